@@ -1,0 +1,537 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE (the parity oracle), NOT product code.
+
+A numpy restatement of the reference's CPU algorithm for the hot path
+(16 kHz PCM -> log-mel -> FastConformer encoder -> CTC / TDT greedy decode),
+written from the reference sources (Frikallo/parakeet.cpp @ 40bbd7e, axiom @
+286b305); every function cites the file:line it follows.  It is pinned in
+tests/test_oracle.py against
+
+  * the reference's own known-answer tests that apply at this boundary
+    (tests/test_all.cpp:759-872 CTCDecode.*, :1003-1030 PositionEmbedding.*,
+    :45-129 GroupTimestamps.* / TimestampTypes.*), and
+  * golden vectors produced by the UNMODIFIED reference compiled here
+    (oracle/_ref/libpkref.so, built by oracle/Makefile; generator script
+    tests/golden/make_golden.py), committed under tests/golden/.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
+this module.  The product (parakeet.cpp_b200/) never does.
+
+Numerics: everything is float32 like the reference, except where the reference
+itself uses double (mel filterbank construction, audio.cpp:40-94; convolution
+accumulators, axiom operations.cpp:3074,3252).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+F32 = np.float32
+
+
+# ----------------------------------------------------------------------------
+# Config presets                                     include/parakeet/config.hpp
+# ----------------------------------------------------------------------------
+@dataclass
+class Config:
+    """EncoderConfig + heads (config.hpp:9-75); presets at :77-116."""
+    mel_bins: int = 80
+    sub_channels: int = 256
+    d_model: int = 512
+    n_layers: int = 17
+    n_heads: int = 8
+    ff: int = 2048
+    conv_k: int = 9
+    vocab: int = 1025          # incl. blank = vocab-1
+    pred_hidden: int = 640
+    lstm_layers: int = 1
+    joint_hidden: int = 640
+    durations: tuple = (0, 1, 2, 3, 4)
+    has_ctc: bool = True
+    joint_prefix: str = "tdt_joint_."   # ParakeetTDTCTC (tdt_ctc.cpp:5-9)
+    name: str = "tdt-ctc-110m"
+
+
+def make_110m_config() -> Config:          # config.hpp:77-95
+    return Config()
+
+
+def make_tdt_600m_config() -> Config:      # config.hpp:98-116, tdt.cpp:28-32
+    return Config(mel_bins=128, d_model=1024, n_layers=24, n_heads=8, ff=4096,
+                  vocab=8193, lstm_layers=2, has_ctc=False, joint_prefix="joint_.",
+                  name="tdt-600m")
+
+
+def make_tiny_config() -> Config:
+    """Not a reference preset: a small shape for fast unit tests only."""
+    return Config(mel_bins=80, sub_channels=32, d_model=64, n_layers=2, n_heads=4, ff=128,
+                  vocab=33, pred_hidden=48, joint_hidden=40, name="tiny")
+
+
+# ----------------------------------------------------------------------------
+# Mel front end                                                  src/audio.cpp
+# ----------------------------------------------------------------------------
+def _hz_to_mel(f: float) -> float:          # audio.cpp:25-30
+    return f / (200.0 / 3.0) if f < 1000.0 else 15.0 + math.log(f / 1000.0) / 0.06875177742094912
+
+
+def _mel_to_hz(m: float) -> float:          # audio.cpp:32-37
+    return m * (200.0 / 3.0) if m < 15.0 else 1000.0 * math.exp((m - 15.0) * 0.06875177742094912)
+
+
+def mel_filterbank(n_freqs: int = 257, n_mels: int = 80, sr: float = 16000.0,
+                   f_min: float = 0.0, f_max: float = 8000.0) -> np.ndarray:
+    """Slaney filterbank, built in double, stored fp32, (n_freqs, n_mels). audio.cpp:40-94."""
+    mel_min, mel_max = _hz_to_mel(f_min), _hz_to_mel(f_max)
+    mel_pts = [mel_min + i * (mel_max - mel_min) / (n_mels + 1) for i in range(n_mels + 2)]
+    hz = [_mel_to_hz(m) for m in mel_pts]
+    freqs = [i * float(sr) / (2.0 * (n_freqs - 1)) for i in range(n_freqs)]
+    fb = np.zeros((n_freqs, n_mels), dtype=F32)
+    for m in range(n_mels):
+        left, center, right = hz[m], hz[m + 1], hz[m + 2]
+        enorm = 2.0 / (right - left)
+        for f in range(n_freqs):
+            fr = freqs[f]
+            val = 0.0
+            if left <= fr <= center and center > left:
+                val = (fr - left) / (center - left)
+            elif center < fr <= right and right > center:
+                val = (right - fr) / (right - center)
+            fb[f, m] = F32(val * enorm)
+    return fb
+
+
+def hann_window(M: int) -> np.ndarray:
+    """Symmetric (periodic=False) Hann, double formula cast to fp32. axiom fft.cpp:1117-1142."""
+    N = max(M - 1, 1)
+    i = np.arange(M, dtype=np.float64)
+    return (0.5 - 0.5 * np.cos(2.0 * math.pi * i / N)).astype(F32)
+
+
+def n_mel_frames(n_samples: int, hop: int = 160) -> int:
+    """center=True STFT: 1 + floor(N / hop) (fft.cpp:1505-1524 with pad n_fft/2 each side)."""
+    return 1 + n_samples // hop
+
+
+def log_mel_unnormalised(pcm: np.ndarray, n_mels: int = 80) -> np.ndarray:
+    """Steps 1-5 of preprocess_audio (audio.cpp:100-136) -> (n_mels, n_frames) fp32."""
+    n_fft, win_len, hop = 512, 400, 160
+    x = np.asarray(pcm, dtype=F32)
+    pre = np.empty_like(x)                                   # :104-114
+    pre[0] = x[0]
+    pre[1:] = x[1:] - F32(0.97) * x[:-1]
+    pad = n_fft // 2                                         # fft.cpp:1505-1513 reflect
+    sig = np.pad(pre, (pad, pad), mode="reflect")
+    win = np.zeros(n_fft, dtype=F32)                         # fft.cpp:1539-1547 centred pad
+    lp = (n_fft - win_len) // 2
+    win[lp:lp + win_len] = hann_window(win_len)
+    n_frames = (len(sig) - n_fft) // hop + 1
+    idx = np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]
+    frames = sig[idx] * win[None, :]                         # fft.cpp:1561-1575
+    spec = np.fft.rfft(frames.astype(F32), n=n_fft, axis=1).astype(np.complex64)
+    mag = np.abs(spec).astype(F32)                           # audio.cpp:123-124
+    power = (mag * mag).T                                    # (257, n_frames)
+    fb = mel_filterbank(n_fft // 2 + 1, n_mels)              # :126-130
+    mel = fb.T.astype(F32) @ power                           # :132
+    return np.log(mel + F32(5.96046448e-8)).astype(F32)      # :135-136
+
+
+def preprocess_audio(pcm: np.ndarray, n_mels: int = 80) -> np.ndarray:
+    """preprocess_audio (audio.cpp:100-158) -> (n_frames, n_mels) fp32."""
+    lm = log_mel_unnormalised(pcm, n_mels)
+    n = lm.shape[1]
+    mean = lm.mean(axis=1, keepdims=True, dtype=F32)         # :142
+    c = lm - mean
+    var = (c * c).sum(axis=1, keepdims=True, dtype=F32) / F32(n - 1)   # :146-147 unbiased
+    feat = c / (np.sqrt(var) + F32(1e-5))                    # :148 eps outside sqrt
+    return np.ascontiguousarray(feat.T.astype(F32))          # :156
+
+
+# ----------------------------------------------------------------------------
+# axiom primitives                       third_party/axiom/src/tensor/operations.cpp
+# ----------------------------------------------------------------------------
+def linear(x, w, b=None):
+    """nn::Linear: x W^T + b, W = (out, in). axiom linear.cpp:15-27."""
+    y = x.astype(F32) @ w.T.astype(F32)
+    return y + b if b is not None else y
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    """Biased variance, eps inside sqrt. operations.cpp:1796-1809."""
+    mu = x.mean(axis=-1, keepdims=True, dtype=F32)
+    c = x - mu
+    var = (c * c).mean(axis=-1, keepdims=True, dtype=F32)
+    return (c / np.sqrt(var + F32(eps)) * w + b).astype(F32)
+
+
+def sigmoid(x):
+    return (F32(1) / (F32(1) + np.exp(-x.astype(F32)))).astype(F32)
+
+
+def silu(x):
+    return (x * sigmoid(x)).astype(F32)
+
+
+def softmax(x, axis=-1):
+    """Max-subtracted softmax. cpu_operations.cpp:3101-3231."""
+    m = x.max(axis=axis, keepdims=True)
+    e = np.exp((x - m).astype(F32))
+    return (e / e.sum(axis=axis, keepdims=True, dtype=F32)).astype(F32)
+
+
+def log_softmax(x, axis=-1):
+    m = x.max(axis=axis, keepdims=True)
+    s = (x - m).astype(F32)
+    return (s - np.log(np.exp(s).sum(axis=axis, keepdims=True, dtype=F32))).astype(F32)
+
+
+def conv_out_len(L: int, k: int = 3, s: int = 2, p: int = 1) -> int:
+    """operations.cpp:3191-3196: floor((L + 2p - k) / s) + 1."""
+    return (L + 2 * p - k) // s + 1
+
+
+def conv2d(x, w, b, stride, pad, groups=1):
+    """Cross-correlation, zero pad, fp64 accumulate. operations.cpp:3133-3326.
+    x (C_in, H, W), w (C_out, C_in/g, kh, kw) -> (C_out, H', W')."""
+    C_in, H, W = x.shape
+    C_out, cg, kh, kw = w.shape
+    Ho, Wo = conv_out_len(H, kh, stride, pad), conv_out_len(W, kw, stride, pad)
+    xp = np.zeros((C_in, H + 2 * pad, W + 2 * pad), dtype=np.float64)
+    xp[:, pad:pad + H, pad:pad + W] = x
+    out = np.zeros((C_out, Ho, Wo), dtype=np.float64)
+    opg = C_out // groups
+    for g in range(groups):
+        xs = xp[g * cg:(g + 1) * cg]
+        ws = w[g * opg:(g + 1) * opg].astype(np.float64)
+        for i in range(kh):
+            for j in range(kw):
+                patch = xs[:, i:i + stride * Ho:stride, j:j + stride * Wo:stride]   # (cg, Ho, Wo)
+                out[g * opg:(g + 1) * opg] += np.einsum("oc,chw->ohw", ws[:, :, i, j], patch)
+    if b is not None:
+        out += b.astype(np.float64)[:, None, None]
+    return out.astype(F32)
+
+
+def depthwise_conv2d(x, w, b, stride, pad):
+    """groups = C specialisation of conv2d (same arithmetic, vectorised)."""
+    C, H, W = x.shape
+    kh, kw = w.shape[2], w.shape[3]
+    Ho, Wo = conv_out_len(H, kh, stride, pad), conv_out_len(W, kw, stride, pad)
+    xp = np.zeros((C, H + 2 * pad, W + 2 * pad), dtype=np.float64)
+    xp[:, pad:pad + H, pad:pad + W] = x
+    out = np.zeros((C, Ho, Wo), dtype=np.float64)
+    for i in range(kh):
+        for j in range(kw):
+            out += w[:, 0, i, j].astype(np.float64)[:, None, None] * \
+                xp[:, i:i + stride * Ho:stride, j:j + stride * Wo:stride]
+    out += b.astype(np.float64)[:, None, None]
+    return out.astype(F32)
+
+
+def depthwise_conv1d(x, w, b, pad):
+    """conv1d groups=C, stride 1. operations.cpp:2960-3127. x (C, T), w (C,1,k)."""
+    C, T = x.shape
+    k = w.shape[2]
+    xp = np.zeros((C, T + 2 * pad), dtype=np.float64)
+    xp[:, pad:pad + T] = x
+    out = np.zeros((C, T + 2 * pad - k + 1), dtype=np.float64)
+    for j in range(k):
+        out += w[:, 0, j].astype(np.float64)[:, None] * xp[:, j:j + out.shape[1]]
+    out += b.astype(np.float64)[:, None]
+    return out.astype(F32)
+
+
+# ----------------------------------------------------------------------------
+# FastConformer encoder                                         src/encoder.cpp
+# ----------------------------------------------------------------------------
+def sinusoidal_position_embedding(seq_len: int, d_model: int) -> np.ndarray:
+    """encoder.cpp:9-30: row r <-> relative position seq_len-1-r; fp32 arithmetic."""
+    total = 2 * seq_len - 1
+    pe = np.zeros((total, d_model), dtype=F32)
+    pos = (F32(seq_len - 1) - np.arange(total, dtype=F32)).astype(F32)
+    i = np.arange(0, d_model, 2, dtype=F32)
+    div = np.exp(i * (F32(-math.log(F32(10000.0))) / F32(d_model))).astype(F32)
+    ang = (pos[:, None] * div[None, :]).astype(F32)
+    pe[:, 0::2] = np.sin(ang)
+    pe[:, 1::2] = np.cos(ang)[:, : d_model // 2]
+    return pe
+
+
+def conv_subsampling(W, feats, cfg: Config, return_stages=False):
+    """ConvSubsampling::forward, encoder.cpp:219-241 (ReLU, not SiLU). feats (T, mel)."""
+    p = "encoder_.subsampling_."
+    x = feats[None, :, :]                                             # (1, T, F)
+    x = np.maximum(conv2d(x, W[p + "conv1_.weight"], W[p + "conv1_.bias"], 2, 1), 0)
+    s1 = x
+    x = depthwise_conv2d(x, W[p + "dw1_.weight"], W[p + "dw1_.bias"], 2, 1)
+    d1 = x
+    x = np.maximum(conv2d(x, W[p + "conv2_.weight"], W[p + "conv2_.bias"], 1, 0), 0)
+    x = depthwise_conv2d(x, W[p + "dw2_.weight"], W[p + "dw2_.bias"], 2, 1)
+    x = np.maximum(conv2d(x, W[p + "conv3_.weight"], W[p + "conv3_.bias"], 1, 0), 0)
+    C, T, Fq = x.shape
+    flat = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(T, C * Fq)   # :236-238
+    out = linear(flat, W[p + "proj_.weight"], W[p + "proj_.bias"]).astype(F32)
+    if return_stages:
+        return out, dict(conv1=s1, dw1=d1)
+    return out
+
+
+def feed_forward(W, p, x):
+    """FeedForward::forward, encoder.cpp:39-46."""
+    h = layer_norm(x, W[p + "norm_.weight"], W[p + "norm_.bias"])
+    h = silu(linear(h, W[p + "fc1_.weight"], W[p + "fc1_.bias"]))
+    h = linear(h, W[p + "fc2_.weight"], W[p + "fc2_.bias"])
+    return (x + h * F32(0.5)).astype(F32)
+
+
+def rel_shift(x):
+    """ConformerAttention::rel_shift, encoder.cpp:85-109, literally. x (H, T, 2T-1)."""
+    H, T, P = x.shape
+    padded = np.concatenate([np.zeros((H, T, 1), dtype=x.dtype), x], axis=2)   # pad left 1
+    padded = padded.reshape(H, P + 1, T)[:, 1:, :]
+    return padded.reshape(H, T, P)[:, :, :T]
+
+
+def conformer_attention(W, p, x, pos_emb, cfg: Config):
+    """ConformerAttention::forward / rel_position_attention, encoder.cpp:111-186."""
+    T, d = x.shape
+    H = cfg.n_heads
+    hd = d // H
+    h = layer_norm(x, W[p + "norm_.weight"], W[p + "norm_.bias"])
+    q = linear(h, W[p + "mha_.q_proj.weight"], W[p + "mha_.q_proj.bias"]).reshape(T, H, hd).transpose(1, 0, 2)
+    k = linear(h, W[p + "mha_.k_proj.weight"], W[p + "mha_.k_proj.bias"]).reshape(T, H, hd).transpose(1, 0, 2)
+    v = linear(h, W[p + "mha_.v_proj.weight"], W[p + "mha_.v_proj.bias"]).reshape(T, H, hd).transpose(1, 0, 2)
+    u = W[p + "pos_bias_u_"].reshape(H, 1, hd)
+    vb = W[p + "pos_bias_v_"].reshape(H, 1, hd)
+    ac = (q + u) @ k.transpose(0, 2, 1)                                  # (H, T, T)
+    pp = linear(pos_emb, W[p + "pos_proj_.weight"]).reshape(2 * T - 1, H, hd).transpose(1, 0, 2)
+    bd = rel_shift((q + vb) @ pp.transpose(0, 2, 1))                     # (H, T, T)
+    scores = ((ac + bd) * F32(1.0 / math.sqrt(hd))).astype(F32)
+    a = softmax(scores, axis=-1)
+    o = (a @ v).transpose(1, 0, 2).reshape(T, d)
+    o = linear(o, W[p + "mha_.out_proj.weight"], W[p + "mha_.out_proj.bias"])
+    return (x + o).astype(F32)
+
+
+def conformer_conv(W, p, x, cfg: Config):
+    """ConformerConvModule::forward, encoder.cpp:59-75; BN eval axiom normalization.cpp:48-104."""
+    d = x.shape[1]
+    h = layer_norm(x, W[p + "norm_.weight"], W[p + "norm_.bias"])
+    h = linear(h, W[p + "pointwise_conv1_.weight"][:, :, 0], W[p + "pointwise_conv1_.bias"])  # (T, 2d)
+    h = (h[:, :d] * sigmoid(h[:, d:])).astype(F32)                       # GLU operations.cpp:1450-1476
+    h = depthwise_conv1d(h.T, W[p + "depthwise_conv_.weight"], W[p + "depthwise_conv_.bias"],
+                         (cfg.conv_k - 1) // 2).T                        # (T, d)
+    mean, var = W[p + "batch_norm_.running_mean"], W[p + "batch_norm_.running_var"]
+    h = ((h - mean) / np.sqrt(var + F32(1e-5)) * W[p + "batch_norm_.weight"] + W[p + "batch_norm_.bias"]).astype(F32)
+    h = silu(h)
+    h = linear(h, W[p + "pointwise_conv2_.weight"][:, :, 0], W[p + "pointwise_conv2_.bias"])
+    return (x + h).astype(F32)
+
+
+def conformer_block(W, i, x, pos_emb, cfg: Config):
+    """ConformerBlock::forward, encoder.cpp:196-204."""
+    p = f"encoder_.layers_.{i}."
+    x = feed_forward(W, p + "ffn1_.", x)
+    x = conformer_attention(W, p + "attn_.", x, pos_emb, cfg)
+    x = conformer_conv(W, p + "conv_.", x, cfg)
+    x = feed_forward(W, p + "ffn2_.", x)
+    return layer_norm(x, W[p + "final_norm_.weight"], W[p + "final_norm_.bias"])
+
+
+def encoder_forward(W, feats, cfg: Config, return_layers=False):
+    """FastConformerEncoder::forward, encoder.cpp:253-271. feats (n_frames, mel) -> (T', d)."""
+    x = conv_subsampling(W, feats, cfg)
+    pos = sinusoidal_position_embedding(x.shape[0], x.shape[1])
+    layers = []
+    sub = x
+    for i in range(cfg.n_layers):
+        x = conformer_block(W, i, x, pos, cfg)
+        if return_layers:
+            layers.append(x)
+    if return_layers:
+        return x, sub, np.stack(layers)
+    return x
+
+
+def encoder_len(n_frames: int) -> int:
+    """Three stride-2 k3 p1 stages (encoder.cpp:208-217)."""
+    t = n_frames
+    for _ in range(3):
+        t = conv_out_len(t)
+    return t
+
+
+# ----------------------------------------------------------------------------
+# CTC head + greedy                                               src/ctc.cpp
+# ----------------------------------------------------------------------------
+def ctc_log_probs(W, enc):
+    """CTCDecoder::forward, ctc.cpp:12-25 (k=1 Conv1d + log_softmax)."""
+    w = W["ctc_decoder_.proj_.weight"][:, :, 0]
+    return log_softmax(linear(enc, w, W["ctc_decoder_.proj_.bias"]), axis=-1)
+
+
+def first_argmax(row) -> int:
+    """Strict '>' scan: first maximum wins. ctc.cpp:59-66."""
+    return int(np.argmax(row))     # np.argmax returns the first occurrence
+
+
+def ctc_greedy_decode(lp, blank=1024):
+    """ctc_greedy_decode, ctc.cpp:40-75. lp (T, V) -> list[int]."""
+    out, prev = [], -1
+    for t in range(lp.shape[0]):
+        best = first_argmax(lp[t])
+        if best != blank and best != prev:
+            out.append(best)
+        prev = best
+    return out
+
+
+def ctc_greedy_decode_with_timestamps(lp, blank=1024):
+    """ctc.cpp:79-127 -> list of (id, start_frame, end_frame, confidence)."""
+    toks, prev = [], -1
+    T = lp.shape[0]
+    for t in range(T):
+        best = first_argmax(lp[t])
+        if best != prev:
+            if prev != -1 and prev != blank and toks:
+                toks[-1][2] = t - 1
+            if best != blank:
+                toks.append([best, t, t, float(np.exp(F32(lp[t, best])))])
+        prev = best
+    if toks:
+        toks[-1][2] = T - 1
+    return [tuple(t) for t in toks]
+
+
+# ----------------------------------------------------------------------------
+# Prediction net + TDT joint + greedy      src/rnnt.cpp src/lstm.cpp src/tdt.cpp
+# ----------------------------------------------------------------------------
+def lstm_cell(W, p, x, h, c):
+    """LSTMCell::forward, lstm.cpp:11-29: gates i,f,g,o; one merged bias."""
+    g = linear(x, W[p + "input_proj_.weight"], W[p + "input_proj_.bias"]) + linear(h, W[p + "hidden_proj_.weight"])
+    H = h.shape[-1]
+    i, f, gg, o = g[..., :H], g[..., H:2 * H], g[..., 2 * H:3 * H], g[..., 3 * H:]
+    c2 = (sigmoid(f) * c + sigmoid(i) * np.tanh(gg)).astype(F32)
+    h2 = (sigmoid(o) * np.tanh(c2)).astype(F32)
+    return h2, c2
+
+
+def prediction_step(W, token, states, cfg: Config):
+    """RNNTPrediction::step rnnt.cpp:22-28 -> LSTM::step lstm.cpp:40-49."""
+    x = W["prediction_.embed_.weight"][token]
+    new = []
+    for l in range(cfg.lstm_layers):
+        h, c = lstm_cell(W, f"prediction_.lstm_.cells_.{l}.", x, *states[l])
+        new.append((h, c))
+        x = h
+    return x, new
+
+
+def tdt_joint(W, enc_t, pred, cfg: Config):
+    """TDTJoint::forward, tdt.cpp:15-24 (pred_proj_ has no bias)."""
+    p = cfg.joint_prefix
+    z = linear(enc_t, W[p + "enc_proj_.weight"], W[p + "enc_proj_.bias"]) + linear(pred, W[p + "pred_proj_.weight"])
+    z = np.maximum(z, 0).astype(F32)
+    lab = log_softmax(linear(z, W[p + "label_proj_.weight"], W[p + "label_proj_.bias"]))
+    dur = log_softmax(linear(z, W[p + "duration_proj_.weight"], W[p + "duration_proj_.bias"]))
+    return lab, dur
+
+
+def tdt_greedy_decode(W, enc, cfg: Config, max_symbols=10, with_timestamps=False, max_steps=100000):
+    """tdt_greedy_decode(_with_timestamps), tdt.cpp:36-110 / :122-201, quirks and all:
+    state revert on blank, blank advances max(skip,1), no forced advance after
+    max_symbols zero-duration emissions (the frame is re-entered)."""
+    T = enc.shape[0]
+    blank = cfg.vocab - 1
+    H = cfg.pred_hidden
+    states = [(np.zeros(H, F32), np.zeros(H, F32)) for _ in range(cfg.lstm_layers)]
+    token, t, out, steps = blank, 0, [], 0
+    while t < T:
+        for _sym in range(max_symbols):
+            steps += 1
+            if steps > max_steps:
+                raise RuntimeError("tdt_greedy_decode: livelock (reference quirk iv)")
+            saved = states
+            pred, states = prediction_step(W, token, states, cfg)
+            lab, dur = tdt_joint(W, enc[t], pred, cfg)
+            tok = first_argmax(lab)
+            di = first_argmax(dur)
+            skip = cfg.durations[di] if di < len(cfg.durations) else 1
+            if tok == blank:
+                states = saved
+                t += max(skip, 1)
+                break
+            if with_timestamps:
+                out.append((tok, t, min(t + max(skip, 1) - 1, T - 1), float(np.exp(F32(lab[tok])))))
+            else:
+                out.append(tok)
+            token = tok
+            if skip > 0:
+                t += skip
+                break
+    return out
+
+
+# ----------------------------------------------------------------------------
+# Tokenizer + word timestamps (host-side)    src/vocab.cpp src/timestamp.cpp
+# ----------------------------------------------------------------------------
+SP_MARK = "▁"
+
+
+def load_vocab(path):
+    """Tokenizer::load, vocab.cpp:10-27 (piece<TAB>score lines)."""
+    pieces = []
+    with open(path, "rb") as f:
+        for raw in f.read().split(b"\n"):
+            line = raw.decode("utf-8", errors="surrogateescape")
+            if "\t" in line:
+                pieces.append(line.split("\t")[0])
+            elif line:
+                pieces.append(line)
+    return pieces
+
+
+def detokenize(ids, pieces):
+    """Tokenizer::decode, vocab.cpp:29-64."""
+    s = "".join(pieces[i] if 0 <= i < len(pieces) else f"[{i}]" for i in ids)
+    s = s.replace(SP_MARK, " ")
+    return s[1:] if s.startswith(" ") else s
+
+
+def group_timestamps(tokens, pieces):
+    """group_timestamps(Words), timestamp.cpp:24-75; frame = 0.08 s (timestamp.hpp:31-35).
+    tokens: iterable of (id, start, end, conf) -> list of (word, start_s, end_s, conf)."""
+    tokens = list(tokens)
+    if not tokens:
+        return []
+    words, cur = [], ""
+    ws, we, wc = tokens[0][1], tokens[0][2], 1.0
+    f2s = lambda fr: float(F32(fr) * F32(0.08))
+    for (tid, st, en, cf) in tokens:
+        if tid < 0 or tid >= len(pieces):
+            continue
+        piece = pieces[tid]
+        new_word = piece.startswith(SP_MARK)
+        if new_word and cur:
+            words.append((cur, f2s(ws), f2s(we), wc))
+            cur, ws, wc = "", st, 1.0
+        cur += piece[1:] if new_word else piece
+        we = en
+        wc = min(wc, cf)
+    if cur:
+        words.append((cur, f2s(ws), f2s(we), wc))
+    return words
+
+
+# ----------------------------------------------------------------------------
+# Whole path (Transcriber::transcribe, transcribe.hpp:99-179), one utterance
+# ----------------------------------------------------------------------------
+def transcribe(W, pcm, cfg: Config, decoder="ctc", timestamps=False):
+    feats = preprocess_audio(pcm, cfg.mel_bins)
+    enc = encoder_forward(W, feats, cfg)
+    if decoder == "ctc":
+        lp = ctc_log_probs(W, enc)
+        return ctc_greedy_decode_with_timestamps(lp, cfg.vocab - 1) if timestamps \
+            else ctc_greedy_decode(lp, cfg.vocab - 1)
+    return tdt_greedy_decode(W, enc, cfg, with_timestamps=timestamps)

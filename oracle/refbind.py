@@ -1,0 +1,148 @@
+"""oracle/refbind.py -- TEST INFRASTRUCTURE: ctypes binding of oracle/_ref/libpkref.so,
+the UNMODIFIED reference compiled from /root/reference by oracle/Makefile plus the
+C-ABI harness oracle/ref_harness.cpp.  Importers: tests/, tests/golden/make_golden.py,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libpkref.so")
+_f = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_d = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.pkref_last_error.restype = C.c_char_p
+        L.pkref_load.restype = C.c_void_p
+        L.pkref_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.pkref_free.argtypes = [C.c_void_p]
+        L.pkref_mel.argtypes = [_f, C.c_int64, C.c_int, _f]
+        L.pkref_posemb.argtypes = [C.c_int, C.c_int, _f]
+        L.pkref_encode.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _f]
+        L.pkref_encode_layers.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _f, _f]
+        L.pkref_ctc_logprobs.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, _f]
+        L.pkref_ctc_greedy.argtypes = [_f, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i, _i, _i, _f, _i]
+        L.pkref_tdt_greedy.argtypes = [C.c_void_p, _f, C.c_int, C.c_int, C.c_int, C.c_int, _i, _i, _i, _f]
+        L.pkref_detok.argtypes = [C.c_void_p, _i, C.c_int, C.c_char_p, C.c_int]
+        L.pkref_group_words.argtypes = [C.c_void_p, _i, _i, _i, _f, C.c_int, C.c_char_p, C.c_int, _f, _f, _f]
+        L.pkref_transcribe.argtypes = [C.c_void_p, _f, C.c_int64, C.c_int, C.c_int, _i, _d]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc is None or rc < 0:
+        raise RuntimeError("reference: " + lib().pkref_last_error().decode())
+    return rc
+
+
+def mel(pcm, n_mels=80):
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    out = np.zeros((1 + len(pcm) // 160 + 2, n_mels), np.float32)
+    n = _check(lib().pkref_mel(pcm, len(pcm), n_mels, out))
+    return out[:n].copy()
+
+
+def posemb(T, d):
+    out = np.zeros((2 * T - 1, d), np.float32)
+    _check(lib().pkref_posemb(T, d, out))
+    return out
+
+
+def ctc_greedy(lp, blank, with_ts=False):
+    lp = np.ascontiguousarray(lp, np.float32)
+    if lp.ndim == 2:
+        lp = lp[None]
+    B, T, V = lp.shape
+    ids = np.zeros((B, T), np.int32); st = np.zeros((B, T), np.int32); en = np.zeros((B, T), np.int32)
+    cf = np.zeros((B, T), np.float32); lens = np.zeros(B, np.int32)
+    _check(lib().pkref_ctc_greedy(lp, B, T, V, blank, int(with_ts), ids, st, en, cf, lens))
+    res = []
+    for b in range(B):
+        n = lens[b]
+        if with_ts:
+            res.append([(int(ids[b, i]), int(st[b, i]), int(en[b, i]), float(cf[b, i])) for i in range(n)])
+        else:
+            res.append([int(x) for x in ids[b, :n]])
+    return res
+
+
+class RefModel:
+    """Reference ParakeetTDTCTC (preset 0) / ParakeetTDT (preset 1) + Tokenizer."""
+
+    def __init__(self, weights_path, vocab_path="", preset=0):
+        self.h = lib().pkref_load(weights_path.encode(), (vocab_path or "").encode(), preset)
+        if not self.h:
+            raise RuntimeError("reference: " + lib().pkref_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().pkref_free(self.h)
+            self.h = None
+
+    def encode(self, feats, d_model):
+        feats = np.ascontiguousarray(feats, np.float32)
+        out = np.zeros((feats.shape[0], d_model), np.float32)
+        T = _check(lib().pkref_encode(self.h, feats, feats.shape[0], feats.shape[1], out))
+        return out[:T].copy()
+
+    def encode_layers(self, feats, d_model, n_layers, T):
+        feats = np.ascontiguousarray(feats, np.float32)
+        sub = np.zeros((T, d_model), np.float32)
+        lay = np.zeros((n_layers, T, d_model), np.float32)
+        _check(lib().pkref_encode_layers(self.h, feats, feats.shape[0], feats.shape[1], sub, lay))
+        return sub, lay
+
+    def ctc_logprobs(self, enc, vocab):
+        enc = np.ascontiguousarray(enc, np.float32)
+        out = np.zeros((enc.shape[0], vocab), np.float32)
+        _check(lib().pkref_ctc_logprobs(self.h, enc, enc.shape[0], enc.shape[1], out))
+        return out
+
+    def tdt_greedy(self, enc, with_ts=False, cap=8192):
+        enc = np.ascontiguousarray(enc, np.float32)
+        ids = np.zeros(cap, np.int32); st = np.zeros(cap, np.int32); en = np.zeros(cap, np.int32)
+        cf = np.zeros(cap, np.float32)
+        n = _check(lib().pkref_tdt_greedy(self.h, enc, enc.shape[0], enc.shape[1], int(with_ts), cap, ids, st, en, cf))
+        if with_ts:
+            return [(int(ids[i]), int(st[i]), int(en[i]), float(cf[i])) for i in range(n)]
+        return [int(x) for x in ids[:n]]
+
+    def detok(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().pkref_detok(self.h, ids, len(ids), buf, len(buf)))
+        return buf.value.decode("utf-8")
+
+    def group_words(self, toks):
+        n = len(toks)
+        ids = np.array([t[0] for t in toks], np.int32); st = np.array([t[1] for t in toks], np.int32)
+        en = np.array([t[2] for t in toks], np.int32); cf = np.array([t[3] for t in toks], np.float32)
+        buf = C.create_string_buffer(1 << 16)
+        ws = np.zeros(max(n, 1), np.float32); we = np.zeros(max(n, 1), np.float32); wc = np.zeros(max(n, 1), np.float32)
+        k = _check(lib().pkref_group_words(self.h, ids, st, en, cf, n, buf, len(buf), ws, we, wc))
+        words = buf.value.decode("utf-8").split("\n")[:k]
+        return [(words[i], float(ws[i]), float(we[i]), float(wc[i])) for i in range(k)]
+
+    def transcribe(self, pcm, decoder="ctc", cap=8192):
+        """Reference Transcriber::transcribe path, stage-timed -> (ids, [pre_ms, enc_ms, dec_ms])."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        ids = np.zeros(cap, np.int32); ms = np.zeros(3, np.float64)
+        n = _check(lib().pkref_transcribe(self.h, pcm, len(pcm), 0 if decoder == "ctc" else 1, cap, ids, ms))
+        return [int(x) for x in ids[:n]], ms.tolist()
