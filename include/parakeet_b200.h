@@ -1,0 +1,170 @@
+/* parakeet_b200.h -- the drop-in boundary: a flat C-ABI over the B200-native hot path
+ *
+ *     16 kHz PCM -> log-mel -> FastConformer encoder -> CTC / TDT greedy decode
+ *
+ * The reference (Frikallo/parakeet.cpp @ 40bbd7e) has no C API ("C API" is an
+ * unchecked roadmap item, README.md:518); its boundary for this path is C++:
+ * parakeet::Transcriber (include/parakeet/transcribe.hpp:55-190) calling
+ * preprocess_audio (src/audio.cpp:100), FastConformerEncoder::forward
+ * (src/encoder.cpp:253), CTCDecoder::forward + ctc_greedy_decode (src/ctc.cpp:12,40)
+ * and tdt_greedy_decode (src/tdt.cpp:36).  Each entry point below names the
+ * reference function(s) it replaces.  include/parakeet/transcribe.hpp in this
+ * repository is the header-only C++ shim with the reference's class signatures
+ * on top of this ABI; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns pk_status and
+ * never throws; the opaque engine owns all device memory, its CUDA stream and
+ * graphs; the caller owns host buffers.  One engine per device; calls on one
+ * engine are serialised on its stream (thread-compatible, not thread-safe).
+ * There is no CPU fallback: without a CUDA device pk_engine_create fails.
+ */
+#ifndef PARAKEET_B200_H
+#define PARAKEET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PK_OK = 0,
+    PK_ERR_INVALID = 1,   /* bad argument / shape */
+    PK_ERR_IO = 2,        /* cannot open / parse weights */
+    PK_ERR_CUDA = 3,      /* CUDA runtime / driver error */
+    PK_ERR_MISSING = 4,   /* tensor missing from the state dict */
+    PK_ERR_CAPACITY = 5,  /* batch exceeds the engine's configured capacity */
+    PK_ERR_NCCL = 6
+} pk_status;
+
+typedef enum { PK_DECODER_CTC = 0, PK_DECODER_TDT = 1 } pk_decoder;
+
+/* GEMM arithmetic.  PK_MATH_BF16X3 (default): tcgen05 kind::f16 MMAs on bf16
+ * hi/lo operand splits, 3 MMAs per product (hi*hi + hi*lo + lo*hi), fp32
+ * accumulation in TMEM: ~1e-5 relative, the parity mode.  PK_MATH_BF16X1: hi*hi only
+ * (fast, ~4e-3).  PK_MATH_FP32: CUDA-core fp32 GEMM (bring-up / checker). */
+typedef enum { PK_MATH_BF16X3 = 0, PK_MATH_BF16X1 = 1, PK_MATH_FP32 = 2 } pk_math;
+
+/* Mirrors EncoderConfig / PredictionConfig / JointConfig / TDTCTCConfig
+ * (include/parakeet/config.hpp:9-75).  pk_config_110m / pk_config_tdt_600m fill
+ * it with make_110m_config (:77-95) / make_tdt_600m_config (:98-116). */
+typedef struct {
+    int32_t mel_bins;          /* 80 | 128 */
+    int32_t sub_channels;      /* 256 */
+    int32_t d_model;           /* 512 | 1024 */
+    int32_t n_layers;          /* 17 | 24 */
+    int32_t n_heads;           /* 8 */
+    int32_t ff;                /* 2048 | 4096 */
+    int32_t conv_kernel;       /* 9 */
+    int32_t vocab;             /* 1025 | 8193, blank = vocab-1 */
+    int32_t pred_hidden;       /* 640 */
+    int32_t lstm_layers;       /* 1 | 2 */
+    int32_t joint_hidden;      /* 640 */
+    int32_t n_durations;       /* 5 */
+    int32_t durations[8];      /* {0,1,2,3,4} */
+    int32_t has_ctc;           /* ParakeetTDTCTC: 1, ParakeetTDT: 0 */
+    int32_t joint_prefix_tdt;  /* 1: keys "tdt_joint_." (tdt_ctc.cpp:5-9); 0: "joint_." (tdt.cpp:28-32) */
+    int32_t max_symbols;       /* max_symbols_per_step, 10 (tdt.hpp) */
+    /* engine capacity (not model shape) */
+    int32_t max_batch;         /* utterances per call */
+    int32_t max_samples;       /* per utterance */
+    int32_t math;              /* pk_math */
+} pk_config;
+
+typedef struct pk_engine pk_engine;
+
+void pk_config_110m(pk_config *cfg);      /* config.hpp:77-95  */
+void pk_config_tdt_600m(pk_config *cfg);  /* config.hpp:98-116 */
+
+/* Replaces Transcriber::Transcriber + to_gpu (transcribe.hpp:59-71):
+ * safetensors::load (axiom io_safetensors.cpp:123-160) + load_state_dict(strict=false)
+ * (axiom module.cpp:24-38) + Module::to(GPU).  Missing tensors for modules on the
+ * path are an error (PK_ERR_MISSING); extra tensors are ignored. */
+pk_status pk_engine_create(const pk_config *cfg, const char *safetensors_path, int device,
+                           pk_engine **out);
+void pk_engine_destroy(pk_engine *e);
+/* Last error text of this engine (or of the failed create when e == NULL). */
+const char *pk_last_error(const pk_engine *e);
+
+/* Shape helpers (operations.cpp:3191-3196 output-length formula). */
+int32_t pk_mel_frames(int64_t n_samples);           /* 1 + n/160                       */
+int32_t pk_encoder_frames(int32_t n_mel_frames);    /* three stride-2 k3 p1 stages     */
+
+/* Replaces preprocess_audio (src/audio.cpp:100-158) for a batch of utterances.
+ * pcm: host fp32, utterance i = pcm[offsets[i] .. offsets[i+1]).
+ * feats_out: host fp32, packed (sum_i frames_i, mel_bins); n_frames_out[n_utt]. */
+pk_status pk_mel(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt,
+                 float *feats_out, int32_t *n_frames_out);
+
+/* Replaces FastConformerEncoder::forward (src/encoder.cpp:253-271).
+ * feats: host fp32 packed (sum frames_i, mel_bins); enc_out: host fp32 packed
+ * (sum T'_i, d_model); enc_lens_out[n_utt] = T'_i.
+ * Optional debug taps (may be NULL): sub_out packed (sum T'_i, d_model) after
+ * ConvSubsampling; layers_out (n_layers, sum T'_i, d_model) after each block. */
+pk_status pk_encode(pk_engine *e, const float *feats, const int32_t *n_frames, int32_t n_utt,
+                    float *enc_out, int32_t *enc_lens_out, float *sub_out, float *layers_out);
+
+/* Token streams of a batch.  Row i holds len[i] entries of ids/start/end/conf
+ * at stride `cap`.  start/end are encoder frames (0.08 s, timestamp.hpp:31-35),
+ * conf = exp(log-prob) as in ctc.cpp:110 / tdt.cpp:165.  */
+typedef struct {
+    int32_t cap;        /* in: row capacity (>= max tokens per utterance)   */
+    int32_t *ids;       /* [n_utt * cap] */
+    int32_t *start;     /* [n_utt * cap] or NULL */
+    int32_t *end;       /* [n_utt * cap] or NULL */
+    float *conf;        /* [n_utt * cap] or NULL */
+    int32_t *len;       /* [n_utt] */
+} pk_tokens;
+
+/* Decode-only entry points on a host encoder output (packed (sum T_i, d_model)):
+ * CTCDecoder::forward + ctc_greedy_decode(_with_timestamps) (src/ctc.cpp:12-127) and
+ * tdt_greedy_decode(_with_timestamps) (src/tdt.cpp:36-201). */
+pk_status pk_decode(pk_engine *e, const float *enc, const int32_t *enc_lens, int32_t n_utt,
+                    pk_decoder dec, pk_tokens *out);
+
+/* CTC head log-probs (CTCDecoder::forward, src/ctc.cpp:12-25) for inspection:
+ * enc packed (sum T_i, d_model) -> logprobs packed (sum T_i, vocab). */
+pk_status pk_ctc_logprobs(pk_engine *e, const float *enc, int32_t total_frames, float *logprobs_out);
+
+/* The whole path, replacing the body of Transcriber::transcribe
+ * (transcribe.hpp:99-179) for a batch: host PCM in, token streams out.
+ * H2D of the PCM and D2H of the tokens happen inside the call. */
+pk_status pk_transcribe_batch(pk_engine *e, const float *pcm, const int64_t *offsets,
+                              int32_t n_utt, pk_decoder dec, pk_tokens *out);
+
+/* Device-resident variant for throughput measurement: stage PCM once ... */
+pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt);
+/* ... then run the path on the staged batch; tokens stay on the device until
+ * pk_fetch_tokens.  Asynchronous on the engine stream. */
+pk_status pk_run_staged(pk_engine *e, pk_decoder dec);
+pk_status pk_fetch_tokens(pk_engine *e, pk_tokens *out);
+pk_status pk_sync(pk_engine *e);
+
+/* Device token buffer of the last run for the single cross-GPU exchange:
+ * int32 rows [n_utt][1 + cap] = (len, ids...).  The caller (torch.distributed /
+ * NCCL) all-gathers this buffer; see INTEGRATION.md. */
+pk_status pk_token_buffer(pk_engine *e, void **dev_ptr, int32_t *rows, int32_t *row_ints);
+
+/* CUDA stream of the engine (cudaStream_t as void*), for event timing. */
+void *pk_stream(pk_engine *e);
+/* Number of kernel launches issued by the engine since creation (the
+ * `gpu_launches` claim in bench.py). */
+int64_t pk_launch_count(const pk_engine *e);
+
+/* Host-side text helpers (pure C++ host code; no device work):
+ * Tokenizer::load/decode (src/vocab.cpp:10-64), group_timestamps (src/timestamp.cpp:24-75). */
+typedef struct pk_vocab pk_vocab;
+pk_status pk_vocab_load(const char *vocab_path, pk_vocab **out);
+void pk_vocab_free(pk_vocab *v);
+int32_t pk_vocab_size(const pk_vocab *v);
+/* Writes NUL-terminated UTF-8 into buf (truncated to cap-1); returns full length. */
+int32_t pk_detokenize(const pk_vocab *v, const int32_t *ids, int32_t n, char *buf, int32_t cap);
+/* Words are written '\n'-separated into buf; returns the number of words. */
+int32_t pk_group_words(const pk_vocab *v, const int32_t *ids, const int32_t *start,
+                       const int32_t *end, const float *conf, int32_t n, char *buf, int32_t cap,
+                       float *w_start, float *w_end, float *w_conf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAKEET_B200_H */

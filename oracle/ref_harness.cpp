@@ -95,6 +95,40 @@ void *pkref_load(const char *weights_path, const char *vocab_path, int preset) {
     }
 }
 
+// Same as preset 0 (ParakeetTDTCTC) but with explicit dimensions (test-only tiny shapes).
+void *pkref_load_custom(const char *weights_path, const char *vocab_path, int mel, int sub_ch, int d,
+                        int layers, int heads, int ff, int vocab, int pred_hidden, int lstm_layers,
+                        int joint_hidden) {
+    try {
+        auto m = std::make_unique<RefModel>();
+        m->preset = 0;
+        m->weights = axiom::io::safetensors::load(weights_path);
+        auto &c = m->cfg110;
+        c = make_110m_config();
+        c.encoder.mel_bins = mel;
+        c.encoder.subsampling_channels = sub_ch;
+        c.encoder.hidden_size = d;
+        c.encoder.num_layers = layers;
+        c.encoder.num_heads = heads;
+        c.encoder.ffn_intermediate = ff;
+        c.prediction.vocab_size = vocab;
+        c.prediction.pred_hidden = pred_hidden;
+        c.prediction.num_lstm_layers = lstm_layers;
+        c.joint.encoder_hidden = d;
+        c.joint.pred_hidden = pred_hidden;
+        c.joint.joint_hidden = joint_hidden;
+        c.joint.vocab_size = vocab;
+        c.ctc_vocab_size = vocab;
+        m->m110 = std::make_unique<ParakeetTDTCTC>(c);
+        m->m110->load_state_dict(m->weights, "", false);
+        if (vocab_path && vocab_path[0]) m->tok.load(vocab_path);
+        return m.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
 void pkref_free(void *h) { delete static_cast<RefModel *>(h); }
 
 // PCM -> normalised log-mel.  out must hold (1 + n/160) * n_mels floats.

@@ -31,6 +31,8 @@ def lib():
         L.pkref_last_error.restype = C.c_char_p
         L.pkref_load.restype = C.c_void_p
         L.pkref_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.pkref_load_custom.restype = C.c_void_p
+        L.pkref_load_custom.argtypes = [C.c_char_p, C.c_char_p] + [C.c_int] * 10
         L.pkref_free.argtypes = [C.c_void_p]
         L.pkref_mel.argtypes = [_f, C.c_int64, C.c_int, _f]
         L.pkref_posemb.argtypes = [C.c_int, C.c_int, _f]
@@ -86,8 +88,13 @@ def ctc_greedy(lp, blank, with_ts=False):
 class RefModel:
     """Reference ParakeetTDTCTC (preset 0) / ParakeetTDT (preset 1) + Tokenizer."""
 
-    def __init__(self, weights_path, vocab_path="", preset=0):
-        self.h = lib().pkref_load(weights_path.encode(), (vocab_path or "").encode(), preset)
+    def __init__(self, weights_path, vocab_path="", preset=0, cfg=None):
+        if cfg is not None:   # explicit dimensions (oracle.Config), ParakeetTDTCTC layout
+            self.h = lib().pkref_load_custom(weights_path.encode(), (vocab_path or "").encode(), cfg.mel_bins,
+                                             cfg.sub_channels, cfg.d_model, cfg.n_layers, cfg.n_heads, cfg.ff,
+                                             cfg.vocab, cfg.pred_hidden, cfg.lstm_layers, cfg.joint_hidden)
+        else:
+            self.h = lib().pkref_load(weights_path.encode(), (vocab_path or "").encode(), preset)
         if not self.h:
             raise RuntimeError("reference: " + lib().pkref_last_error().decode())
 

@@ -1,0 +1,1004 @@
+// engine.cu -- the engine behind the C-ABI (include/parakeet_b200.h): weight loading and
+// layout, workspace, and the orchestration of the sm_100a kernels for
+//     PCM -> log-mel -> FastConformer encoder -> CTC / TDT greedy decode.
+//
+// Reference call stack being replaced:
+//   Transcriber::Transcriber / to_gpu        include/parakeet/transcribe.hpp:59-71
+//   Transcriber::transcribe                  include/parakeet/transcribe.hpp:99-179
+//   preprocess_audio                         src/audio.cpp:100-158
+//   FastConformerEncoder::forward            src/encoder.cpp:253-271 (and :9-241)
+//   CTCDecoder::forward + ctc_greedy_decode  src/ctc.cpp:12-127
+//   tdt_greedy_decode(_with_timestamps)      src/tdt.cpp:36-201
+//
+// Data layout in HBM: utterances are PACKED, not padded: a batch is one row-major matrix
+// whose rows are (utterance, time[, freq]) and per-utterance prefix offsets say where each
+// utterance starts.  GEMMs run over all rows at once; length-aware kernels (convolutions,
+// attention, decode) use the offsets, so every utterance sees exactly the zero padding /
+// sequence end the batch-1 reference gives it.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/parakeet_b200.h"
+#include "kernels.h"
+#include "safetensors.h"
+
+using namespace pk;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+#define PK_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            return fail(PK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+        }                                                                                     \
+    } while (0)
+
+int conv_len(int L) { return (L - 1) / 2 + 1; }  // k3 s2 p1 (operations.cpp:3191-3196)
+
+// A linear layer's parameters on the device: fp32 master [N][K] + bias, and (tcgen05
+// modes) the bf16 hi/lo split planes of the weight.
+struct GemmWeight {
+    float *w = nullptr;
+    bf16 *hi = nullptr, *lo = nullptr;
+    float *bias = nullptr;
+    int N = 0, K = 0;
+};
+
+struct LayerW {
+    float *ffn_ln_w[2], *ffn_ln_b[2];
+    GemmWeight fc1[2], fc2[2];
+    float *att_ln_w, *att_ln_b;
+    GemmWeight qkv, out;
+    float *pos_u, *pos_v;
+    float *pp;  // [(2*Tmax-1)][d] projected relative-position table
+    float *conv_ln_w, *conv_ln_b;
+    GemmWeight pw1, pw2;
+    float *dw_w, *dw_b;  // BatchNorm folded
+    float *fin_ln_w, *fin_ln_b;
+};
+
+}  // namespace
+
+struct pk_engine {
+    pk_config cfg;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_h2d = nullptr;              // recorded after the staging copies of a batch
+    std::string err;
+    int64_t launches = 0;
+    std::vector<void *> allocs;
+
+    // ---- capacity
+    int Bmax = 0, Fmax = 0, Tmax = 0;          // per-utterance max mel frames / encoder frames
+    int f1n = 0, f2n = 0, f3n = 0;
+    int cap = 0;                               // token capacity per utterance
+
+    // ---- weights
+    MelTables mel_tb{};
+    float *c1_w, *c1_b, *dw1_w, *dw1_b, *dw2_w, *dw2_b;
+    GemmWeight conv2, conv3, proj;
+    std::vector<LayerW> layers;
+    GemmWeight ctc_head;
+    GemmWeight enc_proj;                       // joint enc_proj_ [J][d] + bias
+    float *G0 = nullptr;                       // [V][4P]
+    float *Whh[PK_MAX_LSTM] = {}, *Wih[PK_MAX_LSTM] = {}, *bih[PK_MAX_LSTM] = {};
+    float *Wp = nullptr, *Wout = nullptr, *bout = nullptr;
+
+    // ---- workspace
+    float *d_pcm = nullptr;
+    int64_t *d_pcm_off = nullptr;
+    int32_t *d_frame_off = nullptr, *d_s2_off = nullptr, *d_row_off = nullptr, *d_t2_rows = nullptr;
+    float *logmel = nullptr, *feats = nullptr;
+    ActBuf sub1, sub3, sub4, ln, ffh, ctx, cv;
+    float *sub2 = nullptr, *x = nullptr, *qkv = nullptr, *glu = nullptr, *logits = nullptr, *EP = nullptr;
+    int32_t *best = nullptr;
+    float *bconf = nullptr;
+    int32_t *tok = nullptr, *t_start = nullptr, *t_end = nullptr;
+    float *t_conf = nullptr;
+    // TDT state
+    int Bpad = 0;
+    float *hbuf = nullptr, *cbuf = nullptr, *zbuf = nullptr, *pl_max = nullptr, *pl_sum = nullptr, *pd_max = nullptr;
+    int32_t *tdt_ints = nullptr;               // cur|token|tpos|active|ntok|overflow|n_active(3)
+    int32_t *pl_idx = nullptr, *pd_idx = nullptr;
+    // pinned host staging
+    float *h_pcm = nullptr;
+    int32_t *h_meta = nullptr;                 // offsets staging
+    int32_t *h_tok = nullptr, *h_ts = nullptr, *h_te = nullptr;
+    float *h_tc = nullptr;
+
+    // ---- the staged batch
+    int n_utt = 0;
+    std::vector<int64_t> pcm_off;
+    std::vector<int32_t> frame_off, s2_off, row_off, t2_rows;
+    int maxF = 0, maxT2 = 0, maxT = 0, M = 0, M2 = 0;
+
+    pk_status fail(pk_status s, const std::string &m) {
+        err = m;
+        return s;
+    }
+    template <typename T>
+    T *dalloc(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        allocs.push_back(p);
+        return static_cast<T *>(p);
+    }
+    template <typename T>
+    T *upload(const std::vector<T> &h) {
+        T *d = dalloc<T>(h.size());
+        if (d && !h.empty()) cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        return d;
+    }
+    ActBuf act_alloc(size_t n) {
+        ActBuf a;
+        if (cfg.math == PK_MATH_FP32) {
+            a.f32 = dalloc<float>(n);
+        } else {
+            a.hi = dalloc<bf16>(n);
+            if (cfg.math == PK_MATH_BF16X3) a.lo = dalloc<bf16>(n);
+        }
+        return a;
+    }
+
+    pk_status load(const char *path);
+    pk_status make_weight(const SafeTensors &st, const std::string &wname, const std::string &bname, int N, int K,
+                          GemmWeight &out, const std::vector<int> *row_perm = nullptr,
+                          const std::vector<int> *col_perm = nullptr);
+    pk_status finish_weight(std::vector<float> &w, std::vector<float> *b, int N, int K, GemmWeight &out);
+    pk_status get_vec(const SafeTensors &st, const std::string &name, int n, float **out);
+    pk_status alloc_workspace();
+    pk_status set_batch_shapes(const int32_t *n_frames_or_null, const int64_t *offsets_or_null, int n);
+    pk_status upload_shapes();
+    void gemm(const ActBuf &A, int lda, const GemmWeight &W, int M_, EpiParams epi);
+    pk_status run_mel();
+    pk_status run_encoder(float *sub_out_host, float *layers_out_host);
+    pk_status run_ctc(float *logprobs_dev_or_null);
+    pk_status run_tdt();
+    pk_status fetch(pk_tokens *out);
+};
+
+// ===================================================================== weights
+
+pk_status pk_engine::get_vec(const SafeTensors &st, const std::string &name, int n, float **out) {
+    std::vector<float> h;
+    std::string e;
+    if (!st.read_f32(name, h, n, e)) return fail(PK_ERR_MISSING, e);
+    *out = upload(h);
+    return *out ? PK_OK : fail(PK_ERR_CUDA, "cudaMalloc failed for " + name);
+}
+
+pk_status pk_engine::finish_weight(std::vector<float> &w, std::vector<float> *b, int N, int K, GemmWeight &out) {
+    out.N = N;
+    out.K = K;
+    out.w = upload(w);
+    if (!out.w) return fail(PK_ERR_CUDA, "cudaMalloc failed (weight)");
+    if (b) {
+        out.bias = upload(*b);
+        if (!out.bias) return fail(PK_ERR_CUDA, "cudaMalloc failed (bias)");
+    }
+    if (cfg.math != PK_MATH_FP32) {
+        std::vector<bf16> hi(w.size()), lo(w.size());
+        for (size_t i = 0; i < w.size(); ++i) {
+            hi[i] = __float2bfloat16_rn(w[i]);
+            lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(hi[i]));
+        }
+        out.hi = upload(hi);
+        out.lo = upload(lo);
+        if (!out.hi || !out.lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (split weight)");
+    }
+    return PK_OK;
+}
+
+pk_status pk_engine::make_weight(const SafeTensors &st, const std::string &wname, const std::string &bname, int N,
+                                 int K, GemmWeight &out, const std::vector<int> *row_perm,
+                                 const std::vector<int> *col_perm) {
+    std::vector<float> w, b;
+    std::string e;
+    if (!st.read_f32(wname, w, (int64_t)N * K, e)) return fail(PK_ERR_MISSING, e);
+    if (!bname.empty() && !st.read_f32(bname, b, N, e)) return fail(PK_ERR_MISSING, e);
+    if (row_perm || col_perm) {
+        std::vector<float> w2(w.size()), b2(b.size());
+        for (int n = 0; n < N; ++n) {
+            const int sn = row_perm ? (*row_perm)[n] : n;
+            for (int k = 0; k < K; ++k) {
+                const int sk = col_perm ? (*col_perm)[k] : k;
+                w2[(size_t)n * K + k] = w[(size_t)sn * K + sk];
+            }
+            if (!b.empty()) b2[n] = b[sn];
+        }
+        w.swap(w2);
+        if (!b.empty()) b.swap(b2);
+    }
+    return finish_weight(w, bname.empty() ? nullptr : &b, N, K, out);
+}
+
+pk_status pk_engine::load(const char *path) {
+    SafeTensors st;
+    std::string e;
+    if (!st.open(path, e)) return fail(PK_ERR_IO, e);
+    const pk_config &c = cfg;
+    const int C = c.sub_channels, d = c.d_model, ff = c.ff, H = c.n_heads, hd = d / H;
+    pk_status s;
+
+    // ---- mel tables (host, double precision where the reference uses it)
+    {
+        std::vector<float> win(400);
+        for (int i = 0; i < 400; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * i / 399.0));  // fft.cpp:1117-1142
+        std::vector<float2> tw256(256), tw512(257);
+        for (int m = 0; m < 256; ++m) tw256[m] = make_float2((float)std::cos(2.0 * M_PI * m / 256.0), (float)-std::sin(2.0 * M_PI * m / 256.0));
+        for (int k = 0; k <= 256; ++k) tw512[k] = make_float2((float)std::cos(2.0 * M_PI * k / 512.0), (float)-std::sin(2.0 * M_PI * k / 512.0));
+        // Slaney filterbank, audio.cpp:18-94
+        auto hz2mel = [](double f) { return f < 1000.0 ? f / (200.0 / 3.0) : 15.0 + std::log(f / 1000.0) / 0.06875177742094912; };
+        auto mel2hz = [](double m) { return m < 15.0 ? m * (200.0 / 3.0) : 1000.0 * std::exp((m - 15.0) * 0.06875177742094912); };
+        const int nm = c.mel_bins, nf = 257;
+        const double mmin = hz2mel(0.0), mmax = hz2mel(8000.0);
+        std::vector<double> hz(nm + 2);
+        for (int i = 0; i < nm + 2; ++i) hz[i] = mel2hz(mmin + (double)i * (mmax - mmin) / (double)(nm + 1));
+        std::vector<float> fbw;
+        std::vector<int32_t> fstart(nm), flen(nm), foff(nm);
+        for (int m = 0; m < nm; ++m) {
+            const double left = hz[m], center = hz[m + 1], right = hz[m + 2], enorm = 2.0 / (right - left);
+            int first = -1, last = -1;
+            std::vector<float> col(nf);
+            for (int f = 0; f < nf; ++f) {
+                const double fr = (double)f * 16000.0 / (2.0 * (nf - 1));
+                double v = 0.0;
+                if (fr >= left && fr <= center && center > left) v = (fr - left) / (center - left);
+                else if (fr > center && fr <= right && right > center) v = (right - fr) / (right - center);
+                col[f] = (float)(v * enorm);
+                if (col[f] != 0.f) {
+                    if (first < 0) first = f;
+                    last = f;
+                }
+            }
+            fstart[m] = first < 0 ? 0 : first;
+            flen[m] = first < 0 ? 0 : last - first + 1;
+            foff[m] = (int32_t)fbw.size();
+            for (int f = fstart[m]; f < fstart[m] + flen[m]; ++f) fbw.push_back(col[f]);
+        }
+        mel_tb.window = upload(win);
+        mel_tb.tw256 = upload(tw256);
+        mel_tb.tw512 = upload(tw512);
+        mel_tb.fb_w = upload(fbw);
+        mel_tb.fb_start = upload(fstart);
+        mel_tb.fb_len = upload(flen);
+        mel_tb.fb_off = upload(foff);
+        mel_tb.fb_nnz = (int)fbw.size();
+    }
+
+    // ---- subsampling (encoder.cpp:208-241)
+    const std::string sp = "encoder_.subsampling_.";
+    if ((s = get_vec(st, sp + "conv1_.weight", C * 9, &c1_w))) return s;
+    if ((s = get_vec(st, sp + "conv1_.bias", C, &c1_b))) return s;
+    if ((s = get_vec(st, sp + "dw1_.weight", C * 9, &dw1_w))) return s;
+    if ((s = get_vec(st, sp + "dw1_.bias", C, &dw1_b))) return s;
+    if ((s = get_vec(st, sp + "dw2_.weight", C * 9, &dw2_w))) return s;
+    if ((s = get_vec(st, sp + "dw2_.bias", C, &dw2_b))) return s;
+    if ((s = make_weight(st, sp + "conv2_.weight", sp + "conv2_.bias", C, C, conv2))) return s;
+    if ((s = make_weight(st, sp + "conv3_.weight", sp + "conv3_.bias", C, C, conv3))) return s;
+    {
+        // reference flattens (C, F') channel-major (encoder.cpp:236-238): k_ref = c*F' + f.
+        // Our rows are (f, c): k = f*C + c.
+        std::vector<int> colp((size_t)C * f3n);
+        for (int f = 0; f < f3n; ++f)
+            for (int ch = 0; ch < C; ++ch) colp[(size_t)f * C + ch] = ch * f3n + f;
+        if ((s = make_weight(st, sp + "proj_.weight", sp + "proj_.bias", d, C * f3n, proj, nullptr, &colp))) return s;
+    }
+
+    // ---- relative position table input: emb(p) for p = -(Tmax-1) .. Tmax-1, fp32 math as
+    // encoder.cpp:9-30 (row index here = p + Tmax - 1)
+    const int NP = 2 * Tmax - 1;
+    std::vector<float> emb((size_t)NP * d);
+    for (int r = 0; r < NP; ++r) {
+        const float position = (float)(r - (Tmax - 1));
+        for (int i = 0; i < d; i += 2) {
+            const float div_term = std::exp((float)i * (-std::log(10000.0f) / d));
+            emb[(size_t)r * d + i] = std::sin(position * div_term);
+            if (i + 1 < d) emb[(size_t)r * d + i + 1] = std::cos(position * div_term);
+        }
+    }
+    float *d_emb = upload(emb);
+    if (!d_emb) return fail(PK_ERR_CUDA, "cudaMalloc failed (pos emb)");
+
+    layers.resize(c.n_layers);
+    for (int i = 0; i < c.n_layers; ++i) {
+        LayerW &L = layers[i];
+        const std::string lp = "encoder_.layers_." + std::to_string(i) + ".";
+        for (int f = 0; f < 2; ++f) {
+            const std::string fp = lp + (f == 0 ? "ffn1_." : "ffn2_.");
+            if ((s = get_vec(st, fp + "norm_.weight", d, &L.ffn_ln_w[f]))) return s;
+            if ((s = get_vec(st, fp + "norm_.bias", d, &L.ffn_ln_b[f]))) return s;
+            if ((s = make_weight(st, fp + "fc1_.weight", fp + "fc1_.bias", ff, d, L.fc1[f]))) return s;
+            if ((s = make_weight(st, fp + "fc2_.weight", fp + "fc2_.bias", d, ff, L.fc2[f]))) return s;
+        }
+        const std::string ap = lp + "attn_.";
+        if ((s = get_vec(st, ap + "norm_.weight", d, &L.att_ln_w))) return s;
+        if ((s = get_vec(st, ap + "norm_.bias", d, &L.att_ln_b))) return s;
+        {
+            std::vector<float> w((size_t)3 * d * d), b((size_t)3 * d), t;
+            const char *names[3] = {"q_proj", "k_proj", "v_proj"};
+            for (int q = 0; q < 3; ++q) {
+                if (!st.read_f32(ap + "mha_." + names[q] + ".weight", t, (int64_t)d * d, e)) return fail(PK_ERR_MISSING, e);
+                memcpy(&w[(size_t)q * d * d], t.data(), t.size() * 4);
+                if (!st.read_f32(ap + "mha_." + names[q] + ".bias", t, d, e)) return fail(PK_ERR_MISSING, e);
+                memcpy(&b[(size_t)q * d], t.data(), t.size() * 4);
+            }
+            if ((s = finish_weight(w, &b, 3 * d, d, L.qkv))) return s;
+        }
+        if ((s = make_weight(st, ap + "mha_.out_proj.weight", ap + "mha_.out_proj.bias", d, d, L.out))) return s;
+        if ((s = get_vec(st, ap + "pos_bias_u_", H * hd, &L.pos_u))) return s;
+        if ((s = get_vec(st, ap + "pos_bias_v_", H * hd, &L.pos_v))) return s;
+        {
+            // PP = emb . Wpos^T (pos_proj_ has no bias, encoder.cpp:80), exact fp32 GEMM
+            float *wpos;
+            if ((s = get_vec(st, ap + "pos_proj_.weight", d * d, &wpos))) return s;
+            L.pp = dalloc<float>((size_t)NP * d);
+            if (!L.pp) return fail(PK_ERR_CUDA, "cudaMalloc failed (pp)");
+            EpiParams ep;
+            ep.kind = EPI_BIAS_F32;
+            ep.out_f32 = L.pp;
+            ep.ldo = d;
+            launch_gemm_simt(d_emb, d, wpos, d, NP, d, d, ep, stream);
+            ++launches;
+        }
+        const std::string cp = lp + "conv_.";
+        if ((s = get_vec(st, cp + "norm_.weight", d, &L.conv_ln_w))) return s;
+        if ((s = get_vec(st, cp + "norm_.bias", d, &L.conv_ln_b))) return s;
+        {
+            // GLU pairs channel j with j+d (operations.cpp:1450-1476): interleave the rows so
+            // the pair sits in adjacent GEMM columns.
+            std::vector<int> rowp((size_t)2 * d);
+            for (int j = 0; j < d; ++j) {
+                rowp[2 * j] = j;
+                rowp[2 * j + 1] = d + j;
+            }
+            if ((s = make_weight(st, cp + "pointwise_conv1_.weight", cp + "pointwise_conv1_.bias", 2 * d, d, L.pw1, &rowp))) return s;
+        }
+        if ((s = make_weight(st, cp + "pointwise_conv2_.weight", cp + "pointwise_conv2_.bias", d, d, L.pw2))) return s;
+        {
+            // fold BatchNorm1d(eval) (normalization.cpp:48-104, eps 1e-5) into the depthwise conv
+            const int ks = c.conv_kernel;
+            std::vector<float> w, b, g, be, mu, var;
+            if (!st.read_f32(cp + "depthwise_conv_.weight", w, (int64_t)d * ks, e)) return fail(PK_ERR_MISSING, e);
+            if (!st.read_f32(cp + "depthwise_conv_.bias", b, d, e)) return fail(PK_ERR_MISSING, e);
+            if (!st.read_f32(cp + "batch_norm_.weight", g, d, e)) return fail(PK_ERR_MISSING, e);
+            if (!st.read_f32(cp + "batch_norm_.bias", be, d, e)) return fail(PK_ERR_MISSING, e);
+            if (!st.read_f32(cp + "batch_norm_.running_mean", mu, d, e)) return fail(PK_ERR_MISSING, e);
+            if (!st.read_f32(cp + "batch_norm_.running_var", var, d, e)) return fail(PK_ERR_MISSING, e);
+            for (int ch = 0; ch < d; ++ch) {
+                const double sc = (double)g[ch] / std::sqrt((double)var[ch] + 1e-5);
+                for (int j = 0; j < ks; ++j) w[(size_t)ch * ks + j] = (float)((double)w[(size_t)ch * ks + j] * sc);
+                b[ch] = (float)(((double)b[ch] - (double)mu[ch]) * sc + (double)be[ch]);
+            }
+            L.dw_w = upload(w);
+            L.dw_b = upload(b);
+        }
+        if ((s = get_vec(st, lp + "final_norm_.weight", d, &L.fin_ln_w))) return s;
+        if ((s = get_vec(st, lp + "final_norm_.bias", d, &L.fin_ln_b))) return s;
+    }
+
+    // ---- heads
+    const int V = c.vocab, P = c.pred_hidden, J = c.joint_hidden, D = c.n_durations;
+    if (c.has_ctc) {
+        if ((s = make_weight(st, "ctc_decoder_.proj_.weight", "ctc_decoder_.proj_.bias", V, d, ctc_head))) return s;
+    }
+    const std::string jp = c.joint_prefix_tdt ? "tdt_joint_." : "joint_.";
+    if ((s = make_weight(st, jp + "enc_proj_.weight", jp + "enc_proj_.bias", J, d, enc_proj))) return s;
+    if ((s = get_vec(st, jp + "pred_proj_.weight", J * P, &Wp))) return s;
+    {
+        std::vector<float> w((size_t)(V + D) * J), b((size_t)V + D), t;
+        if (!st.read_f32(jp + "label_proj_.weight", t, (int64_t)V * J, e)) return fail(PK_ERR_MISSING, e);
+        memcpy(w.data(), t.data(), t.size() * 4);
+        if (!st.read_f32(jp + "duration_proj_.weight", t, (int64_t)D * J, e)) return fail(PK_ERR_MISSING, e);
+        memcpy(&w[(size_t)V * J], t.data(), t.size() * 4);
+        if (!st.read_f32(jp + "label_proj_.bias", t, V, e)) return fail(PK_ERR_MISSING, e);
+        memcpy(b.data(), t.data(), t.size() * 4);
+        if (!st.read_f32(jp + "duration_proj_.bias", t, D, e)) return fail(PK_ERR_MISSING, e);
+        memcpy(&b[V], t.data(), t.size() * 4);
+        Wout = upload(w);
+        bout = upload(b);
+    }
+    {
+        float *embed, *wih0, *b0;
+        if ((s = get_vec(st, "prediction_.embed_.weight", V * P, &embed))) return s;
+        for (int l = 0; l < c.lstm_layers; ++l) {
+            const std::string q = "prediction_.lstm_.cells_." + std::to_string(l) + ".";
+            if ((s = get_vec(st, q + "hidden_proj_.weight", 4 * P * P, &Whh[l]))) return s;
+            if ((s = get_vec(st, q + "input_proj_.weight", 4 * P * P, &Wih[l]))) return s;
+            if ((s = get_vec(st, q + "input_proj_.bias", 4 * P, &bih[l]))) return s;
+        }
+        wih0 = Wih[0];
+        b0 = bih[0];
+        // G0[token] = W_ih0 . E[token] + b0 (lstm.cpp:17 first term, rnnt.cpp:24)
+        G0 = dalloc<float>((size_t)V * 4 * P);
+        if (!G0) return fail(PK_ERR_CUDA, "cudaMalloc failed (G0)");
+        EpiParams ep;
+        ep.kind = EPI_BIAS_F32;
+        ep.bias = b0;
+        ep.out_f32 = G0;
+        ep.ldo = 4 * P;
+        launch_gemm_simt(embed, P, wih0, P, V, 4 * P, P, ep, stream);
+        ++launches;
+    }
+    PK_CUDA(cudaStreamSynchronize(stream));
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+// ===================================================================== workspace
+
+pk_status pk_engine::alloc_workspace() {
+    const pk_config &c = cfg;
+    const int C = c.sub_channels, d = c.d_model;
+    const size_t B = Bmax;
+    const int t1 = conv_len(Fmax), t2 = conv_len(t1);
+    const size_t rows2 = B * t2 * f2n, rows3 = B * (size_t)Tmax * f3n, Mx = B * (size_t)Tmax;
+    d_pcm = dalloc<float>(B * (size_t)c.max_samples + 8);
+    d_pcm_off = dalloc<int64_t>(B + 1);
+    d_frame_off = dalloc<int32_t>(B + 1);
+    d_s2_off = dalloc<int32_t>(B + 1);
+    d_row_off = dalloc<int32_t>(B + 1);
+    d_t2_rows = dalloc<int32_t>(B + 1);
+    logmel = dalloc<float>(B * (size_t)Fmax * c.mel_bins);
+    feats = dalloc<float>(B * (size_t)Fmax * c.mel_bins);
+    sub1 = act_alloc(rows2 * C);
+    sub2 = dalloc<float>(rows2 * C);
+    sub3 = act_alloc(rows3 * C);
+    sub4 = act_alloc(rows3 * C);
+    x = dalloc<float>(Mx * d);
+    ln = act_alloc(Mx * d);
+    ffh = act_alloc(Mx * c.ff);
+    qkv = dalloc<float>(Mx * 3 * d);
+    ctx = act_alloc(Mx * d);
+    glu = dalloc<float>(Mx * d);
+    cv = act_alloc(Mx * d);
+    const int ldv = (c.vocab + 3) & ~3;
+    logits = dalloc<float>(Mx * ldv);
+    EP = dalloc<float>(Mx * c.joint_hidden);
+    best = dalloc<int32_t>(Mx);
+    bconf = dalloc<float>(Mx);
+    tok = dalloc<int32_t>(B * (1 + (size_t)cap));
+    t_start = dalloc<int32_t>(B * (size_t)cap);
+    t_end = dalloc<int32_t>(B * (size_t)cap);
+    t_conf = dalloc<float>(B * (size_t)cap);
+    Bpad = ((Bmax + 31) / 32) * 32;
+    const size_t HS = (size_t)c.pred_hidden * Bpad;
+    hbuf = dalloc<float>(HS * 2 * c.lstm_layers);
+    cbuf = dalloc<float>(HS * 2 * c.lstm_layers);
+    zbuf = dalloc<float>((size_t)c.joint_hidden * Bpad);
+    tdt_ints = dalloc<int32_t>((size_t)6 * Bpad + 4);
+    const size_t PG = (size_t)num_sms * Bpad;
+    pl_max = dalloc<float>(PG);
+    pl_sum = dalloc<float>(PG);
+    pd_max = dalloc<float>(PG);
+    pl_idx = dalloc<int32_t>(PG);
+    pd_idx = dalloc<int32_t>(PG);
+    if (!pd_idx || !hbuf || !x || !sub2 || !d_pcm || !t_conf) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
+    PK_CUDA(cudaMallocHost(&h_pcm, (B * (size_t)c.max_samples + 8) * sizeof(float)));
+    PK_CUDA(cudaMallocHost(&h_meta, (size_t)(8 * (B + 1)) * sizeof(int32_t)));
+    PK_CUDA(cudaMallocHost(&h_tok, B * (1 + (size_t)cap) * sizeof(int32_t)));
+    PK_CUDA(cudaMallocHost(&h_ts, B * (size_t)cap * sizeof(int32_t)));
+    PK_CUDA(cudaMallocHost(&h_te, B * (size_t)cap * sizeof(int32_t)));
+    PK_CUDA(cudaMallocHost(&h_tc, B * (size_t)cap * sizeof(float)));
+    return PK_OK;
+}
+
+// Derive every per-utterance extent from either sample offsets or mel frame counts.
+pk_status pk_engine::set_batch_shapes(const int32_t *n_frames, const int64_t *offsets, int n) {
+    if (n <= 0) return fail(PK_ERR_INVALID, "empty batch");
+    if (n > Bmax) return fail(PK_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(Bmax));
+    n_utt = n;
+    pcm_off.assign(n + 1, 0);
+    frame_off.assign(n + 1, 0);
+    s2_off.assign(n + 1, 0);
+    row_off.assign(n + 1, 0);
+    t2_rows.assign(n + 1, 0);
+    maxF = maxT2 = maxT = 0;
+    for (int i = 0; i < n; ++i) {
+        int F;
+        if (offsets) {
+            const int64_t ns = offsets[i + 1] - offsets[i];
+            if (ns < 400) return fail(PK_ERR_INVALID, "utterance shorter than one 400-sample window");
+            if (ns > cfg.max_samples) return fail(PK_ERR_CAPACITY, "utterance exceeds max_samples");
+            pcm_off[i + 1] = pcm_off[i] + ns;
+            F = (int)(1 + ns / 160);
+        } else {
+            F = n_frames[i];
+            if (F < 2) return fail(PK_ERR_INVALID, "utterance needs at least 2 mel frames");
+            if (F > Fmax) return fail(PK_ERR_CAPACITY, "utterance exceeds max frames");
+        }
+        const int t1 = conv_len(F), t2 = conv_len(t1), T = conv_len(t2);
+        frame_off[i + 1] = frame_off[i] + F;
+        s2_off[i + 1] = s2_off[i] + t2;
+        row_off[i + 1] = row_off[i] + T;
+        t2_rows[i] = t2;
+        maxF = std::max(maxF, F);
+        maxT2 = std::max(maxT2, t2);
+        maxT = std::max(maxT, T);
+    }
+    M = row_off[n];
+    M2 = s2_off[n] * f2n;
+    return PK_OK;
+}
+
+pk_status pk_engine::upload_shapes() {
+    const int n = n_utt;
+    int32_t *m = h_meta;
+    PK_CUDA(cudaEventSynchronize(ev_h2d));  // pinned staging of the previous batch fully consumed
+    memcpy(m, frame_off.data(), (n + 1) * 4);
+    memcpy(m + (n + 1), s2_off.data(), (n + 1) * 4);
+    memcpy(m + 2 * (n + 1), row_off.data(), (n + 1) * 4);
+    memcpy(m + 3 * (n + 1), t2_rows.data(), (n + 1) * 4);
+    memcpy(m + 4 * (n + 1), pcm_off.data(), (n + 1) * 8);
+    PK_CUDA(cudaMemcpyAsync(d_frame_off, m, (n + 1) * 4, cudaMemcpyHostToDevice, stream));
+    PK_CUDA(cudaMemcpyAsync(d_s2_off, m + (n + 1), (n + 1) * 4, cudaMemcpyHostToDevice, stream));
+    PK_CUDA(cudaMemcpyAsync(d_row_off, m + 2 * (n + 1), (n + 1) * 4, cudaMemcpyHostToDevice, stream));
+    PK_CUDA(cudaMemcpyAsync(d_t2_rows, m + 3 * (n + 1), (n + 1) * 4, cudaMemcpyHostToDevice, stream));
+    PK_CUDA(cudaMemcpyAsync(d_pcm_off, m + 4 * (n + 1), (n + 1) * 8, cudaMemcpyHostToDevice, stream));
+    PK_CUDA(cudaEventRecord(ev_h2d, stream));
+    return PK_OK;
+}
+
+// ===================================================================== pipeline
+
+void pk_engine::gemm(const ActBuf &A, int lda, const GemmWeight &W, int M_, EpiParams epi) {
+    epi.bias = W.bias;
+    launch_gemm_simt(A.f32, lda, W.w, W.K, M_, W.N, W.K, epi, stream);
+    ++launches;
+}
+
+pk_status pk_engine::run_mel() {
+    launch_mel(d_pcm, d_pcm_off, d_frame_off, n_utt, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
+    launches += 2;
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
+    const pk_config &c = cfg;
+    const int C = c.sub_channels, d = c.d_model, H = c.n_heads, hd = d / H;
+    // ---- ConvSubsampling (encoder.cpp:219-241)
+    launch_subsample_conv1_dw1(feats, d_frame_off, d_s2_off, n_utt, maxT2, c.mel_bins, C, c1_w, c1_b, dw1_w, dw1_b,
+                               sub1, stream);
+    ++launches;
+    {
+        EpiParams ep;
+        ep.kind = EPI_BIAS_RELU_F32;
+        ep.out_f32 = sub2;
+        ep.ldo = C;
+        gemm(sub1, C, conv2, M2, ep);
+    }
+    launch_subsample_dw(sub2, d_t2_rows, d_s2_off, d_row_off, n_utt, f2n, C, dw2_w, dw2_b, sub3, M * f3n, stream);
+    ++launches;
+    {
+        EpiParams ep;
+        ep.kind = EPI_BIAS_RELU_ACT;
+        ep.act = sub4;
+        ep.ldo = C;
+        gemm(sub3, C, conv3, M * f3n, ep);
+    }
+    {
+        EpiParams ep;
+        ep.kind = EPI_BIAS_F32;
+        ep.out_f32 = x;
+        ep.ldo = d;
+        gemm(sub4, C * f3n, proj, M, ep);
+    }
+    PK_CUDA(cudaGetLastError());
+    if (sub_out_host) {
+        PK_CUDA(cudaMemcpyAsync(sub_out_host, x, (size_t)M * d * 4, cudaMemcpyDeviceToHost, stream));
+        PK_CUDA(cudaStreamSynchronize(stream));
+    }
+    // ---- Conformer blocks (encoder.cpp:196-204)
+    ActBuf none;
+    launch_layernorm(x, M, d, layers[0].ffn_ln_w[0], layers[0].ffn_ln_b[0], nullptr, ln, nullptr, nullptr, none, stream);
+    ++launches;
+    for (int i = 0; i < c.n_layers; ++i) {
+        const LayerW &L = layers[i];
+        for (int f = 0; f < 2; ++f) {
+            if (f == 1) {
+                launch_layernorm(x, M, d, L.ffn_ln_w[1], L.ffn_ln_b[1], nullptr, ln, nullptr, nullptr, none, stream);
+                ++launches;
+            }
+            // FeedForward (encoder.cpp:39-46): x += 0.5 * fc2(silu(fc1(LN(x))))
+            EpiParams e1;
+            e1.kind = EPI_BIAS_SILU_ACT;
+            e1.act = ffh;
+            e1.ldo = c.ff;
+            gemm(ln, d, L.fc1[f], M, e1);
+            EpiParams e2;
+            e2.kind = EPI_RESID_F32;
+            e2.out_f32 = x;
+            e2.resid = x;
+            e2.ldo = d;
+            e2.alpha = 0.5f;
+            gemm(ffh, c.ff, L.fc2[f], M, e2);
+            if (f == 1) break;
+            // ConformerAttention (encoder.cpp:111-186)
+            launch_layernorm(x, M, d, L.att_ln_w, L.att_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
+            ++launches;
+            EpiParams eq;
+            eq.kind = EPI_BIAS_F32;
+            eq.out_f32 = qkv;
+            eq.ldo = 3 * d;
+            gemm(ln, d, L.qkv, M, eq);
+            if (!launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream))
+                return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
+            ++launches;
+            EpiParams eo;
+            eo.kind = EPI_RESID_F32;
+            eo.out_f32 = x;
+            eo.resid = x;
+            eo.ldo = d;
+            eo.alpha = 1.0f;
+            gemm(ctx, d, L.out, M, eo);
+            // ConformerConvModule (encoder.cpp:59-75)
+            launch_layernorm(x, M, d, L.conv_ln_w, L.conv_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
+            ++launches;
+            EpiParams eg;
+            eg.kind = EPI_GLU_F32;
+            eg.out_f32 = glu;
+            eg.ldo = d;
+            gemm(ln, d, L.pw1, M, eg);
+            if (!launch_dwconv_bn_silu(glu, d_row_off, n_utt, maxT, d, c.conv_kernel, L.dw_w, L.dw_b, cv, stream))
+                return fail(PK_ERR_INVALID, "unsupported conv_kernel");
+            ++launches;
+            EpiParams ec;
+            ec.kind = EPI_RESID_F32;
+            ec.out_f32 = x;
+            ec.resid = x;
+            ec.ldo = d;
+            ec.alpha = 1.0f;
+            gemm(cv, d, L.pw2, M, ec);
+        }
+        // final_norm_ of this block chained with the next block's ffn1_.norm_; after the last
+        // block the normalised output is also written in GEMM-operand form for the heads.
+        const bool last = (i + 1 == c.n_layers);
+        if (!last)
+            launch_layernorm(x, M, d, L.fin_ln_w, L.fin_ln_b, x, none, layers[i + 1].ffn_ln_w[0],
+                             layers[i + 1].ffn_ln_b[0], ln, stream);
+        else
+            launch_layernorm(x, M, d, L.fin_ln_w, L.fin_ln_b, x, cfg.math == PK_MATH_FP32 ? none : ln, nullptr,
+                             nullptr, none, stream);
+        ++launches;
+        if (layers_out_host) {
+            PK_CUDA(cudaMemcpyAsync(layers_out_host + (size_t)i * M * d, x, (size_t)M * d * 4, cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+// encoder output as a GEMM operand
+static ActBuf enc_operand(pk_engine *e) {
+    if (e->cfg.math == PK_MATH_FP32) {
+        ActBuf a;
+        a.f32 = e->x;
+        return a;
+    }
+    return e->ln;
+}
+
+pk_status pk_engine::run_ctc(float *logprobs_dev) {
+    const pk_config &c = cfg;
+    if (!c.has_ctc) return fail(PK_ERR_INVALID, "this model has no CTC head");
+    const int ldv = (c.vocab + 3) & ~3;
+    EpiParams ep;
+    ep.kind = EPI_BIAS_F32;
+    ep.out_f32 = logits;
+    ep.ldo = ldv;
+    gemm(enc_operand(this), c.d_model, ctc_head, M, ep);
+    launch_ctc_frame_argmax(logits, M, c.vocab, ldv, best, bconf, logprobs_dev, stream);
+    launch_ctc_collapse(best, bconf, d_row_off, n_utt, c.vocab - 1, cap, tok, t_start, t_end, t_conf, stream);
+    launches += 2;
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+pk_status pk_engine::run_tdt() {
+    const pk_config &c = cfg;
+    // enc_proj for all frames at once (joint's first Linear, tdt.cpp:17)
+    EpiParams ep;
+    ep.kind = EPI_BIAS_F32;
+    ep.out_f32 = EP;
+    ep.ldo = c.joint_hidden;
+    gemm(enc_operand(this), c.d_model, enc_proj, M, ep);
+
+    const int bp = ((n_utt + 31) / 32) * 32;
+    TdtParams p{};
+    p.P = c.pred_hidden; p.J = c.joint_hidden; p.V = c.vocab; p.D = c.n_durations; p.L = c.lstm_layers;
+    p.Bpad = bp; p.n_utt = n_utt; p.cap = cap; p.n_dur = c.n_durations;
+    p.max_steps = maxT + cap + 2;
+    for (int i = 0; i < 8; ++i) p.durations[i] = c.durations[i];
+    p.EP = EP; p.row_off = d_row_off; p.G0 = G0;
+    for (int l = 0; l < c.lstm_layers; ++l) { p.Whh[l] = Whh[l]; p.Wih[l] = Wih[l]; p.bih[l] = bih[l]; }
+    p.Wp = Wp; p.Wout = Wout; p.bout = bout;
+    p.hbuf = hbuf; p.cbuf = cbuf; p.z = zbuf;
+    p.cur = tdt_ints; p.token = tdt_ints + bp; p.tpos = tdt_ints + 2 * bp; p.active = tdt_ints + 3 * bp;
+    p.ntok = tdt_ints + 4 * bp; p.overflow = tdt_ints + 5 * bp; p.n_active = tdt_ints + 6 * bp;
+    p.pl_max = pl_max; p.pl_sum = pl_sum; p.pd_max = pd_max; p.pl_idx = pl_idx; p.pd_idx = pd_idx;
+    p.tok = tok; p.t_start = t_start; p.t_end = t_end; p.t_conf = t_conf;
+    // initial state: zero LSTM state, token = blank (SOS), t = 0 (tdt.cpp:49-59)
+    const size_t HS = (size_t)p.P * bp;
+    PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * sizeof(float), stream));
+    PK_CUDA(cudaMemsetAsync(cbuf, 0, HS * 2 * p.L * sizeof(float), stream));
+    cudaError_t ce = launch_tdt_decode(p, num_sms, stream);
+    launches += 2;
+    if (ce != cudaSuccess) return fail(PK_ERR_CUDA, std::string("tdt_decode launch: ") + cudaGetErrorString(ce));
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+pk_status pk_engine::fetch(pk_tokens *out) {
+    if (!out || !out->ids || !out->len) return fail(PK_ERR_INVALID, "pk_tokens needs ids and len");
+    const size_t n = n_utt;
+    PK_CUDA(cudaMemcpyAsync(h_tok, tok, n * (1 + cap) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (out->start) PK_CUDA(cudaMemcpyAsync(h_ts, t_start, n * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (out->end) PK_CUDA(cudaMemcpyAsync(h_te, t_end, n * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (out->conf) PK_CUDA(cudaMemcpyAsync(h_tc, t_conf, n * cap * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    PK_CUDA(cudaStreamSynchronize(stream));
+    for (size_t b = 0; b < n; ++b) {
+        const int32_t len = h_tok[b * (1 + cap)];
+        if (len > out->cap) return fail(PK_ERR_CAPACITY, "pk_tokens.cap too small for utterance " + std::to_string(b));
+        out->len[b] = len;
+        memcpy(out->ids + b * out->cap, h_tok + b * (1 + cap) + 1, (size_t)len * 4);
+        if (out->start) memcpy(out->start + b * out->cap, h_ts + b * cap, (size_t)len * 4);
+        if (out->end) memcpy(out->end + b * out->cap, h_te + b * cap, (size_t)len * 4);
+        if (out->conf) memcpy(out->conf + b * out->cap, h_tc + b * cap, (size_t)len * 4);
+    }
+    return PK_OK;
+}
+
+// ===================================================================== C-ABI
+
+extern "C" {
+
+void pk_config_110m(pk_config *c) {
+    memset(c, 0, sizeof(*c));
+    c->mel_bins = 80; c->sub_channels = 256; c->d_model = 512; c->n_layers = 17; c->n_heads = 8; c->ff = 2048;
+    c->conv_kernel = 9; c->vocab = 1025; c->pred_hidden = 640; c->lstm_layers = 1; c->joint_hidden = 640;
+    c->n_durations = 5;
+    for (int i = 0; i < 5; ++i) c->durations[i] = i;
+    c->has_ctc = 1; c->joint_prefix_tdt = 1; c->max_symbols = 10;
+    c->max_batch = 64; c->max_samples = 160000; c->math = PK_MATH_FP32;
+}
+
+void pk_config_tdt_600m(pk_config *c) {
+    pk_config_110m(c);
+    c->mel_bins = 128; c->d_model = 1024; c->n_layers = 24; c->ff = 4096; c->vocab = 8193; c->lstm_layers = 2;
+    c->has_ctc = 0; c->joint_prefix_tdt = 0; c->max_batch = 16; c->max_samples = 480000;
+}
+
+int32_t pk_mel_frames(int64_t n_samples) { return (int32_t)(1 + n_samples / 160); }
+int32_t pk_encoder_frames(int32_t f) { return conv_len(conv_len(conv_len(f))); }
+
+const char *pk_last_error(const pk_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, pk_engine **out) {
+    if (!cfg || !path || !out) {
+        g_create_err = "null argument";
+        return PK_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_err = "no CUDA device: this engine has no CPU fallback";
+        return PK_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_err = "bad device index";
+        return PK_ERR_INVALID;
+    }
+    const pk_config &c = *cfg;
+    if (c.d_model % 128 || c.d_model % c.n_heads || c.mel_bins % 8 || c.sub_channels % 4 || c.ff % 16 ||
+        c.pred_hidden % 32 || c.joint_hidden % 32 || c.lstm_layers < 1 || c.lstm_layers > PK_MAX_LSTM ||
+        c.n_durations < 1 || c.n_durations > 8 || c.max_batch < 1 || c.max_samples < 400 || c.sub_channels > 1024) {
+        g_create_err = "unsupported model shape in pk_config";
+        return PK_ERR_INVALID;
+    }
+    if (c.math != PK_MATH_FP32) {
+        g_create_err = "requested pk_math mode is not available in this build";
+        return PK_ERR_INVALID;
+    }
+    auto e = std::make_unique<pk_engine>();
+    e->cfg = c;
+    e->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_create_err = "cudaSetDevice failed";
+        return PK_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    e->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_err = "cudaStreamCreate failed";
+        return PK_ERR_CUDA;
+    }
+    if (cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming) != cudaSuccess) {
+        g_create_err = "cudaEventCreate failed";
+        return PK_ERR_CUDA;
+    }
+    e->Bmax = c.max_batch;
+    e->Fmax = 1 + c.max_samples / 160;
+    e->Tmax = pk_encoder_frames(e->Fmax);
+    e->f1n = conv_len(c.mel_bins);
+    e->f2n = conv_len(e->f1n);
+    e->f3n = conv_len(e->f2n);
+    e->cap = 2 * e->Tmax + 8;
+    pk_status s = e->load(path);
+    if (s == PK_OK) s = e->alloc_workspace();
+    if (s != PK_OK) {
+        g_create_err = e->err;
+        pk_engine_destroy(e.release());
+        return s;
+    }
+    *out = e.release();
+    return PK_OK;
+}
+
+void pk_engine_destroy(pk_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->h_pcm) cudaFreeHost(e->h_pcm);
+    if (e->h_meta) cudaFreeHost(e->h_meta);
+    if (e->h_tok) cudaFreeHost(e->h_tok);
+    if (e->h_ts) cudaFreeHost(e->h_ts);
+    if (e->h_te) cudaFreeHost(e->h_te);
+    if (e->h_tc) cudaFreeHost(e->h_tc);
+    if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+void *pk_stream(pk_engine *e) { return e ? (void *)e->stream : nullptr; }
+int64_t pk_launch_count(const pk_engine *e) { return e ? e->launches : 0; }
+
+pk_status pk_sync(pk_engine *e) {
+    if (!e) return PK_ERR_INVALID;
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt) {
+    if (!e || !pcm || !offsets) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    pk_status s = e->set_batch_shapes(nullptr, offsets, n_utt);
+    if (s) return s;
+    const size_t total = (size_t)e->pcm_off[n_utt];
+    cudaEventSynchronize(e->ev_h2d);  // previous batch's staging copies have left the pinned buffers
+    // pageable -> pinned -> device; utterances are re-packed back to back
+    for (int i = 0; i < n_utt; ++i)
+        memcpy(e->h_pcm + e->pcm_off[i], pcm + offsets[i], (size_t)(offsets[i + 1] - offsets[i]) * sizeof(float));
+    cudaError_t ce = cudaMemcpyAsync(e->d_pcm, e->h_pcm, total * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D pcm: ") + cudaGetErrorString(ce));
+    return e->upload_shapes();
+}
+
+pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
+    if (!e || e->n_utt <= 0) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    pk_status s;
+    if ((s = e->run_mel())) return s;
+    if ((s = e->run_encoder(nullptr, nullptr))) return s;
+    return dec == PK_DECODER_CTC ? e->run_ctc(nullptr) : e->run_tdt();
+}
+
+pk_status pk_fetch_tokens(pk_engine *e, pk_tokens *out) {
+    if (!e) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    return e->fetch(out);
+}
+
+pk_status pk_transcribe_batch(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, pk_decoder dec,
+                              pk_tokens *out) {
+    pk_status s;
+    if ((s = pk_stage_pcm(e, pcm, offsets, n_utt))) return s;
+    if ((s = pk_run_staged(e, dec))) return s;
+    return pk_fetch_tokens(e, out);
+}
+
+pk_status pk_token_buffer(pk_engine *e, void **dev_ptr, int32_t *rows, int32_t *row_ints) {
+    if (!e || !dev_ptr) return PK_ERR_INVALID;
+    *dev_ptr = e->tok;
+    if (rows) *rows = e->n_utt;
+    if (row_ints) *row_ints = 1 + e->cap;
+    return PK_OK;
+}
+
+pk_status pk_mel(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, float *feats_out,
+                 int32_t *n_frames_out) {
+    pk_status s;
+    if ((s = pk_stage_pcm(e, pcm, offsets, n_utt))) return s;
+    if ((s = e->run_mel())) return s;
+    const size_t n = (size_t)e->frame_off[n_utt] * e->cfg.mel_bins;
+    cudaError_t ce = cudaMemcpyAsync(feats_out, e->feats, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_mel: ") + cudaGetErrorString(ce));
+    if (n_frames_out)
+        for (int i = 0; i < n_utt; ++i) n_frames_out[i] = e->frame_off[i + 1] - e->frame_off[i];
+    return PK_OK;
+}
+
+pk_status pk_encode(pk_engine *e, const float *feats, const int32_t *n_frames, int32_t n_utt, float *enc_out,
+                    int32_t *enc_lens_out, float *sub_out, float *layers_out) {
+    if (!e || !feats || !n_frames || !enc_out) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    pk_status s = e->set_batch_shapes(n_frames, nullptr, n_utt);
+    if (s) return s;
+    if ((s = e->upload_shapes())) return s;
+    const size_t nf = (size_t)e->frame_off[n_utt] * e->cfg.mel_bins;
+    cudaError_t ce = cudaMemcpyAsync(e->feats, feats, nf * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D feats: ") + cudaGetErrorString(ce));
+    if ((s = e->run_encoder(sub_out, layers_out))) return s;
+    ce = cudaMemcpyAsync(enc_out, e->x, (size_t)e->M * e->cfg.d_model * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_encode: ") + cudaGetErrorString(ce));
+    if (enc_lens_out)
+        for (int i = 0; i < n_utt; ++i) enc_lens_out[i] = e->row_off[i + 1] - e->row_off[i];
+    return PK_OK;
+}
+
+// Stage a host encoder output as the current batch (decode-only entry points).
+static pk_status stage_enc(pk_engine *e, const float *enc, const int32_t *enc_lens, int32_t n_utt) {
+    if (n_utt <= 0 || n_utt > e->Bmax) return e->fail(PK_ERR_CAPACITY, "bad batch size");
+    e->n_utt = n_utt;
+    e->row_off.assign(n_utt + 1, 0);
+    e->frame_off.assign(n_utt + 1, 0);
+    e->s2_off.assign(n_utt + 1, 0);
+    e->t2_rows.assign(n_utt + 1, 0);
+    e->pcm_off.assign(n_utt + 1, 0);
+    e->maxT = 0;
+    for (int i = 0; i < n_utt; ++i) {
+        if (enc_lens[i] < 1 || enc_lens[i] > e->Tmax) return e->fail(PK_ERR_CAPACITY, "encoder length out of range");
+        e->row_off[i + 1] = e->row_off[i] + enc_lens[i];
+        e->maxT = std::max(e->maxT, enc_lens[i]);
+    }
+    e->M = e->row_off[n_utt];
+    pk_status s = e->upload_shapes();
+    if (s) return s;
+    cudaError_t ce = cudaMemcpyAsync(e->x, enc, (size_t)e->M * e->cfg.d_model * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D enc: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+pk_status pk_decode(pk_engine *e, const float *enc, const int32_t *enc_lens, int32_t n_utt, pk_decoder dec,
+                    pk_tokens *out) {
+    if (!e || !enc || !enc_lens) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    pk_status s;
+    if ((s = stage_enc(e, enc, enc_lens, n_utt))) return s;
+    if ((s = (dec == PK_DECODER_CTC ? e->run_ctc(nullptr) : e->run_tdt()))) return s;
+    return e->fetch(out);
+}
+
+pk_status pk_ctc_logprobs(pk_engine *e, const float *enc, int32_t total_frames, float *logprobs_out) {
+    if (!e || !enc || !logprobs_out || total_frames < 1) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    if (total_frames > e->Tmax) return e->fail(PK_ERR_CAPACITY, "pk_ctc_logprobs: more than Tmax frames");
+    pk_status s;
+    int32_t len = total_frames;
+    if ((s = stage_enc(e, enc, &len, 1))) return s;
+    // the [M][V] log-prob matrix lands in the (idle) qkv workspace
+    if ((size_t)e->M * e->cfg.vocab > (size_t)e->Bmax * e->Tmax * 3 * e->cfg.d_model)
+        return e->fail(PK_ERR_CAPACITY, "pk_ctc_logprobs: workspace too small");
+    if ((s = e->run_ctc(e->qkv))) return s;
+    cudaError_t ce = cudaMemcpyAsync(logprobs_out, e->qkv, (size_t)e->M * e->cfg.vocab * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_ctc_logprobs: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+}  // extern "C"

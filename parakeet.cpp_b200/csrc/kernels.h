@@ -1,0 +1,77 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (one .cu per op group).
+#pragma once
+#include "pk_common.cuh"
+
+#define PK_MAX_LSTM 4
+
+namespace pk {
+
+// ------------------------------------------------------------------ mel.cu (K1, K2)
+struct MelTables {
+    const float *window;    // [400] symmetric Hann (fp32 of the double formula)
+    const float2 *tw256;    // [256] exp(-2 pi i m / 256)
+    const float2 *tw512;    // [257] exp(-2 pi i k / 512)
+    const float *fb_w;      // non-zero filterbank weights, filter-major
+    const int32_t *fb_start, *fb_len, *fb_off;   // [n_mels]
+    int fb_nnz;
+};
+size_t mel_smem_bytes(const MelTables &tb);
+void launch_mel(const float *pcm, const int64_t *pcm_off, const int32_t *frame_off, int n_utt, int max_frames,
+                int n_mels, const MelTables &tb, float *logmel, float *feats, cudaStream_t st);
+
+// ------------------------------------------------------------------ subsample.cu (K3, K4)
+void launch_subsample_conv1_dw1(const float *feats, const int32_t *frame_off, const int32_t *s2_off, int n_utt,
+                                int max_t2, int mel, int C, const float *w1, const float *b1, const float *wd,
+                                const float *bd, ActBuf out, cudaStream_t st);
+void launch_subsample_dw(const float *in, const int32_t *in_rows, const int32_t *in_off, const int32_t *out_off,
+                         int n_utt, int fin, int C, const float *wd, const float *bd, ActBuf out,
+                         int total_out_rows, cudaStream_t st);
+
+// ------------------------------------------------------------------ gemm_simt.cu / gemm_tc.cu (K5)
+void launch_gemm_simt(const float *A, int lda, const float *W, int ldw, int M, int N, int K,
+                      const EpiParams &epi, cudaStream_t st);
+
+// ------------------------------------------------------------------ norm_conv.cu (K6, K8)
+void launch_layernorm(const float *x, int M, int d, const float *w1, const float *b1, float *out1_f32,
+                      ActBuf out1_act, const float *w2, const float *b2, ActBuf out2_act, cudaStream_t st);
+bool launch_dwconv_bn_silu(const float *g, const int32_t *row_off, int n_utt, int max_T, int d, int ks,
+                           const float *w, const float *bias, ActBuf out, cudaStream_t st);
+
+// ------------------------------------------------------------------ attention.cu (K7)
+bool launch_relpos_attention(const float *qkv, int ld_qkv, const int32_t *row_off, int n_utt, int max_T,
+                             int n_heads, int head_dim, const float *pp, int tmax, const float *bu,
+                             const float *bv, int d_model, ActBuf out, cudaStream_t st);
+
+// ------------------------------------------------------------------ ctc.cu (K9)
+void launch_ctc_frame_argmax(const float *logits, int M, int V, int ld, int32_t *best, float *conf,
+                             float *logprobs, cudaStream_t st);
+void launch_ctc_collapse(const int32_t *best, const float *conf, const int32_t *row_off, int n_utt, int blank,
+                         int cap, int32_t *tok, int32_t *t_start, int32_t *t_end, float *t_conf, cudaStream_t st);
+
+// ------------------------------------------------------------------ tdt.cu (K10)
+struct TdtParams {
+    int P, J, V, D, L, Bpad, n_utt, cap, max_steps, n_dur;
+    int out_in_smem, smem_lstm_floats;       // filled by launch_tdt_decode
+    int durations[8];
+    const float *EP;                          // [M][J] enc_proj(enc) + bias
+    const int32_t *row_off;                   // [n_utt+1]
+    const float *G0;                          // [V][4P] W_ih0 . E[token] + b0
+    const float *Whh[PK_MAX_LSTM];            // [4P][P]
+    const float *Wih[PK_MAX_LSTM];            // [4P][P] (layers >= 1)
+    const float *bih[PK_MAX_LSTM];            // [4P]    (layers >= 1)
+    const float *Wp;                          // [J][P]
+    const float *Wout;                        // [V+D][J]
+    const float *bout;                        // [V+D]
+    float *hbuf, *cbuf;                       // [L][2][P][Bpad]
+    float *z;                                 // [J][Bpad]
+    int32_t *cur, *token, *tpos, *active, *ntok, *overflow;   // [Bpad]
+    float *pl_max, *pl_sum, *pd_max;          // [grid][Bpad]
+    int32_t *pl_idx, *pd_idx;
+    int32_t *n_active;                        // [3]
+    int32_t *tok;                             // [n_utt][1+cap]
+    int32_t *t_start, *t_end;                 // [n_utt][cap]
+    float *t_conf;
+};
+cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
+
+}  // namespace pk

@@ -1,0 +1,147 @@
+// pk_common.cuh -- shared declarations for the sm_100a kernels of the hot path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pk {
+
+typedef __nv_bfloat16 bf16;
+
+// An activation that feeds a GEMM as the A operand.  In PK_MATH_FP32 mode only
+// `f32` is set; in the tcgen05 modes the producer kernel writes the bf16 hi/lo
+// split planes (hi = rn(x), lo = rn(x - hi)), which cost the same bytes as fp32.
+struct ActBuf {
+    float *f32 = nullptr;
+    bf16 *hi = nullptr;
+    bf16 *lo = nullptr;
+};
+
+__device__ __forceinline__ void store_act(const ActBuf &o, size_t idx, float v) {
+    if (o.f32) o.f32[idx] = v;
+    if (o.hi) {
+        bf16 h = __float2bfloat16_rn(v);
+        o.hi[idx] = h;
+        if (o.lo) o.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// 4 consecutive elements (idx multiple of 4): vectorised stores.
+__device__ __forceinline__ void store_act4(const ActBuf &o, size_t idx, float4 v) {
+    if (o.f32) *reinterpret_cast<float4 *>(o.f32 + idx) = v;
+    if (o.hi) {
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 hp;
+        hp.x = *reinterpret_cast<uint32_t *>(&h01);
+        hp.y = *reinterpret_cast<uint32_t *>(&h23);
+        *reinterpret_cast<uint2 *>(o.hi + idx) = hp;
+        if (o.lo) {
+            float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
+            __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+            uint2 lp;
+            lp.x = *reinterpret_cast<uint32_t *>(&l01);
+            lp.y = *reinterpret_cast<uint32_t *>(&l23);
+            *reinterpret_cast<uint2 *>(o.lo + idx) = lp;
+        }
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- GEMM epilogues
+// out = epi(A[M,K] . W[N,K]^T + bias).  All epilogues see 4 consecutive columns
+// of one row (col0 % 4 == 0) so GLU pairs and vector stores stay in-thread.
+enum EpiKind : int {
+    EPI_BIAS_F32 = 0,      // out_f32[row, col] = acc + bias
+    EPI_BIAS_RELU_F32 = 1, // relu -> out_f32
+    EPI_BIAS_RELU_ACT = 2, // relu -> act (feeds the next GEMM)
+    EPI_BIAS_SILU_ACT = 3, // silu -> act
+    EPI_RESID_F32 = 4,     // out_f32[row, col] = resid[row, col] + alpha * (acc + bias)
+    EPI_GLU_F32 = 5,       // columns interleaved (a0,b0,a1,b1..): out_f32[row, col/2] = a * sigmoid(b)
+    EPI_BIAS_ACT = 6,      // acc + bias -> act
+};
+
+struct EpiParams {
+    int kind = EPI_BIAS_F32;
+    const float *bias = nullptr;  // [N] (interleaved order for GLU)
+    float *out_f32 = nullptr;
+    int ldo = 0;                  // leading dimension of out_f32 / act / resid (elements)
+    ActBuf act;
+    const float *resid = nullptr;
+    float alpha = 1.0f;
+};
+
+__device__ __forceinline__ void epilogue4(const EpiParams &p, int row, int col0, int N, float4 acc) {
+    if (col0 >= N) return;
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    const bool full = (col0 + 3 < N);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (p.bias && col0 + i < N) v[i] += p.bias[col0 + i];
+    switch (p.kind) {
+    case EPI_BIAS_RELU_F32:
+    case EPI_BIAS_RELU_ACT:
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+        break;
+    case EPI_BIAS_SILU_ACT:
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = siluf_(v[i]);
+        break;
+    default:
+        break;
+    }
+    const size_t base = (size_t)row * p.ldo + col0;
+    switch (p.kind) {
+    case EPI_BIAS_F32:
+    case EPI_BIAS_RELU_F32:
+        if (full && (p.ldo & 3) == 0) {
+            *reinterpret_cast<float4 *>(p.out_f32 + base) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int i = 0; i < 4 && col0 + i < N; ++i) p.out_f32[base + i] = v[i];
+        }
+        break;
+    case EPI_BIAS_RELU_ACT:
+    case EPI_BIAS_SILU_ACT:
+    case EPI_BIAS_ACT:
+        if (full && (p.ldo & 3) == 0) {
+            store_act4(p.act, base, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+            for (int i = 0; i < 4 && col0 + i < N; ++i) store_act(p.act, base + i, v[i]);
+        }
+        break;
+    case EPI_RESID_F32:
+        if (full && (p.ldo & 3) == 0) {
+            float4 r = *reinterpret_cast<const float4 *>(p.resid + base);
+            *reinterpret_cast<float4 *>(p.out_f32 + base) =
+                make_float4(r.x + p.alpha * v[0], r.y + p.alpha * v[1], r.z + p.alpha * v[2],
+                            r.w + p.alpha * v[3]);
+        } else {
+            for (int i = 0; i < 4 && col0 + i < N; ++i)
+                p.out_f32[base + i] = p.resid[base + i] + p.alpha * v[i];
+        }
+        break;
+    case EPI_GLU_F32: {
+        // N is even and col0 % 4 == 0, so both pairs are in range together.
+        const size_t ob = (size_t)row * p.ldo + (col0 >> 1);
+        p.out_f32[ob] = v[0] * sigmoidf_(v[1]);
+        if (col0 + 2 < N) p.out_f32[ob + 1] = v[2] * sigmoidf_(v[3]);
+        break;
+    }
+    }
+}
+
+}  // namespace pk

@@ -1,0 +1,454 @@
+"""ctypes binding of libparakeet_b200.so and a Python mirror of the reference's
+high-level API (include/parakeet/transcribe.hpp:23-190 in the reference):
+
+    Transcriber(weights_path, vocab_path, config=make_110m_config())
+    .to_gpu()
+    .transcribe(samples | path, decoder=Decoder.TDT, timestamps=False) -> TranscribeResult
+    .transcribe(samples | path, TranscribeOptions(...))
+
+plus `transcribe_batch`, which the reference lacks (it is batch-1 only,
+transcribe.hpp:170-171).  There is no CPU path: if the CUDA library or a device
+is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libparakeet_b200.so")
+
+
+class _PkConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "mel_bins", "sub_channels", "d_model", "n_layers", "n_heads", "ff", "conv_kernel", "vocab",
+        "pred_hidden", "lstm_layers", "joint_hidden", "n_durations")] + [("durations", C.c_int32 * 8)] + \
+        [(n, C.c_int32) for n in ("has_ctc", "joint_prefix_tdt", "max_symbols", "max_batch", "max_samples", "math")]
+
+
+class _PkTokens(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("ids", C.POINTER(C.c_int32)), ("start", C.POINTER(C.c_int32)),
+                ("end", C.POINTER(C.c_int32)), ("conf", C.POINTER(C.c_float)), ("len", C.POINTER(C.c_int32))]
+
+
+EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engine_destroy", "pk_last_error",
+           "pk_mel_frames", "pk_encoder_frames", "pk_mel", "pk_encode", "pk_decode", "pk_ctc_logprobs",
+           "pk_transcribe_batch", "pk_stage_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
+           "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
+           "pk_detokenize", "pk_group_words"]
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA extension; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} is missing: build it with `python parakeet.cpp_b200/build.py` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(p)
+    vp, i32p, f32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int64)
+    L.pk_config_110m.argtypes = [C.POINTER(_PkConfig)]
+    L.pk_config_tdt_600m.argtypes = [C.POINTER(_PkConfig)]
+    L.pk_engine_create.argtypes = [C.POINTER(_PkConfig), C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.pk_engine_destroy.argtypes = [vp]
+    L.pk_last_error.argtypes = [vp]
+    L.pk_last_error.restype = C.c_char_p
+    L.pk_mel_frames.argtypes = [C.c_int64]
+    L.pk_encoder_frames.argtypes = [C.c_int32]
+    L.pk_mel.argtypes = [vp, f32p, i64p, C.c_int32, f32p, i32p]
+    L.pk_encode.argtypes = [vp, f32p, i32p, C.c_int32, f32p, i32p, f32p, f32p]
+    L.pk_decode.argtypes = [vp, f32p, i32p, C.c_int32, C.c_int, C.POINTER(_PkTokens)]
+    L.pk_ctc_logprobs.argtypes = [vp, f32p, C.c_int32, f32p]
+    L.pk_transcribe_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int, C.POINTER(_PkTokens)]
+    L.pk_stage_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
+    L.pk_run_staged.argtypes = [vp, C.c_int]
+    L.pk_fetch_tokens.argtypes = [vp, C.POINTER(_PkTokens)]
+    L.pk_sync.argtypes = [vp]
+    L.pk_token_buffer.argtypes = [vp, C.POINTER(vp), i32p, i32p]
+    L.pk_stream.argtypes = [vp]
+    L.pk_stream.restype = vp
+    L.pk_launch_count.argtypes = [vp]
+    L.pk_launch_count.restype = C.c_int64
+    L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.pk_vocab_free.argtypes = [vp]
+    L.pk_vocab_size.argtypes = [vp]
+    L.pk_detokenize.argtypes = [vp, i32p, C.c_int32, C.c_char_p, C.c_int32]
+    L.pk_group_words.argtypes = [vp, i32p, i32p, i32p, f32p, C.c_int32, C.c_char_p, C.c_int32, f32p, f32p, f32p]
+    _lib = L
+    return L
+
+
+# ------------------------------------------------------------------ configs (config.hpp)
+class Math(enum.IntEnum):
+    BF16X3 = 0
+    BF16X1 = 1
+    FP32 = 2
+
+
+@dataclass
+class ModelConfig:
+    """EncoderConfig + PredictionConfig + JointConfig (reference config.hpp:9-75)."""
+    mel_bins: int = 80
+    sub_channels: int = 256
+    d_model: int = 512
+    n_layers: int = 17
+    n_heads: int = 8
+    ff: int = 2048
+    conv_k: int = 9
+    vocab: int = 1025
+    pred_hidden: int = 640
+    lstm_layers: int = 1
+    joint_hidden: int = 640
+    durations: tuple = (0, 1, 2, 3, 4)
+    has_ctc: bool = True
+    joint_prefix: str = "tdt_joint_."
+    name: str = "tdt-ctc-110m"
+    # engine capacity
+    max_batch: int = 64
+    max_samples: int = 160000
+    math: int = int(Math.FP32)
+
+    def to_c(self) -> _PkConfig:
+        c = _PkConfig()
+        c.mel_bins, c.sub_channels, c.d_model, c.n_layers = self.mel_bins, self.sub_channels, self.d_model, self.n_layers
+        c.n_heads, c.ff, c.conv_kernel, c.vocab = self.n_heads, self.ff, self.conv_k, self.vocab
+        c.pred_hidden, c.lstm_layers, c.joint_hidden = self.pred_hidden, self.lstm_layers, self.joint_hidden
+        c.n_durations = len(self.durations)
+        for i, d in enumerate(self.durations):
+            c.durations[i] = d
+        c.has_ctc = int(self.has_ctc)
+        c.joint_prefix_tdt = int(self.joint_prefix == "tdt_joint_.")
+        c.max_symbols = 10
+        c.max_batch, c.max_samples, c.math = self.max_batch, self.max_samples, int(self.math)
+        return c
+
+
+def make_110m_config(**kw) -> ModelConfig:           # config.hpp:77-95
+    return ModelConfig(**kw)
+
+
+def make_tdt_600m_config(**kw) -> ModelConfig:       # config.hpp:98-116
+    base = dict(mel_bins=128, d_model=1024, n_layers=24, ff=4096, vocab=8193, lstm_layers=2, has_ctc=False,
+                joint_prefix="joint_.", name="tdt-600m", max_batch=16, max_samples=480000)
+    base.update(kw)
+    return ModelConfig(**base)
+
+
+def make_tiny_config(**kw) -> ModelConfig:
+    """Small test-only shape (not a reference preset)."""
+    base = dict(sub_channels=32, d_model=128, n_layers=2, n_heads=2, ff=256, vocab=33, pred_hidden=64,
+                joint_hidden=64, name="tiny", max_batch=8, max_samples=64000)
+    base.update(kw)
+    return ModelConfig(**base)
+
+
+# ------------------------------------------------------------------ result types (timestamp.hpp, transcribe.hpp)
+class Decoder(enum.IntEnum):          # transcribe.hpp:34
+    CTC = 0
+    TDT = 1
+
+
+@dataclass
+class TimestampedToken:               # timestamp.hpp:11-18
+    token_id: int
+    start_frame: int
+    end_frame: int
+    confidence: float = 1.0
+
+
+@dataclass
+class WordTimestamp:                  # timestamp.hpp:20-27
+    word: str
+    start: float
+    end: float
+    confidence: float = 1.0
+
+
+@dataclass
+class TranscribeResult:               # transcribe.hpp:23-30
+    text: str = ""
+    token_ids: List[int] = field(default_factory=list)
+    timestamped_tokens: List[TimestampedToken] = field(default_factory=list)
+    word_timestamps: List[WordTimestamp] = field(default_factory=list)
+
+
+@dataclass
+class TranscribeOptions:              # transcribe.hpp:38-43
+    decoder: Decoder = Decoder.TDT
+    timestamps: bool = False
+    boost_phrases: List[str] = field(default_factory=list)
+    boost_score: float = 5.0
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _i64p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _pack(arrs: Sequence[np.ndarray]):
+    arrs = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in arrs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    off[1:] = np.cumsum([len(a) for a in arrs])
+    return (np.concatenate(arrs) if arrs else np.zeros(0, np.float32)), off
+
+
+def read_wav(path: str) -> np.ndarray:
+    """16 kHz mono PCM16 / float32 WAV -> fp32 in [-1, 1] (the subset of read_audio,
+    src/audio_io.cpp:453-483, the configs need; int16 is divided by 32768 like dr_wav)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise RuntimeError("Unsupported audio format (only RIFF/WAVE here): " + path)
+    pos, fmt, pcm = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+        body = data[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", body[:16])
+        elif cid == b"data":
+            pcm = body
+        pos += 8 + size + (size & 1)
+    if fmt is None or pcm is None:
+        raise RuntimeError("malformed WAV: " + path)
+    tag, ch, sr, _, _, bits = fmt
+    if sr != 16000:
+        raise RuntimeError(f"Sample rate mismatch: audio={sr} expected=16000")
+    if tag == 1 and bits == 16:
+        x = np.frombuffer(pcm, "<i2").astype(np.float32) / np.float32(32768.0)
+    elif tag == 3 and bits == 32:
+        x = np.frombuffer(pcm, "<f4").astype(np.float32)
+    else:
+        raise RuntimeError("unsupported WAV encoding")
+    if ch > 1:
+        x = x.reshape(-1, ch).mean(axis=1).astype(np.float32)
+    return x
+
+
+class Engine:
+    """Thin object wrapper over the C-ABI (one engine per device)."""
+
+    def __init__(self, cfg: ModelConfig, weights_path: str, device: int = 0):
+        self.L = load_library()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        cc = cfg.to_c()
+        st = self.L.pk_engine_create(C.byref(cc), weights_path.encode(), device, C.byref(self.h))
+        if st != 0:
+            raise RuntimeError(f"pk_engine_create failed ({st}): " + self.L.pk_last_error(None).decode())
+        self.Tmax = self.L.pk_encoder_frames(self.L.pk_mel_frames(cfg.max_samples))
+        self.cap = 2 * self.Tmax + 8
+
+    def close(self):
+        if self.h:
+            self.L.pk_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what):
+        if st != 0:
+            raise RuntimeError(f"{what} failed ({st}): " + self.L.pk_last_error(self.h).decode())
+
+    # -- stage-level entry points (parity taps)
+    def mel(self, pcms: Sequence[np.ndarray]) -> List[np.ndarray]:
+        buf, off = _pack(pcms)
+        nfr = np.zeros(len(pcms), np.int32)
+        total = sum(1 + len(p) // 160 for p in pcms)
+        out = np.zeros((total, self.cfg.mel_bins), np.float32)
+        self._check(self.L.pk_mel(self.h, _f32p(buf), _i64p(off), len(pcms), _f32p(out), _i32p(nfr)), "pk_mel")
+        res, o = [], 0
+        for n in nfr:
+            res.append(out[o:o + n].copy())
+            o += n
+        return res
+
+    def encode(self, feats: Sequence[np.ndarray], taps: bool = False):
+        nfr = np.array([f.shape[0] for f in feats], np.int32)
+        buf = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float32) for f in feats], axis=0))
+        lens = [self.L.pk_encoder_frames(int(n)) for n in nfr]
+        Mx, d = sum(lens), self.cfg.d_model
+        out = np.zeros((Mx, d), np.float32)
+        olen = np.zeros(len(feats), np.int32)
+        sub = np.zeros((Mx, d), np.float32) if taps else None
+        lay = np.zeros((self.cfg.n_layers, Mx, d), np.float32) if taps else None
+        self._check(self.L.pk_encode(self.h, _f32p(buf), _i32p(nfr), len(feats), _f32p(out), _i32p(olen),
+                                     _f32p(sub) if taps else None, _f32p(lay) if taps else None), "pk_encode")
+        offs = np.concatenate([[0], np.cumsum(olen)])
+        encs = [out[offs[i]:offs[i + 1]].copy() for i in range(len(feats))]
+        if taps:
+            return encs, [sub[offs[i]:offs[i + 1]].copy() for i in range(len(feats))], \
+                [lay[:, offs[i]:offs[i + 1]].copy() for i in range(len(feats))]
+        return encs
+
+    def _tokens(self, n):
+        cap = self.cap
+        arrs = dict(ids=np.zeros((n, cap), np.int32), start=np.zeros((n, cap), np.int32),
+                    end=np.zeros((n, cap), np.int32), conf=np.zeros((n, cap), np.float32), len=np.zeros(n, np.int32))
+        t = _PkTokens(cap, _i32p(arrs["ids"]), _i32p(arrs["start"]), _i32p(arrs["end"]), _f32p(arrs["conf"]),
+                      _i32p(arrs["len"]))
+        return t, arrs
+
+    @staticmethod
+    def _unpack(arrs, n):
+        out = []
+        for b in range(n):
+            k = int(arrs["len"][b])
+            out.append([TimestampedToken(int(arrs["ids"][b, i]), int(arrs["start"][b, i]), int(arrs["end"][b, i]),
+                                         float(arrs["conf"][b, i])) for i in range(k)])
+        return out
+
+    def decode(self, encs: Sequence[np.ndarray], decoder: Decoder) -> List[List[TimestampedToken]]:
+        lens = np.array([e.shape[0] for e in encs], np.int32)
+        buf = np.ascontiguousarray(np.concatenate([np.asarray(e, np.float32) for e in encs], axis=0))
+        t, arrs = self._tokens(len(encs))
+        self._check(self.L.pk_decode(self.h, _f32p(buf), _i32p(lens), len(encs), int(decoder), C.byref(t)), "pk_decode")
+        return self._unpack(arrs, len(encs))
+
+    def ctc_logprobs(self, enc: np.ndarray) -> np.ndarray:
+        enc = np.ascontiguousarray(enc, np.float32)
+        out = np.zeros((enc.shape[0], self.cfg.vocab), np.float32)
+        self._check(self.L.pk_ctc_logprobs(self.h, _f32p(enc), enc.shape[0], _f32p(out)), "pk_ctc_logprobs")
+        return out
+
+    # -- the whole path
+    def transcribe_batch(self, pcms: Sequence[np.ndarray], decoder: Decoder) -> List[List[TimestampedToken]]:
+        buf, off = _pack(pcms)
+        t, arrs = self._tokens(len(pcms))
+        self._check(self.L.pk_transcribe_batch(self.h, _f32p(buf), _i64p(off), len(pcms), int(decoder), C.byref(t)),
+                    "pk_transcribe_batch")
+        return self._unpack(arrs, len(pcms))
+
+    # -- device-resident variant (bench)
+    def stage(self, buf: np.ndarray, off: np.ndarray):
+        self._check(self.L.pk_stage_pcm(self.h, _f32p(buf), _i64p(off), len(off) - 1), "pk_stage_pcm")
+
+    def run_staged(self, decoder: Decoder):
+        self._check(self.L.pk_run_staged(self.h, int(decoder)), "pk_run_staged")
+
+    def fetch(self, n) -> List[List[TimestampedToken]]:
+        t, arrs = self._tokens(n)
+        self._check(self.L.pk_fetch_tokens(self.h, C.byref(t)), "pk_fetch_tokens")
+        return self._unpack(arrs, n)
+
+    def sync(self):
+        self._check(self.L.pk_sync(self.h), "pk_sync")
+
+    def launch_count(self) -> int:
+        return int(self.L.pk_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.L.pk_stream(self.h) or 0)
+
+    def token_buffer(self):
+        p, rows, ints = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._check(self.L.pk_token_buffer(self.h, C.byref(p), C.byref(rows), C.byref(ints)), "pk_token_buffer")
+        return int(p.value), rows.value, ints.value
+
+
+class Tokenizer:
+    """Tokenizer::load / decode (src/vocab.cpp:10-64) via the C-ABI host helpers."""
+
+    def __init__(self, vocab_path: Optional[str] = None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        if vocab_path:
+            self.load(vocab_path)
+
+    def load(self, vocab_path: str):
+        if self.L.pk_vocab_load(vocab_path.encode(), C.byref(self.h)) != 0:
+            raise RuntimeError("Cannot open vocab file: " + vocab_path)      # vocab.cpp:13
+
+    def loaded(self) -> bool:
+        return bool(self.h) and self.L.pk_vocab_size(self.h) > 0
+
+    def decode(self, ids: Sequence[int]) -> str:
+        a = np.ascontiguousarray(ids, np.int32)
+        buf = C.create_string_buffer(64 + 64 * max(len(a), 1))
+        self.L.pk_detokenize(self.h, _i32p(a), len(a), buf, len(buf))
+        return buf.value.decode("utf-8")
+
+    def group_words(self, toks: Sequence[TimestampedToken]) -> List[WordTimestamp]:
+        n = len(toks)
+        ids = np.array([t.token_id for t in toks], np.int32)
+        st = np.array([t.start_frame for t in toks], np.int32)
+        en = np.array([t.end_frame for t in toks], np.int32)
+        cf = np.array([t.confidence for t in toks], np.float32)
+        buf = C.create_string_buffer(64 + 64 * max(n, 1))
+        ws, we, wc = (np.zeros(max(n, 1), np.float32) for _ in range(3))
+        k = self.L.pk_group_words(self.h, _i32p(ids), _i32p(st), _i32p(en), _f32p(cf), n, buf, len(buf), _f32p(ws),
+                                  _f32p(we), _f32p(wc))
+        words = buf.value.decode("utf-8").split("\n")[:k]
+        return [WordTimestamp(words[i], float(ws[i]), float(we[i]), float(wc[i])) for i in range(k)]
+
+
+class Transcriber:
+    """Python mirror of parakeet::Transcriber / TDTTranscriber (transcribe.hpp:55-299)."""
+
+    def __init__(self, weights_path: str, vocab_path: str, config: Optional[ModelConfig] = None, device: int = 0):
+        self.config = config or make_110m_config()
+        self.engine = Engine(self.config, weights_path, device)
+        self.tokenizer = Tokenizer(vocab_path) if vocab_path else Tokenizer()
+
+    def to_gpu(self):
+        """The reference moves the module tree to Metal here (transcribe.hpp:68-71); this
+        engine only ever lives on the CUDA device, so this is a checked no-op."""
+        return self
+
+    def _result(self, toks, timestamps):
+        r = TranscribeResult()
+        r.token_ids = [t.token_id for t in toks]
+        if timestamps:
+            r.timestamped_tokens = list(toks)
+        if self.tokenizer.loaded():
+            r.text = self.tokenizer.decode(r.token_ids)
+            if timestamps:
+                r.word_timestamps = self.tokenizer.group_words(toks)
+        return r
+
+    def transcribe(self, audio, decoder=Decoder.TDT, timestamps: bool = False) -> TranscribeResult:
+        if isinstance(decoder, TranscribeOptions):
+            opts = decoder
+        else:
+            opts = TranscribeOptions(decoder=decoder, timestamps=timestamps)
+        if opts.boost_phrases:
+            raise NotImplementedError("phrase boosting is outside the B200 hot path (SURVEY.md section 8f.3)")
+        samples = read_wav(audio) if isinstance(audio, str) else np.asarray(audio, np.float32)
+        dec = opts.decoder if self.config.has_ctc else Decoder.TDT
+        toks = self.engine.transcribe_batch([samples], dec)[0]
+        return self._result(toks, opts.timestamps)
+
+    def transcribe_batch(self, audios, decoder=Decoder.TDT, timestamps: bool = False) -> List[TranscribeResult]:
+        pcms = [read_wav(a) if isinstance(a, str) else np.asarray(a, np.float32) for a in audios]
+        out = []
+        B = self.config.max_batch
+        for i in range(0, len(pcms), B):
+            for toks in self.engine.transcribe_batch(pcms[i:i + B], decoder):
+                out.append(self._result(toks, timestamps))
+        return out
+
+
+TDTTranscriber = Transcriber   # transcribe.hpp:200-299 (same surface, TDT only)

@@ -76,13 +76,17 @@ def tensor_specs(cfg):
     return s
 
 
-def make_weights(cfg, seed=0, gain=1.0, head_gain=4.0, out_gain=0.25):
+def make_weights(cfg, seed=0, gain=1.0, head_gain=4.0, out_gain=0.25, blank_bias=None, ctc_blank_bias=None):
     """dict name -> ndarray.  N(0, gain/sqrt(fan_in)) matrices; LayerNorm/BN scale
     ~1; small biases; the q/k/pos projections get a larger gain so attention is
     peaked (time-local) instead of uniform, and the classification heads get
     `head_gain` so arg-max margins sit well above fp32 re-association noise."""
     rng = np.random.default_rng(seed)
     W = {}
+    if blank_bias is None:          # keeps the TDT token rate near one per 2-4 frames
+        blank_bias = 6.0 if cfg.vocab > 100 else 1.0
+    if ctc_blank_bias is None:
+        ctc_blank_bias = 12.0 if cfg.vocab > 100 else 7.0
     for name, shape, kind in tensor_specs(cfg):
         if kind == "i64":
             W[name] = np.array(1000, dtype=np.int64)
@@ -109,12 +113,14 @@ def make_weights(cfg, seed=0, gain=1.0, head_gain=4.0, out_gain=0.25):
             a = 0.5 * rng.standard_normal(shape)
         elif kind == "lab_b":
             a = 0.1 * rng.standard_normal(shape)
-            a[-1] = 6.0                      # blank is the commonest TDT label
+            a[-1] = blank_bias               # blank is the commonest TDT label
         elif kind == "dur_b":
             a = np.array([-2.0, 2.0, 1.0, 0.0, -1.0])[: shape[0]] + 0.1 * rng.standard_normal(shape)
         else:                                # "b"
             a = 0.1 * rng.standard_normal(shape)
         W[name] = a.astype(F32)
+    if "ctc_decoder_.proj_.bias" in W:
+        W["ctc_decoder_.proj_.bias"][-1] = ctc_blank_bias
     return W
 
 

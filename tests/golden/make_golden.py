@@ -1,0 +1,97 @@
+"""Generates tests/golden/golden_v1.npz from the UNMODIFIED reference compiled here
+(oracle/_ref/libpkref.so <- /root/reference via oracle/Makefile).
+
+    python tests/golden/make_golden.py
+
+The reference ships no numeric golden vectors for mel / encoder (SURVEY.md section 4:
+its tests pin shapes and decode-loop logic only), so these are produced by running
+the reference itself on seeded synthetic checkpoints / audio
+(parakeet.cpp_b200/synth.py; same seeds as the tests' fixtures).  The fixtures pin
+oracle/oracle.py (tests/test_oracle.py, CPU) and the CUDA path (tests/test_gpu_parity.py).
+/root/reference is not needed to *consume* the fixtures.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import __graft_entry__ as ge  # noqa: E402
+import oracle as O  # noqa: E402
+import refbind as R  # noqa: E402
+
+ge.load_package()
+from parakeet_cpp_b200 import synth  # noqa: E402
+
+
+def toks_arr(toks):
+    return np.array([[t[0], t[1], t[2]] for t in toks], np.int32).reshape(-1, 3), \
+        np.array([t[3] for t in toks], np.float32)
+
+
+def run_model(out, tag, ocfg, seed, clips, td, custom):
+    W = synth.make_weights(ocfg, seed=seed)
+    wp = os.path.join(td, tag + ".safetensors")
+    synth.save_safetensors(wp, W)
+    pieces = synth.make_vocab(ocfg.vocab - 1, seed=seed)
+    vp = os.path.join(td, tag + ".vocab.txt")
+    synth.save_vocab(vp, pieces)
+    m = R.RefModel(wp, vp, 0, cfg=ocfg if custom else None)
+    for ci, (n, aseed) in enumerate(clips):
+        k = f"{tag}.c{ci}."
+        pcm = synth.make_audio(n, aseed)
+        feats = R.mel(pcm, ocfg.mel_bins)
+        T = O.encoder_len(feats.shape[0])
+        sub, lay = m.encode_layers(feats, ocfg.d_model, ocfg.n_layers, T)
+        enc = m.encode(feats, ocfg.d_model)
+        assert np.array_equal(enc, lay[-1])
+        lp = m.ctc_logprobs(enc, ocfg.vocab)
+        ctc = R.ctc_greedy(lp, ocfg.vocab - 1, True)[0]
+        tdt = m.tdt_greedy(enc, True)
+        out[k + "n_samples"] = np.array([n, aseed], np.int64)
+        out[k + "mel"] = feats.astype(np.float16) if feats.size > 50000 else feats
+        out[k + "mel_stats"] = np.array([feats.mean(), feats.std(), np.abs(feats).max(), feats[::7, ::3].sum()], np.float64)
+        out[k + "sub"] = sub if sub.size < 70000 else sub[::8]
+        out[k + "layers_first_last"] = np.stack([lay[0], lay[-1]]) if lay[0].size < 70000 else np.stack([lay[0][::8], lay[-1][::8]])
+        out[k + "enc"] = enc
+        out[k + "ctc_lp_max"] = lp.max(axis=1)
+        out[k + "ctc_argmax"] = lp.argmax(axis=1).astype(np.int32)
+        out[k + "ctc_tok"], out[k + "ctc_conf"] = toks_arr(ctc)
+        out[k + "tdt_tok"], out[k + "tdt_conf"] = toks_arr(tdt)
+        out[k + "ctc_text"] = np.frombuffer(m.detok([t[0] for t in ctc]).encode(), np.uint8)
+        out[k + "tdt_text"] = np.frombuffer(m.detok([t[0] for t in tdt]).encode(), np.uint8)
+        words = m.group_words(tdt)
+        out[k + "tdt_words"] = np.frombuffer("\n".join(w[0] for w in words).encode(), np.uint8)
+        out[k + "tdt_word_times"] = np.array([[w[1], w[2], w[3]] for w in words], np.float32).reshape(-1, 3)
+        print(tag, ci, "frames", feats.shape[0], "T", T, "ctc", len(ctc), "tdt", len(tdt))
+    m.close()
+
+
+def main():
+    out = {}
+    out["posemb_5_4"] = R.posemb(5, 4)
+    out["posemb_10_64"] = R.posemb(10, 64)
+    # decode-loop vectors of the reference's own tests (tests/test_all.cpp:759-872), run
+    # through the reference to record the full timestamped answers
+    V = 1025
+    for name, pattern in (("collapse", [10, 10, 1024, 10, 10, 20]), ("with_ts", [5, 5, 1024, 8, 8, 8]),
+                          ("all_blank", [1024] * 10), ("single", [42, 42, 42, 1024, 1024])):
+        lp = np.full((len(pattern), V), -10.0, np.float32)
+        for t, p in enumerate(pattern):
+            lp[t, p] = 0.0
+        r = R.ctc_greedy(lp, 1024, True)[0]
+        out[f"ctc_ka.{name}.pattern"] = np.array(pattern, np.int32)
+        out[f"ctc_ka.{name}.tok"], out[f"ctc_ka.{name}.conf"] = toks_arr(r)
+    with tempfile.TemporaryDirectory() as td:
+        run_model(out, "tiny", O.make_tiny_config(), 3, [(32000, 11), (20000, 12), (400, 13), (64000, 14)], td, True)
+        run_model(out, "m110", O.make_110m_config(), 0, [(160000, 1000)], td, False)
+    path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/parakeet_b200.h declares (no compute without a GPU), presets match the
+reference's config.hpp, the host-side text helpers match the oracle, and the product
+fails loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "parakeet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.load_library()
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/parakeet_b200.h but not exported"
+    assert set(pkg.engine.EXPORTS) == set(syms)
+
+
+def test_presets_match_reference_config(pkg):
+    L = pkg.load_library()
+    c = pkg.engine._PkConfig()
+    L.pk_config_110m(C.byref(c))           # config.hpp:77-95
+    assert (c.mel_bins, c.sub_channels, c.d_model, c.n_layers, c.n_heads, c.ff, c.conv_kernel) == (80, 256, 512, 17, 8, 2048, 9)
+    assert (c.vocab, c.pred_hidden, c.lstm_layers, c.joint_hidden, c.n_durations) == (1025, 640, 1, 640, 5)
+    assert list(c.durations)[:5] == [0, 1, 2, 3, 4] and c.has_ctc == 1 and c.joint_prefix_tdt == 1
+    L.pk_config_tdt_600m(C.byref(c))       # config.hpp:98-116
+    assert (c.mel_bins, c.d_model, c.n_layers, c.ff, c.vocab, c.lstm_layers, c.has_ctc, c.joint_prefix_tdt) == \
+        (128, 1024, 24, 4096, 8193, 2, 0, 0)
+    py = pkg.make_110m_config().to_c()
+    L.pk_config_110m(C.byref(c))
+    for f, _ in pkg.engine._PkConfig._fields_:
+        if f in ("durations", "max_batch", "max_samples", "math"):
+            continue
+        assert getattr(py, f) == getattr(c, f), f
+
+
+def test_shape_helpers(pkg, O):
+    L = pkg.load_library()
+    for n in (400, 401, 16000, 159999, 160000, 160001, 480000):
+        assert L.pk_mel_frames(n) == O.n_mel_frames(n)
+        assert L.pk_encoder_frames(L.pk_mel_frames(n)) == O.encoder_len(O.n_mel_frames(n))
+    assert L.pk_encoder_frames(1001) == 126 and L.pk_encoder_frames(3001) == 376
+
+
+def test_text_helpers_match_oracle(pkg, O, tiny):
+    tok = pkg.engine.Tokenizer(tiny.vocab_path)
+    assert tok.loaded()
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        n = int(rng.integers(0, 30))
+        ids = rng.integers(0, tiny.ocfg.vocab - 1, n).tolist()
+        if n > 3:
+            ids[2] = 9999        # out-of-range -> "[9999]" (vocab.cpp:33-36)
+        assert tok.decode(ids) == O.detokenize(ids, tiny.pieces)
+        start = np.cumsum(rng.integers(0, 4, n)).tolist()
+        toks = [pkg.TimestampedToken(i, s, s + int(rng.integers(0, 3)), float(rng.random())) for i, s in zip(ids, start)]
+        got = tok.group_words(toks)
+        want = O.group_timestamps([(t.token_id, t.start_frame, t.end_frame, t.confidence) for t in toks], tiny.pieces)
+        assert [w.word for w in got] == [w[0] for w in want]
+        assert np.allclose([[w.start, w.end, w.confidence] for w in got], [[w[1], w[2], w[3]] for w in want], rtol=1e-6) or not want
+
+
+def test_vocab_missing_file_raises(pkg):
+    with pytest.raises(RuntimeError):
+        pkg.engine.Tokenizer("/nonexistent/vocab.txt")
+
+
+def test_safetensors_errors_are_reported(pkg, tiny, tmp_path):
+    """Loader error paths that do not need a device come back as status + message...
+    but without a GPU pk_engine_create refuses first: the product has no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        pkg.Engine(tiny.cfg, tiny.weights_path, 0)
+
+
+def test_read_wav_roundtrip(pkg, synth, tmp_path):
+    import struct
+    pcm = synth.make_audio(16000, 5)
+    i16 = np.round(pcm * 32768.0).astype(np.int16)
+    p = tmp_path / "a.wav"
+    with open(p, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + 2 * len(i16)) + b"WAVEfmt " +
+                struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"data" + struct.pack("<I", 2 * len(i16)))
+        f.write(i16.tobytes())
+    assert np.array_equal(pkg.engine.read_wav(str(p)), pcm)
+
+
+def test_synth_checkpoint_layout(O, synth):
+    """705 tensors / 114.6 M parameters for 110m."""
+    specs = synth.tensor_specs(O.make_110m_config())
+    assert len(specs) == 705
+    n = sum(int(np.prod(s)) for _, s, k in specs if k != "i64")
+    assert abs(n - 114.6e6) < 0.1e6

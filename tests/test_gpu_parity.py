@@ -1,0 +1,227 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against the oracle
+on the same seeded inputs, against the committed golden fixtures produced by the
+compiled reference, and -- at the BASELINE batch size -- through size-independent
+properties (batch invariance, determinism).
+
+Tolerances: tokens / frames / argmax are bit-exact; floating point uses the north-star
+bound "encoder activations within 1e-3 rel fp32" (max-abs error / max-abs reference), and
+tighter where the arithmetic is exact fp32.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ENC_TOL = 1e-3        # north_star tolerance for encoder activations
+MEL_TOL = 2e-3        # abs, on unit-variance normalised features
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _tt(toks):
+    return [(t.token_id, t.start_frame, t.end_frame) for t in toks]
+
+
+@pytest.fixture(scope="module")
+def eng_tiny(pkg, tiny):
+    e = pkg.Engine(tiny.cfg, tiny.weights_path, 0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng110(pkg, m110):
+    e = pkg.Engine(m110.cfg, m110.weights_path, 0)
+    yield e
+    e.close()
+
+
+# ------------------------------------------------------------------ mel front end (K1/K2)
+@pytest.mark.parametrize("lengths", [[16000], [400], [401, 559, 560, 561], [32000, 20000, 64000, 12345, 8000, 16001]])
+def test_mel_matches_oracle(eng_tiny, O, synth, lengths):
+    pcms = [synth.make_audio(n, 100 + i) for i, n in enumerate(lengths)]
+    got = eng_tiny.mel(pcms)
+    for pcm, g in zip(pcms, got):
+        want = O.preprocess_audio(pcm)
+        assert g.shape == want.shape
+        if want.shape[0] > 3:
+            assert np.abs(g - want).max() < MEL_TOL
+        else:   # 3 frames: sigma ~ 0 bins amplify fp32 noise by 1e5; compare what is stable
+            assert np.isfinite(g).all()
+
+
+def test_mel_matches_reference_golden(eng_tiny, synth, golden):
+    for ci in (0, 1, 3):
+        n, aseed = (int(v) for v in golden[f"tiny.c{ci}.n_samples"])
+        got = eng_tiny.mel([synth.make_audio(n, aseed)])[0]
+        assert np.abs(got - golden[f"tiny.c{ci}.mel"]).max() < MEL_TOL
+
+
+def test_mel_edge_signals(eng_tiny, O):
+    rng = np.random.default_rng(0)
+    sil = (1e-4 * rng.standard_normal(16000)).astype(np.float32)          # near-silence
+    loud = np.clip(rng.standard_normal(16000), -1, 1).astype(np.float32)  # full-scale noise
+    imp = np.zeros(16000, np.float32); imp[8000] = 1.0; imp += (1e-3 * rng.standard_normal(16000)).astype(np.float32)
+    for pcm in (sil, loud, imp):
+        g = eng_tiny.mel([pcm])[0]
+        assert np.abs(g - O.preprocess_audio(pcm)).max() < 5e-3
+
+
+# ------------------------------------------------------------------ encoder
+def test_encoder_tiny_layers_match_oracle_and_golden(eng_tiny, O, tiny, golden):
+    for ci in (0, 1, 2, 3):
+        k = f"tiny.c{ci}."
+        feats = golden[k + "mel"].astype(np.float32)
+        encs, subs, lays = eng_tiny.encode([feats], taps=True)
+        enc_o, sub_o, lay_o = O.encoder_forward(tiny.W, feats, tiny.ocfg, return_layers=True)
+        assert _rel(subs[0], sub_o) < 1e-4
+        for i in range(tiny.ocfg.n_layers):
+            assert _rel(lays[0][i], lay_o[i]) < ENC_TOL
+        assert _rel(encs[0], golden[k + "enc"]) < ENC_TOL
+        assert _rel(subs[0], golden[k + "sub"]) < 1e-4
+
+
+def test_encoder_ragged_batch_equals_singles(eng_tiny, O, synth, tiny):
+    """Packed batch == each utterance alone (the reference is batch-1): padding, conv edges
+    and attention extents are per utterance."""
+    pcms = [synth.make_audio(n, 200 + i) for i, n in enumerate([64000, 400, 20000, 33333, 8000])]
+    feats = [O.preprocess_audio(p) for p in pcms]
+    batch = eng_tiny.encode(feats)
+    for f, b in zip(feats, batch):
+        single = eng_tiny.encode([f])[0]
+        assert np.array_equal(single, b)
+        assert _rel(b, O.encoder_forward(tiny.W, f, tiny.ocfg)) < ENC_TOL
+
+
+def test_encoder_110m_matches_reference_golden(eng110, O, m110, synth, golden):
+    k = "m110.c0."
+    n, aseed = (int(v) for v in golden[k + "n_samples"])
+    feats = O.preprocess_audio(synth.make_audio(n, aseed))
+    encs, subs, lays = eng110.encode([feats], taps=True)
+    assert encs[0].shape == (126, 512)
+    assert _rel(subs[0][::8], golden[k + "sub"]) < 1e-4
+    fl = golden[k + "layers_first_last"]
+    assert _rel(lays[0][0][::8], fl[0]) < ENC_TOL
+    assert _rel(lays[0][-1][::8], fl[1]) < ENC_TOL
+    assert _rel(encs[0], golden[k + "enc"]) < ENC_TOL
+
+
+# ------------------------------------------------------------------ CTC head + greedy (K9)
+def test_ctc_logprobs_and_tokens(eng_tiny, eng110, O, tiny, m110, golden):
+    for eng, mdl, tag, cis in ((eng_tiny, tiny, "tiny", (0, 1, 2, 3)), (eng110, m110, "m110", (0,))):
+        for ci in cis:
+            k = f"{tag}.c{ci}."
+            enc = golden[k + "enc"]
+            lp = eng.ctc_logprobs(enc)
+            want = O.ctc_log_probs(mdl.W, enc)
+            assert np.abs(lp - want).max() < 1e-3
+            assert np.array_equal(lp.argmax(1), golden[k + "ctc_argmax"])
+            toks = eng.decode([enc], 0)[0]
+            assert [list(t) for t in _tt(toks)] == golden[k + "ctc_tok"].tolist()
+            assert np.allclose([t.confidence for t in toks], golden[k + "ctc_conf"], rtol=1e-3)
+
+
+def test_ctc_known_answer_patterns(pkg, eng_tiny, O, tiny, golden):
+    """The reference's CTCDecode.* vectors need log-probs as input; the C-ABI decodes from
+    encoder output, so drive it with encoder rows that make the head emit the pattern:
+    checked against the oracle's collapse of the engine's own per-frame argmax."""
+    rng = np.random.default_rng(1)
+    enc = rng.standard_normal((40, tiny.ocfg.d_model)).astype(np.float32)
+    enc[10:14] = enc[10]       # repeated frames -> repeated argmax -> collapse
+    enc[20:23] = enc[5]
+    lp = O.ctc_log_probs(tiny.W, enc)
+    want = O.ctc_greedy_decode_with_timestamps(lp, tiny.ocfg.vocab - 1)
+    got = eng_tiny.decode([enc], 0)[0]
+    assert _tt(got) == [w[:3] for w in want]
+
+
+# ------------------------------------------------------------------ TDT greedy (K10)
+def test_tdt_tokens_match_reference_golden(eng_tiny, eng110, golden):
+    for eng, tag, cis in ((eng_tiny, "tiny", (0, 1, 2, 3)), (eng110, "m110", (0,))):
+        for ci in cis:
+            k = f"{tag}.c{ci}."
+            toks = eng.decode([golden[k + "enc"]], 1)[0]
+            assert [list(t) for t in _tt(toks)] == golden[k + "tdt_tok"].tolist()
+            assert np.allclose([t.confidence for t in toks], golden[k + "tdt_conf"], rtol=1e-3)
+
+
+def test_tdt_batch_lockstep_equals_singles(eng_tiny, O, tiny):
+    rng = np.random.default_rng(2)
+    encs = [rng.standard_normal((T, tiny.ocfg.d_model)).astype(np.float32) for T in (51, 1, 7, 33, 20, 2, 40, 13)]
+    got = eng_tiny.decode(encs, 1)
+    for e, g in zip(encs, got):
+        want = O.tdt_greedy_decode(tiny.W, e, tiny.ocfg, with_timestamps=True)
+        assert _tt(g) == [w[:3] for w in want]
+        assert np.allclose([t.confidence for t in g], [w[3] for w in want], rtol=1e-3)
+
+
+# ------------------------------------------------------------------ whole path through the public API
+def test_transcriber_api_matches_reference_golden(pkg, tiny, synth, golden):
+    t = pkg.Transcriber(tiny.weights_path, tiny.vocab_path, tiny.cfg)
+    t.to_gpu()
+    for ci in (0, 1, 3):
+        k = f"tiny.c{ci}."
+        n, aseed = (int(v) for v in golden[k + "n_samples"])
+        pcm = synth.make_audio(n, aseed)
+        r = t.transcribe(pcm, pkg.Decoder.TDT, True)
+        assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == golden[k + "tdt_tok"].tolist()
+        assert r.text == bytes(golden[k + "tdt_text"]).decode()
+        assert "\n".join(w.word for w in r.word_timestamps) == bytes(golden[k + "tdt_words"]).decode()
+        if r.word_timestamps:
+            assert np.allclose([[w.start, w.end, w.confidence] for w in r.word_timestamps], golden[k + "tdt_word_times"], rtol=1e-3)
+        r2 = t.transcribe(pcm, pkg.Decoder.CTC)
+        assert r2.token_ids == golden[k + "ctc_tok"][:, 0].tolist()
+        assert r2.text == bytes(golden[k + "ctc_text"]).decode()
+        assert r2.timestamped_tokens == []           # timestamps=false leaves them empty (transcribe.hpp:152-176)
+    t.engine.close()
+
+
+def test_transcribe_110m_whole_path_tokens(pkg, m110, synth, golden):
+    t = pkg.Transcriber(m110.weights_path, m110.vocab_path, m110.cfg)
+    k = "m110.c0."
+    n, aseed = (int(v) for v in golden[k + "n_samples"])
+    pcm = synth.make_audio(n, aseed)
+    r = t.transcribe(pcm, pkg.Decoder.CTC, True)
+    assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == golden[k + "ctc_tok"].tolist()
+    assert r.text == bytes(golden[k + "ctc_text"]).decode()
+    r = t.transcribe(pcm, pkg.Decoder.TDT, True)
+    assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == golden[k + "tdt_tok"].tolist()
+    t.engine.close()
+
+
+def test_full_batch_properties(pkg, m110, synth):
+    """BASELINE size (64 x 10 s): batch invariance and determinism, no oracle needed."""
+    cfg = pkg.make_110m_config(max_batch=64)
+    e = pkg.Engine(cfg, m110.weights_path, 0)
+    pcms = [synth.make_audio(160000, 1000 + i) for i in range(64)]
+    for dec in (0, 1):
+        a = e.transcribe_batch(pcms, dec)
+        b = e.transcribe_batch(pcms, dec)
+        assert [_tt(x) for x in a] == [_tt(x) for x in b]                 # deterministic
+        sub = e.transcribe_batch([pcms[5], pcms[63], pcms[0]], dec)
+        assert [_tt(x) for x in sub] == [_tt(a[5]), _tt(a[63]), _tt(a[0])]  # batch-invariant
+        for x in a:
+            assert all(0 <= t.token_id < 1024 for t in x)
+            assert all(0 <= t.start_frame <= t.end_frame <= 125 for t in x)
+            assert all(x[i].start_frame <= x[i + 1].start_frame for i in range(len(x) - 1))
+    e.close()
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_error_statuses(pkg, eng_tiny, tiny, synth, tmp_path):
+    with pytest.raises(RuntimeError, match="max_samples|capacity|exceeds"):
+        eng_tiny.transcribe_batch([synth.make_audio(tiny.cfg.max_samples + 160, 1)], 0)
+    with pytest.raises(RuntimeError, match="window|shorter"):
+        eng_tiny.transcribe_batch([np.zeros(100, np.float32)], 0)
+    with pytest.raises(RuntimeError, match="max_batch|exceeds"):
+        eng_tiny.transcribe_batch([synth.make_audio(800, i) for i in range(tiny.cfg.max_batch + 1)], 0)
+    with pytest.raises(RuntimeError, match="cannot open"):
+        pkg.Engine(tiny.cfg, str(tmp_path / "nope.safetensors"), 0)
+    bad = dict(tiny.W)
+    bad.pop("encoder_.layers_.1.attn_.pos_bias_u_")
+    p = str(tmp_path / "missing.safetensors")
+    synth.save_safetensors(p, bad)
+    with pytest.raises(RuntimeError, match="missing tensor"):
+        pkg.Engine(tiny.cfg, p, 0)

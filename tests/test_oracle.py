@@ -1,0 +1,179 @@
+"""CPU tests that PIN THE ORACLE (oracle/oracle.py) before it is trusted:
+  (1) the reference's own known-answer tests that apply at this boundary
+      (/root/reference/tests/test_all.cpp: CTCDecode.* :759-872, PositionEmbedding.* :1003-1030,
+       GroupTimestamps.* / TimestampTypes.* :45-129, Tokenizer.DecodeOutOfRange :470-477),
+  (2) golden vectors produced by the unmodified reference compiled here
+      (tests/golden/golden_v1.npz <- tests/golden/make_golden.py),
+  (3) when oracle/_ref/libpkref.so is present, the live compiled reference.
+"""
+import numpy as np
+import pytest
+
+
+def _lp_from_pattern(pattern, V=1025):
+    lp = np.full((len(pattern), V), -10.0, np.float32)
+    for t, p in enumerate(pattern):
+        lp[t, p] = 0.0
+    return lp
+
+
+# ---------------------------------------------------------------- (1) reference known-answer tests
+def test_ctc_all_blanks(O):                       # CTCDecode.AllBlanks
+    assert O.ctc_greedy_decode(_lp_from_pattern([1024] * 10)) == []
+
+
+def test_ctc_single_token(O):                     # CTCDecode.SingleToken
+    assert O.ctc_greedy_decode(_lp_from_pattern([42, 42, 42, 1024, 1024])) == [42]
+
+
+def test_ctc_collapse_repeats(O):                 # CTCDecode.CollapseRepeats
+    assert O.ctc_greedy_decode(_lp_from_pattern([10, 10, 1024, 10, 10, 20])) == [10, 10, 20]
+
+
+def test_ctc_with_timestamps(O):                  # CTCDecode.WithTimestamps
+    r = O.ctc_greedy_decode_with_timestamps(_lp_from_pattern([5, 5, 1024, 8, 8, 8]))
+    assert [(t[0], t[1]) for t in r] == [(5, 0), (8, 3)]
+
+
+def test_ctc_batch(O):                            # CTCDecode.BatchDecode
+    assert O.ctc_greedy_decode(_lp_from_pattern([5] * 4)) == [5]
+    assert O.ctc_greedy_decode(_lp_from_pattern([1024] * 4)) == []
+
+
+def test_ctc_first_max_wins(O):                   # strict '>' scan, ctc.cpp:59-66
+    lp = np.zeros((1, 1025), np.float32)
+    assert O.ctc_greedy_decode(lp) == [0]
+
+
+def test_posemb_shape_values_center(O):           # PositionEmbedding.{Shape,Values,CenterRow}
+    pe = O.sinusoidal_position_embedding(10, 64)
+    assert pe.shape == (19, 64)
+    pe = O.sinusoidal_position_embedding(5, 4)
+    assert np.all(pe >= -1.001) and np.all(pe <= 1.001)
+    assert abs(pe[4, 0]) < 1e-5
+
+
+def test_frame_to_seconds_and_grouping(O):        # TimestampTypes.FrameToSeconds, GroupTimestamps.*
+    M = O.SP_MARK
+    assert O.group_timestamps([], []) == []
+    w = O.group_timestamps([(0, 5, 10, 1.0)], [M + "hello"])
+    assert len(w) == 1 and w[0][0] == "hello"
+    assert w[0][1] == pytest.approx(np.float32(5) * np.float32(0.08)) and w[0][2] == pytest.approx(0.8)
+    w = O.group_timestamps([(0, 0, 2, 1.0), (1, 5, 8, 1.0), (2, 12, 15, 1.0)], [M + "the", M + "quick", M + "fox"])
+    assert [x[0] for x in w] == ["the", "quick", "fox"]
+    w = O.group_timestamps([(0, 0, 3, 0.9), (1, 4, 6, 0.5)], [M + "run", "ning"])
+    assert len(w) == 1 and w[0][0] == "running" and w[0][1] == 0.0
+    assert w[0][2] == pytest.approx(np.float32(6) * np.float32(0.08)) and w[0][3] == pytest.approx(0.5)
+    w = O.group_timestamps([(999, 0, 1, 1.0), (0, 2, 4, 1.0)], [M + "hello"])      # OutOfRangeTokenId
+    assert len(w) == 1 and w[0][0] == "hello"
+
+
+def test_detokenize(O):                           # Tokenizer.DecodeEmpty / DecodeOutOfRange
+    M = O.SP_MARK
+    assert O.detokenize([], ["a"]) == ""
+    assert O.detokenize([9999], ["a"]) == "[9999]"
+    assert O.detokenize([0, 1, 2], [M + "he", "llo", M + "you"]) == "hello you"
+
+
+def test_preset_values(O):                        # Config.* (test_all.cpp:135-194)
+    c = O.make_110m_config()
+    assert (c.d_model, c.n_layers, c.n_heads, c.ff, c.vocab, c.lstm_layers, c.pred_hidden) == (512, 17, 8, 2048, 1025, 1, 640)
+    c = O.make_tdt_600m_config()
+    assert (c.mel_bins, c.d_model, c.n_layers, c.ff, c.vocab, c.lstm_layers) == (128, 1024, 24, 4096, 8193, 2)
+
+
+# ---------------------------------------------------------------- (2) golden vectors from the compiled reference
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_golden_posemb(O, golden):
+    assert np.abs(O.sinusoidal_position_embedding(5, 4) - golden["posemb_5_4"]).max() < 2e-6
+    assert np.abs(O.sinusoidal_position_embedding(10, 64) - golden["posemb_10_64"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("name", ["collapse", "with_ts", "all_blank", "single"])
+def test_golden_ctc_known_answers(O, golden, name):
+    lp = _lp_from_pattern(golden[f"ctc_ka.{name}.pattern"])
+    r = O.ctc_greedy_decode_with_timestamps(lp)
+    tok = golden[f"ctc_ka.{name}.tok"]
+    assert [[t[0], t[1], t[2]] for t in r] == tok.tolist()
+    assert np.allclose([t[3] for t in r], golden[f"ctc_ka.{name}.conf"], rtol=1e-6)
+
+
+def _golden_clip(O, synth, golden, tag, ci, ocfg, seed):
+    k = f"{tag}.c{ci}."
+    n, aseed = (int(v) for v in golden[k + "n_samples"])
+    W = synth.make_weights(ocfg, seed=seed)
+    pcm = synth.make_audio(n, aseed)
+    return k, W, pcm
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_golden_tiny_whole_path(O, synth, golden, ci):
+    ocfg = O.make_tiny_config()
+    k, W, pcm = _golden_clip(O, synth, golden, "tiny", ci, ocfg, 3)
+    feats = O.preprocess_audio(pcm, ocfg.mel_bins)
+    assert feats.shape == golden[k + "mel"].shape
+    if feats.shape[0] > 3:   # the 3-frame clip has near-zero variance bins: 1/(sigma+1e-5) amplifies fp32 noise
+        assert np.abs(feats - golden[k + "mel"]).max() < 2e-3
+    enc, sub, lay = O.encoder_forward(W, golden[k + "mel"].astype(np.float32), ocfg, return_layers=True)
+    assert _rel(sub, golden[k + "sub"]) < 2e-5
+    assert _rel(lay[0], golden[k + "layers_first_last"][0]) < 2e-5
+    assert _rel(enc, golden[k + "enc"]) < 5e-5
+    genc = golden[k + "enc"]
+    lp = O.ctc_log_probs(W, genc)
+    assert np.array_equal(lp.argmax(1), golden[k + "ctc_argmax"])
+    assert np.abs(lp.max(1) - golden[k + "ctc_lp_max"]).max() < 1e-4
+    ctc = O.ctc_greedy_decode_with_timestamps(lp, ocfg.vocab - 1)
+    assert [[t[0], t[1], t[2]] for t in ctc] == golden[k + "ctc_tok"].tolist()
+    assert np.allclose([t[3] for t in ctc], golden[k + "ctc_conf"], rtol=1e-4)
+    tdt = O.tdt_greedy_decode(W, genc, ocfg, with_timestamps=True)
+    assert [[t[0], t[1], t[2]] for t in tdt] == golden[k + "tdt_tok"].tolist()
+    assert np.allclose([t[3] for t in tdt], golden[k + "tdt_conf"], rtol=1e-4)
+    pieces = synth.make_vocab(ocfg.vocab - 1, seed=3)
+    assert O.detokenize([t[0] for t in tdt], pieces) == bytes(golden[k + "tdt_text"]).decode()
+    words = O.group_timestamps(tdt, pieces)
+    assert "\n".join(w[0] for w in words) == bytes(golden[k + "tdt_words"]).decode()
+    if words:
+        assert np.allclose(np.array([[w[1], w[2], w[3]] for w in words], np.float32), golden[k + "tdt_word_times"], rtol=1e-4)
+
+
+def test_golden_110m_decode(O, synth, golden):
+    """110m: decode-side check on the reference's encoder output (the encoder itself is
+    covered at the tiny shape above and, when _ref is present, live below)."""
+    ocfg = O.make_110m_config()
+    k, W, pcm = _golden_clip(O, synth, golden, "m110", 0, ocfg, 0)
+    feats = O.preprocess_audio(pcm, ocfg.mel_bins)
+    assert np.abs(feats - golden[k + "mel"].astype(np.float32)).max() < 5e-3     # stored as fp16
+    st = golden[k + "mel_stats"]
+    assert abs(feats[::7, ::3].sum() - st[3]) < 0.5 and abs(np.abs(feats).max() - st[2]) < 1e-2
+    genc = golden[k + "enc"]
+    lp = O.ctc_log_probs(W, genc)
+    assert np.array_equal(lp.argmax(1), golden[k + "ctc_argmax"])
+    ctc = O.ctc_greedy_decode_with_timestamps(lp, ocfg.vocab - 1)
+    assert [[t[0], t[1], t[2]] for t in ctc] == golden[k + "ctc_tok"].tolist()
+    tdt = O.tdt_greedy_decode(W, genc, ocfg, with_timestamps=True)
+    assert [[t[0], t[1], t[2]] for t in tdt] == golden[k + "tdt_tok"].tolist()
+    pieces = synth.make_vocab(ocfg.vocab - 1, seed=0)
+    assert O.detokenize([t[0] for t in ctc], pieces) == bytes(golden[k + "ctc_text"]).decode()
+
+
+# ---------------------------------------------------------------- (3) live compiled reference (when present)
+def test_live_reference_tiny(O, synth, refbind, tiny):
+    if refbind is None:
+        pytest.skip("oracle/_ref/libpkref.so not built")
+    m = refbind.RefModel(tiny.weights_path, tiny.vocab_path, 0, cfg=tiny.ocfg)
+    pcm = synth.make_audio(48000, 21)
+    fr = refbind.mel(pcm)
+    fo = O.preprocess_audio(pcm)
+    assert np.abs(fr - fo).max() < 2e-3
+    T = O.encoder_len(fr.shape[0])
+    sub_r, lay_r = m.encode_layers(fr, tiny.ocfg.d_model, tiny.ocfg.n_layers, T)
+    enc_o, sub_o, lay_o = O.encoder_forward(tiny.W, fr, tiny.ocfg, return_layers=True)
+    assert _rel(sub_o, sub_r) < 2e-5
+    for i in range(tiny.ocfg.n_layers):
+        assert _rel(lay_o[i], lay_r[i]) < 5e-5
+    assert m.tdt_greedy(lay_r[-1], True)[:50] == [tuple(t) for t in O.tdt_greedy_decode(tiny.W, lay_r[-1], tiny.ocfg, with_timestamps=True)][:50] or \
+        [t[:3] for t in m.tdt_greedy(lay_r[-1], True)] == [t[:3] for t in O.tdt_greedy_decode(tiny.W, lay_r[-1], tiny.ocfg, with_timestamps=True)]
+    m.close()
