@@ -137,7 +137,12 @@ struct pk_engine {
     template <typename T>
     T *upload(const std::vector<T> &h) {
         T *d = dalloc<T>(h.size());
-        if (d && !h.empty()) cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        // On the engine's own (non-blocking) stream, then wait: a legacy-stream cudaMemcpy from
+        // pageable memory may still be in flight when a kernel on `stream` starts.
+        if (d && !h.empty()) {
+            cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+            cudaStreamSynchronize(stream);
+        }
         return d;
     }
     ActBuf act_alloc(size_t n) {
@@ -602,6 +607,9 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
     }
     // ---- Conformer blocks (encoder.cpp:196-204)
     ActBuf none;
+    // PK_DEBUG_SUBBLOCKS=n (bisecting aid): stop after n residual sub-blocks; x is returned as is.
+    int dbg_stop = -1, dbg_cnt = 0;
+    if (const char *ev = getenv("PK_DEBUG_SUBBLOCKS")) dbg_stop = atoi(ev);
     launch_layernorm(x, M, d, layers[0].ffn_ln_w[0], layers[0].ffn_ln_b[0], nullptr, ln, nullptr, nullptr, none, stream);
     ++launches;
     for (int i = 0; i < c.n_layers; ++i) {
@@ -624,6 +632,7 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             e2.ldo = d;
             e2.alpha = 0.5f;
             gemm(ffh, c.ff, L.fc2[f], M, e2);
+            if (++dbg_cnt == dbg_stop) return PK_OK;
             if (f == 1) break;
             // ConformerAttention (encoder.cpp:111-186)
             launch_layernorm(x, M, d, L.att_ln_w, L.att_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
@@ -643,6 +652,7 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             eo.ldo = d;
             eo.alpha = 1.0f;
             gemm(ctx, d, L.out, M, eo);
+            if (++dbg_cnt == dbg_stop) return PK_OK;
             // ConformerConvModule (encoder.cpp:59-75)
             launch_layernorm(x, M, d, L.conv_ln_w, L.conv_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
             ++launches;
@@ -661,6 +671,7 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             ec.ldo = d;
             ec.alpha = 1.0f;
             gemm(cv, d, L.pw2, M, ec);
+            if (++dbg_cnt == dbg_stop) return PK_OK;
         }
         // final_norm_ of this block chained with the next block's ffn1_.norm_; after the last
         // block the normalised output is also written in GEMM-operand form for the heads.

@@ -67,7 +67,7 @@ subsample_conv1_dw1_kernel(const float *__restrict__ feats, const int32_t *__res
         for (int r = 0; r < 7; ++r) colprev[r] = Srow[r * stride + 1];  // col -1 (zero pad)
         float p2[3], p1[3] = {0.f, 0.f, 0.f}, cur[3];
         p2[0] = p2[1] = p2[2] = 0.f;
-        const size_t orow = ((size_t)s2_off[b] + (size_t)t2 * f2n);
+        const size_t orow = ((size_t)s2_off[b] + (size_t)t2) * f2n;
         for (int f1 = 0; f1 < 2 * f2n; ++f1) {
             float2 nw[7];
 #pragma unroll
