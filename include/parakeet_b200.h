@@ -151,6 +151,15 @@ void *pk_stream(pk_engine *e);
  * `gpu_launches` claim in bench.py). */
 int64_t pk_launch_count(const pk_engine *e);
 
+/* Measurement aids (bench.py): per-kernel-class device time measured with CUDA events on
+ * the engine stream between begin/end (classes in pk_profile_names() order, comma
+ * separated; ms / launch counts / algorithmic GEMM flops summed per class), and an L2
+ * flush (writes a 256 MiB scratch buffer on the engine stream). */
+pk_status pk_profile_begin(pk_engine *e);
+pk_status pk_profile_end(pk_engine *e, double *ms, int64_t *counts, double *flops, int32_t n);
+const char *pk_profile_names(void);
+pk_status pk_flush_l2(pk_engine *e);
+
 /* Host-side text helpers (pure C++ host code; no device work):
  * Tokenizer::load/decode (src/vocab.cpp:10-64), group_timestamps (src/timestamp.cpp:24-75). */
 typedef struct pk_vocab pk_vocab;

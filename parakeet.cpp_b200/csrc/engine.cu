@@ -78,6 +78,9 @@ struct pk_engine {
     std::string err;
     int64_t launches = 0;
     std::vector<void *> allocs;
+    void *l2_scratch = nullptr;
+    size_t l2_scratch_bytes = 0;
+    int64_t l2_flushes = 0;
 
     // ---- capacity
     int Bmax = 0, Fmax = 0, Tmax = 0;          // per-utterance max mel frames / encoder frames
@@ -122,6 +125,28 @@ struct pk_engine {
     std::vector<int64_t> pcm_off;
     std::vector<int32_t> frame_off, s2_off, row_off, t2_rows;
     int maxF = 0, maxT2 = 0, maxT = 0, M = 0, M2 = 0;
+
+    // ---- optional per-kernel-class timing (CUDA events on the engine stream)
+    enum { CAT_MEL, CAT_SUBSAMPLE, CAT_GEMM, CAT_LAYERNORM, CAT_ATTENTION, CAT_DWCONV, CAT_CTC, CAT_TDT, CAT_N };
+    struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t prof_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    struct Scope {
+        pk_engine *e; int idx = -1;
+        Scope(pk_engine *e_, int cat, double flops = 0.0) : e(e_) {
+            if (!e->prof_on) return;
+            ProfRec r{cat, e->prof_event(), e->prof_event(), flops};
+            cudaEventRecord(r.a, e->stream);
+            idx = (int)e->prof.size();
+            e->prof.push_back(r);
+        }
+        ~Scope() { if (idx >= 0) cudaEventRecord(e->prof[idx].b, e->stream); }
+    };
 
     pk_status fail(pk_status s, const std::string &m) {
         err = m;
@@ -559,23 +584,34 @@ pk_status pk_engine::upload_shapes() {
 
 void pk_engine::gemm(const ActBuf &A, int lda, const GemmWeight &W, int M_, EpiParams epi) {
     epi.bias = W.bias;
+    Scope sc(this, CAT_GEMM, 2.0 * M_ * W.N * W.K);
     launch_gemm_simt(A.f32, lda, W.w, W.K, M_, W.N, W.K, epi, stream);
     ++launches;
 }
 
 pk_status pk_engine::run_mel() {
+    Scope sc(this, CAT_MEL);
     launch_mel(d_pcm, d_pcm_off, d_frame_off, n_utt, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
     launches += 2;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
 
+#define PK_LN(...)                              \
+    do {                                        \
+        Scope _sc(this, CAT_LAYERNORM);         \
+        launch_layernorm(__VA_ARGS__);          \
+    } while (0)
+
 pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
     const pk_config &c = cfg;
     const int C = c.sub_channels, d = c.d_model, H = c.n_heads, hd = d / H;
     // ---- ConvSubsampling (encoder.cpp:219-241)
-    launch_subsample_conv1_dw1(feats, d_frame_off, d_s2_off, n_utt, maxT2, c.mel_bins, C, c1_w, c1_b, dw1_w, dw1_b,
-                               sub1, stream);
+    {
+        Scope sc(this, CAT_SUBSAMPLE);
+        launch_subsample_conv1_dw1(feats, d_frame_off, d_s2_off, n_utt, maxT2, c.mel_bins, C, c1_w, c1_b, dw1_w, dw1_b,
+                                   sub1, stream);
+    }
     ++launches;
     {
         EpiParams ep;
@@ -584,7 +620,10 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
         ep.ldo = C;
         gemm(sub1, C, conv2, M2, ep);
     }
-    launch_subsample_dw(sub2, d_t2_rows, d_s2_off, d_row_off, n_utt, f2n, C, dw2_w, dw2_b, sub3, M * f3n, stream);
+    {
+        Scope sc(this, CAT_SUBSAMPLE);
+        launch_subsample_dw(sub2, d_t2_rows, d_s2_off, d_row_off, n_utt, f2n, C, dw2_w, dw2_b, sub3, M * f3n, stream);
+    }
     ++launches;
     {
         EpiParams ep;
@@ -610,13 +649,13 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
     // PK_DEBUG_SUBBLOCKS=n (bisecting aid): stop after n residual sub-blocks; x is returned as is.
     int dbg_stop = -1, dbg_cnt = 0;
     if (const char *ev = getenv("PK_DEBUG_SUBBLOCKS")) dbg_stop = atoi(ev);
-    launch_layernorm(x, M, d, layers[0].ffn_ln_w[0], layers[0].ffn_ln_b[0], nullptr, ln, nullptr, nullptr, none, stream);
+    PK_LN(x, M, d, layers[0].ffn_ln_w[0], layers[0].ffn_ln_b[0], nullptr, ln, nullptr, nullptr, none, stream);
     ++launches;
     for (int i = 0; i < c.n_layers; ++i) {
         const LayerW &L = layers[i];
         for (int f = 0; f < 2; ++f) {
             if (f == 1) {
-                launch_layernorm(x, M, d, L.ffn_ln_w[1], L.ffn_ln_b[1], nullptr, ln, nullptr, nullptr, none, stream);
+                PK_LN(x, M, d, L.ffn_ln_w[1], L.ffn_ln_b[1], nullptr, ln, nullptr, nullptr, none, stream);
                 ++launches;
             }
             // FeedForward (encoder.cpp:39-46): x += 0.5 * fc2(silu(fc1(LN(x))))
@@ -635,15 +674,18 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             if (++dbg_cnt == dbg_stop) return PK_OK;
             if (f == 1) break;
             // ConformerAttention (encoder.cpp:111-186)
-            launch_layernorm(x, M, d, L.att_ln_w, L.att_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
+            PK_LN(x, M, d, L.att_ln_w, L.att_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
             ++launches;
             EpiParams eq;
             eq.kind = EPI_BIAS_F32;
             eq.out_f32 = qkv;
             eq.ldo = 3 * d;
             gemm(ln, d, L.qkv, M, eq);
-            if (!launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream))
-                return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
+            {
+                Scope sc(this, CAT_ATTENTION);
+                if (!launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream))
+                    return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
+            }
             ++launches;
             EpiParams eo;
             eo.kind = EPI_RESID_F32;
@@ -654,15 +696,18 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             gemm(ctx, d, L.out, M, eo);
             if (++dbg_cnt == dbg_stop) return PK_OK;
             // ConformerConvModule (encoder.cpp:59-75)
-            launch_layernorm(x, M, d, L.conv_ln_w, L.conv_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
+            PK_LN(x, M, d, L.conv_ln_w, L.conv_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
             ++launches;
             EpiParams eg;
             eg.kind = EPI_GLU_F32;
             eg.out_f32 = glu;
             eg.ldo = d;
             gemm(ln, d, L.pw1, M, eg);
-            if (!launch_dwconv_bn_silu(glu, d_row_off, n_utt, maxT, d, c.conv_kernel, L.dw_w, L.dw_b, cv, stream))
-                return fail(PK_ERR_INVALID, "unsupported conv_kernel");
+            {
+                Scope sc(this, CAT_DWCONV);
+                if (!launch_dwconv_bn_silu(glu, d_row_off, n_utt, maxT, d, c.conv_kernel, L.dw_w, L.dw_b, cv, stream))
+                    return fail(PK_ERR_INVALID, "unsupported conv_kernel");
+            }
             ++launches;
             EpiParams ec;
             ec.kind = EPI_RESID_F32;
@@ -677,10 +722,10 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
         // block the normalised output is also written in GEMM-operand form for the heads.
         const bool last = (i + 1 == c.n_layers);
         if (!last)
-            launch_layernorm(x, M, d, L.fin_ln_w, L.fin_ln_b, x, none, layers[i + 1].ffn_ln_w[0],
+            PK_LN(x, M, d, L.fin_ln_w, L.fin_ln_b, x, none, layers[i + 1].ffn_ln_w[0],
                              layers[i + 1].ffn_ln_b[0], ln, stream);
         else
-            launch_layernorm(x, M, d, L.fin_ln_w, L.fin_ln_b, x, cfg.math == PK_MATH_FP32 ? none : ln, nullptr,
+            PK_LN(x, M, d, L.fin_ln_w, L.fin_ln_b, x, cfg.math == PK_MATH_FP32 ? none : ln, nullptr,
                              nullptr, none, stream);
         ++launches;
         if (layers_out_host) {
@@ -710,8 +755,11 @@ pk_status pk_engine::run_ctc(float *logprobs_dev) {
     ep.out_f32 = logits;
     ep.ldo = ldv;
     gemm(enc_operand(this), c.d_model, ctc_head, M, ep);
-    launch_ctc_frame_argmax(logits, M, c.vocab, ldv, best, bconf, logprobs_dev, stream);
-    launch_ctc_collapse(best, bconf, d_row_off, n_utt, c.vocab - 1, cap, tok, t_start, t_end, t_conf, stream);
+    {
+        Scope sc(this, CAT_CTC);
+        launch_ctc_frame_argmax(logits, M, c.vocab, ldv, best, bconf, logprobs_dev, stream);
+        launch_ctc_collapse(best, bconf, d_row_off, n_utt, c.vocab - 1, cap, tok, t_start, t_end, t_conf, stream);
+    }
     launches += 2;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
@@ -744,7 +792,11 @@ pk_status pk_engine::run_tdt() {
     const size_t HS = (size_t)p.P * bp;
     PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * sizeof(float), stream));
     PK_CUDA(cudaMemsetAsync(cbuf, 0, HS * 2 * p.L * sizeof(float), stream));
-    cudaError_t ce = launch_tdt_decode(p, num_sms, stream);
+    cudaError_t ce;
+    {
+        Scope sc(this, CAT_TDT);
+        ce = launch_tdt_decode(p, num_sms, stream);
+    }
     launches += 2;
     if (ce != cudaSuccess) return fail(PK_ERR_CUDA, std::string("tdt_decode launch: ") + cudaGetErrorString(ce));
     PK_CUDA(cudaGetLastError());
@@ -862,6 +914,8 @@ void pk_engine_destroy(pk_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->allocs) cudaFree(p);
+    for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->h_pcm) cudaFreeHost(e->h_pcm);
     if (e->h_meta) cudaFreeHost(e->h_meta);
     if (e->h_tok) cudaFreeHost(e->h_tok);
@@ -875,6 +929,45 @@ void pk_engine_destroy(pk_engine *e) {
 
 void *pk_stream(pk_engine *e) { return e ? (void *)e->stream : nullptr; }
 int64_t pk_launch_count(const pk_engine *e) { return e ? e->launches : 0; }
+
+pk_status pk_profile_begin(pk_engine *e) {
+    if (!e) return PK_ERR_INVALID;
+    e->prof_on = true;
+    return PK_OK;
+}
+
+pk_status pk_profile_end(pk_engine *e, double *ms, int64_t *counts, double *flops, int32_t n) {
+    if (!e || !ms || !counts || n < pk_engine::CAT_N) return PK_ERR_INVALID;
+    cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < n; ++i) { ms[i] = 0; counts[i] = 0; if (flops) flops[i] = 0; }
+    for (auto &r : e->prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cat] += t;
+        counts[r.cat] += 1;
+        if (flops) flops[r.cat] += r.flops;
+        e->ev_pool.push_back(r.a);
+        e->ev_pool.push_back(r.b);
+    }
+    e->prof.clear();
+    e->prof_on = false;
+    return PK_OK;
+}
+
+const char *pk_profile_names(void) { return "mel,subsample,gemm,layernorm,attention,dwconv,ctc,tdt"; }
+
+pk_status pk_flush_l2(pk_engine *e) {
+    if (!e) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    if (!e->l2_scratch) {
+        e->l2_scratch_bytes = (size_t)256 << 20;   // > 126 MB L2
+        if (cudaMalloc(&e->l2_scratch, e->l2_scratch_bytes) != cudaSuccess) return e->fail(PK_ERR_CUDA, "cudaMalloc (L2 scratch)");
+        e->allocs.push_back(e->l2_scratch);
+    }
+    cudaError_t ce = cudaMemsetAsync(e->l2_scratch, (int)(++e->l2_flushes & 0xff), e->l2_scratch_bytes, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("L2 flush: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
 
 pk_status pk_sync(pk_engine *e) {
     if (!e) return PK_ERR_INVALID;

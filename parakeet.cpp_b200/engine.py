@@ -43,7 +43,8 @@ class _PkTokens(C.Structure):
 EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engine_destroy", "pk_last_error",
            "pk_mel_frames", "pk_encoder_frames", "pk_mel", "pk_encode", "pk_decode", "pk_ctc_logprobs",
            "pk_transcribe_batch", "pk_stage_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
-           "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
+           "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
+           "pk_profile_names", "pk_flush_l2", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
            "pk_detokenize", "pk_group_words"]
 
 _lib = None
@@ -82,6 +83,10 @@ def load_library():
     L.pk_stream.restype = vp
     L.pk_launch_count.argtypes = [vp]
     L.pk_launch_count.restype = C.c_int64
+    L.pk_profile_begin.argtypes = [vp]
+    L.pk_profile_end.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double), C.c_int32]
+    L.pk_profile_names.restype = C.c_char_p
+    L.pk_flush_l2.argtypes = [vp]
     L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pk_vocab_free.argtypes = [vp]
     L.pk_vocab_size.argtypes = [vp]
@@ -356,6 +361,20 @@ class Engine:
 
     def sync(self):
         self._check(self.L.pk_sync(self.h), "pk_sync")
+
+    def flush_l2(self):
+        self._check(self.L.pk_flush_l2(self.h), "pk_flush_l2")
+
+    def profile_begin(self):
+        self._check(self.L.pk_profile_begin(self.h), "pk_profile_begin")
+
+    def profile_end(self):
+        """-> {class: (ms, launches, gemm_flops)} summed since profile_begin()."""
+        names = self.L.pk_profile_names().decode().split(",")
+        n = len(names)
+        ms = (C.c_double * n)(); cnt = (C.c_int64 * n)(); fl = (C.c_double * n)()
+        self._check(self.L.pk_profile_end(self.h, ms, cnt, fl, n), "pk_profile_end")
+        return {names[i]: (ms[i], int(cnt[i]), fl[i]) for i in range(n)}
 
     def launch_count(self) -> int:
         return int(self.L.pk_launch_count(self.h))
