@@ -160,6 +160,11 @@ pk_status pk_profile_end(pk_engine *e, double *ms, int64_t *counts, double *flop
 const char *pk_profile_names(void);
 pk_status pk_flush_l2(pk_engine *e);
 
+/* GPU self-check of the tcgen05 GEMM kernel against the fp32 CUDA-core GEMM on seeded
+ * random data (epi_kind: EpiKind of csrc/pk_common.cuh; math: PK_MATH_BF16X3 | PK_MATH_BF16X1). */
+pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int math, uint32_t seed,
+                           float *max_err, float *max_ref);
+
 /* Host-side text helpers (pure C++ host code; no device work):
  * Tokenizer::load/decode (src/vocab.cpp:10-64), group_timestamps (src/timestamp.cpp:24-75). */
 typedef struct pk_vocab pk_vocab;

@@ -65,7 +65,7 @@ def make_tdt_600m_config() -> Config:      # config.hpp:98-116, tdt.cpp:28-32
 
 def make_tiny_config() -> Config:
     """Not a reference preset: a small shape for fast unit tests only."""
-    return Config(mel_bins=80, sub_channels=32, d_model=128, n_layers=2, n_heads=2, ff=256,
+    return Config(mel_bins=80, sub_channels=64, d_model=128, n_layers=2, n_heads=2, ff=256,
                   vocab=33, pred_hidden=64, joint_hidden=64, name="tiny")
 
 

@@ -52,6 +52,12 @@ struct GemmWeight {
     bf16 *hi = nullptr, *lo = nullptr;
     float *bias = nullptr;
     int N = 0, K = 0;
+    TcOperand tc;   // TMA tensor maps of hi/lo (tcgen05 modes)
+};
+
+// An activation buffer that feeds GEMMs, with its TMA tensor maps (tcgen05 modes).
+struct Act : ActBuf {
+    TcOperand tc;
 };
 
 struct LayerW {
@@ -103,7 +109,7 @@ struct pk_engine {
     int64_t *d_pcm_off = nullptr;
     int32_t *d_frame_off = nullptr, *d_s2_off = nullptr, *d_row_off = nullptr, *d_t2_rows = nullptr;
     float *logmel = nullptr, *feats = nullptr;
-    ActBuf sub1, sub3, sub4, ln, ffh, ctx, cv;
+    Act sub1, sub3, sub4, ln, ffh, ctx, cv;
     float *sub2 = nullptr, *x = nullptr, *qkv = nullptr, *glu = nullptr, *logits = nullptr, *EP = nullptr;
     int32_t *best = nullptr;
     float *bconf = nullptr;
@@ -170,13 +176,16 @@ struct pk_engine {
         }
         return d;
     }
-    ActBuf act_alloc(size_t n) {
-        ActBuf a;
+    // [rows][K] activation that feeds a GEMM as the A operand
+    Act act_alloc(size_t rows, size_t K) {
+        Act a;
+        const size_t n = rows * K;
         if (cfg.math == PK_MATH_FP32) {
             a.f32 = dalloc<float>(n);
         } else {
             a.hi = dalloc<bf16>(n);
             if (cfg.math == PK_MATH_BF16X3) a.lo = dalloc<bf16>(n);
+            if (a.hi && !make_tc_operand(&a.tc, a.hi, a.lo, rows, K, 128)) a.hi = nullptr;   // reported by the caller
         }
         return a;
     }
@@ -190,7 +199,8 @@ struct pk_engine {
     pk_status alloc_workspace();
     pk_status set_batch_shapes(const int32_t *n_frames_or_null, const int64_t *offsets_or_null, int n);
     pk_status upload_shapes();
-    void gemm(const ActBuf &A, int lda, const GemmWeight &W, int M_, EpiParams epi);
+    void gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiParams epi);
+    pk_status gemm_err = PK_OK;
     pk_status run_mel();
     pk_status run_encoder(float *sub_out_host, float *layers_out_host);
     pk_status run_ctc(float *logprobs_dev_or_null);
@@ -226,6 +236,9 @@ pk_status pk_engine::finish_weight(std::vector<float> &w, std::vector<float> *b,
         out.hi = upload(hi);
         out.lo = upload(lo);
         if (!out.hi || !out.lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (split weight)");
+        if (K % 64 != 0) return fail(PK_ERR_INVALID, "tcgen05 GEMM needs K % 64 == 0");
+        if (!make_tc_operand(&out.tc, out.hi, out.lo, N, K, tc_tile_n(N)))
+            return fail(PK_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight");
     }
     return PK_OK;
 }
@@ -482,17 +495,18 @@ pk_status pk_engine::alloc_workspace() {
     d_t2_rows = dalloc<int32_t>(B + 1);
     logmel = dalloc<float>(B * (size_t)Fmax * c.mel_bins);
     feats = dalloc<float>(B * (size_t)Fmax * c.mel_bins);
-    sub1 = act_alloc(rows2 * C);
+    sub1 = act_alloc(rows2, C);
     sub2 = dalloc<float>(rows2 * C);
-    sub3 = act_alloc(rows3 * C);
-    sub4 = act_alloc(rows3 * C);
+    sub3 = act_alloc(rows3, C);
+    sub4 = act_alloc(rows3, C);
+    if (cfg.math != PK_MATH_FP32 && sub4.hi && !make_tc_operand(&sub4.tc, sub4.hi, sub4.lo, Mx, (size_t)C * f3n, 128)) sub4.hi = nullptr;   // viewed as [M][C*F'] by proj_
     x = dalloc<float>(Mx * d);
-    ln = act_alloc(Mx * d);
-    ffh = act_alloc(Mx * c.ff);
+    ln = act_alloc(Mx, d);
+    ffh = act_alloc(Mx, c.ff);
     qkv = dalloc<float>(Mx * 3 * d);
-    ctx = act_alloc(Mx * d);
+    ctx = act_alloc(Mx, d);
     glu = dalloc<float>(Mx * d);
-    cv = act_alloc(Mx * d);
+    cv = act_alloc(Mx, d);
     const int ldv = (c.vocab + 3) & ~3;
     logits = dalloc<float>(Mx * ldv);
     EP = dalloc<float>(Mx * c.joint_hidden);
@@ -515,6 +529,8 @@ pk_status pk_engine::alloc_workspace() {
     pl_idx = dalloc<int32_t>(PG);
     pd_idx = dalloc<int32_t>(PG);
     if (!pd_idx || !hbuf || !x || !sub2 || !d_pcm || !t_conf) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
+    if (cfg.math != PK_MATH_FP32 && (!sub1.hi || !sub3.hi || !sub4.hi || !ln.hi || !ffh.hi || !ctx.hi || !cv.hi))
+        return fail(PK_ERR_CUDA, "workspace: cudaMalloc or cuTensorMapEncodeTiled failed for an activation operand");
     PK_CUDA(cudaMallocHost(&h_pcm, (B * (size_t)c.max_samples + 8) * sizeof(float)));
     PK_CUDA(cudaMallocHost(&h_meta, (size_t)(8 * (B + 1)) * sizeof(int32_t)));
     PK_CUDA(cudaMallocHost(&h_tok, B * (1 + (size_t)cap) * sizeof(int32_t)));
@@ -582,10 +598,15 @@ pk_status pk_engine::upload_shapes() {
 
 // ===================================================================== pipeline
 
-void pk_engine::gemm(const ActBuf &A, int lda, const GemmWeight &W, int M_, EpiParams epi) {
+void pk_engine::gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiParams epi) {
     epi.bias = W.bias;
     Scope sc(this, CAT_GEMM, 2.0 * M_ * W.N * W.K);
-    launch_gemm_simt(A.f32, lda, W.w, W.K, M_, W.N, W.K, epi, stream);
+    if (cfg.math == PK_MATH_FP32) {
+        launch_gemm_simt(A.f32, lda, W.w, W.K, M_, W.N, W.K, epi, stream);
+    } else {
+        cudaError_t ce = launch_gemm_tc(A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, epi, stream);
+        if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(ce));
+    }
     ++launches;
 }
 
@@ -737,9 +758,9 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
 }
 
 // encoder output as a GEMM operand
-static ActBuf enc_operand(pk_engine *e) {
+static Act enc_operand(pk_engine *e) {
     if (e->cfg.math == PK_MATH_FP32) {
-        ActBuf a;
+        Act a;
         a.f32 = e->x;
         return a;
     }
@@ -834,7 +855,7 @@ void pk_config_110m(pk_config *c) {
     c->n_durations = 5;
     for (int i = 0; i < 5; ++i) c->durations[i] = i;
     c->has_ctc = 1; c->joint_prefix_tdt = 1; c->max_symbols = 10;
-    c->max_batch = 64; c->max_samples = 160000; c->math = PK_MATH_FP32;
+    c->max_batch = 64; c->max_samples = 160000; c->math = PK_MATH_BF16X3;
 }
 
 void pk_config_tdt_600m(pk_config *c) {
@@ -869,8 +890,8 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
         g_create_err = "unsupported model shape in pk_config";
         return PK_ERR_INVALID;
     }
-    if (c.math != PK_MATH_FP32) {
-        g_create_err = "requested pk_math mode is not available in this build";
+    if (c.math != PK_MATH_FP32 && c.math != PK_MATH_BF16X3 && c.math != PK_MATH_BF16X1) {
+        g_create_err = "unknown pk_math mode";
         return PK_ERR_INVALID;
     }
     auto e = std::make_unique<pk_engine>();
@@ -969,6 +990,81 @@ pk_status pk_flush_l2(pk_engine *e) {
     return PK_OK;
 }
 
+// Runs one GEMM through the tcgen05 kernel and through the fp32 CUDA-core kernel on seeded
+// random data and returns max |tc - fp32| and max |fp32| (GPU self-check used by the tests).
+pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int math, uint32_t seed, float *max_err,
+                           float *max_ref) {
+    if (cudaSetDevice(device) != cudaSuccess) return PK_ERR_CUDA;
+    if (K % 64 != 0 || (epi_kind == EPI_GLU_F32 && (N & 1))) return PK_ERR_INVALID;
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    const bool act_out = epi_kind == EPI_BIAS_RELU_ACT || epi_kind == EPI_BIAS_SILU_ACT || epi_kind == EPI_BIAS_ACT;
+    const int No = epi_kind == EPI_GLU_F32 ? N / 2 : N;
+    std::vector<float> hA((size_t)M * K), hW((size_t)N * K), hb(N), hr((size_t)M * No);
+    uint32_t sd = seed * 2654435761u + 12345u;
+    auto rnd = [&]() { sd = sd * 1664525u + 1013904223u; return ((sd >> 8) & 0xffff) / 32768.0f - 1.0f; };
+    for (auto &v : hA) v = rnd();
+    for (auto &v : hW) v = rnd() * 0.1f;
+    for (auto &v : hb) v = rnd();
+    for (auto &v : hr) v = rnd();
+    float *dA, *dW, *db, *dr, *o_ref, *o_tc;
+    bf16 *Ah, *Al, *Wh, *Wl, *oh, *ol;
+    cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dW, hW.size() * 4); cudaMalloc(&db, hb.size() * 4);
+    cudaMalloc(&dr, hr.size() * 4); cudaMalloc(&o_ref, hr.size() * 4); cudaMalloc(&o_tc, hr.size() * 4);
+    cudaMalloc(&Ah, hA.size() * 2); cudaMalloc(&Al, hA.size() * 2); cudaMalloc(&Wh, hW.size() * 2); cudaMalloc(&Wl, hW.size() * 2);
+    cudaMalloc(&oh, hr.size() * 2); cudaMalloc(&ol, hr.size() * 2);
+    cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, hW.data(), hW.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dr, hr.data(), hr.size() * 4, cudaMemcpyHostToDevice);
+    cudaDeviceSynchronize();
+    ActBuf sa; sa.hi = Ah; sa.lo = Al;
+    ActBuf sw; sw.hi = Wh; sw.lo = Wl;
+    launch_split(dA, hA.size(), sa, st);
+    launch_split(dW, hW.size(), sw, st);
+    EpiParams ep;
+    ep.kind = epi_kind; ep.bias = db; ep.ldo = No; ep.resid = dr; ep.alpha = 0.5f;
+    ep.out_f32 = o_ref;
+    ActBuf ref_act; ref_act.f32 = o_ref;
+    ep.act = ref_act;
+    launch_gemm_simt(dA, K, dW, K, M, N, K, ep, st);
+    TcOperand ta, tw;
+    pk_status rc = PK_OK;
+    if (!make_tc_operand(&ta, Ah, Al, M, K, 128) || !make_tc_operand(&tw, Wh, Wl, N, K, tc_tile_n(N))) rc = PK_ERR_CUDA;
+    if (rc == PK_OK) {
+        ep.out_f32 = o_tc;
+        ActBuf tc_act; tc_act.hi = oh; tc_act.lo = ol;
+        ep.act = tc_act;
+        if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st) != cudaSuccess) rc = PK_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = PK_ERR_CUDA;
+    if (rc == PK_OK) {
+        std::vector<float> r(hr.size()), t(hr.size());
+        cudaMemcpy(r.data(), o_ref, r.size() * 4, cudaMemcpyDeviceToHost);
+        if (act_out) {
+            std::vector<bf16> h(hr.size()), l(hr.size());
+            cudaMemcpy(h.data(), oh, h.size() * 2, cudaMemcpyDeviceToHost);
+            cudaMemcpy(l.data(), ol, l.size() * 2, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < t.size(); ++i) t[i] = __bfloat162float(h[i]) + __bfloat162float(l[i]);
+        } else {
+            cudaMemcpy(t.data(), o_tc, t.size() * 4, cudaMemcpyDeviceToHost);
+        }
+        float me = 0.f, mr = 0.f;
+        for (size_t i = 0; i < t.size(); ++i) {
+            const float e = std::fabs(t[i] - r[i]);
+            if (!(e <= me)) me = e;            // NaN-propagating max
+            mr = std::max(mr, std::fabs(r[i]));
+        }
+        *max_err = me;
+        *max_ref = mr;
+    }
+    for (void *p : {(void *)dA, (void *)dW, (void *)db, (void *)dr, (void *)o_ref, (void *)o_tc, (void *)Ah, (void *)Al,
+                    (void *)Wh, (void *)Wl, (void *)oh, (void *)ol})
+        cudaFree(p);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
 pk_status pk_sync(pk_engine *e) {
     if (!e) return PK_ERR_INVALID;
     cudaError_t ce = cudaStreamSynchronize(e->stream);
@@ -995,6 +1091,7 @@ pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
     if (!e || e->n_utt <= 0) return PK_ERR_INVALID;
     cudaSetDevice(e->device);
     pk_status s;
+    if (e->gemm_err) return e->gemm_err;
     if ((s = e->run_mel())) return s;
     if ((s = e->run_encoder(nullptr, nullptr))) return s;
     return dec == PK_DECODER_CTC ? e->run_ctc(nullptr) : e->run_tdt();
@@ -1075,6 +1172,7 @@ static pk_status stage_enc(pk_engine *e, const float *enc, const int32_t *enc_le
     if (s) return s;
     cudaError_t ce = cudaMemcpyAsync(e->x, enc, (size_t)e->M * e->cfg.d_model * sizeof(float), cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D enc: ") + cudaGetErrorString(ce));
+    if (e->cfg.math != PK_MATH_FP32) launch_split(e->x, (size_t)e->M * e->cfg.d_model, e->ln, e->stream);
     return PK_OK;
 }
 

@@ -1,0 +1,284 @@
+// gemm_tc.cu -- K5: the tensor-core GEMM of the encoder, hand-written for sm_100a:
+//     C = epi(A[M,K] . W[N,K]^T + bias)
+// TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory -> tcgen05.mma (UMMA, one
+// issuing thread, cta_group::1, M=128 x N=BN x K=16 per instruction) -> fp32 accumulator in
+// TMEM -> tcgen05.ld -> fused epilogue (pk_common.cuh: bias / ReLU / SiLU / GLU / residual,
+// output either fp32 or the bf16 hi/lo operand planes of the next GEMM).
+//
+// Arithmetic (pk_math): operands are bf16 hi/lo SPLITS of the fp32 values
+// (hi = rn_bf16(x), lo = rn_bf16(x - hi); weights split once at load, activations split by
+// the producing kernel's epilogue).  PK_MATH_BF16X3 issues three MMAs per product,
+//     A_hi.W_hi + A_hi.W_lo + A_lo.W_hi      (fp32 accumulate in TMEM)
+// which keeps ~16 mantissa bits (measured: encoder output 8e-6 rel vs 4e-3 for plain bf16
+// and 6e-4 for TF32) -- the reference is an fp32 CPU build and parity is token-identical.
+// PK_MATH_BF16X1 issues only A_hi.W_hi.
+//
+// Structure (one output tile per CTA, 192 threads):
+//   warp 0      TMA producer   : waits empty[s], arms full[s] with the byte count, issues
+//                                the 2 or 4 tile loads of k-block kb into stage s
+//   warp 1      MMA issuer     : allocates TMEM; waits full[s]; 4 x (1|3) tcgen05.mma per
+//                                k-block; tcgen05.commit -> empty[s]; last commit -> acc_full
+//   warps 2..5  epilogue       : wait acc_full; tcgen05.ld 32 lanes x 32 columns at a time
+//                                (warp w owns TMEM lanes 32*(w%4)..); epilogue4 per 4 columns
+// Every spin-wait is bounded and traps, so a protocol bug is an error, not a hung GPU.
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace pk {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();   // ~seconds: protocol error, fail instead of hanging
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of 128 B, SWIZZLE_128B (as written by TMA):
+// 8-row core groups are 1024 B apart (SBO); LBO unused for swizzled K-major (1);
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  (cute mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
+    d |= (uint64_t)1 << 16;                           // leading byte offset (>>4) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset (>>4)  [32,46)
+    d |= (uint64_t)1 << 46;                           // version = 1               [46,48)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B              [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int NPASS>
+struct TcCfg {
+    static constexpr int A_BYTES = BM * BK * 2;                 // one plane, 16 KB
+    static constexpr int W_BYTES = BN * BK * 2;
+    static constexpr int PLANES = (NPASS == 3) ? 2 : 1;
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
+               int K, EpiParams epi) {
+    using C = TcCfg<BN, NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int nkb = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation: BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::STAGES;
+                const uint32_t ph = (kb / C::STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
+                mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
+                tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
+                if (NPASS == 3) {
+                    tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0);
+                    tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::STAGES;
+                const uint32_t ph = (kb / C::STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t st = smem_u32(tiles + (size_t)s * C::STAGE_BYTES);
+                const uint64_t a_hi = umma_desc_sw128(st), w_hi = umma_desc_sw128(st + C::A_BYTES);
+                const uint64_t a_lo = umma_desc_sw128(st + C::A_BYTES + C::W_BYTES);
+                const uint64_t w_lo = umma_desc_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, encoded >>4
+                    umma_bf16(tmem_base, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+                    if (NPASS == 3) {
+                        umma_bf16(tmem_base, a_hi + koff, w_lo + koff, idesc, 1);
+                        umma_bf16(tmem_base, a_lo + koff, w_hi + koff, idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);          // frees the stage when these MMAs retire
+            }
+            umma_commit(acc_full);               // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        mbar_wait(acc_full, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    epilogue4(epi, row, n0 + c * 32 + j * 4, N,
+                              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int BN, int NPASS>
+cudaError_t launch_t(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
+    using C = TcCfg<BN, NPASS>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
+    gemm_tc_kernel<BN, NPASS><<<grid, TC_THREADS, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || !hi || (K % 8) != 0) return false;
+    const cuuint64_t gdim[2] = {K, rows};
+    const cuuint64_t gstr[1] = {K * sizeof(bf16)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (fn(&out->hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16 *>(hi), gdim, gstr, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    out->has_lo = lo != nullptr;
+    if (lo && fn(&out->lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16 *>(lo), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    out->box_rows = box_rows;
+    return true;
+}
+
+int tc_tile_n(int N) { return N <= 64 ? 64 : 128; }
+
+cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
+                           const EpiParams &epi, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    if (K % BK != 0 || A.box_rows != BM) return cudaErrorInvalidValue;
+    if (split3 && !(A.has_lo && W.has_lo)) return cudaErrorInvalidValue;
+    if (W.box_rows == 128) return split3 ? launch_t<128, 3>(A, W, M, N, K, epi, st) : launch_t<128, 1>(A, W, M, N, K, epi, st);
+    if (W.box_rows == 64) return split3 ? launch_t<64, 3>(A, W, M, N, K, epi, st) : launch_t<64, 1>(A, W, M, N, K, epi, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pk

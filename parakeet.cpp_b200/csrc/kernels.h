@@ -1,5 +1,7 @@
 // kernels.h -- host-callable launchers of the sm_100a kernels (one .cu per op group).
 #pragma once
+#include <cuda.h>
+
 #include "pk_common.cuh"
 
 #define PK_MAX_LSTM 4
@@ -31,7 +33,21 @@ void launch_subsample_dw(const float *in, const int32_t *in_rows, const int32_t 
 void launch_gemm_simt(const float *A, int lda, const float *W, int ldw, int M, int N, int K,
                       const EpiParams &epi, cudaStream_t st);
 
+// tcgen05 path (gemm_tc.cu): a K-major bf16 matrix [rows][K] as TMA tensor maps of its hi
+// (and lo) split planes, box = 64 (K) x box_rows, SWIZZLE_128B.
+struct TcOperand {
+    CUtensorMap hi, lo;
+    bool has_lo = false;
+    uint32_t box_rows = 0;
+};
+bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t rows, uint64_t K, uint32_t box_rows);
+int tc_tile_n(int N);   // N-tile (= box_rows of the weight operand) chosen for an [N][K] weight
+cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
+                           const EpiParams &epi, cudaStream_t st);
+
 // ------------------------------------------------------------------ norm_conv.cu (K6, K8)
+// fp32 -> bf16 hi/lo operand planes (n multiple of 4)
+void launch_split(const float *x, size_t n, ActBuf out, cudaStream_t st);
 void launch_layernorm(const float *x, int M, int d, const float *w1, const float *b1, float *out1_f32,
                       ActBuf out1_act, const float *w2, const float *b2, ActBuf out2_act, cudaStream_t st);
 bool launch_dwconv_bn_silu(const float *g, const int32_t *row_off, int n_utt, int max_T, int d, int ks,

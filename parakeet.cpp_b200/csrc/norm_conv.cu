@@ -106,7 +106,18 @@ __global__ void dwconv_bn_silu_kernel(const float *__restrict__ g, const int32_t
     store_act4(out, (size_t)(r0 + t) * d + c, make_float4(siluf_(acc.x), siluf_(acc.y), siluf_(acc.z), siluf_(acc.w)));
 }
 
+__global__ void split_kernel(const float *__restrict__ x, size_t n4, ActBuf out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) store_act4(out, i * 4, reinterpret_cast<const float4 *>(x)[i]);
+}
+
 }  // namespace
+
+void launch_split(const float *x, size_t n, ActBuf out, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    if (n4 == 0) return;
+    split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, n4, out);
+}
 
 void launch_layernorm(const float *x, int M, int d, const float *w1, const float *b1, float *out1_f32,
                       ActBuf out1_act, const float *w2, const float *b2, ActBuf out2_act, cudaStream_t st) {

@@ -44,7 +44,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_mel_frames", "pk_encoder_frames", "pk_mel", "pk_encode", "pk_decode", "pk_ctc_logprobs",
            "pk_transcribe_batch", "pk_stage_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
-           "pk_profile_names", "pk_flush_l2", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
+           "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
            "pk_detokenize", "pk_group_words"]
 
 _lib = None
@@ -87,6 +87,7 @@ def load_library():
     L.pk_profile_end.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double), C.c_int32]
     L.pk_profile_names.restype = C.c_char_p
     L.pk_flush_l2.argtypes = [vp]
+    L.pk_selftest_gemm.argtypes = [C.c_int] * 6 + [C.c_uint32, f32p, f32p]
     L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pk_vocab_free.argtypes = [vp]
     L.pk_vocab_size.argtypes = [vp]
@@ -124,7 +125,7 @@ class ModelConfig:
     # engine capacity
     max_batch: int = 64
     max_samples: int = 160000
-    math: int = int(Math.FP32)
+    math: int = int(Math.BF16X3)
 
     def to_c(self) -> _PkConfig:
         c = _PkConfig()
@@ -154,7 +155,7 @@ def make_tdt_600m_config(**kw) -> ModelConfig:       # config.hpp:98-116
 
 def make_tiny_config(**kw) -> ModelConfig:
     """Small test-only shape (not a reference preset)."""
-    base = dict(sub_channels=32, d_model=128, n_layers=2, n_heads=2, ff=256, vocab=33, pred_hidden=64,
+    base = dict(sub_channels=64, d_model=128, n_layers=2, n_heads=2, ff=256, vocab=33, pred_hidden=64,
                 joint_hidden=64, name="tiny", max_batch=8, max_samples=64000)
     base.update(kw)
     return ModelConfig(**base)
@@ -196,6 +197,16 @@ class TranscribeOptions:              # transcribe.hpp:38-43
     timestamps: bool = False
     boost_phrases: List[str] = field(default_factory=list)
     boost_score: float = 5.0
+
+
+def selftest_gemm(M, N, K, epi_kind, math=0, seed=1, device=0):
+    """-> (max_abs_err, max_abs_ref) of the tcgen05 GEMM vs the fp32 CUDA-core GEMM."""
+    L = load_library()
+    e, r = C.c_float(), C.c_float()
+    st = L.pk_selftest_gemm(device, M, N, K, epi_kind, math, seed, C.byref(e), C.byref(r))
+    if st != 0:
+        raise RuntimeError(f"pk_selftest_gemm failed ({st})")
+    return e.value, r.value
 
 
 def _f32p(a):

@@ -84,9 +84,9 @@ def make_weights(cfg, seed=0, gain=1.0, head_gain=4.0, out_gain=0.25, blank_bias
     rng = np.random.default_rng(seed)
     W = {}
     if blank_bias is None:          # keeps the TDT token rate near one per 2-4 frames
-        blank_bias = 6.0 if cfg.vocab > 100 else 1.0
+        blank_bias = 5.0 if cfg.vocab > 100 else 2.5
     if ctc_blank_bias is None:
-        ctc_blank_bias = 12.0 if cfg.vocab > 100 else 7.0
+        ctc_blank_bias = 12.0 if cfg.vocab > 100 else 5.0
     for name, shape, kind in tensor_specs(cfg):
         if kind == "i64":
             W[name] = np.array(1000, dtype=np.int64)
@@ -102,6 +102,10 @@ def make_weights(cfg, seed=0, gain=1.0, head_gain=4.0, out_gain=0.25, blank_bias
             a = rng.standard_normal(shape) * (2.0 * gain / np.sqrt(fan_in))
         elif kind == "head":
             a = rng.standard_normal(shape) * (head_gain / np.sqrt(fan_in))
+            if name.startswith(cfg.joint_prefix):
+                # zero-mean rows: the (positive-mean) ReLU joint activation then adds no constant
+                # per-class offset, so labels/durations follow the input instead of a few classes
+                a = a - a.reshape(shape[0], -1).mean(axis=1).reshape((shape[0],) + (1,) * (len(shape) - 1))
         elif kind == "emb":
             a = rng.standard_normal(shape)
             a[-1] = 0.0                      # blank/SOS row is zero in real checkpoints
@@ -115,7 +119,9 @@ def make_weights(cfg, seed=0, gain=1.0, head_gain=4.0, out_gain=0.25, blank_bias
             a = 0.1 * rng.standard_normal(shape)
             a[-1] = blank_bias               # blank is the commonest TDT label
         elif kind == "dur_b":
-            a = np.array([-2.0, 2.0, 1.0, 0.0, -1.0])[: shape[0]] + 0.1 * rng.standard_normal(shape)
+            # duration 0 ("emit again on this frame") must stay rare: the reference never forces an
+            # advance (tdt.cpp:66-104), so a zero-duration fixed point livelocks it
+            a = np.array([-3.5, 1.0, 0.5, 0.0, -0.5])[: shape[0]] + 0.1 * rng.standard_normal(shape)
         else:                                # "b"
             a = 0.1 * rng.standard_normal(shape)
         W[name] = a.astype(F32)

@@ -24,18 +24,44 @@ def _tt(toks):
     return [(t.token_id, t.start_frame, t.end_frame) for t in toks]
 
 
+MATH = {"bf16x3": 0, "fp32": 2}     # pk_math: the tcgen05 parity mode and the fp32 CUDA-core mode
+
+
+@pytest.fixture(scope="module", params=["bf16x3", "fp32"])
+def math_mode(request):
+    return request.param
+
+
 @pytest.fixture(scope="module")
-def eng_tiny(pkg, tiny):
-    e = pkg.Engine(tiny.cfg, tiny.weights_path, 0)
+def eng_tiny(pkg, tiny, math_mode):
+    import dataclasses
+    e = pkg.Engine(dataclasses.replace(tiny.cfg, math=MATH[math_mode]), tiny.weights_path, 0)
     yield e
     e.close()
 
 
 @pytest.fixture(scope="module")
-def eng110(pkg, m110):
-    e = pkg.Engine(m110.cfg, m110.weights_path, 0)
+def eng110(pkg, m110, math_mode):
+    import dataclasses
+    e = pkg.Engine(dataclasses.replace(m110.cfg, math=MATH[math_mode]), m110.weights_path, 0)
     yield e
     e.close()
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM kernel (K5) in isolation
+EPI = dict(BIAS_F32=0, RELU_F32=1, RELU_ACT=2, SILU_ACT=3, RESID=4, GLU=5, BIAS_ACT=6)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, "BIAS_F32"), (300, 256, 256, "RELU_F32"), (126, 1025, 512, "BIAS_F32"),
+                                       (777, 2048, 512, "SILU_ACT"), (513, 512, 2048, "RESID"), (256, 1024, 512, "GLU"),
+                                       (130, 64, 64, "BIAS_ACT"), (1, 640, 512, "BIAS_F32"), (8064, 512, 2560, "BIAS_F32"),
+                                       (5020, 256, 256, "RELU_ACT")])
+def test_tcgen05_gemm_matches_fp32_gemm(pkg, M, N, K, epi):
+    from parakeet_cpp_b200.engine import selftest_gemm
+    err, ref = selftest_gemm(M, N, K, EPI[epi], 0)
+    assert err / ref < 5e-5, (err, ref)          # bf16 hi/lo split, 3 MMAs: ~16 mantissa bits
+    err1, _ = selftest_gemm(M, N, K, EPI[epi], 1)
+    assert err1 / ref < 2e-2                     # plain bf16 operands
 
 
 # ------------------------------------------------------------------ mel front end (K1/K2)
@@ -153,14 +179,19 @@ def test_tdt_batch_lockstep_equals_singles(eng_tiny, O, tiny):
     encs = [rng.standard_normal((T, tiny.ocfg.d_model)).astype(np.float32) for T in (51, 1, 7, 33, 20, 2, 40, 13)]
     got = eng_tiny.decode(encs, 1)
     for e, g in zip(encs, got):
-        want = O.tdt_greedy_decode(tiny.W, e, tiny.ocfg, with_timestamps=True)
+        try:
+            want = O.tdt_greedy_decode(tiny.W, e, tiny.ocfg, with_timestamps=True, max_steps=4000)
+        except RuntimeError:      # the reference algorithm livelocks on this input (tdt.cpp:66-104): no oracle
+            assert len(g) == eng_tiny.cap
+            continue
         assert _tt(g) == [w[:3] for w in want]
         assert np.allclose([t.confidence for t in g], [w[3] for w in want], rtol=1e-3)
 
 
 # ------------------------------------------------------------------ whole path through the public API
-def test_transcriber_api_matches_reference_golden(pkg, tiny, synth, golden):
-    t = pkg.Transcriber(tiny.weights_path, tiny.vocab_path, tiny.cfg)
+def test_transcriber_api_matches_reference_golden(pkg, tiny, synth, golden, math_mode):
+    import dataclasses
+    t = pkg.Transcriber(tiny.weights_path, tiny.vocab_path, dataclasses.replace(tiny.cfg, math=MATH[math_mode]))
     t.to_gpu()
     for ci in (0, 1, 3):
         k = f"tiny.c{ci}."
@@ -179,8 +210,9 @@ def test_transcriber_api_matches_reference_golden(pkg, tiny, synth, golden):
     t.engine.close()
 
 
-def test_transcribe_110m_whole_path_tokens(pkg, m110, synth, golden):
-    t = pkg.Transcriber(m110.weights_path, m110.vocab_path, m110.cfg)
+def test_transcribe_110m_whole_path_tokens(pkg, m110, synth, golden, math_mode):
+    import dataclasses
+    t = pkg.Transcriber(m110.weights_path, m110.vocab_path, dataclasses.replace(m110.cfg, math=MATH[math_mode]))
     k = "m110.c0."
     n, aseed = (int(v) for v in golden[k + "n_samples"])
     pcm = synth.make_audio(n, aseed)
@@ -192,9 +224,9 @@ def test_transcribe_110m_whole_path_tokens(pkg, m110, synth, golden):
     t.engine.close()
 
 
-def test_full_batch_properties(pkg, m110, synth):
+def test_full_batch_properties(pkg, m110, synth, math_mode):
     """BASELINE size (64 x 10 s): batch invariance and determinism, no oracle needed."""
-    cfg = pkg.make_110m_config(max_batch=64)
+    cfg = pkg.make_110m_config(max_batch=64, math=MATH[math_mode])
     e = pkg.Engine(cfg, m110.weights_path, 0)
     pcms = [synth.make_audio(160000, 1000 + i) for i in range(64)]
     for dec in (0, 1):

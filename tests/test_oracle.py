@@ -164,7 +164,7 @@ def test_live_reference_tiny(O, synth, refbind, tiny):
     if refbind is None:
         pytest.skip("oracle/_ref/libpkref.so not built")
     m = refbind.RefModel(tiny.weights_path, tiny.vocab_path, 0, cfg=tiny.ocfg)
-    pcm = synth.make_audio(48000, 21)
+    pcm = synth.make_audio(48000, 22)
     fr = refbind.mel(pcm)
     fo = O.preprocess_audio(pcm)
     assert np.abs(fr - fo).max() < 2e-3
