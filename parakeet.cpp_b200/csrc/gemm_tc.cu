@@ -13,13 +13,18 @@
 // and 6e-4 for TF32) -- the reference is an fp32 CPU build and parity is token-identical.
 // PK_MATH_BF16X1 issues only A_hi.W_hi.
 //
-// Structure (one output tile per CTA, 192 threads):
+// Structure (persistent, one CTA per SM, 320 threads, static round-robin tile schedule):
 //   warp 0      TMA producer   : waits empty[s], arms full[s] with the byte count, issues
 //                                the 2 or 4 tile loads of k-block kb into stage s
-//   warp 1      MMA issuer     : allocates TMEM; waits full[s]; 4 x (1|3) tcgen05.mma per
-//                                k-block; tcgen05.commit -> empty[s]; last commit -> acc_full
-//   warps 2..5  epilogue       : wait acc_full; tcgen05.ld 32 lanes x 32 columns at a time
-//                                (warp w owns TMEM lanes 32*(w%4)..); epilogue4 per 4 columns
+//   warp 1      MMA issuer     : allocates TMEM (2 x BN columns: the accumulator is double
+//                                buffered); per tile waits acc_empty[b]; per k-block waits
+//                                full[s], 4 x (1|3) tcgen05.mma, tcgen05.commit -> empty[s];
+//                                after the last k-block tcgen05.commit -> acc_full[b]
+//   warps 2..9  epilogue       : wait acc_full[b]; tcgen05.ld 32 lanes x 16 columns (warp w owns
+//                                TMEM lanes 32*(w%4).., half (w-2)/4 of the columns); release
+//                                acc_empty[b] after the last read; transpose through shared
+//                                memory so global stores are row-contiguous; epilogue4 per 4 cols
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Every spin-wait is bounded and traps, so a protocol bug is an error, not a hung GPU.
 #include <cuda.h>
 
@@ -31,7 +36,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,42 +109,70 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int EPI_WARPS = 8;                    // two per TMEM lane quarter, each half of the columns
+constexpr int TC_THREADS_P = 64 + EPI_WARPS * 32;
+constexpr int STG_LD = 20;                      // staging row stride (floats): 16 columns + pad
+
 template <int BN, int NPASS>
 struct TcCfg {
     static constexpr int A_BYTES = BM * BK * 2;                 // one plane, 16 KB
     static constexpr int W_BYTES = BN * BK * 2;
     static constexpr int PLANES = (NPASS == 3) ? 2 : 1;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;   // epilogue transpose staging
+    static constexpr int AVAIL = 225 * 1024 - STG_BYTES - 1024 - 256;
+    static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
 };
 
+// Persistent: grid = min(#tiles, #SMs); CTA c takes tiles c, c+grid, ...  (n-tile fastest so
+// concurrently running CTAs share the same A rows through L2).  The accumulator is double
+// buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 template <int BN, int NPASS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
                int K, EpiParams epi) {
     using C = TcCfg<BN, NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
-    uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C::STAGES + 1);
+    float *staging = reinterpret_cast<float *>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(staging) + C::STG_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     const int nkb = K / BK;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+    const int num_tiles = tiles_n * tiles_m;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM allocation: BN fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -150,17 +183,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
-                mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
-                tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
-                if (NPASS == 3) {
-                    tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0);
+            uint32_t it = 0;   // global k-block counter across tiles
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                    tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
+                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
+                    if (NPASS == 3) {
+                        tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0);
+                        tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0);
+                    }
                 }
             }
         }
@@ -168,51 +205,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t st = smem_u32(tiles + (size_t)s * C::STAGE_BYTES);
-                const uint64_t a_hi = umma_desc_sw128(st), w_hi = umma_desc_sw128(st + C::A_BYTES);
-                const uint64_t a_lo = umma_desc_sw128(st + C::A_BYTES + C::W_BYTES);
-                const uint64_t w_lo = umma_desc_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_u32(tiles + (size_t)s * C::STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(st), w_hi = umma_desc_sw128(st + C::A_BYTES);
+                    const uint64_t a_lo = umma_desc_sw128(st + C::A_BYTES + C::W_BYTES);
+                    const uint64_t w_lo = umma_desc_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, encoded >>4
-                    umma_bf16(tmem_base, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
-                    if (NPASS == 3) {
-                        umma_bf16(tmem_base, a_hi + koff, w_lo + koff, idesc, 1);
-                        umma_bf16(tmem_base, a_lo + koff, w_hi + koff, idesc, 1);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per K step, encoded >>4
+                        umma_bf16(tmem_d, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+                        if (NPASS == 3) {
+                            umma_bf16(tmem_d, a_hi + koff, w_lo + koff, idesc, 1);
+                            umma_bf16(tmem_d, a_lo + koff, w_hi + koff, idesc, 1);
+                        }
                     }
+                    umma_commit(&empty[s]);          // frees the stage when these MMAs retire
                 }
-                umma_commit(&empty[s]);          // frees the stage when these MMAs retire
+                umma_commit(&acc_full[buf]);         // accumulator of this tile complete
             }
-            umma_commit(acc_full);               // accumulator complete
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        mbar_wait(acc_full, 0);
-        tcgen05_fence_after();
-        const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
+        // ===================== epilogue (warps 2..9) =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                    // which half of the BN columns
+        float *stg = staging + (size_t)ew * 32 * STG_LD;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&acc_full[buf], aph);
+            tcgen05_fence_after();
+            const uint32_t tbase = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (row < M) {
+            for (int c = 0; c < BN / 32; ++c) {      // 16-column chunks of this warp's half
+                const int col = half * (BN / 2) + c * 16;
+                uint32_t v[16];
+                tmem_ld16(tbase + (uint32_t)col, v);
+                if (c == BN / 32 - 1) {              // last TMEM read of this tile: release the buffer
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                // transpose through shared memory: lane = TMEM row -> (8 rows x 4 lanes x float4) stores
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    epilogue4(epi, row, n0 + c * 32 + j * 4, N,
-                              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * j) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + (lane >> 2), cc = (lane & 3) * 4;
+                    const int row = m0 + q * 32 + r;
+                    const float4 val = *reinterpret_cast<const float4 *>(stg + r * STG_LD + cc);
+                    if (row < M) epilogue4(epi, row, n0 + col + cc, N, val);
+                }
+                __syncwarp();
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
 }
 
@@ -241,9 +307,16 @@ cudaError_t launch_t(const TcOperand &A, const TcOperand &W, int M, int N, int K
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int num_tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+    dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    gemm_tc_kernel<BN, NPASS><<<grid, TC_THREADS, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
+    gemm_tc_kernel<BN, NPASS><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
     return cudaGetLastError();
 }
 
