@@ -1,0 +1,329 @@
+// include/parakeet/transcribe.hpp -- header-only C++ drop-in for the reference's high-level
+// API (Frikallo/parakeet.cpp include/parakeet/transcribe.hpp:23-299, config.hpp:9-135,
+// timestamp.hpp:11-35) on top of the B200 C-ABI (include/parakeet_b200.h).
+//
+//   parakeet::Transcriber t("model.safetensors", "vocab.txt");   // transcribe.hpp:59
+//   t.to_gpu();                                                    // :68
+//   auto r = t.transcribe("audio.wav");                           // :74, Decoder::TDT default
+//   auto r2 = t.transcribe(samples, n, parakeet::Decoder::CTC, /*timestamps=*/true);
+//
+// Same class / method names, argument meaning, defaults and error behaviour
+// (std::runtime_error) as the reference.  Differences, all forced by the boundary:
+//   * samples are (const float*, size_t) or std::vector<float> instead of axiom::Tensor
+//     (an axiom::Tensor overload is enabled when <axiom/axiom.hpp> is on the include path);
+//   * the model only ever lives on the CUDA device: to_gpu() is a checked no-op and there
+//     is no CPU fallback;
+//   * transcribe_batch() is an addition (the reference is batch-1, transcribe.hpp:170-171);
+//   * phrase boosting (TranscribeOptions::boost_phrases) is not on the GPU path and throws;
+//   * TDTTranscriber passes blank = vocab-1 like the reference CLI (src/main.cpp:252), not
+//     the header's hard-coded 1024 (transcribe.hpp:256-261) which is wrong for 8193 tokens.
+// Link with libparakeet_b200.so.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <algorithm>
+#include <fstream>
+#include <iterator>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../parakeet_b200.h"
+
+#if __has_include(<axiom/axiom.hpp>)
+#include <axiom/axiom.hpp>
+#define PARAKEET_B200_HAS_AXIOM 1
+#endif
+
+namespace parakeet {
+
+// ─── configs (config.hpp:9-135) ──────────────────────────────────────────────
+struct EncoderConfig {
+    int mel_bins = 80, subsampling_factor = 8, subsampling_channels = 256, hidden_size = 1024, num_layers = 24,
+        num_heads = 8, ffn_intermediate = 4096, conv_kernel_size = 9;
+    float dropout = 0.1f, layer_norm_eps = 1e-5f;
+};
+struct PredictionConfig { int vocab_size = 1025, pred_hidden = 640, num_lstm_layers = 2; float dropout = 0.1f; };
+struct JointConfig { int encoder_hidden = 1024, pred_hidden = 640, joint_hidden = 640, vocab_size = 1025; };
+struct TDTConfig { EncoderConfig encoder; PredictionConfig prediction; JointConfig joint; std::vector<int> durations = {0, 1, 2, 3, 4}; };
+struct TDTCTCConfig { EncoderConfig encoder; PredictionConfig prediction; JointConfig joint; std::vector<int> durations = {0, 1, 2, 3, 4}; int ctc_vocab_size = 1025; };
+
+inline TDTCTCConfig make_110m_config() {       // config.hpp:77-95
+    TDTCTCConfig c;
+    c.encoder.hidden_size = 512; c.encoder.num_layers = 17; c.encoder.num_heads = 8; c.encoder.ffn_intermediate = 2048;
+    c.prediction.num_lstm_layers = 1; c.joint.encoder_hidden = 512;
+    return c;
+}
+inline TDTConfig make_tdt_600m_config() {      // config.hpp:98-116
+    TDTConfig c;
+    c.encoder.mel_bins = 128;
+    c.prediction.vocab_size = 8193; c.joint.vocab_size = 8193;
+    return c;
+}
+
+// ─── timestamps (timestamp.hpp:11-35) ────────────────────────────────────────
+struct TimestampedToken { int token_id; int start_frame; int end_frame; float confidence = 1.0f; };
+struct WordTimestamp { std::string word; float start; float end; float confidence = 1.0f; };
+constexpr float FRAME_DURATION_S = 0.08f;
+inline float frame_to_seconds(int frame) { return static_cast<float>(frame) * FRAME_DURATION_S; }
+
+// ─── result / options (transcribe.hpp:23-43) ─────────────────────────────────
+struct TranscribeResult {
+    std::string text;
+    std::vector<int> token_ids;
+    std::vector<TimestampedToken> timestamped_tokens;
+    std::vector<WordTimestamp> word_timestamps;
+};
+enum class Decoder { CTC, TDT };
+struct TranscribeOptions {
+    Decoder decoder = Decoder::TDT;
+    bool timestamps = false;
+    std::vector<std::string> boost_phrases;
+    float boost_score = 5.0f;
+};
+
+// ─── Tokenizer (vocab.hpp) over the C-ABI host helpers ───────────────────────
+class Tokenizer {
+  public:
+    Tokenizer() = default;
+    Tokenizer(const Tokenizer &) = delete;
+    Tokenizer &operator=(const Tokenizer &) = delete;
+    ~Tokenizer() { pk_vocab_free(v_); }
+    void load(const std::string &vocab_path) {
+        pk_vocab_free(v_);
+        v_ = nullptr;
+        if (pk_vocab_load(vocab_path.c_str(), &v_) != PK_OK) throw std::runtime_error("Cannot open vocab file: " + vocab_path);
+    }
+    bool loaded() const { return v_ && pk_vocab_size(v_) > 0; }
+    size_t vocab_size() const { return loaded() ? (size_t)pk_vocab_size(v_) + 1 : 0; }   // +1 blank, like the reference
+    std::string decode(const std::vector<int> &ids) const {
+        std::vector<int32_t> a(ids.begin(), ids.end());
+        std::string buf(64 + 64 * a.size(), '\0');
+        int n = pk_detokenize(v_, a.data(), (int32_t)a.size(), &buf[0], (int32_t)buf.size());
+        buf.resize(n < 0 ? 0 : std::min<size_t>((size_t)n, buf.size() - 1));
+        return buf;
+    }
+    std::vector<WordTimestamp> group(const std::vector<TimestampedToken> &t) const {
+        const int n = (int)t.size();
+        std::vector<int32_t> id(n), st(n), en(n);
+        std::vector<float> cf(n), ws(n + 1), we(n + 1), wc(n + 1);
+        for (int i = 0; i < n; ++i) { id[i] = t[i].token_id; st[i] = t[i].start_frame; en[i] = t[i].end_frame; cf[i] = t[i].confidence; }
+        std::string buf(64 + 64 * (size_t)n, '\0');
+        int k = pk_group_words(v_, id.data(), st.data(), en.data(), cf.data(), n, &buf[0], (int32_t)buf.size(), ws.data(), we.data(), wc.data());
+        std::vector<WordTimestamp> out;
+        size_t pos = 0;
+        for (int i = 0; i < k; ++i) {
+            size_t e = buf.find('\n', pos);
+            out.push_back({buf.substr(pos, e - pos), ws[i], we[i], wc[i]});
+            pos = e + 1;
+        }
+        return out;
+    }
+  private:
+    pk_vocab *v_ = nullptr;
+};
+
+// ─── minimal read_audio (audio_io.hpp): 16 kHz mono PCM16 / float32 WAV ──────
+inline std::vector<float> read_audio(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Cannot open audio file: " + path);
+    std::vector<char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (d.size() < 12 || std::memcmp(d.data(), "RIFF", 4) || std::memcmp(d.data() + 8, "WAVE", 4))
+        throw std::runtime_error("Unsupported audio format (RIFF/WAVE only on this path): " + path);
+    uint16_t tag = 0, ch = 0, bits = 0;
+    uint32_t sr = 0;
+    const char *pcm = nullptr;
+    uint32_t pcm_bytes = 0;
+    for (size_t pos = 12; pos + 8 <= d.size();) {
+        uint32_t sz;
+        std::memcpy(&sz, d.data() + pos + 4, 4);
+        if (!std::memcmp(d.data() + pos, "fmt ", 4) && sz >= 16) {
+            std::memcpy(&tag, d.data() + pos + 8, 2); std::memcpy(&ch, d.data() + pos + 10, 2);
+            std::memcpy(&sr, d.data() + pos + 12, 4); std::memcpy(&bits, d.data() + pos + 22, 2);
+        } else if (!std::memcmp(d.data() + pos, "data", 4)) {
+            pcm = d.data() + pos + 8;
+            pcm_bytes = (uint32_t)std::min<size_t>(sz, d.size() - pos - 8);
+        }
+        pos += 8 + sz + (sz & 1);
+    }
+    if (!pcm || !ch) throw std::runtime_error("malformed WAV: " + path);
+    if (sr != 16000) throw std::runtime_error("Sample rate mismatch: audio=" + std::to_string(sr) + " expected=16000");
+    std::vector<float> mono;
+    if (tag == 1 && bits == 16) {
+        const size_t n = pcm_bytes / 2 / ch;
+        mono.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            float s = 0.f;
+            for (int c = 0; c < ch; ++c) { int16_t v; std::memcpy(&v, pcm + 2 * (i * ch + c), 2); s += (float)v / 32768.0f; }
+            mono[i] = s / (float)ch;
+        }
+    } else if (tag == 3 && bits == 32) {
+        const size_t n = pcm_bytes / 4 / ch;
+        mono.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            float s = 0.f;
+            for (int c = 0; c < ch; ++c) { float v; std::memcpy(&v, pcm + 4 * (i * ch + c), 4); s += v; }
+            mono[i] = s / (float)ch;
+        }
+    } else {
+        throw std::runtime_error("unsupported WAV encoding: " + path);
+    }
+    return mono;
+}
+
+namespace detail {
+
+class EngineHolder {
+  public:
+    EngineHolder(const pk_config &cfg, const std::string &weights, int device) : cfg_(cfg) {
+        if (pk_engine_create(&cfg, weights.c_str(), device, &e_) != PK_OK)
+            throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(nullptr));
+        cap_ = 2 * pk_encoder_frames(pk_mel_frames(cfg.max_samples)) + 8;
+    }
+    EngineHolder(const EngineHolder &) = delete;
+    EngineHolder &operator=(const EngineHolder &) = delete;
+    ~EngineHolder() { pk_engine_destroy(e_); }
+
+    std::vector<std::vector<TimestampedToken>> run(const std::vector<const float *> &pcm, const std::vector<size_t> &n, pk_decoder dec) {
+        const int B = (int)pcm.size();
+        std::vector<int64_t> off(B + 1, 0);
+        for (int i = 0; i < B; ++i) off[i + 1] = off[i] + (int64_t)n[i];
+        std::vector<float> buf((size_t)off[B]);
+        for (int i = 0; i < B; ++i) std::memcpy(buf.data() + off[i], pcm[i], n[i] * sizeof(float));
+        std::vector<int32_t> ids((size_t)B * cap_), st((size_t)B * cap_), en((size_t)B * cap_), len(B);
+        std::vector<float> cf((size_t)B * cap_);
+        pk_tokens t{cap_, ids.data(), st.data(), en.data(), cf.data(), len.data()};
+        if (pk_transcribe_batch(e_, buf.data(), off.data(), B, dec, &t) != PK_OK)
+            throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(e_));
+        std::vector<std::vector<TimestampedToken>> out(B);
+        for (int b = 0; b < B; ++b)
+            for (int i = 0; i < len[b]; ++i)
+                out[b].push_back({ids[(size_t)b * cap_ + i], st[(size_t)b * cap_ + i], en[(size_t)b * cap_ + i], cf[(size_t)b * cap_ + i]});
+        return out;
+    }
+    const pk_config &cfg() const { return cfg_; }
+    pk_engine *raw() { return e_; }
+
+  private:
+    pk_config cfg_;
+    pk_engine *e_ = nullptr;
+    int32_t cap_ = 0;
+};
+
+inline void fill(pk_config &c, const EncoderConfig &e, const PredictionConfig &p, const JointConfig &j, const std::vector<int> &dur) {
+    c.mel_bins = e.mel_bins; c.sub_channels = e.subsampling_channels; c.d_model = e.hidden_size; c.n_layers = e.num_layers;
+    c.n_heads = e.num_heads; c.ff = e.ffn_intermediate; c.conv_kernel = e.conv_kernel_size;
+    c.vocab = j.vocab_size; c.pred_hidden = p.pred_hidden; c.lstm_layers = p.num_lstm_layers; c.joint_hidden = j.joint_hidden;
+    c.n_durations = (int)dur.size();
+    for (size_t i = 0; i < dur.size() && i < 8; ++i) c.durations[i] = dur[i];
+}
+
+template <class Derived>
+class TranscriberBase {
+  public:
+    void to_gpu() {}   // the reference moves weights to Metal here (transcribe.hpp:68-71); we are always on the device
+
+    TranscribeResult transcribe(const std::string &audio_path, const TranscribeOptions &opts) {
+        auto s = read_audio(audio_path);
+        return transcribe(s.data(), s.size(), opts);
+    }
+    TranscribeResult transcribe(const std::vector<float> &samples, const TranscribeOptions &opts) { return transcribe(samples.data(), samples.size(), opts); }
+    TranscribeResult transcribe(const float *samples, size_t n, const TranscribeOptions &opts) {
+        if (!opts.boost_phrases.empty()) throw std::runtime_error("phrase boosting is not available on the B200 path");
+        auto toks = eng_->run({samples}, {n}, self().pick(opts.decoder))[0];
+        return finish(toks, opts.timestamps);
+    }
+    // Not in the reference (batch-1 only): one call for many utterances.
+    std::vector<TranscribeResult> transcribe_batch(const std::vector<std::vector<float>> &utts, Decoder decoder = Decoder::TDT, bool timestamps = false) {
+        std::vector<TranscribeResult> out;
+        const size_t B = (size_t)eng_->cfg().max_batch;
+        for (size_t i = 0; i < utts.size(); i += B) {
+            std::vector<const float *> p;
+            std::vector<size_t> n;
+            for (size_t k = i; k < utts.size() && k < i + B; ++k) { p.push_back(utts[k].data()); n.push_back(utts[k].size()); }
+            for (auto &toks : eng_->run(p, n, self().pick(decoder))) out.push_back(finish(toks, timestamps));
+        }
+        return out;
+    }
+#ifdef PARAKEET_B200_HAS_AXIOM
+    TranscribeResult transcribe(const axiom::Tensor &samples, const TranscribeOptions &opts) {
+        auto c = samples.cpu().ascontiguousarray();
+        return transcribe(c.template typed_data<float>(), c.size(), opts);
+    }
+#endif
+    const Tokenizer &tokenizer() const { return tokenizer_; }
+    pk_engine *engine() { return eng_->raw(); }
+
+  protected:
+    TranscribeResult finish(const std::vector<TimestampedToken> &toks, bool timestamps) {
+        TranscribeResult r;
+        for (auto &t : toks) r.token_ids.push_back(t.token_id);
+        if (timestamps) r.timestamped_tokens = toks;
+        if (tokenizer_.loaded()) {
+            r.text = tokenizer_.decode(r.token_ids);
+            if (timestamps) r.word_timestamps = tokenizer_.group(toks);
+        }
+        return r;
+    }
+    Derived &self() { return static_cast<Derived &>(*this); }
+    std::unique_ptr<EngineHolder> eng_;
+    Tokenizer tokenizer_;
+};
+
+}  // namespace detail
+
+/// parakeet::Transcriber (reference transcribe.hpp:55-190): TDT-CTC hybrid, 110M preset by default.
+class Transcriber : public detail::TranscriberBase<Transcriber> {
+  public:
+    Transcriber(const std::string &weights_path, const std::string &vocab_path, const TDTCTCConfig &config = make_110m_config(),
+                int device = 0, int max_batch = 64, int max_samples = 30 * 16000) {
+        pk_config c;
+        pk_config_110m(&c);
+        detail::fill(c, config.encoder, config.prediction, config.joint, config.durations);
+        c.has_ctc = 1; c.joint_prefix_tdt = 1; c.max_batch = max_batch; c.max_samples = max_samples;
+        eng_ = std::make_unique<detail::EngineHolder>(c, weights_path, device);
+        tokenizer_.load(vocab_path);
+    }
+    using TranscriberBase::transcribe;
+    TranscribeResult transcribe(const std::string &audio_path, Decoder decoder = Decoder::TDT, bool timestamps = false) {
+        TranscribeOptions o; o.decoder = decoder; o.timestamps = timestamps;
+        return TranscriberBase::transcribe(audio_path, o);
+    }
+    TranscribeResult transcribe(const std::vector<float> &samples, Decoder decoder = Decoder::TDT, bool timestamps = false) {
+        TranscribeOptions o; o.decoder = decoder; o.timestamps = timestamps;
+        return TranscriberBase::transcribe(samples, o);
+    }
+    TranscribeResult transcribe(const float *samples, size_t n, Decoder decoder = Decoder::TDT, bool timestamps = false) {
+        TranscribeOptions o; o.decoder = decoder; o.timestamps = timestamps;
+        return TranscriberBase::transcribe(samples, n, o);
+    }
+    pk_decoder pick(Decoder d) const { return d == Decoder::CTC ? PK_DECODER_CTC : PK_DECODER_TDT; }
+};
+
+/// parakeet::TDTTranscriber (reference transcribe.hpp:200-299): TDT-only models (600M multilingual).
+class TDTTranscriber : public detail::TranscriberBase<TDTTranscriber> {
+  public:
+    TDTTranscriber(const std::string &weights_path, const std::string &vocab_path, const TDTConfig &config = make_tdt_600m_config(),
+                   int device = 0, int max_batch = 16, int max_samples = 30 * 16000) {
+        pk_config c;
+        pk_config_tdt_600m(&c);
+        detail::fill(c, config.encoder, config.prediction, config.joint, config.durations);
+        c.has_ctc = 0; c.joint_prefix_tdt = 0; c.max_batch = max_batch; c.max_samples = max_samples;
+        eng_ = std::make_unique<detail::EngineHolder>(c, weights_path, device);
+        tokenizer_.load(vocab_path);
+    }
+    using TranscriberBase::transcribe;
+    TranscribeResult transcribe(const std::string &audio_path, bool timestamps = false) {
+        TranscribeOptions o; o.timestamps = timestamps;
+        return TranscriberBase::transcribe(audio_path, o);
+    }
+    TranscribeResult transcribe(const std::vector<float> &samples, bool timestamps = false) {
+        TranscribeOptions o; o.timestamps = timestamps;
+        return TranscriberBase::transcribe(samples, o);
+    }
+    pk_decoder pick(Decoder) const { return PK_DECODER_TDT; }
+};
+
+}  // namespace parakeet

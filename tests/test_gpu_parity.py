@@ -258,3 +258,37 @@ def test_error_statuses(pkg, eng_tiny, tiny, synth, tmp_path):
     synth.save_safetensors(p, bad)
     with pytest.raises(RuntimeError, match="missing tensor"):
         pkg.Engine(tiny.cfg, p, 0)
+
+
+# ------------------------------------------------------------------ the C++ drop-in shim (include/parakeet/transcribe.hpp)
+def test_cpp_shim(pkg, tiny, synth, golden, tmp_path):
+    """Builds tests/cpp_shim_check.cpp (the reference-style usage: parakeet::Transcriber t(weights, vocab);
+    t.to_gpu(); t.transcribe("audio.wav", Decoder, timestamps)) against the header-only shim + the C-ABI
+    library and compares its tokens / text / words with the reference goldens."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cpp_shim_check")
+    libdir = os.path.dirname(pkg.lib_path())
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp_shim_check.cpp"),
+                    "-L" + libdir, "-lparakeet_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    k = "tiny.c0."
+    n, aseed = (int(v) for v in golden[k + "n_samples"])
+    pcm = synth.make_audio(n, aseed)
+    i16 = np.round(pcm * 32768.0).astype(np.int16)
+    wav = str(tmp_path / "a.wav")
+    with open(wav, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + 2 * len(i16)) + b"WAVEfmt " +
+                struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"data" + struct.pack("<I", 2 * len(i16)))
+        f.write(i16.tobytes())
+    out = subprocess.run([exe, tiny.weights_path, tiny.vocab_path, wav, "tiny"], check=True, capture_output=True, text=True).stdout
+    lines = out.strip().split("\n")
+    tdt = [[int(x) for x in t.split(":")] for t in lines[0].split()[1:]]
+    assert tdt == golden[k + "tdt_tok"].tolist()
+    assert lines[1] == "TEXT " + bytes(golden[k + "tdt_text"]).decode()
+    assert lines[2].split()[1:] == bytes(golden[k + "tdt_words"]).decode().split("\n")
+    ctc = [[int(x) for x in t.split(":")] for t in lines[3].split()[1:]]
+    assert ctc == golden[k + "ctc_tok"].tolist()
+    assert lines[4] == "TEXT " + bytes(golden[k + "ctc_text"]).decode()
+    assert lines[6].startswith("ERR Cannot open audio file")
