@@ -280,6 +280,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm (all GEMM launches of one step)",
                 "achieved": gemm_tflops, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
                 "frac": gemm_tflops / pk["bf16_sus"], "traffic": None,
+                "mma_frac": (3.0 if int(cfg.math) == 0 else 1.0) * gemm_tflops / pk["bf16_sus"] if int(cfg.math) != 2 else None,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9, "launches_per_step": gemm_n // PSTEPS,
                 "avg_launch_ms": gemm_ms / max(gemm_n, 1),
