@@ -160,6 +160,10 @@ pk_status pk_profile_end(pk_engine *e, double *ms, int64_t *counts, double *flop
 const char *pk_profile_names(void);
 pk_status pk_flush_l2(pk_engine *e);
 
+/* Debug aid: cycles CTA 0 of the last TDT decode spent in {P1, B1, P2, B2, P3, B3, P4}; out8[7] =
+ * number of lock-step decode steps. */
+pk_status pk_debug_tdt_phases(pk_engine *e, int64_t *out8);
+
 /* GPU self-check of the tcgen05 GEMM kernel against the fp32 CUDA-core GEMM on seeded
  * random data (epi_kind: EpiKind of csrc/pk_common.cuh; math: PK_MATH_BF16X3 | PK_MATH_BF16X1). */
 pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int math, uint32_t seed,

@@ -117,9 +117,9 @@ struct pk_engine {
     float *t_conf = nullptr;
     // TDT state
     int Bpad = 0;
-    float *hbuf = nullptr, *cbuf = nullptr, *zbuf = nullptr, *pl_max = nullptr, *pl_sum = nullptr, *pd_max = nullptr;
-    int32_t *tdt_ints = nullptr;               // cur|token|tpos|active|ntok|overflow|n_active(3)
-    int32_t *pl_idx = nullptr, *pd_idx = nullptr;
+    float *hbuf = nullptr, *cbuf = nullptr, *zbuf = nullptr, *pl_max = nullptr, *pl_sum = nullptr;
+    int32_t *tdt_ints = nullptr;               // overflow[Bpad] | barrier counter
+    unsigned long long *tdt_keys = nullptr;    // arg-max keys: label[3][Bpad] | duration[3][Bpad]
     // pinned host staging
     float *h_pcm = nullptr;
     int32_t *h_meta = nullptr;                 // offsets staging
@@ -518,17 +518,15 @@ pk_status pk_engine::alloc_workspace() {
     t_conf = dalloc<float>(B * (size_t)cap);
     Bpad = ((Bmax + 31) / 32) * 32;
     const size_t HS = (size_t)c.pred_hidden * Bpad;
-    hbuf = dalloc<float>(HS * 2 * c.lstm_layers);
+    hbuf = dalloc<float>(HS * 2 * c.lstm_layers * TDT_NREP);
     cbuf = dalloc<float>(HS * 2 * c.lstm_layers);
-    zbuf = dalloc<float>((size_t)c.joint_hidden * Bpad);
-    tdt_ints = dalloc<int32_t>((size_t)6 * Bpad + 4);
-    const size_t PG = (size_t)num_sms * Bpad;
+    zbuf = dalloc<float>((size_t)c.joint_hidden * Bpad * TDT_NREP);
+    tdt_ints = dalloc<int32_t>((size_t)Bpad + 4);
+    tdt_keys = dalloc<unsigned long long>((size_t)6 * Bpad + 8);
+    const size_t PG = (size_t)3 * num_sms * Bpad;
     pl_max = dalloc<float>(PG);
     pl_sum = dalloc<float>(PG);
-    pd_max = dalloc<float>(PG);
-    pl_idx = dalloc<int32_t>(PG);
-    pd_idx = dalloc<int32_t>(PG);
-    if (!pd_idx || !hbuf || !x || !sub2 || !d_pcm || !t_conf) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
+    if (!pl_sum || !tdt_keys || !hbuf || !x || !sub2 || !d_pcm || !t_conf) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
     if (cfg.math != PK_MATH_FP32 && (!sub1.hi || !sub3.hi || !sub4.hi || !ln.hi || !ffh.hi || !ctx.hi || !cv.hi))
         return fail(PK_ERR_CUDA, "workspace: cudaMalloc or cuTensorMapEncodeTiled failed for an activation operand");
     PK_CUDA(cudaMallocHost(&h_pcm, (B * (size_t)c.max_samples + 8) * sizeof(float)));
@@ -805,13 +803,14 @@ pk_status pk_engine::run_tdt() {
     for (int l = 0; l < c.lstm_layers; ++l) { p.Whh[l] = Whh[l]; p.Wih[l] = Wih[l]; p.bih[l] = bih[l]; }
     p.Wp = Wp; p.Wout = Wout; p.bout = bout;
     p.hbuf = hbuf; p.cbuf = cbuf; p.z = zbuf;
-    p.cur = tdt_ints; p.token = tdt_ints + bp; p.tpos = tdt_ints + 2 * bp; p.active = tdt_ints + 3 * bp;
-    p.ntok = tdt_ints + 4 * bp; p.overflow = tdt_ints + 5 * bp; p.n_active = tdt_ints + 6 * bp;
-    p.pl_max = pl_max; p.pl_sum = pl_sum; p.pd_max = pd_max; p.pl_idx = pl_idx; p.pd_idx = pd_idx;
+    p.overflow = tdt_ints; p.bar = reinterpret_cast<unsigned int *>(tdt_ints + Bpad);
+    p.pl_max = pl_max; p.pl_sum = pl_sum;
+    p.key_lab = tdt_keys; p.key_dur = tdt_keys + 3 * (size_t)Bpad;
+    p.dbg = reinterpret_cast<long long *>(tdt_keys + 6 * (size_t)Bpad);
     p.tok = tok; p.t_start = t_start; p.t_end = t_end; p.t_conf = t_conf;
     // initial state: zero LSTM state, token = blank (SOS), t = 0 (tdt.cpp:49-59)
     const size_t HS = (size_t)p.P * bp;
-    PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * sizeof(float), stream));
+    PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * TDT_NREP * sizeof(float), stream));
     PK_CUDA(cudaMemsetAsync(cbuf, 0, HS * 2 * p.L * sizeof(float), stream));
     cudaError_t ce;
     {
@@ -1063,6 +1062,20 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
         cudaFree(p);
     cudaStreamDestroy(st);
     return rc;
+}
+
+// Debug aid: cycles CTA 0 of the last TDT decode spent in {P1, B1, P2, B2, P3, B3, P4} and the
+// number of lock-step decode steps (out[7]).
+pk_status pk_debug_tdt_phases(pk_engine *e, int64_t *out8) {
+    if (!e || !out8) return PK_ERR_INVALID;
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(out8, e->tdt_keys + 6 * (size_t)e->Bpad, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost);
+    if (getenv("PK_DEBUG_TDT_INNER")) {
+        long long d[8];
+        tdt_debug_fetch(d);
+        fprintf(stderr, "tdt inner: loop cycles %lld tail cycles %lld calls %lld | loop by site R>10: %lld R==5: %lld other: %lld\n", d[0], d[1], d[2], d[3], d[4], d[5]);
+    }
+    return PK_OK;
 }
 
 pk_status pk_sync(pk_engine *e) {

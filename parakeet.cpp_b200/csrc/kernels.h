@@ -5,6 +5,7 @@
 #include "pk_common.cuh"
 
 #define PK_MAX_LSTM 4
+#define TDT_NREP 8   // replicas of the TDT h / z vectors (see tdt.cu)
 
 namespace pk {
 
@@ -78,16 +79,19 @@ struct TdtParams {
     const float *Wp;                          // [J][P]
     const float *Wout;                        // [V+D][J]
     const float *bout;                        // [V+D]
-    float *hbuf, *cbuf;                       // [L][2][P][Bpad]
-    float *z;                                 // [J][Bpad]
-    int32_t *cur, *token, *tpos, *active, *ntok, *overflow;   // [Bpad]
-    float *pl_max, *pl_sum, *pd_max;          // [grid][Bpad]
-    int32_t *pl_idx, *pd_idx;
-    int32_t *n_active;                        // [3]
+    float *hbuf;                              // [NREP][L][2][Bpad][P] LSTM h (two planes per utterance)
+    float *cbuf;                              // [L][2][Bpad][P]       LSTM c
+    float *z;                                 // [NREP][Bpad][J]       joint hidden
+    int32_t *overflow;                        // [Bpad]
+    float *pl_max, *pl_sum;                   // [3][grid][Bpad] per-CTA (max, sum-exp) partials
+    unsigned long long *key_lab, *key_dur;    // [3][Bpad] packed (value, index) arg-max keys
+    unsigned int *bar;                        // grid barrier counter
+    long long *dbg;                           // [8] optional: CTA-0 cycles per phase, steps
     int32_t *tok;                             // [n_utt][1+cap]
     int32_t *t_start, *t_end;                 // [n_utt][cap]
     float *t_conf;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
+void tdt_debug_fetch(long long *out8);
 
 }  // namespace pk

@@ -19,17 +19,16 @@
 //
 // Design (weights-stationary): the grid is one CTA per SM; every CTA keeps its slice of
 // W_hh / W_ih / pred_proj / label+duration rows in shared memory for the whole decode and
-// only the tiny per-utterance vectors (h, z; stored [k][utterance] so a warp lane is an
-// utterance) travel through L2 between the phases of a step, separated by grid barriers:
-//   P1 LSTM gates + cell (per layer)   P2 joint hidden   P3 logits -> per-CTA partial
-//   argmax / sum-exp                    P4 per-utterance reduction + state update.
+// only the tiny per-utterance vectors (h, z; [utterance][k]) travel through L2 (staged into
+// shared memory by a cp.async ring; a warp lane is an utterance) between the phases of a step, separated by grid barriers:
+//   P1 LSTM gates + cell (per layer) | P2 joint hidden | P3 logits -> per-CTA (max, sum-exp)
+//   partials + atomicMax of packed (value, index) keys | P4 state update, replicated in every
+//   CTA from the keys (no barrier before the next P1; confidences are finalised one phase later
+//   from the partials, in a fixed order, by the CTA that owns the utterance).
+// Three monotonic-counter grid barriers per step (cooperative launch guarantees co-residency).
 // enc_proj(enc)+bias for all frames and the layer-0 input table W_ih.E[token]+b for all
 // tokens are precomputed by GEMMs (engine.cu).
-#include <cooperative_groups.h>
-
 #include "kernels.h"
-
-namespace cg = cooperative_groups;
 
 namespace pk {
 namespace {
@@ -38,60 +37,162 @@ constexpr int RMAX = 20;   // rows accumulated per pass (5 LSTM units x 4 gates)
 constexpr int NWARP = 8;
 constexpr int BCH = 64;    // utterances per pass (2 per lane)
 
-// out(r, b) = sum_k W[r][k] * x_b[k] for r < R (R <= RMAX), b in [bc, bc+64).
-// W rows are contiguous [R][K] (shared or global); xsrc(b) -> pointer to x_b[0] with
-// element stride Bpad.  K-split across the 8 warps, partials reduced through `red`.
-template <typename XSrc, typename Fin>
-__device__ __forceinline__ void rows_times_batch(const float *W, int R, int K, int Bpad, int bc, XSrc xsrc,
-                                                 float *red, Fin fin) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kch = K / NWARP, k0 = warp * kch;
-    const int b0 = bc + lane, b1 = bc + 32 + lane;
-    const bool has0 = b0 < Bpad, has1 = b1 < Bpad;
-    const float *x0 = xsrc(has0 ? b0 : 0), *x1 = xsrc(has1 ? b1 : 0);
-    float acc[RMAX][2];
-#pragma unroll
-    for (int r = 0; r < RMAX; ++r) acc[r][0] = acc[r][1] = 0.f;
-    for (int k = k0; k < k0 + kch; k += 4) {
-        float xa[4], xb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            xa[i] = x0[(size_t)(k + i) * Bpad];
-            xb[i] = x1[(size_t)(k + i) * Bpad];
-        }
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-            if (r < R) {
-                const float4 w = *reinterpret_cast<const float4 *>(W + (size_t)r * K + k);
-                acc[r][0] = fmaf(w.x, xa[0], acc[r][0]);
-                acc[r][0] = fmaf(w.y, xa[1], acc[r][0]);
-                acc[r][0] = fmaf(w.z, xa[2], acc[r][0]);
-                acc[r][0] = fmaf(w.w, xa[3], acc[r][0]);
-                acc[r][1] = fmaf(w.x, xb[0], acc[r][1]);
-                acc[r][1] = fmaf(w.y, xb[1], acc[r][1]);
-                acc[r][1] = fmaf(w.z, xb[2], acc[r][1]);
-                acc[r][1] = fmaf(w.w, xb[3], acc[r][1]);
-            }
+constexpr int KC = NWARP * 4;   // k-values staged per chunk (4 per warp)
+constexpr int NST = 4;          // cp.async ring depth
+constexpr int XLD = KC + 4;     // staged row stride (floats): 16 B aligned, conflict-free float4 reads
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool WS>
+__device__ __forceinline__ float4 load_w4(const float *p) {
+    if (WS) {
+        float4 v;   // weights never change during the kernel: not volatile, so loads can be batched ahead of the FMAs
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return v;
     }
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+// out(r, b) = sum_k W[r][k] * x_b[k] for r < R (R <= RMAX), b in [bc, bc+64).
+// W rows are contiguous [R][K] (shared memory when WS, else global).  xsrc(b) -> pointer to the
+// K contiguous floats of utterance b (global; lives in L2).  x is streamed through a 4-deep
+// cp.async ring in shared memory, 64 utterances x 32 k-values per chunk (16-byte copies that
+// bypass L1; a warp fetches 4 full lines), so the L2 latency is paid once per phase; within a chunk warp w owns k = 4w..4w+3
+// (K-split) and a lane owns utterances (lane, lane+32).  Partials are reduced across the 8
+// warps through `red`.
+__device__ long long g_tdt_dbg[8];
+
+// RB = compile-time bound on the rows of this call (the row loop is fully unrolled and the
+// compiler if-converts `r < R`, so every unrolled row costs its FMAs whether it is live or not).
+template <int RB, bool WS, typename XSrc, typename Fin>
+__device__ __forceinline__ void rows_times_batch_rb(const float *W, int R, int K, int Bpad, int bc, XSrc xsrc,
+                                                    float *xs, float *red, Fin fin) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = K / KC;
+    // this thread copies 16-byte piece `pc` of staged rows b_a and b_a + 32 (a warp = 4 full 128 B lines)
+    const int pc = threadIdx.x & 7, b_a = threadIdx.x >> 3;
+    const bool va = (bc + b_a) < Bpad, vb = (bc + b_a + 32) < Bpad;
+    const float *xa_src = xsrc(va ? bc + b_a : 0) + pc * 4;
+    const float *xb_src = xsrc(vb ? bc + b_a + 32 : 0) + pc * 4;
+    auto issue = [&](int c) {
+        if (c < nchunks) {
+            float *dst = xs + (size_t)(c % NST) * BCH * XLD + pc * 4;
+            if (va) cp_async16(dst + b_a * XLD, xa_src + c * KC);
+            if (vb) cp_async16(dst + (b_a + 32) * XLD, xb_src + c * KC);
+        }
+        cp_async_commit();
+    };
+    float acc[RB][2];
+    const long long t0 = clock64();
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r)
+    for (int r = 0; r < RB; ++r) acc[r][0] = acc[r][1] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) issue(c);
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();                       // chunk c landed for everyone; chunk c-1 fully consumed
+        issue(c + NST - 1);
+        const float *xc = xs + (size_t)(c % NST) * BCH * XLD + warp * 4;
+        const float4 xa = *reinterpret_cast<const float4 *>(xc + lane * XLD);
+        const float4 xb = *reinterpret_cast<const float4 *>(xc + (lane + 32) * XLD);
+        const int k = c * KC + warp * 4;
+        // rows in groups of up to 5: issue the group's weight loads first, then its 40 FMAs, so the
+        // shared-memory latency is paid once per group instead of once per row
+#pragma unroll
+        for (int r0 = 0; r0 < RB; r0 += 5) {
+            float4 w[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (r0 + j < RB) w[j] = load_w4<WS>(W + (size_t)min(r0 + j, R - 1) * K + k);
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+                if (r0 + j < RB) {
+                    const int r = r0 + j;
+                    acc[r][0] = fmaf(w[j].x, xa.x, acc[r][0]);
+                    acc[r][1] = fmaf(w[j].x, xb.x, acc[r][1]);
+                    acc[r][0] = fmaf(w[j].y, xa.y, acc[r][0]);
+                    acc[r][1] = fmaf(w[j].y, xb.y, acc[r][1]);
+                    acc[r][0] = fmaf(w[j].z, xa.z, acc[r][0]);
+                    acc[r][1] = fmaf(w[j].z, xb.z, acc[r][1]);
+                    acc[r][0] = fmaf(w[j].w, xa.w, acc[r][0]);
+                    acc[r][1] = fmaf(w[j].w, xb.w, acc[r][1]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    const long long t1 = clock64();
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
         if (r < R) {
             red[(warp * RMAX + r) * BCH + lane] = acc[r][0];
             red[(warp * RMAX + r) * BCH + 32 + lane] = acc[r][1];
         }
     __syncthreads();
     for (int idx = threadIdx.x; idx < R * BCH; idx += blockDim.x) {
-        const int r = idx / BCH, bb = idx % BCH;
+        const int r = idx / BCH, b2 = idx % BCH;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < NWARP; ++w) s += red[(w * RMAX + r) * BCH + bb];
-        if (bc + bb < Bpad) fin(r, bc + bb, s);
+        for (int w = 0; w < NWARP; ++w) s += red[(w * RMAX + r) * BCH + b2];
+        if (bc + b2 < Bpad) fin(r, bc + b2, s);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        g_tdt_dbg[0] += t1 - t0;
+        g_tdt_dbg[1] += clock64() - t1;
+        g_tdt_dbg[2] += 1;
+        const int site = (K == 0) ? 0 : (R > 10 ? 3 : (R == 5 ? 4 : 5));
+        g_tdt_dbg[site] += t1 - t0;
+    }
+}
+
+template <bool WS, typename XSrc, typename Fin>
+__device__ __forceinline__ void rows_times_batch(const float *W, int R, int K, int Bpad, int bc, XSrc xsrc,
+                                                 float *xs, float *red, Fin fin) {
+    if (R <= 5) rows_times_batch_rb<5, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+    else if (R <= 8) rows_times_batch_rb<8, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+    else if (R <= 12) rows_times_batch_rb<12, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+    else rows_times_batch_rb<RMAX, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+}
+
+// Monotonic-counter grid barrier (all CTAs are co-resident: cooperative launch).  Cheaper than
+// cooperative_groups' grid.sync() and traps instead of hanging if a CTA never arrives.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v, spin = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (++spin > (1u << 28)) __trap();
+        } while (v < target);
+        __threadfence();
     }
     __syncthreads();
 }
 
+// (value, index) packed so that atomicMax picks the larger value and, on ties, the SMALLER index
+// (the reference's strict '>' scans keep the first maximum).
+__device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
+    unsigned int u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx);
+}
+__device__ __forceinline__ void unpack_key(unsigned long long k, float &v, int &idx) {
+    unsigned int u = (unsigned int)(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    v = __uint_as_float(u);
+    idx = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFu));
+}
+
 __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) float sm[];
     const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
     const int P = p.P, J = p.J, V = p.V, D = p.D, L = p.L, Bpad = p.Bpad;
@@ -103,12 +204,15 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
     const int OPC = (NO + G - 1) / G;
     const int o0 = min(g * OPC, NO), o1 = min(o0 + OPC, NO);
 
-    // ---- shared memory carve-up: [red][gates][weights...]
+    // ---- shared memory carve-up: [red][gates][state][weights...]
     float *red = sm;                               // [NWARP][RMAX][BCH]
     float *gsm = red + NWARP * RMAX * BCH;         // [RMAX][BCH] gate pre-activations / logits
-    float *wsm = gsm + RMAX * BCH;
+    float *xs = gsm + RMAX * BCH;                  // [NST][BCH][XLD] cp.async ring for the x vectors
+    int *s_cur = reinterpret_cast<int *>(xs + NST * BCH * XLD);   // replicated decode state, [Bpad] each
+    int *s_token = s_cur + Bpad, *s_tpos = s_token + Bpad, *s_active = s_tpos + Bpad, *s_ntok = s_active + Bpad;
+    int *s_pend = s_ntok + Bpad;                   // slot of a token whose confidence is still pending (-1: none)
+    float *wsm = reinterpret_cast<float *>(s_pend + Bpad);
     const int nU = u1 - u0;
-    // per layer: Whh rows (nU*4, K=P); layers >= 1 also Wih rows
     float *w_hh[PK_MAX_LSTM], *w_ih[PK_MAX_LSTM];
     {
         float *cur = wsm;
@@ -139,27 +243,74 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
     } else {
         w_o = p.Wout + (size_t)o0 * J;
     }
+    for (int b = tid; b < Bpad; b += blockDim.x) {           // initial state (tdt.cpp:49-59)
+        s_cur[b] = 0;
+        s_token[b] = V - 1;
+        s_tpos[b] = 0;
+        s_active[b] = b < p.n_utt ? 1 : 0;
+        s_ntok[b] = 0;
+        s_pend[b] = -1;
+    }
     __syncthreads();
 
     const size_t HS = (size_t)P * Bpad;  // one h/c plane
+    // All CTAs read the same h / z lines in the same microsecond, and an L2 slice serialises
+    // requests to one line: the vectors are therefore kept in NREP replicas (writers store every
+    // replica, CTA g reads replica g % NREP), which spreads the readers of a line 8 ways.
+    const int rep = g % TDT_NREP;
+    const size_t HREP = (size_t)L * 2 * HS, ZREP = (size_t)J * Bpad;
+    const float *h_rd = p.hbuf + (size_t)rep * HREP;
+    const float *z_rd = p.z + (size_t)rep * ZREP;
+    const size_t KB = (size_t)Bpad;      // one key buffer
+    const size_t PB = (size_t)G * Bpad;  // one partial buffer
+    unsigned int nbar = 0;
+    // deferred confidence: 1 / sum_q lsum_q * exp(lmax_q - gmax) over the per-CTA partials of `buf`
+    auto finalize_conf = [&](int buf) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int b = g + warp * G; b < p.n_utt; b += G * NWARP) {   // utterances owned by this CTA (b % G == g)
+            const int slot = s_pend[b];
+            if (slot < 0) continue;
+            float gmax = -INFINITY;
+            for (int q = lane; q < G; q += 32) gmax = fmaxf(gmax, p.pl_max[buf * PB + (size_t)q * Bpad + b]);
+            gmax = warp_max(gmax);
+            float s = 0.f;
+            for (int q = lane; q < G; q += 32) {
+                const float m = p.pl_max[buf * PB + (size_t)q * Bpad + b];
+                if (m > -INFINITY) s += p.pl_sum[buf * PB + (size_t)q * Bpad + b] * expf(m - gmax);
+            }
+            s = warp_sum(s);
+            if (lane == 0) p.t_conf[(size_t)b * p.cap + slot] = 1.0f / s;
+        }
+    };
+
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    auto tick = [&](int slot) {   // phase timing of CTA 0 (debug aid, p.dbg may be null)
+        const long long now = clock64();
+        tacc[slot] += now - tprev;
+        tprev = now;
+    };
     int step = 0;
     for (;; ++step) {
-        if (g == 0 && tid == 0) p.n_active[(step + 1) % 3] = 0;
+        const int kb = step % 3;
+        if (g == 0)   // reset the key buffer of the NEXT step (last read two barriers ago)
+            for (int b = tid; b < Bpad; b += blockDim.x) {
+                p.key_lab[((step + 1) % 3) * KB + b] = 0ull;
+                p.key_dur[((step + 1) % 3) * KB + b] = 0ull;
+            }
         // ================= P1: LSTM layers =================
         for (int l = 0; l < L; ++l) {
             for (int bc = 0; bc < Bpad; bc += BCH) {
                 const int R = nU * 4;
                 if (R > 0) {
-                    // recurrent part: W_hh . h_l(current)
-                    rows_times_batch(
+                    rows_times_batch<true>(
                         w_hh[l], R, P, Bpad, bc,
-                        [&](int b) { return p.hbuf + ((size_t)(l * 2 + p.cur[b])) * HS + b; }, red,
+                        [&](int b) { return h_rd + ((size_t)(l * 2 + s_cur[b])) * HS + (size_t)b * P; }, xs, red,
                         [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v; });
                     if (l > 0) {  // input part: W_ih . h'_{l-1}(new)
-                        rows_times_batch(
+                        rows_times_batch<true>(
                             w_ih[l], R, P, Bpad, bc,
-                            [&](int b) { return p.hbuf + ((size_t)((l - 1) * 2 + (1 - p.cur[b]))) * HS + b; },
-                            red, [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] += v; });
+                            [&](int b) { return h_rd + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; },
+                            xs, red, [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] += v; });
                     }
                     __syncthreads();
                     for (int idx = tid; idx < nU * BCH; idx += blockDim.x) {
@@ -169,51 +320,64 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                         float gi = gsm[(ul * 4 + 0) * BCH + bb], gf = gsm[(ul * 4 + 1) * BCH + bb];
                         float gg = gsm[(ul * 4 + 2) * BCH + bb], go = gsm[(ul * 4 + 3) * BCH + bb];
                         if (l == 0) {
-                            const float *row = p.G0 + (size_t)p.token[b] * 4 * P;
+                            const float *row = p.G0 + (size_t)s_token[b] * 4 * P;
                             gi += row[u]; gf += row[P + u]; gg += row[2 * P + u]; go += row[3 * P + u];
                         } else {
                             const float *bi = p.bih[l];
                             gi += bi[u]; gf += bi[P + u]; gg += bi[2 * P + u]; go += bi[3 * P + u];
                         }
-                        const int cu = p.cur[b];
-                        const float c_old = p.cbuf[((size_t)(l * 2 + cu)) * HS + (size_t)u * Bpad + b];
+                        const int cu = s_cur[b];
+                        const float c_old = p.cbuf[((size_t)(l * 2 + cu)) * HS + (size_t)b * P + u];
                         const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
                         const float h_new = sigmoidf_(go) * tanhf(c_new);
-                        p.cbuf[((size_t)(l * 2 + 1 - cu)) * HS + (size_t)u * Bpad + b] = c_new;
-                        p.hbuf[((size_t)(l * 2 + 1 - cu)) * HS + (size_t)u * Bpad + b] = h_new;
+                        p.cbuf[((size_t)(l * 2 + 1 - cu)) * HS + (size_t)b * P + u] = c_new;
+                        for (int rr = 0; rr < TDT_NREP; ++rr)
+                            p.hbuf[(size_t)rr * HREP + ((size_t)(l * 2 + 1 - cu)) * HS + (size_t)b * P + u] = h_new;
                     }
                     __syncthreads();
                 }
             }
-            grid.sync();
+            tick(0);
+            grid_barrier(p.bar, G * (++nbar));
+            tick(1);
         }
+        // confidences of the tokens emitted in the previous step (partials are complete now)
+        if (step > 0) finalize_conf((step - 1) % 3);
+        __syncthreads();
+        for (int b = tid; b < Bpad; b += blockDim.x) s_pend[b] = -1;
         // ================= P2: joint hidden z = relu(EP[t] + Wp . h') =================
         for (int bc = 0; bc < Bpad; bc += BCH)
             for (int rg = j0; rg < j1; rg += RMAX) {
                 const int R = min(RMAX, j1 - rg);
-                rows_times_batch(
+                rows_times_batch<true>(
                     w_p + (size_t)(rg - j0) * P, R, P, Bpad, bc,
-                    [&](int b) { return p.hbuf + ((size_t)((L - 1) * 2 + (1 - p.cur[b]))) * HS + b; }, red,
+                    [&](int b) { return h_rd + ((size_t)((L - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; }, xs, red,
                     [&](int r, int b, float v) {
                         float e = 0.f;
                         if (b < p.n_utt) {
                             const int T = p.row_off[b + 1] - p.row_off[b];
-                            const int t = min(p.tpos[b], T - 1);
+                            const int t = min(s_tpos[b], T - 1);
                             e = p.EP[(size_t)(p.row_off[b] + t) * J + rg + r];
                         }
-                        p.z[(size_t)(rg + r) * Bpad + b] = fmaxf(v + e, 0.f);
+                        const float zv = fmaxf(v + e, 0.f);
+                        for (int rr = 0; rr < TDT_NREP; ++rr) p.z[(size_t)rr * ZREP + (size_t)b * J + rg + r] = zv;
                     });
             }
-        grid.sync();
-        // ================= P3: logits + per-CTA partial reductions =================
+        tick(2);
+        grid_barrier(p.bar, G * (++nbar));
+        tick(3);
+        // ================= P3: logits -> per-CTA partials + global arg-max keys =================
         for (int bc = 0; bc < Bpad; bc += BCH) {
             float lmax = -INFINITY, lsum = 0.f, dmax = -INFINITY;
             int lidx = 0x7fffffff, didx = 0x7fffffff;
             for (int rg = o0; rg < o1; rg += RMAX) {
                 const int R = min(RMAX, o1 - rg);
-                rows_times_batch(
-                    w_o + (size_t)(rg - o0) * J, R, J, Bpad, bc, [&](int b) { return p.z + b; }, red,
-                    [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v + p.bout[rg + r]; });
+                auto xz = [&](int b) { return z_rd + (size_t)b * J; };
+                auto fl = [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v + p.bout[rg + r]; };
+                if (p.out_in_smem)
+                    rows_times_batch<true>(w_o + (size_t)(rg - o0) * J, R, J, Bpad, bc, xz, xs, red, fl);
+                else
+                    rows_times_batch<false>(w_o + (size_t)(rg - o0) * J, R, J, Bpad, bc, xz, xs, red, fl);
                 __syncthreads();
                 if (tid < BCH) {
                     for (int r = 0; r < R; ++r) {
@@ -236,90 +400,80 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                 __syncthreads();
             }
             if (tid < BCH && bc + tid < Bpad) {
-                const size_t o = (size_t)g * Bpad + bc + tid;
-                p.pl_max[o] = lmax; p.pl_idx[o] = lidx; p.pl_sum[o] = lsum;
-                p.pd_max[o] = dmax; p.pd_idx[o] = didx;
-            }
-        }
-        grid.sync();
-        // ================= P4: per-utterance argmax + state update (one warp each) ============
-        {
-            const int warp = tid >> 5, lane = tid & 31;
-            for (int b = g * NWARP + warp; b < p.n_utt; b += G * NWARP) {
-                if (!p.active[b]) continue;
-                float lmax = -INFINITY, dmax = -INFINITY;
-                int lidx = 0x7fffffff, didx = 0x7fffffff;
-                for (int q = lane; q < G; q += 32) {
-                    const size_t o = (size_t)q * Bpad + b;
-                    const float m = p.pl_max[o];
-                    const int i = p.pl_idx[o];
-                    if (m > lmax || (m == lmax && i < lidx)) { lmax = m; lidx = i; }
-                    const float dm = p.pd_max[o];
-                    const int di = p.pd_idx[o];
-                    if (dm > dmax || (dm == dmax && di < didx)) { dmax = dm; didx = di; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float m = __shfl_xor_sync(0xffffffffu, lmax, o);
-                    const int i = __shfl_xor_sync(0xffffffffu, lidx, o);
-                    if (m > lmax || (m == lmax && i < lidx)) { lmax = m; lidx = i; }
-                    const float dm = __shfl_xor_sync(0xffffffffu, dmax, o);
-                    const int di = __shfl_xor_sync(0xffffffffu, didx, o);
-                    if (dm > dmax || (dm == dmax && di < didx)) { dmax = dm; didx = di; }
-                }
-                float s = 0.f;
-                for (int q = lane; q < G; q += 32) {
-                    const size_t o = (size_t)q * Bpad + b;
-                    const float m = p.pl_max[o];
-                    if (m > -INFINITY) s += p.pl_sum[o] * expf(m - lmax);
-                }
-                s = warp_sum(s);
-                if (lane == 0) {
-                    const int T = p.row_off[b + 1] - p.row_off[b];
-                    const int skip = (didx < p.n_dur) ? p.durations[didx] : 1;
-                    int t = p.tpos[b];
-                    bool act = true;
-                    if (lidx == V - 1) {            // blank: state reverts (cur unchanged)
-                        t += max(skip, 1);
-                    } else {
-                        const int n = p.ntok[b];
-                        if (n < p.cap) {
-                            int32_t *row = p.tok + (size_t)b * (1 + p.cap);
-                            row[1 + n] = lidx;
-                            p.t_start[(size_t)b * p.cap + n] = t;
-                            p.t_end[(size_t)b * p.cap + n] = min(t + max(skip, 1) - 1, T - 1);
-                            p.t_conf[(size_t)b * p.cap + n] = 1.0f / s;
-                            row[0] = n + 1;
-                        }
-                        p.ntok[b] = n + 1;
-                        p.token[b] = lidx;
-                        p.cur[b] = 1 - p.cur[b];     // commit the new LSTM state
-                        t += skip;
-                        if (n + 1 >= p.cap) { act = false; p.overflow[b] = 1; }
-                    }
-                    p.tpos[b] = t;
-                    if (t >= T) act = false;
-                    p.active[b] = act ? 1 : 0;
-                    if (act) atomicAdd(&p.n_active[step % 3], 1);
+                const int b = bc + tid;
+                p.pl_max[kb * PB + (size_t)g * Bpad + b] = lmax;
+                p.pl_sum[kb * PB + (size_t)g * Bpad + b] = lsum;
+                if (b < p.n_utt && s_active[b]) {
+                    if (lmax > -INFINITY) atomicMax(&p.key_lab[kb * KB + b], pack_key(lmax, lidx));
+                    if (dmax > -INFINITY) atomicMax(&p.key_dur[kb * KB + b], pack_key(dmax, didx));
                 }
             }
         }
-        grid.sync();
-        if (p.n_active[step % 3] == 0 || step + 1 >= p.max_steps) break;
+        tick(4);
+        grid_barrier(p.bar, G * (++nbar));
+        tick(5);
+        // ================= P4 (replicated in every CTA): state update =================
+        int any = 0;
+        for (int b = tid; b < p.n_utt; b += blockDim.x) {
+            if (!s_active[b]) continue;
+            float lmax, dmax;
+            int lidx, didx;
+            unpack_key(p.key_lab[kb * KB + b], lmax, lidx);
+            unpack_key(p.key_dur[kb * KB + b], dmax, didx);
+            const int T = p.row_off[b + 1] - p.row_off[b];
+            const int skip = (didx < p.n_dur) ? p.durations[didx] : 1;
+            int t = s_tpos[b];
+            bool act = true;
+            if (lidx == V - 1) {                 // blank: LSTM state reverts (cur unchanged)
+                t += max(skip, 1);
+            } else {
+                const int n = s_ntok[b];
+                if (n < p.cap && (b % G) == g) { // the owner CTA writes the token; confidence follows
+                    int32_t *row = p.tok + (size_t)b * (1 + p.cap);
+                    row[1 + n] = lidx;
+                    p.t_start[(size_t)b * p.cap + n] = t;
+                    p.t_end[(size_t)b * p.cap + n] = min(t + max(skip, 1) - 1, T - 1);
+                    row[0] = n + 1;
+                }
+                if (n < p.cap) s_pend[b] = n;
+                s_ntok[b] = n + 1;
+                s_token[b] = lidx;
+                s_cur[b] = 1 - s_cur[b];         // commit the new LSTM state
+                t += skip;
+                if (n + 1 >= p.cap) {
+                    act = false;
+                    if ((b % G) == g) p.overflow[b] = 1;
+                }
+            }
+            s_tpos[b] = t;
+            if (t >= T) act = false;
+            s_active[b] = act ? 1 : 0;
+            any |= act ? 1 : 0;
+        }
+        any = __syncthreads_or(any);
+        tick(6);
+        if (!any || step + 1 >= p.max_steps) break;
     }
+    if (p.dbg && g == 0 && tid == 0) {
+        for (int i = 0; i < 7; ++i) p.dbg[i] = tacc[i];
+        p.dbg[7] = step + 1;
+    }
+    // confidences of the last step's tokens: every CTA's partials must be visible first
+    grid_barrier(p.bar, G * (++nbar));
+    finalize_conf(step % 3);
 }
 
 __global__ void tdt_init_kernel(TdtParams p) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < 3) p.n_active[b] = 0;
-    if (b >= p.Bpad) return;
-    p.cur[b] = 0;
-    p.token[b] = p.V - 1;   // SOS = blank (tdt.cpp:56-58)
-    p.tpos[b] = 0;
-    p.active[b] = b < p.n_utt ? 1 : 0;
-    p.ntok[b] = 0;
-    p.overflow[b] = 0;
-    if (b < p.n_utt) p.tok[(size_t)b * (1 + p.cap)] = 0;
+    if (b == 0) *p.bar = 0u;
+    if (b < 3 * p.Bpad) {
+        p.key_lab[b] = 0ull;
+        p.key_dur[b] = 0ull;
+    }
+    if (b < p.n_utt) {
+        p.tok[(size_t)b * (1 + p.cap)] = 0;
+        p.overflow[b] = 0;
+    }
 }
 
 }  // namespace
@@ -328,15 +482,21 @@ size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, int *lstm
     const int UPC = (p.P + grid - 1) / grid, JPC = (p.J + grid - 1) / grid, OPC = (p.V + p.D + grid - 1) / grid;
     size_t lstm = 0;
     for (int l = 0; l < p.L; ++l) lstm += (size_t)UPC * 4 * p.P * (l > 0 ? 2 : 1);
-    size_t base = (size_t)NWARP * RMAX * BCH + RMAX * BCH + lstm + (size_t)JPC * p.P;
+    size_t base = (size_t)NWARP * RMAX * BCH + RMAX * BCH + (size_t)NST * BCH * XLD + 6 * (size_t)p.Bpad + lstm + (size_t)JPC * p.P;
     size_t with_out = base + (size_t)OPC * p.J;
     *lstm_floats = (int)lstm;
-    if (with_out * sizeof(float) <= 200 * 1024) {
+    if (with_out * sizeof(float) <= 225 * 1024) {
         *out_in_smem = true;
         return with_out * sizeof(float);
     }
     *out_in_smem = false;
     return base * sizeof(float);
+}
+
+void tdt_debug_fetch(long long *out8) {
+    cudaMemcpyFromSymbol(out8, g_tdt_dbg, sizeof(long long) * 8);
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_tdt_dbg, z, sizeof(z));
 }
 
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st) {
@@ -355,7 +515,7 @@ cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st) {
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tdt_decode_kernel, NWARP * 32, smem);
     if (err != cudaSuccess) return err;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    tdt_init_kernel<<<(p.Bpad + 127) / 128, 128, 0, st>>>(p);
+    tdt_init_kernel<<<(3 * p.Bpad + 127) / 128, 128, 0, st>>>(p);
     void *args[] = {&p};
     return cudaLaunchCooperativeKernel((void *)tdt_decode_kernel, dim3(grid), dim3(NWARP * 32), args, smem, st);
 }

@@ -44,7 +44,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_mel_frames", "pk_encoder_frames", "pk_mel", "pk_encode", "pk_decode", "pk_ctc_logprobs",
            "pk_transcribe_batch", "pk_stage_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
-           "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
+           "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
            "pk_detokenize", "pk_group_words"]
 
 _lib = None
@@ -87,6 +87,7 @@ def load_library():
     L.pk_profile_end.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double), C.c_int32]
     L.pk_profile_names.restype = C.c_char_p
     L.pk_flush_l2.argtypes = [vp]
+    L.pk_debug_tdt_phases.argtypes = [vp, i64p]
     L.pk_selftest_gemm.argtypes = [C.c_int] * 6 + [C.c_uint32, f32p, f32p]
     L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pk_vocab_free.argtypes = [vp]
@@ -386,6 +387,11 @@ class Engine:
         ms = (C.c_double * n)(); cnt = (C.c_int64 * n)(); fl = (C.c_double * n)()
         self._check(self.L.pk_profile_end(self.h, ms, cnt, fl, n), "pk_profile_end")
         return {names[i]: (ms[i], int(cnt[i]), fl[i]) for i in range(n)}
+
+    def tdt_phases(self):
+        a = np.zeros(8, np.int64)
+        self._check(self.L.pk_debug_tdt_phases(self.h, _i64p(a)), "pk_debug_tdt_phases")
+        return a
 
     def launch_count(self) -> int:
         return int(self.L.pk_launch_count(self.h))
