@@ -893,6 +893,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
         g_create_err = "unknown pk_math mode";
         return PK_ERR_INVALID;
     }
+    if (const char *ev = getenv("PK_GEMM_2CTA")) tc_set_2cta(atoi(ev) != 0);
     auto e = std::make_unique<pk_engine>();
     e->cfg = c;
     e->device = device;
@@ -994,6 +995,7 @@ pk_status pk_flush_l2(pk_engine *e) {
 pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int math, uint32_t seed, float *max_err,
                            float *max_ref) {
     if (cudaSetDevice(device) != cudaSuccess) return PK_ERR_CUDA;
+    if (const char *ev = getenv("PK_GEMM_2CTA")) tc_set_2cta(atoi(ev) != 0);
     if (K % 64 != 0 || (epi_kind == EPI_GLU_F32 && (N & 1))) return PK_ERR_INVALID;
     cudaStream_t st;
     cudaStreamCreate(&st);
@@ -1092,10 +1094,25 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
     if (s) return s;
     const size_t total = (size_t)e->pcm_off[n_utt];
     cudaEventSynchronize(e->ev_h2d);  // previous batch's staging copies have left the pinned buffers
-    // pageable -> pinned -> device; utterances are re-packed back to back
-    for (int i = 0; i < n_utt; ++i)
-        memcpy(e->h_pcm + e->pcm_off[i], pcm + offsets[i], (size_t)(offsets[i + 1] - offsets[i]) * sizeof(float));
-    cudaError_t ce = cudaMemcpyAsync(e->d_pcm, e->h_pcm, total * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    // Is the caller's buffer already page-locked and packed back to back?  Then DMA straight from it.
+    bool packed = true;
+    for (int i = 0; i < n_utt; ++i) packed = packed && (offsets[i] - offsets[0] == e->pcm_off[i]);
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // an unregistered host pointer is not an error for us
+    cudaError_t ce = cudaSuccess;
+    if (pinned && packed) {
+        ce = cudaMemcpyAsync(e->d_pcm, pcm + offsets[0], total * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    } else {
+        // pageable -> pinned staging -> device, utterance by utterance so the DMA of utterance i
+        // overlaps the host copy of utterance i+1; utterances are re-packed back to back
+        for (int i = 0; i < n_utt && ce == cudaSuccess; ++i) {
+            const size_t ns = (size_t)(offsets[i + 1] - offsets[i]);
+            memcpy(e->h_pcm + e->pcm_off[i], pcm + offsets[i], ns * sizeof(float));
+            ce = cudaMemcpyAsync(e->d_pcm + e->pcm_off[i], e->h_pcm + e->pcm_off[i], ns * sizeof(float),
+                                 cudaMemcpyHostToDevice, e->stream);
+        }
+    }
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D pcm: ") + cudaGetErrorString(ce));
     return e->upload_shapes();
 }

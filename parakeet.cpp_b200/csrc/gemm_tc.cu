@@ -142,7 +142,7 @@ struct TcCfg {
 // Persistent: grid = min(#tiles, #SMs); CTA c takes tiles c, c+grid, ...  (n-tile fastest so
 // concurrently running CTAs share the same A rows through L2).  The accumulator is double
 // buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int NPASS>
+template <int BN, int NPASS, int EK>
 __global__ void __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
@@ -250,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {      // 16-column chunks of this warp's half
                 const int col = half * (BN / 2) + c * 16;
+                const bool interior = (n0 + col + 16 <= N) && ((epi.ldo & 3) == 0) && ((N & 3) == 0);
                 uint32_t v[16];
                 tmem_ld16(tbase + (uint32_t)col, v);
                 if (c == BN / 32 - 1) {              // last TMEM read of this tile: release the buffer
@@ -269,7 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const int r = i * 8 + (lane >> 2), cc = (lane & 3) * 4;
                     const int row = m0 + q * 32 + r;
                     const float4 val = *reinterpret_cast<const float4 *>(stg + r * STG_LD + cc);
-                    if (row < M) epilogue4(epi, row, n0 + col + cc, N, val);
+                    if (row < M) {
+                        if (interior) epilogue4_fast<EK>(epi, row, n0 + col + cc, val);
+                        else epilogue4(epi, row, n0 + col + cc, N, val);
+                    }
                 }
                 __syncwarp();
             }
@@ -279,6 +283,217 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================
+// 2-CTA variant (cta_group::2): a CTA PAIR (cluster 2x1x1, the two SMs of a TPC) computes a
+// 256 x 256 output tile with one UMMA M=256 x N=256 x K=16 per instruction.  Each CTA stages only
+// ITS half of both operands (its 128 rows of A, its 128 rows of W) -- the same 64 KB per k-block
+// as the 1-CTA kernel -- but the pair produces 4x the outputs, so the L2->SM operand traffic per
+// flop is halved (the 1-CTA kernel is L2-bandwidth-bound with the 4 split planes: 85 B/cycle/SM
+// needed vs ~43 available).  Roles per CTA as above; only the leader (cluster rank 0) issues
+// MMAs; the peer's TMA loads complete on the LEADER's full barrier; tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs; each CTA drains its own 128 TMEM
+// lanes; the leader's acc_empty barrier collects the arrivals of both epilogues.
+constexpr int BN2 = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *tm, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int NPASS>
+struct Tc2Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;                 // this CTA's 128 rows of A, one plane
+    static constexpr int W_BYTES = (BN2 / 2) * BK * 2;          // this CTA's 128 rows of W, one plane
+    static constexpr int PLANES = (NPASS == 3) ? 2 : 1;
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
+    static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+    static constexpr int AVAIL = 225 * 1024 - STG_BYTES - 1024 - 256;
+    static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 2 * BN2;                   // 512: double-buffered 256-column accumulator
+};
+
+template <int NPASS, int EK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS_P, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
+                int K, EpiParams epi) {
+    using C = Tc2Cfg<NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *staging = reinterpret_cast<float *>(tiles + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(staging) + C::STG_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int nkb = K / BK;
+    const int tiles_n = (N + BN2 - 1) / BN2, tiles_m = (M + 2 * BM - 1) / (2 * BM);
+    const int num_tiles = tiles_n * tiles_m;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 2);              // leader producer (arrive + expect_tx) + peer producer (remote arrive)
+            mbar_init(&empty[s], 1);             // multicast tcgen05.commit from the leader
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);          // multicast tcgen05.commit from the leader
+            mbar_init(&acc_empty[b], 2 * EPI_WARPS);   // both CTAs' epilogue warps (leader's copy is the one used)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // both CTAs of the pair allocate (same warp id, same columns)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync();                              // barriers of both CTAs initialised before any remote arrive
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
+                const int n0 = (tile % tiles_n) * BN2 + (int)rank * (BN2 / 2);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
+                    const uint32_t lbar = mapa_rank(smem_u32(&full[s]), 0);   // the leader's full barrier
+                    if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+                    else mbar_arrive_cluster(lbar);
+                    tma_load_2d_2sm(st, &tmA_hi, lbar, kb * BK, m0);
+                    tma_load_2d_2sm(st + C::A_BYTES, &tmW_hi, lbar, kb * BK, n0);
+                    if (NPASS == 3) {
+                        tma_load_2d_2sm(st + C::A_BYTES + C::W_BYTES, &tmA_lo, lbar, kb * BK, m0);
+                        tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, lbar, kb * BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs, ++tcount) {
+                const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN2;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_u32(tiles + (size_t)s * C::STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(st), w_hi = umma_desc_sw128(st + C::A_BYTES);
+                    const uint64_t a_lo = umma_desc_sw128(st + C::A_BYTES + C::W_BYTES);
+                    const uint64_t w_lo = umma_desc_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_bf16_2sm(tmem_d, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+                        if (NPASS == 3) {
+                            umma_bf16_2sm(tmem_d, a_hi + koff, w_lo + koff, idesc, 1);
+                            umma_bf16_2sm(tmem_d, a_lo + koff, w_hi + koff, idesc, 1);
+                        }
+                    }
+                    umma_commit_2sm(&empty[s]);      // frees stage s in both CTAs
+                }
+                umma_commit_2sm(&acc_full[buf]);     // accumulator ready in both CTAs
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of both CTAs) =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        float *stg = staging + (size_t)ew * 32 * STG_LD;
+        const uint32_t lempty0 = mapa_rank(smem_u32(&acc_empty[0]), 0), lempty1 = mapa_rank(smem_u32(&acc_empty[1]), 0);
+        uint32_t tcount = 0;
+        for (int tile = pair; tile < num_tiles; tile += npairs, ++tcount) {
+            const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN2;
+            const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&acc_full[buf], aph);
+            tcgen05_fence_after();
+            const uint32_t tbase = tmem_base + buf * BN2 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN2 / 32; ++c) {
+                const int col = half * (BN2 / 2) + c * 16;
+                const bool interior = (n0 + col + 16 <= N) && ((epi.ldo & 3) == 0) && ((N & 3) == 0);
+                uint32_t v[16];
+                tmem_ld16(tbase + (uint32_t)col, v);
+                if (c == BN2 / 32 - 1) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * j) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + (lane >> 2), cc = (lane & 3) * 4;
+                    const int row = m0 + q * 32 + r;
+                    const float4 val = *reinterpret_cast<const float4 *>(stg + r * STG_LD + cc);
+                    if (row < M) {
+                        if (interior) epilogue4_fast<EK>(epi, row, n0 + col + cc, val);
+                        else epilogue4(epi, row, n0 + col + cc, N, val);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync();                              // nobody leaves (or frees TMEM) while the peer may still signal it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
 }
 
@@ -298,12 +513,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int BN, int NPASS>
-cudaError_t launch_t(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
+template <int BN, int NPASS, int EK>
+cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
     using C = TcCfg<BN, NPASS>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         attr = true;
     }
@@ -316,8 +531,56 @@ cudaError_t launch_t(const TcOperand &A, const TcOperand &W, int M, int N, int K
     const int num_tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
     dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    gemm_tc_kernel<BN, NPASS><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
+    gemm_tc_kernel<BN, NPASS, EK><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
     return cudaGetLastError();
+}
+
+template <int NPASS, int EK>
+cudaError_t launch_k2(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
+    using C = Tc2Cfg<NPASS>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<NPASS, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int num_tiles = ((N + BN2 - 1) / BN2) * ((M + 2 * BM - 1) / (2 * BM));
+    const int pairs = num_tiles < num_sms / 2 ? num_tiles : num_sms / 2;
+    const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
+    gemm_tc2_kernel<NPASS, EK><<<dim3(2 * pairs), TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
+    return cudaGetLastError();
+}
+
+#define PK_EPI_SWITCH(CALL)                                              \
+    switch (epi.kind) {                                                  \
+    case EPI_BIAS_F32: return CALL(EPI_BIAS_F32);                        \
+    case EPI_BIAS_RELU_F32: return CALL(EPI_BIAS_RELU_F32);              \
+    case EPI_BIAS_RELU_ACT: return CALL(EPI_BIAS_RELU_ACT);              \
+    case EPI_BIAS_SILU_ACT: return CALL(EPI_BIAS_SILU_ACT);              \
+    case EPI_RESID_F32: return CALL(EPI_RESID_F32);                      \
+    case EPI_GLU_F32: return CALL(EPI_GLU_F32);                          \
+    case EPI_BIAS_ACT: return CALL(EPI_BIAS_ACT);                        \
+    default: return cudaErrorInvalidValue;                               \
+    }
+
+template <int BN, int NPASS>
+cudaError_t launch_t(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
+#define PK_CALL1(EK) launch_k<BN, NPASS, EK>(A, W, M, N, K, epi, st)
+    PK_EPI_SWITCH(PK_CALL1)
+#undef PK_CALL1
+}
+
+template <int NPASS>
+cudaError_t launch_t2(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
+#define PK_CALL2(EK) launch_k2<NPASS, EK>(A, W, M, N, K, epi, st)
+    PK_EPI_SWITCH(PK_CALL2)
+#undef PK_CALL2
 }
 
 }  // namespace
@@ -344,11 +607,16 @@ bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t ro
 
 int tc_tile_n(int N) { return N <= 64 ? 64 : 128; }
 
+static bool g_use_2cta = false;   // measured on B200 (64x10 s): the pair kernel is not faster yet at M = 8064
+void tc_set_2cta(bool on) { g_use_2cta = on; }
+
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (K % BK != 0 || A.box_rows != BM) return cudaErrorInvalidValue;
     if (split3 && !(A.has_lo && W.has_lo)) return cudaErrorInvalidValue;
+    if (W.box_rows == 128 && N >= 256 && g_use_2cta)
+        return split3 ? launch_t2<3>(A, W, M, N, K, epi, st) : launch_t2<1>(A, W, M, N, K, epi, st);
     if (W.box_rows == 128) return split3 ? launch_t<128, 3>(A, W, M, N, K, epi, st) : launch_t<128, 1>(A, W, M, N, K, epi, st);
     if (W.box_rows == 64) return split3 ? launch_t<64, 3>(A, W, M, N, K, epi, st) : launch_t<64, 1>(A, W, M, N, K, epi, st);
     return cudaErrorInvalidValue;

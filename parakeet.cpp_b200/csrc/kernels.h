@@ -42,7 +42,8 @@ struct TcOperand {
     uint32_t box_rows = 0;
 };
 bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t rows, uint64_t K, uint32_t box_rows);
-int tc_tile_n(int N);   // N-tile (= box_rows of the weight operand) chosen for an [N][K] weight
+int tc_tile_n(int N);
+void tc_set_2cta(bool on);   // debug/measurement switch: use the cta_group::2 kernel for N >= 256 (default off; PK_GEMM_2CTA=1)   // N-tile (= box_rows of the weight operand) chosen for an [N][K] weight
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st);
 

@@ -359,6 +359,18 @@ class Engine:
                     "pk_transcribe_batch")
         return self._unpack(arrs, len(pcms))
 
+    def transcribe_packed(self, buf: np.ndarray, off: np.ndarray, decoder: Decoder, out=None):
+        """Same call on an already packed host buffer (fp32 samples back to back + int64 offsets;
+        page-locked buffers are DMA'd directly).  Returns the raw token arrays
+        (ids, start, end, conf, len) without building Python objects."""
+        n = len(off) - 1
+        if out is None:
+            out = self._tokens(n)
+        t, arrs = out
+        self._check(self.L.pk_transcribe_batch(self.h, _f32p(buf), _i64p(off), n, int(decoder), C.byref(t)),
+                    "pk_transcribe_batch")
+        return arrs
+
     # -- device-resident variant (bench)
     def stage(self, buf: np.ndarray, off: np.ndarray):
         self._check(self.L.pk_stage_pcm(self.h, _f32p(buf), _i64p(off), len(off) - 1), "pk_stage_pcm")
