@@ -126,6 +126,11 @@ struct pk_engine {
     int32_t *h_tok = nullptr, *h_ts = nullptr, *h_te = nullptr;
     float *h_tc = nullptr;
 
+    // ---- CUDA graphs of the staged pipeline, keyed by (decoder, utterance lengths)
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
+    std::map<std::string, GraphEntry> graphs;
+    bool use_graphs = true;
+
     // ---- the staged batch
     int n_utt = 0;
     std::vector<int64_t> pcm_off;
@@ -896,6 +901,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     if (const char *ev = getenv("PK_GEMM_2CTA")) tc_set_2cta(atoi(ev) != 0);
     auto e = std::make_unique<pk_engine>();
     e->cfg = c;
+    if (const char *ev = getenv("PK_GRAPH")) e->use_graphs = atoi(ev) != 0;
     e->device = device;
     if (cudaSetDevice(device) != cudaSuccess) {
         g_create_err = "cudaSetDevice failed";
@@ -935,6 +941,8 @@ void pk_engine_destroy(pk_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void *p : e->allocs) cudaFree(p);
+    for (auto &kv : e->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->h_pcm) cudaFreeHost(e->h_pcm);
@@ -1117,14 +1125,64 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
     return e->upload_shapes();
 }
 
-pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
-    if (!e || e->n_utt <= 0) return PK_ERR_INVALID;
-    cudaSetDevice(e->device);
+static pk_status run_pipeline(pk_engine *e, pk_decoder dec) {
     pk_status s;
-    if (e->gemm_err) return e->gemm_err;
     if ((s = e->run_mel())) return s;
     if ((s = e->run_encoder(nullptr, nullptr))) return s;
     return dec == PK_DECODER_CTC ? e->run_ctc(nullptr) : e->run_tdt();
+}
+
+// The ~250 launches of one batch are replayed as ONE CUDA graph once a batch shape has been seen
+// twice (first sight runs eagerly, which also completes every lazy one-time initialisation).
+pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
+    if (!e || e->n_utt <= 0) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    if (e->gemm_err) return e->gemm_err;
+    if (!e->use_graphs || e->prof_on) return run_pipeline(e, dec);
+    std::string key(1, dec == PK_DECODER_CTC ? 'c' : 't');
+    key.append(reinterpret_cast<const char *>(e->frame_off.data()), e->frame_off.size() * sizeof(int32_t));
+    auto &g = e->graphs[key];
+    if (g.exec) {
+        cudaError_t ce = cudaGraphLaunch(g.exec, e->stream);
+        if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce));
+        e->launches += g.launches;
+        return PK_OK;
+    }
+    if (g.seen++ == 0) return run_pipeline(e, dec);
+    if (e->graphs.size() > 16) {   // bound the cache: drop everything but this entry
+        for (auto &kv : e->graphs)
+            if (kv.second.exec && &kv.second != &g) cudaGraphExecDestroy(kv.second.exec);
+        pk_engine::GraphEntry keep = g;
+        e->graphs.clear();
+        e->graphs[key] = keep;
+    }
+    auto &gg = e->graphs[key];
+    const int64_t l0 = e->launches;
+    cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce));
+    pk_status s = run_pipeline(e, dec);
+    cudaGraph_t graph = nullptr;
+    ce = cudaStreamEndCapture(e->stream, &graph);
+    if (s != PK_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        e->use_graphs = false;     // capture not possible here: stay on plain launches
+        e->launches = l0;
+        return run_pipeline(e, dec);
+    }
+    gg.launches = e->launches - l0;
+    ce = cudaGraphInstantiate(&gg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        gg.exec = nullptr;
+        cudaGetLastError();
+        e->use_graphs = false;
+        e->launches = l0;
+        return run_pipeline(e, dec);
+    }
+    ce = cudaGraphLaunch(gg.exec, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce));
+    return PK_OK;
 }
 
 pk_status pk_fetch_tokens(pk_engine *e, pk_tokens *out) {
