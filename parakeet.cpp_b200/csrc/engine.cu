@@ -102,6 +102,7 @@ struct pk_engine {
     GemmWeight enc_proj;                       // joint enc_proj_ [J][d] + bias
     float *G0 = nullptr;                       // [V][4P]
     float *Whh[PK_MAX_LSTM] = {}, *Wih[PK_MAX_LSTM] = {}, *bih[PK_MAX_LSTM] = {};
+    float *Whh_um[PK_MAX_LSTM] = {}, *Wih_um[PK_MAX_LSTM] = {};   // unit-major copies (decode kernel)
     float *Wp = nullptr, *Wout = nullptr, *bout = nullptr;
 
     // ---- workspace
@@ -464,6 +465,19 @@ pk_status pk_engine::load(const char *path) {
             const std::string q = "prediction_.lstm_.cells_." + std::to_string(l) + ".";
             if ((s = get_vec(st, q + "hidden_proj_.weight", 4 * P * P, &Whh[l]))) return s;
             if ((s = get_vec(st, q + "input_proj_.weight", 4 * P * P, &Wih[l]))) return s;
+            // unit-major copies for the decode kernel (row = unit*4 + gate; gate order i,f,g,o of lstm.cpp:20-24)
+            {
+                std::vector<float> src, dst((size_t)4 * P * P);
+                for (int which = 0; which < 2; ++which) {
+                    if (!st.read_f32(q + (which ? "input_proj_.weight" : "hidden_proj_.weight"), src, (int64_t)4 * P * P, e)) return fail(PK_ERR_MISSING, e);
+                    for (int u = 0; u < P; ++u)
+                        for (int gt = 0; gt < 4; ++gt)
+                            memcpy(&dst[((size_t)u * 4 + gt) * P], &src[((size_t)gt * P + u) * P], (size_t)P * sizeof(float));
+                    float *d = upload(dst);
+                    if (!d) return fail(PK_ERR_CUDA, "cudaMalloc failed (LSTM weights)");
+                    (which ? Wih_um[l] : Whh_um[l]) = d;
+                }
+            }
             if ((s = get_vec(st, q + "input_proj_.bias", 4 * P, &bih[l]))) return s;
         }
         wih0 = Wih[0];
@@ -805,7 +819,7 @@ pk_status pk_engine::run_tdt() {
     p.max_steps = maxT + cap + 2;
     for (int i = 0; i < 8; ++i) p.durations[i] = c.durations[i];
     p.EP = EP; p.row_off = d_row_off; p.G0 = G0;
-    for (int l = 0; l < c.lstm_layers; ++l) { p.Whh[l] = Whh[l]; p.Wih[l] = Wih[l]; p.bih[l] = bih[l]; }
+    for (int l = 0; l < c.lstm_layers; ++l) { p.Whh[l] = Whh_um[l]; p.Wih[l] = Wih_um[l]; p.bih[l] = bih[l]; }
     p.Wp = Wp; p.Wout = Wout; p.bout = bout;
     p.hbuf = hbuf; p.cbuf = cbuf; p.z = zbuf;
     p.overflow = tdt_ints; p.bar = reinterpret_cast<unsigned int *>(tdt_ints + Bpad);

@@ -69,13 +69,13 @@ void launch_ctc_collapse(const int32_t *best, const float *conf, const int32_t *
 // ------------------------------------------------------------------ tdt.cu (K10)
 struct TdtParams {
     int P, J, V, D, L, Bpad, n_utt, cap, max_steps, n_dur;
-    int out_in_smem, smem_lstm_floats;       // filled by launch_tdt_decode
+    int out_in_smem, wih_in_smem, smem_lstm_floats;   // filled by launch_tdt_decode
     int durations[8];
     const float *EP;                          // [M][J] enc_proj(enc) + bias
     const int32_t *row_off;                   // [n_utt+1]
     const float *G0;                          // [V][4P] W_ih0 . E[token] + b0
-    const float *Whh[PK_MAX_LSTM];            // [4P][P]
-    const float *Wih[PK_MAX_LSTM];            // [4P][P] (layers >= 1)
+    const float *Whh[PK_MAX_LSTM];            // [P*4][P] unit-major: row = unit*4 + gate(i,f,g,o)
+    const float *Wih[PK_MAX_LSTM];            // [P*4][P] unit-major (layers >= 1)
     const float *bih[PK_MAX_LSTM];            // [4P]    (layers >= 1)
     const float *Wp;                          // [J][P]
     const float *Wout;                        // [V+D][J]

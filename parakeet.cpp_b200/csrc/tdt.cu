@@ -213,25 +213,27 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
     int *s_pend = s_ntok + Bpad;                   // slot of a token whose confidence is still pending (-1: none)
     float *wsm = reinterpret_cast<float *>(s_pend + Bpad);
     const int nU = u1 - u0;
-    float *w_hh[PK_MAX_LSTM], *w_ih[PK_MAX_LSTM];
+    // LSTM weights arrive "unit-major" (row = unit*4 + gate, engine.cu), so this CTA's rows
+    // [u0*4, u1*4) are one contiguous block: W_hh always lives in shared memory, W_ih of the
+    // upper layers too when it fits (else it is streamed from L2).
+    const float *w_hh[PK_MAX_LSTM], *w_ih[PK_MAX_LSTM];
     {
         float *cur = wsm;
         for (int l = 0; l < L; ++l) {
+            for (int idx = tid; idx < nU * 4 * P; idx += blockDim.x) cur[idx] = p.Whh[l][(size_t)u0 * 4 * P + idx];
             w_hh[l] = cur;
             cur += (size_t)UPC * 4 * P;
             w_ih[l] = nullptr;
             if (l > 0) {
-                w_ih[l] = cur;
-                cur += (size_t)UPC * 4 * P;
+                if (p.wih_in_smem) {
+                    for (int idx = tid; idx < nU * 4 * P; idx += blockDim.x) cur[idx] = p.Wih[l][(size_t)u0 * 4 * P + idx];
+                    w_ih[l] = cur;
+                    cur += (size_t)UPC * 4 * P;
+                } else {
+                    w_ih[l] = p.Wih[l] + (size_t)u0 * 4 * P;
+                }
             }
         }
-        for (int l = 0; l < L; ++l)
-            for (int idx = tid; idx < nU * 4 * P; idx += blockDim.x) {
-                const int r = idx / P, k = idx % P;
-                const int u = u0 + r / 4, gate = r % 4;
-                w_hh[l][idx] = p.Whh[l][(size_t)(gate * P + u) * P + k];
-                if (l > 0) w_ih[l][idx] = p.Wih[l][(size_t)(gate * P + u) * P + k];
-            }
     }
     float *w_p = wsm + (size_t)p.smem_lstm_floats;          // [JPC][P]
     for (int idx = tid; idx < (j1 - j0) * P; idx += blockDim.x) w_p[idx] = p.Wp[(size_t)j0 * P + idx];
@@ -307,10 +309,10 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                         [&](int b) { return h_rd + ((size_t)(l * 2 + s_cur[b])) * HS + (size_t)b * P; }, xs, red,
                         [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v; });
                     if (l > 0) {  // input part: W_ih . h'_{l-1}(new)
-                        rows_times_batch<true>(
-                            w_ih[l], R, P, Bpad, bc,
-                            [&](int b) { return h_rd + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; },
-                            xs, red, [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] += v; });
+                        auto xh = [&](int b) { return h_rd + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; };
+                        auto fa = [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] += v; };
+                        if (p.wih_in_smem) rows_times_batch<true>(w_ih[l], R, P, Bpad, bc, xh, xs, red, fa);
+                        else rows_times_batch<false>(w_ih[l], R, P, Bpad, bc, xh, xs, red, fa);
                     }
                     __syncthreads();
                     for (int idx = tid; idx < nU * BCH; idx += blockDim.x) {
@@ -478,19 +480,19 @@ __global__ void tdt_init_kernel(TdtParams p) {
 
 }  // namespace
 
-size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, int *lstm_floats) {
+size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, bool *wih_in_smem, int *lstm_floats) {
     const int UPC = (p.P + grid - 1) / grid, JPC = (p.J + grid - 1) / grid, OPC = (p.V + p.D + grid - 1) / grid;
-    size_t lstm = 0;
-    for (int l = 0; l < p.L; ++l) lstm += (size_t)UPC * 4 * p.P * (l > 0 ? 2 : 1);
-    size_t base = (size_t)NWARP * RMAX * BCH + RMAX * BCH + (size_t)NST * BCH * XLD + 6 * (size_t)p.Bpad + lstm + (size_t)JPC * p.P;
-    size_t with_out = base + (size_t)OPC * p.J;
-    *lstm_floats = (int)lstm;
-    if (with_out * sizeof(float) <= 225 * 1024) {
-        *out_in_smem = true;
-        return with_out * sizeof(float);
-    }
-    *out_in_smem = false;
-    return base * sizeof(float);
+    const size_t budget = 225 * 1024 / sizeof(float);
+    size_t fixed = (size_t)NWARP * RMAX * BCH + RMAX * BCH + (size_t)NST * BCH * XLD + 6 * (size_t)p.Bpad;
+    const size_t hh = (size_t)p.L * UPC * 4 * p.P, ih = (size_t)(p.L - 1) * UPC * 4 * p.P;
+    const size_t wp = (size_t)JPC * p.P, wo = (size_t)OPC * p.J;
+    size_t total = fixed + hh + wp;                 // always resident
+    *wih_in_smem = (ih == 0) || (total + ih <= budget);
+    if (*wih_in_smem) total += ih;
+    *lstm_floats = (int)(hh + (*wih_in_smem ? ih : 0));
+    *out_in_smem = total + wo <= budget;
+    if (*out_in_smem) total += wo;
+    return total * sizeof(float);
 }
 
 void tdt_debug_fetch(long long *out8) {
@@ -504,10 +506,11 @@ cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st) {
     int grid = num_sms;
     // every CTA must own <= 5 LSTM units (RMAX = 20 gate rows)
     if ((p.P + grid - 1) / grid * 4 > RMAX) return cudaErrorInvalidConfiguration;
-    bool out_in_smem;
+    bool out_in_smem, wih_in_smem;
     int lstm_floats;
-    size_t smem = tdt_smem_bytes(p, grid, &out_in_smem, &lstm_floats);
+    size_t smem = tdt_smem_bytes(p, grid, &out_in_smem, &wih_in_smem, &lstm_floats);
     p.out_in_smem = out_in_smem ? 1 : 0;
+    p.wih_in_smem = wih_in_smem ? 1 : 0;
     p.smem_lstm_floats = lstm_floats;
     cudaError_t err = cudaFuncSetAttribute(tdt_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

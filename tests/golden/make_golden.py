@@ -32,14 +32,14 @@ def toks_arr(toks):
         np.array([t[3] for t in toks], np.float32)
 
 
-def run_model(out, tag, ocfg, seed, clips, td, custom):
+def run_model(out, tag, ocfg, seed, clips, td, custom, preset=0):
     W = synth.make_weights(ocfg, seed=seed)
     wp = os.path.join(td, tag + ".safetensors")
     synth.save_safetensors(wp, W)
     pieces = synth.make_vocab(ocfg.vocab - 1, seed=seed)
     vp = os.path.join(td, tag + ".vocab.txt")
     synth.save_vocab(vp, pieces)
-    m = R.RefModel(wp, vp, 0, cfg=ocfg if custom else None)
+    m = R.RefModel(wp, vp, preset, cfg=ocfg if custom else None)
     for ci, (n, aseed) in enumerate(clips):
         k = f"{tag}.c{ci}."
         pcm = synth.make_audio(n, aseed)
@@ -48,8 +48,11 @@ def run_model(out, tag, ocfg, seed, clips, td, custom):
         sub, lay = m.encode_layers(feats, ocfg.d_model, ocfg.n_layers, T)
         enc = m.encode(feats, ocfg.d_model)
         assert np.array_equal(enc, lay[-1])
-        lp = m.ctc_logprobs(enc, ocfg.vocab)
-        ctc = R.ctc_greedy(lp, ocfg.vocab - 1, True)[0]
+        if ocfg.has_ctc:
+            lp = m.ctc_logprobs(enc, ocfg.vocab)
+            ctc = R.ctc_greedy(lp, ocfg.vocab - 1, True)[0]
+        else:
+            lp, ctc = np.zeros((enc.shape[0], 1), np.float32), []
         tdt = m.tdt_greedy(enc, True)
         out[k + "n_samples"] = np.array([n, aseed], np.int64)
         out[k + "mel"] = feats.astype(np.float16) if feats.size > 50000 else feats
@@ -93,5 +96,21 @@ def main():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def main_600m():
+    """tdt-600m preset (config.hpp:98-116): one 4 s clip through the compiled reference."""
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        run_model(out, "m600", O.make_tdt_600m_config(), 0, [(64000, 2000)], td, False, preset=1)
+    for k in list(out):
+        if k.endswith(".mel") or k.endswith(".sub") or k.endswith("layers_first_last"):
+            out[k] = out[k].astype(np.float16) if out[k].dtype == np.float32 and out[k].size > 70000 else out[k]
+    path = os.path.join(ROOT, "tests", "golden", "golden_600m_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "600m":
+        main_600m()
+    else:
+        main()

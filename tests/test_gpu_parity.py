@@ -292,3 +292,49 @@ def test_cpp_shim(pkg, tiny, synth, golden, tmp_path):
     assert ctc == golden[k + "ctc_tok"].tolist()
     assert lines[4] == "TEXT " + bytes(golden[k + "ctc_text"]).decode()
     assert lines[6].startswith("ERR Cannot open audio file")
+
+
+# ------------------------------------------------------------------ tdt-600m preset (BASELINE config 3)
+@pytest.fixture(scope="module")
+def m600(tmp_path_factory, pkg, O, synth):
+    import os
+    d = str(tmp_path_factory.mktemp("m600"))
+    ocfg = O.make_tdt_600m_config()
+    W = synth.make_weights(ocfg, seed=0)
+    wp = os.path.join(d, "m600.safetensors")
+    synth.save_safetensors(wp, W)
+    pieces = synth.make_vocab(ocfg.vocab - 1, seed=0)
+    vp = os.path.join(d, "m600.vocab.txt")
+    synth.save_vocab(vp, pieces)
+    return dict(ocfg=ocfg, W=W, weights_path=wp, vocab_path=vp, pieces=pieces)
+
+
+def test_tdt_600m_preset_matches_reference_golden(pkg, O, synth, m600):
+    """make_tdt_600m_config: 128 mels, d=1024, 24 layers, head_dim 128, 2-layer LSTM, 8193 labels,
+    'joint_.' key prefix, no CTC head -- same kernels, checked against the compiled reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_600m_v1.npz"))
+    k = "m600.c0."
+    n, aseed = (int(v) for v in g[k + "n_samples"])
+    pcm = synth.make_audio(n, aseed)
+    cfg = pkg.make_tdt_600m_config(max_batch=4, max_samples=80000)
+    e = pkg.Engine(cfg, m600["weights_path"], 0)
+    feats = e.mel([pcm])[0]
+    assert feats.shape == g[k + "mel"].shape
+    assert np.abs(feats - g[k + "mel"].astype(np.float32)).max() < 5e-3          # golden stored as fp16
+    encs, subs, lays = e.encode([O.preprocess_audio(pcm, 128)], taps=True)
+    genc = g[k + "enc"]
+    assert encs[0].shape == genc.shape
+    assert _rel(encs[0], genc) < ENC_TOL
+    toks = e.decode([genc], 1)[0]
+    assert [list(t) for t in _tt(toks)] == g[k + "tdt_tok"].tolist()
+    assert np.allclose([t.confidence for t in toks], g[k + "tdt_conf"], rtol=1e-3)
+    # whole path + a ragged batch through the public API
+    t = pkg.Transcriber(m600["weights_path"], m600["vocab_path"], cfg)
+    r = t.transcribe(pcm, pkg.Decoder.TDT, True)
+    assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == g[k + "tdt_tok"].tolist()
+    assert r.text == bytes(g[k + "tdt_text"]).decode()
+    rs = t.transcribe_batch([pcm[:40000], pcm, pcm[:16000]], pkg.Decoder.TDT)
+    assert rs[1].token_ids == r.token_ids
+    e.close()
+    t.engine.close()

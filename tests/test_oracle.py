@@ -177,3 +177,19 @@ def test_live_reference_tiny(O, synth, refbind, tiny):
     assert m.tdt_greedy(lay_r[-1], True)[:50] == [tuple(t) for t in O.tdt_greedy_decode(tiny.W, lay_r[-1], tiny.ocfg, with_timestamps=True)][:50] or \
         [t[:3] for t in m.tdt_greedy(lay_r[-1], True)] == [t[:3] for t in O.tdt_greedy_decode(tiny.W, lay_r[-1], tiny.ocfg, with_timestamps=True)]
     m.close()
+
+
+def test_golden_600m_decode(O, synth):
+    """tdt-600m preset: the oracle's 2-layer LSTM / 8193-label TDT decode on the reference's encoder output."""
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_600m_v1.npz")
+    if not os.path.exists(p):
+        pytest.skip("600m golden not generated")
+    g = np.load(p)
+    ocfg = O.make_tdt_600m_config()
+    specs = {n: s for n, s, _ in synth.tensor_specs(ocfg)}
+    rng_needed = [n for n in specs if n.startswith("prediction_.") or n.startswith("joint_.")]
+    W = synth.make_weights(ocfg, seed=0)
+    tdt = O.tdt_greedy_decode({k: W[k] for k in rng_needed}, g["m600.c0.enc"], ocfg, with_timestamps=True)
+    assert [[t[0], t[1], t[2]] for t in tdt] == g["m600.c0.tdt_tok"].tolist()
+    assert np.allclose([t[3] for t in tdt], g["m600.c0.tdt_conf"], rtol=1e-4)
