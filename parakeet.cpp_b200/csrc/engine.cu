@@ -67,6 +67,7 @@ struct LayerW {
     GemmWeight qkv, out;
     float *pos_u, *pos_v;
     float *pp;  // [(2*Tmax-1)][d] projected relative-position table
+    bf16 *pp_hi = nullptr, *pp_lo = nullptr;   // its bf16 split planes (tensor-core attention)
     float *conv_ln_w, *conv_ln_b;
     GemmWeight pw1, pw2;
     float *dw_w, *dw_b;  // BatchNorm folded
@@ -131,6 +132,7 @@ struct pk_engine {
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;
+    bool attn_tc = true;                       // mma.sync attention for head_dim 64 (PK_ATTN_TC=0: fp32 kernel)
 
     // ---- the staged batch
     int n_utt = 0;
@@ -400,6 +402,16 @@ pk_status pk_engine::load(const char *path) {
             ep.ldo = d;
             launch_gemm_simt(d_emb, d, wpos, d, NP, d, d, ep, stream);
             ++launches;
+            if (cfg.math != PK_MATH_FP32 && hd == 64) {
+                L.pp_hi = dalloc<bf16>((size_t)NP * d);
+                L.pp_lo = dalloc<bf16>((size_t)NP * d);
+                if (!L.pp_hi || !L.pp_lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (pp planes)");
+                ActBuf sp;
+                sp.hi = L.pp_hi;
+                sp.lo = L.pp_lo;
+                launch_split(L.pp, (size_t)NP * d, sp, stream);
+                ++launches;
+            }
         }
         const std::string cp = lp + "conv_.";
         if ((s = get_vec(st, cp + "norm_.weight", d, &L.conv_ln_w))) return s;
@@ -721,8 +733,10 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             gemm(ln, d, L.qkv, M, eq);
             {
                 Scope sc(this, CAT_ATTENTION);
-                if (!launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream))
-                    return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
+                const bool ok = (L.pp_hi && attn_tc)
+                    ? launch_relpos_attention_tc(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, L.pos_u, L.pos_v, d, ctx, stream)
+                    : launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream);
+                if (!ok) return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
             }
             ++launches;
             EpiParams eo;
@@ -916,6 +930,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     auto e = std::make_unique<pk_engine>();
     e->cfg = c;
     if (const char *ev = getenv("PK_GRAPH")) e->use_graphs = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_ATTN_TC")) e->attn_tc = atoi(ev) != 0;
     e->device = device;
     if (cudaSetDevice(device) != cudaSuccess) {
         g_create_err = "cudaSetDevice failed";
@@ -1059,6 +1074,21 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
         ActBuf tc_act; tc_act.hi = oh; tc_act.lo = ol;
         ep.act = tc_act;
         if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st) != cudaSuccess) rc = PK_ERR_CUDA;
+        if (rc == PK_OK && getenv("PK_SELFTEST_TIME")) {   // warm, back-to-back timing of the tcgen05 launch
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            const int reps = 20;
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < reps; ++i) launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st);
+            cudaEventRecord(e1, st);
+            cudaStreamSynchronize(st);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double us = 1e3 * ms / reps, tf = 2.0 * M * N * K / (us * 1e-6) / 1e12;
+            fprintf(stderr, "gemm_tc M=%d N=%d K=%d epi=%d math=%d: %.1f us  %.1f TFLOP/s algorithmic (x%d MMA)\n", M, N, K,
+                    epi_kind, math, us, tf, math == PK_MATH_BF16X3 ? 3 : 1);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = PK_ERR_CUDA;
     if (rc == PK_OK) {

@@ -109,22 +109,120 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread.  Issue only; the caller overlaps
+// the TMEM read latency with other work and calls tmem_wait_ld() before touching v[].
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *v) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int STG_LD = 20;                      // epilogue staging row stride (floats): 16 columns + pad
+// Explicit shared-space accesses for the epilogue staging (the compiler otherwise emits generic
+// LD/ST: the pointer is derived from a uintptr_t-aligned base).
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+// Global operands of one 16-column chunk (this lane: 4 rows x 4 columns), issued one chunk AHEAD of
+// their use so that the L2 round trip overlaps the previous chunk's transpose / math / stores.
+template <int EK>
+__device__ __forceinline__ void epi_load(const EpiParams &epi, int rb, int gc, int M, bool ok, float4 &b, float4 (&r)[4]) {
+    b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EK == EPI_RESID_F32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (ok) {
+        if (epi.bias) b = __ldg(reinterpret_cast<const float4 *>(epi.bias + gc));
+        if (EK == EPI_RESID_F32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rb + i * 8 < M) r[i] = *reinterpret_cast<const float4 *>(epi.resid + (size_t)(rb + i * 8) * epi.ldo + gc);
+        }
+    }
+}
+
+// Epilogue of one warp's slab of an accumulator tile: TMEM lanes [32q, 32q+32) x NCOLS fp32 columns
+// starting at `taddr`; output rows row0.., global columns gcol0...  TMEM is read 32 columns at a time,
+// one group ahead of the group being processed; each group is transposed through this warp's staging
+// buffer in two 16-column chunks (lane = TMEM row  ->  8 rows x 4 lanes x float4) so that global stores
+// are 64 B-contiguous per row.  `release()` is called once, as soon as the last TMEM read has landed,
+// so the MMA warp can start refilling this accumulator buffer while the tail is still being stored.
+template <int NCOLS, int EK, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, int row0, int gcol0, int M, int N,
+                                              const EpiParams &epi, int lane, ReleaseFn release) {
+    constexpr int NG = NCOLS / 32;
+    static_assert(NCOLS % 32 == 0 && NG >= 1, "slab width");
+    const int cc = (lane & 3) * 4, rb = row0 + (lane >> 2);
+    const bool vec_ok = ((epi.ldo & 3) == 0) && ((N & 3) == 0);
+    uint32_t v[2][32];
+    tmem_ld32_issue(taddr, v[0]);
+    float4 bias_c, res_c[4];
+    epi_load<EK>(epi, rb, gcol0 + cc, M, vec_ok && gcol0 + 16 <= N, bias_c, res_c);
+    tmem_wait_ld();
+    if (NG == 1) release();
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (g + 1 < NG) tmem_ld32_issue(taddr + (uint32_t)(g + 1) * 32u, v[(g + 1) & 1]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int gc0 = gcol0 + g * 32 + c * 16;
+            const bool interior = vec_ok && (gc0 + 16 <= N);
+            const bool has_next = (g * 2 + c + 1 < NG * 2);
+            float4 bias_n = bias_c, res_n[4];
+            if (has_next) epi_load<EK>(epi, rb, gc0 + 16 + cc, M, vec_ok && gc0 + 32 <= N, bias_n, res_n);
+            const uint32_t *vv = &v[g & 1][c * 16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                sts128(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
+            __syncwarp();
+            float4 val[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) val[i] = lds128(stg_s + (uint32_t)((i * 8 + (lane >> 2)) * STG_LD + cc) * 4u);
+            if (interior) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) val[i] = epi_math<EK>(val[i], bias_c, res_c[i], epi.alpha);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (rb + i * 8 < M) epi_store<EK>(epi, rb + i * 8, gc0 + cc, val[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (rb + i * 8 < M) epilogue4(epi, rb + i * 8, gc0 + cc, N, val[i]);
+            }
+            __syncwarp();
+            if (has_next) {
+                bias_c = bias_n;
+                if (EK == EPI_RESID_F32) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) res_c[i] = res_n[i];
+                }
+            }
+        }
+        if (g + 1 < NG) {
+            tmem_wait_ld();
+            if (g + 2 == NG) release();
+        }
+    }
+}
 constexpr int EPI_WARPS = 8;                    // two per TMEM lane quarter, each half of the columns
 constexpr int TC_THREADS_P = 64 + EPI_WARPS * 32;
-constexpr int STG_LD = 20;                      // staging row stride (floats): 16 columns + pad
 
 template <int BN, int NPASS>
 struct TcCfg {
@@ -239,44 +337,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ew = warp - 2;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int half = ew >> 2;                    // which half of the BN columns
-        float *stg = staging + (size_t)ew * 32 * STG_LD;
+        const uint32_t stg_s = smem_u32(staging + (size_t)ew * 32 * STG_LD);   // explicit .shared accesses
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
-            const uint32_t tbase = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {      // 16-column chunks of this warp's half
-                const int col = half * (BN / 2) + c * 16;
-                const bool interior = (n0 + col + 16 <= N) && ((epi.ldo & 3) == 0) && ((N & 3) == 0);
-                uint32_t v[16];
-                tmem_ld16(tbase + (uint32_t)col, v);
-                if (c == BN / 32 - 1) {              // last TMEM read of this tile: release the buffer
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                }
-                // transpose through shared memory: lane = TMEM row -> (8 rows x 4 lanes x float4) stores
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * j) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+            epilogue_slab<BN / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN / 2), M, N, epi, lane, [&]() {
+                tcgen05_fence_before();              // last TMEM read of this tile has landed: release the buffer
                 __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = i * 8 + (lane >> 2), cc = (lane & 3) * 4;
-                    const int row = m0 + q * 32 + r;
-                    const float4 val = *reinterpret_cast<const float4 *>(stg + r * STG_LD + cc);
-                    if (row < M) {
-                        if (interior) epilogue4_fast<EK>(epi, row, n0 + col + cc, val);
-                        else epilogue4(epi, row, n0 + col + cc, N, val);
-                    }
-                }
-                __syncwarp();
-            }
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            });
         }
     }
     tcgen05_fence_before();
@@ -450,7 +523,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        float *stg = staging + (size_t)ew * 32 * STG_LD;
+        const uint32_t stg_s = smem_u32(staging + (size_t)ew * 32 * STG_LD);   // explicit .shared accesses
         const uint32_t lempty0 = mapa_rank(smem_u32(&acc_empty[0]), 0), lempty1 = mapa_rank(smem_u32(&acc_empty[1]), 0);
         uint32_t tcount = 0;
         for (int tile = pair; tile < num_tiles; tile += npairs, ++tcount) {
@@ -458,36 +531,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
-            const uint32_t tbase = tmem_base + buf * BN2 + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN2 / 32; ++c) {
-                const int col = half * (BN2 / 2) + c * 16;
-                const bool interior = (n0 + col + 16 <= N) && ((epi.ldo & 3) == 0) && ((N & 3) == 0);
-                uint32_t v[16];
-                tmem_ld16(tbase + (uint32_t)col, v);
-                if (c == BN2 / 32 - 1) {
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + 4 * j) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            const uint32_t taddr = tmem_base + buf * BN2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN2 / 2));
+            epilogue_slab<BN2 / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN2 / 2), M, N, epi, lane, [&]() {
+                tcgen05_fence_before();
                 __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = i * 8 + (lane >> 2), cc = (lane & 3) * 4;
-                    const int row = m0 + q * 32 + r;
-                    const float4 val = *reinterpret_cast<const float4 *>(stg + r * STG_LD + cc);
-                    if (row < M) {
-                        if (interior) epilogue4_fast<EK>(epi, row, n0 + col + cc, val);
-                        else epilogue4(epi, row, n0 + col + cc, N, val);
-                    }
-                }
-                __syncwarp();
-            }
+                if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);   // leader's barrier counts both CTAs
+            });
         }
     }
     tcgen05_fence_before();

@@ -84,7 +84,8 @@ struct EpiParams {
     float alpha = 1.0f;
 };
 
-__device__ __forceinline__ void epilogue4(const EpiParams &p, int row, int col0, int N, float4 acc) {
+// Generic (edge-tile / run-time-kind) path; out of line so that it does not bloat the hot loops.
+static __device__ __noinline__ void epilogue4(const EpiParams &p, int row, int col0, int N, float4 acc) {
     if (col0 >= N) return;
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
     const bool full = (col0 + 3 < N);
@@ -147,7 +148,14 @@ __device__ __forceinline__ void epilogue4(const EpiParams &p, int row, int col0,
 // Compile-time-specialised fast path of epilogue4 for interior tiles (all 4 columns < N, ldo % 4
 // == 0): vector bias load, __expf / fast reciprocal, no run-time switch.  (GEMM epilogues are
 // instruction-bound on the big-N layers: 16.5 M outputs per fc1 launch.)
-__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// (ex2.approx + rcp.approx: two MUFU ops, branch-free.  __frcp_rn is an IEEE-rounded reciprocal with
+// a per-element slow-path branch, which serialises the whole epilogue.)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 
 template <int KIND>
 __device__ __forceinline__ void epilogue4_fast(const EpiParams &p, int row, int col0, float4 v) {
@@ -173,6 +181,36 @@ __device__ __forceinline__ void epilogue4_fast(const EpiParams &p, int row, int 
     } else if (KIND == EPI_GLU_F32) {
         *reinterpret_cast<float2 *>(p.out_f32 + (size_t)row * p.ldo + (col0 >> 1)) =
             make_float2(v.x * fast_sigmoid(v.y), v.z * fast_sigmoid(v.w));
+    }
+}
+
+// Split form used by the tcgen05 kernels: all global LOADS of a 16-column chunk (bias, residual)
+// are issued before the accumulator is read, then pure math, then all STORES -- otherwise every
+// epilogue4 call waits for its own L2 round trip (loads cannot be hoisted above the previous
+// call's stores: out_f32 may alias resid).
+template <int KIND>
+__device__ __forceinline__ float4 epi_math(float4 v, const float4 &b, const float4 &r, float alpha) {
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if (KIND == EPI_BIAS_RELU_F32 || KIND == EPI_BIAS_RELU_ACT) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    } else if (KIND == EPI_BIAS_SILU_ACT) {
+        v.x *= fast_sigmoid(v.x); v.y *= fast_sigmoid(v.y); v.z *= fast_sigmoid(v.z); v.w *= fast_sigmoid(v.w);
+    } else if (KIND == EPI_RESID_F32) {
+        v = make_float4(r.x + alpha * v.x, r.y + alpha * v.y, r.z + alpha * v.z, r.w + alpha * v.w);
+    } else if (KIND == EPI_GLU_F32) {
+        v = make_float4(v.x * fast_sigmoid(v.y), v.z * fast_sigmoid(v.w), 0.f, 0.f);
+    }
+    return v;
+}
+template <int KIND>
+__device__ __forceinline__ void epi_store(const EpiParams &p, int row, int col0, const float4 &v) {
+    const size_t base = (size_t)row * p.ldo + col0;
+    if (KIND == EPI_BIAS_F32 || KIND == EPI_BIAS_RELU_F32 || KIND == EPI_RESID_F32) {
+        *reinterpret_cast<float4 *>(p.out_f32 + base) = v;
+    } else if (KIND == EPI_GLU_F32) {
+        *reinterpret_cast<float2 *>(p.out_f32 + (size_t)row * p.ldo + (col0 >> 1)) = make_float2(v.x, v.y);
+    } else {
+        store_act4(p.act, base, v);
     }
 }
 
