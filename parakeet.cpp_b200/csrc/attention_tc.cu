@@ -1,5 +1,5 @@
-// attention_tc.cu -- K7 on tensor cores (head_dim 64): the same relative-position attention as
-// attention.cu (reference src/encoder.cpp:111-178, rel_shift :85-109)
+// attention_tc.cu -- K7 on tensor cores (head_dim 64): the relative-position attention of
+// reference src/encoder.cpp:111-178 (rel_shift :85-109)
 //     S[i,j] = ((q_i + u).k_j + (q_i + v).PP[i-j]) / sqrt(hd),  ctx_i = softmax_j(S[i,:]) V
 // with every product on mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) using the same hi/lo
 // operand split as the GEMMs (3 MMAs per product: hi.hi + hi.lo + lo.hi), i.e. ~16 mantissa bits,
@@ -7,49 +7,54 @@
 // 126 x 126 x 64, far below a UMMA tile pipeline's break-even, and the rel_shift needs a per-row
 // skew that is natural in registers/shared memory.
 //
-// One CTA = (64-query tile, head, utterance), 4 warps x 16 query rows.  Per 64-key tile a warp does
+// Operands arrive as bf16 hi/lo planes: the fused q/k/v projection (EPI_QKV_ACT epilogue of the
+// tcgen05 GEMM) writes [M, 4d] = [Qu | Qv | K | V] with Qu = q + pos_bias_u, Qv = q + pos_bias_v, and
+// PP = pos_emb . Wpos^T is split once at load.  So this kernel does no conversions on its inputs:
+// K / V / PP-window tiles are cp.async'ed (16 B) into shared memory, Q fragments are read straight
+// from global memory into registers, all fragments come from ldmatrix (V through .trans).
+//
+// One CTA = (64-query tile, head, utterance), 4 warps x 16 query rows; 93 KB smem -> 2 CTAs per SM
+// (one CTA's tile loads overlap the other's MMAs).  Per 64-key tile a warp does
 //   AC  = Qu . K^T                  16 x 64   (8 n-blocks x 4 k-steps x 3 MMAs)
 //   G   = Qv . PPwin^T              16 x 80   window of relative positions i-j (10 x 4 x 3 MMAs)
 //   S   = AC + skew(G)              G goes through a per-warp smem patch: S[r][jj] += G[r][r+63-jj]
-//   online softmax, P -> bf16 hi/lo A-fragments (C-fragment layout == A-fragment layout)
-//   O  += P . V                     16 x 64   (8 x 4 x 3 MMAs, V staged transposed)
+//   online softmax (base 2), P -> bf16 hi/lo A-fragments (C-fragment layout == A-fragment layout)
+//   O  += P . V                     16 x 64   (8 x 4 x 3 MMAs)
 #include "kernels.h"
 
 namespace pk {
 namespace {
 
-constexpr int HD = 64, BQ = 64, BKV = 64, LDS_ = 72;   // LDS_: smem row stride in bf16 (conflict-free fragment loads)
+constexpr int HD = 64, BQ = 64, BKV = 64, LDS_ = 72;   // LDS_: smem row stride in bf16 (144 B: conflict-free ldmatrix)
 constexpr int NPW = 128;                               // relative-position window rows per (q-tile, k-tile)
 constexpr int LDG_ = 84;                               // G patch row stride (floats)
 constexpr int TCA_THREADS = 128;
 
 struct __align__(16) AttnSmem {
-    bf16 qu_hi[BQ * LDS_], qu_lo[BQ * LDS_], qv_hi[BQ * LDS_], qv_lo[BQ * LDS_];
     bf16 k_hi[BKV * LDS_], k_lo[BKV * LDS_];
-    bf16 vt_hi[HD * LDS_], vt_lo[HD * LDS_];          // [dim][key]
+    bf16 v_hi[BKV * LDS_], v_lo[BKV * LDS_];          // [key][dim]; PV reads it through ldmatrix.trans
     bf16 pp_hi[NPW * LDS_], pp_lo[NPW * LDS_];
     float g[4][16 * LDG_];
 };
 
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// A fragment (16 x 16, row-major source [row][LDS_]) of rows row0.. and columns k0..
-__device__ __forceinline__ void load_a(uint32_t (&a)[4], const bf16 *base, int row0, int k0, int g, int c) {
-    const bf16 *p = base + (row0 + g) * LDS_ + k0 + 2 * c;
-    a[0] = *reinterpret_cast<const uint32_t *>(p);
-    a[1] = *reinterpret_cast<const uint32_t *>(p + 8 * LDS_);
-    a[2] = *reinterpret_cast<const uint32_t *>(p + 8);
-    a[3] = *reinterpret_cast<const uint32_t *>(p + 8 * LDS_ + 8);
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-// B fragment (16 x 8, "col" layout) where B[k][n] = src[n0 + n][k0 + k] (src row-major [n][LDS_])
-__device__ __forceinline__ void load_b(uint32_t (&b)[2], const bf16 *base, int n0, int k0, int g, int c) {
-    const bf16 *p = base + (n0 + g) * LDS_ + k0 + 2 * c;
-    b[0] = *reinterpret_cast<const uint32_t *>(p);
-    b[1] = *reinterpret_cast<const uint32_t *>(p + 8);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// 16-byte async copy; src_bytes = 0 zero-fills the destination (rows outside the utterance / table)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t &lo) {
     __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
@@ -58,16 +63,27 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t 
     hi = *reinterpret_cast<uint32_t *>(&h);
     lo = *reinterpret_cast<uint32_t *>(&l);
 }
-__device__ __forceinline__ void split_store(bf16 *hi, bf16 *lo, int idx, float x) {
-    bf16 h = __float2bfloat16_rn(x);
-    hi[idx] = h;
-    lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__global__ void __launch_bounds__(TCA_THREADS)
-relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int32_t *__restrict__ row_off,
-                           const bf16 *__restrict__ pp_hi, const bf16 *__restrict__ pp_lo, int tmax,
-                           const float *__restrict__ bias_u, const float *__restrict__ bias_v, int d_model, ActBuf out) {
+// B fragments of two adjacent 8-row n-blocks (rows n0..n0+15 of a row-major [n][LDS_] tile) for the
+// 16-wide k-step at k0: r[0], r[1] = (b0, b1) of block n0; r[2], r[3] = (b0, b1) of block n0 + 8.
+__device__ __forceinline__ uint32_t bfrag_addr(const bf16 *base, int n0, int k0, int lane) {
+    return smem_addr(base + (n0 + ((lane >> 4) << 3) + (lane & 7)) * LDS_ + k0 + (((lane >> 3) & 1) << 3));
+}
+// Same for B[k][n] = src[k0 + k][n0 + n] (src row-major [k][LDS_]) through ldmatrix.trans:
+// r[0], r[1] = (b0, b1) of columns n0..n0+7; r[2], r[3] of columns n0+8..n0+15.
+__device__ __forceinline__ uint32_t bfrag_t_addr(const bf16 *base, int k0, int n0, int lane) {
+    return smem_addr(base + (k0 + (((lane >> 3) & 1) << 3) + (lane & 7)) * LDS_ + n0 + ((lane >> 4) << 3));
+}
+
+__global__ void __launch_bounds__(TCA_THREADS, 2)
+relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restrict__ qkv_lo, int ld_qkv,
+                           const int32_t *__restrict__ row_off, const bf16 *__restrict__ pp_hi,
+                           const bf16 *__restrict__ pp_lo, int tmax, int d_model, ActBuf out) {
     extern __shared__ __align__(16) uint8_t smraw[];
     AttnSmem &sm = *reinterpret_cast<AttnSmem *>(smraw);
     const int b = blockIdx.z, h = blockIdx.y;
@@ -75,14 +91,24 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
     const int i0 = blockIdx.x * BQ;
     if (i0 >= T) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    const int wrow = warp * 16;          // this warp's first query row inside the tile
 
-    // ---- query tile: Qu = q + u_h, Qv = q + v_h, split to bf16 hi/lo
-    for (int idx = tid; idx < BQ * HD; idx += TCA_THREADS) {
-        const int i = idx / HD, k = idx % HD;
-        float q = 0.f;
-        if (i0 + i < T) q = qkv[(size_t)(r0 + i0 + i) * ld_qkv + h * HD + k];
-        split_store(sm.qu_hi, sm.qu_lo, i * LDS_ + k, q + bias_u[h * HD + k]);
-        split_store(sm.qv_hi, sm.qv_lo, i * LDS_ + k, q + bias_v[h * HD + k]);
+    // ---- Q fragments (A operand, rows wrow+g / wrow+g+8, 4 k-steps), straight from the planes
+    uint32_t qu_h[4][4], qu_l[4][4], qv_h[4][4], qv_l[4][4];
+    {
+        const int ia = i0 + wrow + g, ib = ia + 8;
+        const size_t oa = (size_t)(r0 + ia) * ld_qkv + h * HD + 2 * c, ob = (size_t)(r0 + ib) * ld_qkv + h * HD + 2 * c;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool okr = ((e & 1) ? ib : ia) < T;
+                const size_t o = ((e & 1) ? ob : oa) + ks * 16 + ((e >> 1) << 3);
+                qu_h[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_hi + o) : 0u;
+                qu_l[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_lo + o) : 0u;
+                qv_h[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_hi + o + d_model) : 0u;
+                qv_l[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_lo + o + d_model) : 0u;
+            }
     }
 
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
@@ -91,35 +117,37 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
     for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
         for (int e = 0; e < 4; ++e) oacc[nb][e] = 0.f;
-    const int wrow = warp * 16;          // this warp's first query row inside the tile
     float *gs = sm.g[warp];
+    const uint32_t sk_hi = smem_addr(sm.k_hi), sk_lo = smem_addr(sm.k_lo), sv_hi = smem_addr(sm.v_hi), sv_lo = smem_addr(sm.v_lo);
+    const uint32_t sp_hi = smem_addr(sm.pp_hi), sp_lo = smem_addr(sm.pp_lo);
 
     for (int j0 = 0; j0 < T; j0 += BKV) {
-        __syncthreads();                 // previous key tile fully consumed (and Q stores visible)
-        for (int idx = tid; idx < BKV * HD; idx += TCA_THREADS) {
-            const int j = idx / HD, k = idx % HD;
-            float kv = 0.f, vv = 0.f;
-            if (j0 + j < T) {
-                const float *row = qkv + (size_t)(r0 + j0 + j) * ld_qkv + h * HD + k;
-                kv = row[d_model];
-                vv = row[2 * d_model];
-            }
-            split_store(sm.k_hi, sm.k_lo, j * LDS_ + k, kv);
-            split_store(sm.vt_hi, sm.vt_lo, k * LDS_ + j, vv);
+        __syncthreads();                 // previous key tile fully consumed
+        // ---- K, V rows j0..j0+63 and the PP window, 16 B per cp.async
+        for (int idx = tid; idx < BKV * 8; idx += TCA_THREADS) {
+            const int j = idx >> 3, ch = idx & 7;
+            const bool ok = (j0 + j < T);
+            const size_t o = (size_t)(r0 + (ok ? j0 + j : 0)) * ld_qkv + 2 * d_model + h * HD + ch * 8;
+            const uint32_t so = (uint32_t)(j * LDS_ + ch * 8) * 2u;
+            const int nb = ok ? 16 : 0;
+            cp_async16(sk_hi + so, qkv_hi + o, nb);
+            cp_async16(sk_lo + so, qkv_lo + o, nb);
+            cp_async16(sv_hi + so, qkv_hi + o + d_model, nb);
+            cp_async16(sv_lo + so, qkv_lo + o + d_model, nb);
         }
         const int pmin = i0 - (j0 + BKV - 1);
-        for (int idx = tid; idx < NPW * (HD / 2); idx += TCA_THREADS) {   // 2 bf16 per thread-iteration
-            const int w = idx / (HD / 2), k2 = (idx % (HD / 2)) * 2;
+        for (int idx = tid; idx < NPW * 8; idx += TCA_THREADS) {
+            const int w = idx >> 3, ch = idx & 7;
             const int prow = pmin + w + tmax - 1;
-            uint32_t vh = 0u, vl = 0u;
-            if (prow >= 0 && prow < 2 * tmax - 1) {
-                const size_t o = (size_t)prow * d_model + h * HD + k2;
-                vh = *reinterpret_cast<const uint32_t *>(pp_hi + o);
-                vl = *reinterpret_cast<const uint32_t *>(pp_lo + o);
-            }
-            *reinterpret_cast<uint32_t *>(sm.pp_hi + w * LDS_ + k2) = vh;
-            *reinterpret_cast<uint32_t *>(sm.pp_lo + w * LDS_ + k2) = vl;
+            const bool ok = (prow >= 0 && prow < 2 * tmax - 1);
+            const size_t o = (size_t)(ok ? prow : 0) * d_model + h * HD + ch * 8;
+            const uint32_t so = (uint32_t)(w * LDS_ + ch * 8) * 2u;
+            const int nb = ok ? 16 : 0;
+            cp_async16(sp_hi + so, pp_hi + o, nb);
+            cp_async16(sp_lo + so, pp_lo + o, nb);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
         // ---- AC = Qu K^T (16 x 64 per warp)
@@ -130,17 +158,17 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
             for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
-            uint32_t ah[4], al[4];
-            load_a(ah, sm.qu_hi, wrow, ks * 16, g, c);
-            load_a(al, sm.qu_lo, wrow, ks * 16, g, c);
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
-                uint32_t bh[2], bl[2];
-                load_b(bh, sm.k_hi, nb * 8, ks * 16, g, c);
-                load_b(bl, sm.k_lo, nb * 8, ks * 16, g, c);
-                mma_bf16(sacc[nb], ah, bh);
-                mma_bf16(sacc[nb], ah, bl);
-                mma_bf16(sacc[nb], al, bh);
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bh[4], bl[4];
+                ldsm_x4(bh, bfrag_addr(sm.k_hi, np * 16, ks * 16, lane));
+                ldsm_x4(bl, bfrag_addr(sm.k_lo, np * 16, ks * 16, lane));
+                mma_bf16(sacc[2 * np], qu_h[ks], bh[0], bh[1]);
+                mma_bf16(sacc[2 * np + 1], qu_h[ks], bh[2], bh[3]);
+                mma_bf16(sacc[2 * np], qu_h[ks], bl[0], bl[1]);
+                mma_bf16(sacc[2 * np + 1], qu_h[ks], bl[2], bl[3]);
+                mma_bf16(sacc[2 * np], qu_l[ks], bh[0], bh[1]);
+                mma_bf16(sacc[2 * np + 1], qu_l[ks], bh[2], bh[3]);
             }
         }
         // ---- G = Qv PPwin^T (16 x 80: window rows wrow .. wrow+79), through the smem patch, skewed into S
@@ -152,17 +180,17 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
                 for (int e = 0; e < 4; ++e) gacc[nb][e] = 0.f;
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks) {
-                uint32_t ah[4], al[4];
-                load_a(ah, sm.qv_hi, wrow, ks * 16, g, c);
-                load_a(al, sm.qv_lo, wrow, ks * 16, g, c);
 #pragma unroll
-                for (int nb = 0; nb < 10; ++nb) {
-                    uint32_t bh[2], bl[2];
-                    load_b(bh, sm.pp_hi, wrow + nb * 8, ks * 16, g, c);
-                    load_b(bl, sm.pp_lo, wrow + nb * 8, ks * 16, g, c);
-                    mma_bf16(gacc[nb], ah, bh);
-                    mma_bf16(gacc[nb], ah, bl);
-                    mma_bf16(gacc[nb], al, bh);
+                for (int np = 0; np < 5; ++np) {
+                    uint32_t bh[4], bl[4];
+                    ldsm_x4(bh, bfrag_addr(sm.pp_hi, wrow + np * 16, ks * 16, lane));
+                    ldsm_x4(bl, bfrag_addr(sm.pp_lo, wrow + np * 16, ks * 16, lane));
+                    mma_bf16(gacc[2 * np], qv_h[ks], bh[0], bh[1]);
+                    mma_bf16(gacc[2 * np + 1], qv_h[ks], bh[2], bh[3]);
+                    mma_bf16(gacc[2 * np], qv_h[ks], bl[0], bl[1]);
+                    mma_bf16(gacc[2 * np + 1], qv_h[ks], bl[2], bl[3]);
+                    mma_bf16(gacc[2 * np], qv_l[ks], bh[0], bh[1]);
+                    mma_bf16(gacc[2 * np + 1], qv_l[ks], bh[2], bh[3]);
                 }
             }
 #pragma unroll
@@ -182,7 +210,8 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
                 }
             __syncwarp();
         }
-        // ---- scale, mask, online softmax (rows g and g+8 of this warp)
+        // ---- scale (1/sqrt(64), folded with log2 e), mask, online softmax in base 2 (rows g and g+8)
+        constexpr float kScale = 0.125f * 1.4426950408889634f;
         float alpha[2];
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -192,22 +221,21 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int jj = nb * 8 + 2 * c + e;
-                    float s = sacc[nb][hrow * 2 + e] * 0.125f;
+                    float s = sacc[nb][hrow * 2 + e] * kScale;
                     s = (j0 + jj < T) ? s : -INFINITY;
                     sacc[nb][hrow * 2 + e] = s;
                     mx = fmaxf(mx, s);
                 }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            const float m_new = fmaxf(m_run[hrow], mx);
-            alpha[hrow] = (m_run[hrow] == -INFINITY) ? 0.f : expf(m_run[hrow] - m_new);
+            const float m_new = fmaxf(m_run[hrow], mx);     // finite: key j0 is always valid
+            alpha[hrow] = ex2_approx(m_run[hrow] - m_new);  // ex2(-inf) = 0 on the first tile
             float sum = 0.f;
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float s = sacc[nb][hrow * 2 + e];
-                    const float pexp = (s == -INFINITY) ? 0.f : expf(s - m_new);
+                    const float pexp = ex2_approx(sacc[nb][hrow * 2 + e] - m_new);
                     sacc[nb][hrow * 2 + e] = pexp;
                     sum += pexp;
                 }
@@ -232,13 +260,16 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
             split2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);
             split2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
-                uint32_t bh[2], bl[2];
-                load_b(bh, sm.vt_hi, nb * 8, kk * 16, g, c);
-                load_b(bl, sm.vt_lo, nb * 8, kk * 16, g, c);
-                mma_bf16(oacc[nb], ph, bh);
-                mma_bf16(oacc[nb], ph, bl);
-                mma_bf16(oacc[nb], pl, bh);
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bh[4], bl[4];
+                ldsm_x4_t(bh, bfrag_t_addr(sm.v_hi, kk * 16, np * 16, lane));
+                ldsm_x4_t(bl, bfrag_t_addr(sm.v_lo, kk * 16, np * 16, lane));
+                mma_bf16(oacc[2 * np], ph, bh[0], bh[1]);
+                mma_bf16(oacc[2 * np + 1], ph, bh[2], bh[3]);
+                mma_bf16(oacc[2 * np], ph, bl[0], bl[1]);
+                mma_bf16(oacc[2 * np + 1], ph, bl[2], bl[3]);
+                mma_bf16(oacc[2 * np], pl, bh[0], bh[1]);
+                mma_bf16(oacc[2 * np + 1], pl, bh[2], bh[3]);
             }
         }
     }
@@ -265,10 +296,10 @@ relpos_attention_tc_kernel(const float *__restrict__ qkv, int ld_qkv, const int3
 
 }  // namespace
 
-bool launch_relpos_attention_tc(const float *qkv, int ld_qkv, const int32_t *row_off, int n_utt, int max_T, int n_heads,
-                                int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax, const float *bu,
-                                const float *bv, int d_model, ActBuf out, cudaStream_t st) {
-    if (head_dim != HD) return false;
+bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt,
+                                int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
+                                int d_model, ActBuf out, cudaStream_t st) {
+    if (head_dim != HD || !qkv_hi || !qkv_lo || !pp_hi || !pp_lo) return false;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(relpos_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -277,8 +308,8 @@ bool launch_relpos_attention_tc(const float *qkv, int ld_qkv, const int32_t *row
         attr = true;
     }
     dim3 grid((max_T + BQ - 1) / BQ, n_heads, n_utt);
-    relpos_attention_tc_kernel<<<grid, TCA_THREADS, sizeof(AttnSmem), st>>>(qkv, ld_qkv, row_off, pp_hi, pp_lo, tmax, bu,
-                                                                          bv, d_model, out);
+    relpos_attention_tc_kernel<<<grid, TCA_THREADS, sizeof(AttnSmem), st>>>(qkv_hi, qkv_lo, ld_qkv, row_off, pp_hi, pp_lo,
+                                                                          tmax, d_model, out);
     return true;
 }
 

@@ -113,6 +113,7 @@ struct pk_engine {
     float *logmel = nullptr, *feats = nullptr;
     Act sub1, sub3, sub4, ln, ffh, ctx, cv;
     float *sub2 = nullptr, *x = nullptr, *qkv = nullptr, *glu = nullptr, *logits = nullptr, *EP = nullptr;
+    bf16 *qkvp_hi = nullptr, *qkvp_lo = nullptr;   // [Mx, 4 d] planes [q+u | q+v | k | v] for the tensor-core attention
     int32_t *best = nullptr;
     float *bconf = nullptr;
     int32_t *tok = nullptr, *t_start = nullptr, *t_end = nullptr;
@@ -535,6 +536,11 @@ pk_status pk_engine::alloc_workspace() {
     ln = act_alloc(Mx, d);
     ffh = act_alloc(Mx, c.ff);
     qkv = dalloc<float>(Mx * 3 * d);
+    if (cfg.math != PK_MATH_FP32 && c.d_model / c.n_heads == 64) {
+        qkvp_hi = dalloc<bf16>(Mx * 4 * d);
+        qkvp_lo = dalloc<bf16>(Mx * 4 * d);
+        if (!qkvp_hi || !qkvp_lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (qkv planes)");
+    }
     ctx = act_alloc(Mx, d);
     glu = dalloc<float>(Mx * d);
     cv = act_alloc(Mx, d);
@@ -726,15 +732,26 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             // ConformerAttention (encoder.cpp:111-186)
             PK_LN(x, M, d, L.att_ln_w, L.att_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
             ++launches;
+            const bool tc_attn = L.pp_hi && qkvp_hi && attn_tc;
             EpiParams eq;
-            eq.kind = EPI_BIAS_F32;
-            eq.out_f32 = qkv;
-            eq.ldo = 3 * d;
+            if (tc_attn) {   // q/k/v land as bf16 hi/lo planes with the position biases already added
+                eq.kind = EPI_QKV_ACT;
+                eq.act.hi = qkvp_hi;
+                eq.act.lo = qkvp_lo;
+                eq.ldo = 4 * d;
+                eq.bias_u = L.pos_u;
+                eq.bias_v = L.pos_v;
+                eq.qcols = d;
+            } else {
+                eq.kind = EPI_BIAS_F32;
+                eq.out_f32 = qkv;
+                eq.ldo = 3 * d;
+            }
             gemm(ln, d, L.qkv, M, eq);
             {
                 Scope sc(this, CAT_ATTENTION);
-                const bool ok = (L.pp_hi && attn_tc)
-                    ? launch_relpos_attention_tc(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, L.pos_u, L.pos_v, d, ctx, stream)
+                const bool ok = tc_attn
+                    ? launch_relpos_attention_tc(qkvp_hi, qkvp_lo, 4 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, d, ctx, stream)
                     : launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream);
                 if (!ok) return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
             }
@@ -1034,10 +1051,13 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     if (cudaSetDevice(device) != cudaSuccess) return PK_ERR_CUDA;
     if (const char *ev = getenv("PK_GEMM_2CTA")) tc_set_2cta(atoi(ev) != 0);
     if (K % 64 != 0 || (epi_kind == EPI_GLU_F32 && (N & 1))) return PK_ERR_INVALID;
+    const int qcols = epi_kind == EPI_QKV_ACT ? N / 3 : 0;     // fused q/k/v projection: N = 3 d, output [M, 4 d]
+    if (epi_kind == EPI_QKV_ACT && (N % 3 != 0 || qcols % 16 != 0)) return PK_ERR_INVALID;
     cudaStream_t st;
     cudaStreamCreate(&st);
-    const bool act_out = epi_kind == EPI_BIAS_RELU_ACT || epi_kind == EPI_BIAS_SILU_ACT || epi_kind == EPI_BIAS_ACT;
-    const int No = epi_kind == EPI_GLU_F32 ? N / 2 : N;
+    const bool act_out = epi_kind == EPI_BIAS_RELU_ACT || epi_kind == EPI_BIAS_SILU_ACT || epi_kind == EPI_BIAS_ACT ||
+                         epi_kind == EPI_QKV_ACT;
+    const int No = epi_kind == EPI_GLU_F32 ? N / 2 : N + qcols;
     std::vector<float> hA((size_t)M * K), hW((size_t)N * K), hb(N), hr((size_t)M * No);
     uint32_t sd = seed * 2654435761u + 12345u;
     auto rnd = [&]() { sd = sd * 1664525u + 1013904223u; return ((sd >> 8) & 0xffff) / 32768.0f - 1.0f; };
@@ -1062,6 +1082,7 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     launch_split(dW, hW.size(), sw, st);
     EpiParams ep;
     ep.kind = epi_kind; ep.bias = db; ep.ldo = No; ep.resid = dr; ep.alpha = 0.5f;
+    ep.bias_u = dr; ep.bias_v = dr + qcols; ep.qcols = qcols;   // (dr holds >= 2 qcols random floats)
     ep.out_f32 = o_ref;
     ActBuf ref_act; ref_act.f32 = o_ref;
     ep.act = ref_act;

@@ -109,17 +109,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread.  Issue only; the caller overlaps
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread.  Issue only; the caller overlaps
 // the TMEM read latency with other work and calls tmem_wait_ld() before touching v[].
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *v) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *v) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -141,86 +138,102 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 
 // Global operands of one 16-column chunk (this lane: 4 rows x 4 columns), issued one chunk AHEAD of
 // their use so that the L2 round trip overlaps the previous chunk's transpose / math / stores.
+struct EpiOperands {
+    float4 b, bu, bv, r[4];
+};
 template <int EK>
-__device__ __forceinline__ void epi_load(const EpiParams &epi, int rb, int gc, int M, bool ok, float4 &b, float4 (&r)[4]) {
-    b = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ void epi_load(const EpiParams &epi, int rb, int gc, int M, bool ok, EpiOperands &o) {
+    o.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EK == EPI_QKV_ACT) o.bu = o.bv = o.b;
     if (EK == EPI_RESID_F32) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) o.r[i] = o.b;
     }
     if (ok) {
-        if (epi.bias) b = __ldg(reinterpret_cast<const float4 *>(epi.bias + gc));
+        if (epi.bias) o.b = __ldg(reinterpret_cast<const float4 *>(epi.bias + gc));
+        if (EK == EPI_QKV_ACT && gc < epi.qcols) {
+            o.bu = __ldg(reinterpret_cast<const float4 *>(epi.bias_u + gc));
+            o.bv = __ldg(reinterpret_cast<const float4 *>(epi.bias_v + gc));
+        }
         if (EK == EPI_RESID_F32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (rb + i * 8 < M) r[i] = *reinterpret_cast<const float4 *>(epi.resid + (size_t)(rb + i * 8) * epi.ldo + gc);
+                if (rb + i * 8 < M) o.r[i] = *reinterpret_cast<const float4 *>(epi.resid + (size_t)(rb + i * 8) * epi.ldo + gc);
         }
     }
 }
 
 // Epilogue of one warp's slab of an accumulator tile: TMEM lanes [32q, 32q+32) x NCOLS fp32 columns
-// starting at `taddr`; output rows row0.., global columns gcol0...  TMEM is read 32 columns at a time,
-// one group ahead of the group being processed; each group is transposed through this warp's staging
-// buffer in two 16-column chunks (lane = TMEM row  ->  8 rows x 4 lanes x float4) so that global stores
-// are 64 B-contiguous per row.  `release()` is called once, as soon as the last TMEM read has landed,
-// so the MMA warp can start refilling this accumulator buffer while the tail is still being stored.
+// starting at `taddr`; output rows row0.., global columns gcol0...  The slab is processed in 16-column
+// chunks; chunk c+1's TMEM read and global operands (bias / residual) are issued before chunk c is
+// transposed through this warp's staging buffer (lane = TMEM row -> 8 rows x 4 lanes x float4, so
+// global stores are 64 B-contiguous per row), which hides both latencies.  The loop is deliberately
+// NOT unrolled: the body is ~150 instructions and the kernels must stay inside the instruction
+// cache.  `release()` is called once, as soon as the last TMEM read has landed, so the MMA warp can
+// start refilling this accumulator buffer while the tail is still being stored.
 template <int NCOLS, int EK, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, int row0, int gcol0, int M, int N,
-                                              const EpiParams &epi, int lane, ReleaseFn release) {
-    constexpr int NG = NCOLS / 32;
-    static_assert(NCOLS % 32 == 0 && NG >= 1, "slab width");
+                                              const EpiParams &epi_param, int lane, ReleaseFn release) {
+    // Register copy of the parameters for the fast path.  (The out-of-line edge path takes the
+    // struct by reference; reading fields through that same object here makes every pointer a
+    // generic-address reload after each store.)
+    const EpiParams epi = epi_param;
+    constexpr int NCH = NCOLS / 16;
+    static_assert(NCOLS % 16 == 0 && NCH >= 1, "slab width");
     const int cc = (lane & 3) * 4, rb = row0 + (lane >> 2);
     const bool vec_ok = ((epi.ldo & 3) == 0) && ((N & 3) == 0);
-    uint32_t v[2][32];
-    tmem_ld32_issue(taddr, v[0]);
-    float4 bias_c, res_c[4];
-    epi_load<EK>(epi, rb, gcol0 + cc, M, vec_ok && gcol0 + 16 <= N, bias_c, res_c);
+    uint32_t vc[16], vn[16];
+    EpiOperands oc, on;
+    tmem_ld16_issue(taddr, vc);
+    epi_load<EK>(epi, rb, gcol0 + cc, M, vec_ok && gcol0 + 16 <= N, oc);
     tmem_wait_ld();
-    if (NG == 1) release();
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        if (g + 1 < NG) tmem_ld32_issue(taddr + (uint32_t)(g + 1) * 32u, v[(g + 1) & 1]);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int gc0 = gcol0 + g * 32 + c * 16;
-            const bool interior = vec_ok && (gc0 + 16 <= N);
-            const bool has_next = (g * 2 + c + 1 < NG * 2);
-            float4 bias_n = bias_c, res_n[4];
-            if (has_next) epi_load<EK>(epi, rb, gc0 + 16 + cc, M, vec_ok && gc0 + 32 <= N, bias_n, res_n);
-            const uint32_t *vv = &v[g & 1][c * 16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                sts128(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
-            __syncwarp();
-            float4 val[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) val[i] = lds128(stg_s + (uint32_t)((i * 8 + (lane >> 2)) * STG_LD + cc) * 4u);
-            if (interior) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) val[i] = epi_math<EK>(val[i], bias_c, res_c[i], epi.alpha);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (rb + i * 8 < M) epi_store<EK>(epi, rb + i * 8, gc0 + cc, val[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (rb + i * 8 < M) epilogue4(epi, rb + i * 8, gc0 + cc, N, val[i]);
-            }
-            __syncwarp();
-            if (has_next) {
-                bias_c = bias_n;
-                if (EK == EPI_RESID_F32) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) res_c[i] = res_n[i];
-                }
-            }
+    if (NCH == 1) release();
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+        const int gc0 = gcol0 + ch * 16;
+        const bool interior = vec_ok && (gc0 + 16 <= N);
+        const bool has_next = ch + 1 < NCH;
+        if (has_next) {
+            tmem_ld16_issue(taddr + (uint32_t)(ch + 1) * 16u, vn);
+            epi_load<EK>(epi, rb, gc0 + 16 + cc, M, vec_ok && gc0 + 32 <= N, on);
         }
-        if (g + 1 < NG) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            sts128(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, vc[4 * j], vc[4 * j + 1], vc[4 * j + 2], vc[4 * j + 3]);
+        __syncwarp();
+        float4 val[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) val[i] = lds128(stg_s + (uint32_t)((i * 8 + (lane >> 2)) * STG_LD + cc) * 4u);
+        if (interior) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) val[i] = epi_math<EK>(val[i], oc.b, oc.r[i], epi.alpha);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rb + i * 8 < M) epi_store<EK>(epi, rb + i * 8, gc0 + cc, val[i], oc.bu, oc.bv);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rb + i * 8 < M) epilogue4(epi_param, rb + i * 8, gc0 + cc, N, val[i]);
+        }
+        __syncwarp();
+        if (has_next) {
             tmem_wait_ld();
-            if (g + 2 == NG) release();
+            if (ch + 2 == NCH) release();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vc[j] = vn[j];
+            oc.b = on.b;
+            if (EK == EPI_QKV_ACT) {
+                oc.bu = on.bu;
+                oc.bv = on.bv;
+            }
+            if (EK == EPI_RESID_F32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) oc.r[i] = on.r[i];
+            }
         }
     }
 }
+
 constexpr int EPI_WARPS = 8;                    // two per TMEM lane quarter, each half of the columns
 constexpr int TC_THREADS_P = 64 + EPI_WARPS * 32;
 
@@ -244,7 +257,7 @@ template <int BN, int NPASS, int EK>
 __global__ void __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-               int K, EpiParams epi) {
+               int K, const __grid_constant__ EpiParams epi) {
     using C = TcCfg<BN, NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -424,7 +437,7 @@ template <int NPASS, int EK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-                int K, EpiParams epi) {
+                int K, const __grid_constant__ EpiParams epi) {
     using C = Tc2Cfg<NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -615,6 +628,7 @@ cudaError_t launch_k2(const TcOperand &A, const TcOperand &W, int M, int N, int 
     case EPI_RESID_F32: return CALL(EPI_RESID_F32);                      \
     case EPI_GLU_F32: return CALL(EPI_GLU_F32);                          \
     case EPI_BIAS_ACT: return CALL(EPI_BIAS_ACT);                        \
+    case EPI_QKV_ACT: return CALL(EPI_QKV_ACT);                          \
     default: return cudaErrorInvalidValue;                               \
     }
 

@@ -61,9 +61,10 @@ bool launch_relpos_attention(const float *qkv, int ld_qkv, const int32_t *row_of
                              const float *bv, int d_model, ActBuf out, cudaStream_t st);
 
 // tensor-core variant (attention_tc.cu, head_dim 64): pp as bf16 hi/lo planes
-bool launch_relpos_attention_tc(const float *qkv, int ld_qkv, const int32_t *row_off, int n_utt, int max_T, int n_heads,
-                                int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax, const float *bu,
-                                const float *bv, int d_model, ActBuf out, cudaStream_t st);
+// qkv_hi / qkv_lo: bf16 planes [M, ld_qkv = 4 d] = [q + u | q + v | k | v] from the EPI_QKV_ACT GEMM epilogue.
+bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt,
+                                int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
+                                int d_model, ActBuf out, cudaStream_t st);
 
 // ------------------------------------------------------------------ ctc.cu (K9)
 void launch_ctc_frame_argmax(const float *logits, int M, int V, int ld, int32_t *best, float *conf,

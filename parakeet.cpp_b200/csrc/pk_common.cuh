@@ -72,6 +72,8 @@ enum EpiKind : int {
     EPI_RESID_F32 = 4,     // out_f32[row, col] = resid[row, col] + alpha * (acc + bias)
     EPI_GLU_F32 = 5,       // columns interleaved (a0,b0,a1,b1..): out_f32[row, col/2] = a * sigmoid(b)
     EPI_BIAS_ACT = 6,      // acc + bias -> act
+    EPI_QKV_ACT = 7,       // fused q/k/v projection for the tensor-core attention: act planes [M, N + qcols] =
+                           // [q + bias_u | q + bias_v | k | v]  (q = acc + bias for col < qcols; encoder.cpp:129-140)
 };
 
 struct EpiParams {
@@ -82,6 +84,8 @@ struct EpiParams {
     ActBuf act;
     const float *resid = nullptr;
     float alpha = 1.0f;
+    const float *bias_u = nullptr, *bias_v = nullptr;   // EPI_QKV_ACT: pos_bias_u / pos_bias_v, [qcols]
+    int qcols = 0;
 };
 
 // Generic (edge-tile / run-time-kind) path; out of line so that it does not bloat the hot loops.
@@ -135,6 +139,17 @@ static __device__ __noinline__ void epilogue4(const EpiParams &p, int row, int c
                 p.out_f32[base + i] = p.resid[base + i] + p.alpha * v[i];
         }
         break;
+    case EPI_QKV_ACT:
+        for (int i = 0; i < 4 && col0 + i < N; ++i) {
+            const int cidx = col0 + i;
+            if (cidx < p.qcols) {
+                store_act(p.act, (size_t)row * p.ldo + cidx, v[i] + p.bias_u[cidx]);
+                store_act(p.act, (size_t)row * p.ldo + cidx + p.qcols, v[i] + p.bias_v[cidx]);
+            } else {
+                store_act(p.act, (size_t)row * p.ldo + cidx + p.qcols, v[i]);
+            }
+        }
+        break;
     case EPI_GLU_F32: {
         // N is even and col0 % 4 == 0, so both pairs are in range together.
         const size_t ob = (size_t)row * p.ldo + (col0 >> 1);
@@ -145,9 +160,7 @@ static __device__ __noinline__ void epilogue4(const EpiParams &p, int row, int c
     }
 }
 
-// Compile-time-specialised fast path of epilogue4 for interior tiles (all 4 columns < N, ldo % 4
-// == 0): vector bias load, __expf / fast reciprocal, no run-time switch.  (GEMM epilogues are
-// instruction-bound on the big-N layers: 16.5 M outputs per fc1 launch.)
+// Compile-time-specialised fast path for interior tiles (all 4 columns < N, ldo % 4 == 0).
 // (ex2.approx + rcp.approx: two MUFU ops, branch-free.  __frcp_rn is an IEEE-rounded reciprocal with
 // a per-element slow-path branch, which serialises the whole epilogue.)
 __device__ __forceinline__ float fast_sigmoid(float x) {
@@ -155,33 +168,6 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return r;
-}
-
-template <int KIND>
-__device__ __forceinline__ void epilogue4_fast(const EpiParams &p, int row, int col0, float4 v) {
-    if (p.bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0));
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    }
-    if (KIND == EPI_BIAS_RELU_F32 || KIND == EPI_BIAS_RELU_ACT) {
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    }
-    if (KIND == EPI_BIAS_SILU_ACT) {
-        v.x *= fast_sigmoid(v.x); v.y *= fast_sigmoid(v.y); v.z *= fast_sigmoid(v.z); v.w *= fast_sigmoid(v.w);
-    }
-    const size_t base = (size_t)row * p.ldo + col0;
-    if (KIND == EPI_BIAS_F32 || KIND == EPI_BIAS_RELU_F32) {
-        *reinterpret_cast<float4 *>(p.out_f32 + base) = v;
-    } else if (KIND == EPI_BIAS_RELU_ACT || KIND == EPI_BIAS_SILU_ACT || KIND == EPI_BIAS_ACT) {
-        store_act4(p.act, base, v);
-    } else if (KIND == EPI_RESID_F32) {
-        const float4 r = *reinterpret_cast<const float4 *>(p.resid + base);
-        *reinterpret_cast<float4 *>(p.out_f32 + base) =
-            make_float4(r.x + p.alpha * v.x, r.y + p.alpha * v.y, r.z + p.alpha * v.z, r.w + p.alpha * v.w);
-    } else if (KIND == EPI_GLU_F32) {
-        *reinterpret_cast<float2 *>(p.out_f32 + (size_t)row * p.ldo + (col0 >> 1)) =
-            make_float2(v.x * fast_sigmoid(v.y), v.z * fast_sigmoid(v.w));
-    }
 }
 
 // Split form used by the tcgen05 kernels: all global LOADS of a 16-column chunk (bias, residual)
@@ -203,9 +189,17 @@ __device__ __forceinline__ float4 epi_math(float4 v, const float4 &b, const floa
     return v;
 }
 template <int KIND>
-__device__ __forceinline__ void epi_store(const EpiParams &p, int row, int col0, const float4 &v) {
+__device__ __forceinline__ void epi_store(const EpiParams &p, int row, int col0, const float4 &v, const float4 &bu,
+                                          const float4 &bv) {
     const size_t base = (size_t)row * p.ldo + col0;
-    if (KIND == EPI_BIAS_F32 || KIND == EPI_BIAS_RELU_F32 || KIND == EPI_RESID_F32) {
+    if (KIND == EPI_QKV_ACT) {
+        if (col0 < p.qcols) {
+            store_act4(p.act, base, make_float4(v.x + bu.x, v.y + bu.y, v.z + bu.z, v.w + bu.w));
+            store_act4(p.act, base + p.qcols, make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w));
+        } else {
+            store_act4(p.act, base + p.qcols, v);
+        }
+    } else if (KIND == EPI_BIAS_F32 || KIND == EPI_BIAS_RELU_F32 || KIND == EPI_RESID_F32) {
         *reinterpret_cast<float4 *>(p.out_f32 + base) = v;
     } else if (KIND == EPI_GLU_F32) {
         *reinterpret_cast<float2 *>(p.out_f32 + (size_t)row * p.ldo + (col0 >> 1)) = make_float2(v.x, v.y);

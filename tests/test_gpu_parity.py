@@ -49,13 +49,13 @@ def eng110(pkg, m110, math_mode):
 
 
 # ------------------------------------------------------------------ tcgen05 GEMM kernel (K5) in isolation
-EPI = dict(BIAS_F32=0, RELU_F32=1, RELU_ACT=2, SILU_ACT=3, RESID=4, GLU=5, BIAS_ACT=6)
+EPI = dict(BIAS_F32=0, RELU_F32=1, RELU_ACT=2, SILU_ACT=3, RESID=4, GLU=5, BIAS_ACT=6, QKV=7)
 
 
 @pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, "BIAS_F32"), (300, 256, 256, "RELU_F32"), (126, 1025, 512, "BIAS_F32"),
                                        (777, 2048, 512, "SILU_ACT"), (513, 512, 2048, "RESID"), (256, 1024, 512, "GLU"),
                                        (130, 64, 64, "BIAS_ACT"), (1, 640, 512, "BIAS_F32"), (8064, 512, 2560, "BIAS_F32"),
-                                       (5020, 256, 256, "RELU_ACT")])
+                                       (5020, 256, 256, "RELU_ACT"), (300, 384, 128, "QKV"), (8064, 1536, 512, "QKV")])
 def test_tcgen05_gemm_matches_fp32_gemm(pkg, M, N, K, epi):
     from parakeet_cpp_b200.engine import selftest_gemm
     err, ref = selftest_gemm(M, N, K, EPI[epi], 0)
