@@ -1145,11 +1145,6 @@ pk_status pk_debug_tdt_phases(pk_engine *e, int64_t *out8) {
     if (!e || !out8) return PK_ERR_INVALID;
     cudaStreamSynchronize(e->stream);
     cudaMemcpy(out8, e->tdt_keys + 6 * (size_t)e->Bpad, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost);
-    if (getenv("PK_DEBUG_TDT_INNER")) {
-        long long d[8];
-        tdt_debug_fetch(d);
-        fprintf(stderr, "tdt inner: loop cycles %lld tail cycles %lld calls %lld | loop by site R>10: %lld R==5: %lld other: %lld\n", d[0], d[1], d[2], d[3], d[4], d[5]);
-    }
     return PK_OK;
 }
 

@@ -99,6 +99,5 @@ struct TdtParams {
     float *t_conf;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
-void tdt_debug_fetch(long long *out8);
 
 }  // namespace pk

@@ -78,32 +78,53 @@ layernorm_kernel(const float *__restrict__ x, int M, int d, const float *__restr
         }
 }
 
+// Depthwise conv over time (k = KS, "same" zero padding inside each utterance) + folded BatchNorm +
+// SiLU (reference src/encoder.cpp:59-75).  A thread owns 4 channels and DW_TT consecutive frames and
+// slides the KS-tap window down the column: DW_TT + KS - 1 float4 loads and one read of its 4 x KS
+// taps for DW_TT x 4 outputs (the previous one-frame-per-thread version re-read both 9x).
+constexpr int DW_TT = 16;
 template <int KS>
-__global__ void dwconv_bn_silu_kernel(const float *__restrict__ g, const int32_t *__restrict__ row_off,
-                                      int d, const float *__restrict__ w /* [d][KS] folded */,
-                                      const float *__restrict__ bias /* [d] folded */, ActBuf out) {
+__global__ void __launch_bounds__(128)
+dwconv_bn_silu_kernel(const float *__restrict__ g, const int32_t *__restrict__ row_off, int d,
+                      const float *__restrict__ w /* [d][KS] folded */, const float *__restrict__ bias /* [d] folded */,
+                      ActBuf out) {
     const int b = blockIdx.z;
     const int r0 = row_off[b], T = row_off[b + 1] - r0;
-    const int t = blockIdx.y * blockDim.y + threadIdx.y;
+    const int t0 = blockIdx.y * DW_TT;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (t >= T || c >= d) return;
-    float4 acc = *reinterpret_cast<const float4 *>(bias + c);
+    if (t0 >= T || c >= d) return;
     float wr[4][KS];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < KS; ++j) wr[q][j] = w[(c + q) * KS + j];
+        for (int j = 0; j < KS; ++j) wr[q][j] = __ldg(w + (c + q) * KS + j);
+    const float4 bs = *reinterpret_cast<const float4 *>(bias + c);
+    float4 win[KS];                      // win[j] = g[t - KS/2 + j]
 #pragma unroll
-    for (int j = 0; j < KS; ++j) {
-        const int tt = t - KS / 2 + j;
-        if (tt < 0 || tt >= T) continue;
-        const float4 x = *reinterpret_cast<const float4 *>(g + (size_t)(r0 + tt) * d + c);
-        acc.x = fmaf(wr[0][j], x.x, acc.x);
-        acc.y = fmaf(wr[1][j], x.y, acc.y);
-        acc.z = fmaf(wr[2][j], x.z, acc.z);
-        acc.w = fmaf(wr[3][j], x.w, acc.w);
+    for (int j = 0; j < KS - 1; ++j) {
+        const int tt = t0 - KS / 2 + j;
+        win[j + 1] = (tt >= 0 && tt < T) ? *reinterpret_cast<const float4 *>(g + (size_t)(r0 + tt) * d + c)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    store_act4(out, (size_t)(r0 + t) * d + c, make_float4(siluf_(acc.x), siluf_(acc.y), siluf_(acc.z), siluf_(acc.w)));
+#pragma unroll
+    for (int i = 0; i < DW_TT; ++i) {
+        const int t = t0 + i;
+        if (t >= T) break;
+#pragma unroll
+        for (int j = 0; j < KS - 1; ++j) win[j] = win[j + 1];
+        const int tn = t + KS / 2;
+        win[KS - 1] = (tn < T) ? *reinterpret_cast<const float4 *>(g + (size_t)(r0 + tn) * d + c)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = bs;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {   // same tap order as the one-frame version (bit-identical sums)
+            acc.x = fmaf(wr[0][j], win[j].x, acc.x);
+            acc.y = fmaf(wr[1][j], win[j].y, acc.y);
+            acc.z = fmaf(wr[2][j], win[j].z, acc.z);
+            acc.w = fmaf(wr[3][j], win[j].w, acc.w);
+        }
+        store_act4(out, (size_t)(r0 + t) * d + c, make_float4(siluf_(acc.x), siluf_(acc.y), siluf_(acc.z), siluf_(acc.w)));
+    }
 }
 
 __global__ void split_kernel(const float *__restrict__ x, size_t n4, ActBuf out) {
@@ -130,8 +151,8 @@ void launch_layernorm(const float *x, int M, int d, const float *w1, const float
 bool launch_dwconv_bn_silu(const float *g, const int32_t *row_off, int n_utt, int max_T, int d, int ks,
                            const float *w, const float *bias, ActBuf out, cudaStream_t st) {
     if (ks != 9) return false;
-    dim3 block(32, 8);
-    dim3 grid((d / 4 + 31) / 32, (max_T + 7) / 8, n_utt);
+    dim3 block(128);
+    dim3 grid((d / 4 + 127) / 128, (max_T + DW_TT - 1) / DW_TT, n_utt);
     dwconv_bn_silu_kernel<9><<<grid, block, 0, st>>>(g, row_off, d, w, bias, out);
     return true;
 }

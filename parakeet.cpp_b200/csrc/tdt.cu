@@ -39,7 +39,9 @@ constexpr int BCH = 64;    // utterances per pass (2 per lane)
 
 constexpr int KC = NWARP * 4;   // k-values staged per chunk (4 per warp)
 constexpr int NST = 4;          // cp.async ring depth
-constexpr int XLD = KC + 4;     // staged row stride (floats): 16 B aligned, conflict-free float4 reads
+constexpr int XLD = KC + 4;     // staged row stride (floats), CUDA-core path: 16 B aligned, conflict-free float4 reads
+constexpr int XLDM = KC + 8;    // staged row stride, tensor-core path: conflict-free float2 A-fragment reads
+constexpr int RPAD = 24;        // RMAX rounded up to whole 8-row MMA n-blocks
 
 __device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -67,8 +69,6 @@ __device__ __forceinline__ float4 load_w4(const float *p) {
 // bypass L1; a warp fetches 4 full lines), so the L2 latency is paid once per phase; within a chunk warp w owns k = 4w..4w+3
 // (K-split) and a lane owns utterances (lane, lane+32).  Partials are reduced across the 8
 // warps through `red`.
-__device__ long long g_tdt_dbg[8];
-
 // RB = compile-time bound on the rows of this call (the row loop is fully unrolled and the
 // compiler if-converts `r < R`, so every unrolled row costs its FMAs whether it is live or not).
 template <int RB, bool WS, typename XSrc, typename Fin>
@@ -90,7 +90,6 @@ __device__ __forceinline__ void rows_times_batch_rb(const float *W, int R, int K
         cp_async_commit();
     };
     float acc[RB][2];
-    const long long t0 = clock64();
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r][0] = acc[r][1] = 0.f;
 #pragma unroll
@@ -127,7 +126,6 @@ __device__ __forceinline__ void rows_times_batch_rb(const float *W, int R, int K
         }
     }
     cp_async_wait<0>();
-    const long long t1 = clock64();
 #pragma unroll
     for (int r = 0; r < RB; ++r)
         if (r < R) {
@@ -143,13 +141,6 @@ __device__ __forceinline__ void rows_times_batch_rb(const float *W, int R, int K
         if (bc + b2 < Bpad) fin(r, bc + b2, s);
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        g_tdt_dbg[0] += t1 - t0;
-        g_tdt_dbg[1] += clock64() - t1;
-        g_tdt_dbg[2] += 1;
-        const int site = (K == 0) ? 0 : (R > 10 ? 3 : (R == 5 ? 4 : 5));
-        g_tdt_dbg[site] += t1 - t0;
-    }
 }
 
 template <bool WS, typename XSrc, typename Fin>
@@ -159,6 +150,107 @@ __device__ __forceinline__ void rows_times_batch(const float *W, int R, int K, i
     else if (R <= 8) rows_times_batch_rb<8, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
     else if (R <= 12) rows_times_batch_rb<12, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
     else rows_times_batch_rb<RMAX, WS>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+}
+
+// ---- tensor-core variant for weights resident in shared memory --------------------------------
+// Same contract as rows_times_batch_rb, on mma.sync.m16n8k16 with the bf16 hi/lo operand split of
+// the encoder GEMMs (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, fp32 accumulate: ~16 mantissa bits).
+//   M = utterances (64 = 4 blocks of 16), N = weight rows (NB blocks of 8), K in chunks of KC = 32.
+//   W is pre-split at kernel start: row r = [hi: K+4 bf16][lo: K+4 bf16] (the +4 pad makes the
+//   32-bit B-fragment reads of 8 rows conflict-free).  x arrives as fp32 [utterance][k] through the
+//   same cp.async ring (row stride XLDM) and is split in registers while building A fragments.
+//   Warp w owns utterance block (w & 3) and k-step (w >> 2) of every chunk; the two k-step halves
+//   are added in `red` in a fixed order.
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2(float2 x, uint32_t &hi, uint32_t &lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(x.x, x.y);
+    float2 hf = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(x.x - hf.x, x.y - hf.y);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+}
+__device__ __forceinline__ uint32_t lds32(const bf16 *p) {
+    uint32_t v;   // weights never change during the kernel: not volatile
+    asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+template <int NB, typename XSrc, typename Fin>
+__device__ __forceinline__ void rows_times_batch_mma(const bf16 *W, int R, int K, int Bpad, int bc, XSrc xsrc,
+                                                     float *xs, float *red, Fin fin) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
+    const int mb = warp & 3, ks = warp >> 2;
+    const int KP = K + 4, RS = 2 * KP;
+    const int nchunks = K / KC;
+    const int pc = threadIdx.x & 7, b_a = threadIdx.x >> 3;
+    const bool va = (bc + b_a) < Bpad, vb = (bc + b_a + 32) < Bpad;
+    const float *xa_src = xsrc(va ? bc + b_a : 0) + pc * 4;
+    const float *xb_src = xsrc(vb ? bc + b_a + 32 : 0) + pc * 4;
+    auto issue = [&](int c) {
+        if (c < nchunks) {
+            float *dst = xs + (size_t)(c % NST) * BCH * XLDM + pc * 4;
+            if (va) cp_async16(dst + b_a * XLDM, xa_src + c * KC);
+            if (vb) cp_async16(dst + (b_a + 32) * XLDM, xb_src + c * KC);
+        }
+        cp_async_commit();
+    };
+    float acc[NB][4];
+    const bf16 *wrow[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+        wrow[nb] = W + (size_t)min(nb * 8 + g, R - 1) * RS + ks * 16 + 2 * cq;   // rows >= R: clamped, discarded
+    }
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) issue(c);
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();                       // chunk c landed for everyone; chunk c-1 fully consumed
+        issue(c + NST - 1);
+        const float *xc = xs + (size_t)(c % NST) * BCH * XLDM + (mb * 16 + g) * XLDM + ks * 16 + 2 * cq;
+        uint32_t ah[4], al[4];
+        split2(*reinterpret_cast<const float2 *>(xc), ah[0], al[0]);
+        split2(*reinterpret_cast<const float2 *>(xc + 8 * XLDM), ah[1], al[1]);
+        split2(*reinterpret_cast<const float2 *>(xc + 8), ah[2], al[2]);
+        split2(*reinterpret_cast<const float2 *>(xc + 8 * XLDM + 8), ah[3], al[3]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            const bf16 *wp = wrow[nb] + c * KC;
+            const uint32_t b0h = lds32(wp), b1h = lds32(wp + 8), b0l = lds32(wp + KP), b1l = lds32(wp + KP + 8);
+            mma_bf16(acc[nb], ah, b0h, b1h);
+            mma_bf16(acc[nb], ah, b0l, b1l);
+            mma_bf16(acc[nb], al, b0h, b1h);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        const int n = nb * 8 + 2 * cq, u = mb * 16 + g;
+        red[(ks * RPAD + n) * BCH + u] = acc[nb][0];
+        red[(ks * RPAD + n + 1) * BCH + u] = acc[nb][1];
+        red[(ks * RPAD + n) * BCH + u + 8] = acc[nb][2];
+        red[(ks * RPAD + n + 1) * BCH + u + 8] = acc[nb][3];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < R * BCH; idx += blockDim.x) {
+        const int r = idx / BCH, b2 = idx % BCH;
+        const float s = red[r * BCH + b2] + red[(RPAD + r) * BCH + b2];
+        if (bc + b2 < Bpad) fin(r, bc + b2, s);
+    }
+    __syncthreads();
+}
+
+template <typename XSrc, typename Fin>
+__device__ __forceinline__ void rows_times_batch_s(const bf16 *W, int R, int K, int Bpad, int bc, XSrc xsrc, float *xs,
+                                                   float *red, Fin fin) {
+    if (R <= 8) rows_times_batch_mma<1>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+    else if (R <= 16) rows_times_batch_mma<2>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
+    else rows_times_batch_mma<3>(W, R, K, Bpad, bc, xsrc, xs, red, fin);
 }
 
 // Monotonic-counter grid barrier (all CTAs are co-resident: cooperative launch).  Cheaper than
@@ -207,8 +299,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
     // ---- shared memory carve-up: [red][gates][state][weights...]
     float *red = sm;                               // [NWARP][RMAX][BCH]
     float *gsm = red + NWARP * RMAX * BCH;         // [RMAX][BCH] gate pre-activations / logits
-    float *xs = gsm + RMAX * BCH;                  // [NST][BCH][XLD] cp.async ring for the x vectors
-    int *s_cur = reinterpret_cast<int *>(xs + NST * BCH * XLD);   // replicated decode state, [Bpad] each
+    float *xs = gsm + RMAX * BCH;                  // [NST][BCH][XLDM] cp.async ring for the x vectors
+    int *s_cur = reinterpret_cast<int *>(xs + NST * BCH * XLDM);  // replicated decode state, [Bpad] each
     int *s_token = s_cur + Bpad, *s_tpos = s_token + Bpad, *s_active = s_tpos + Bpad, *s_ntok = s_active + Bpad;
     int *s_pend = s_ntok + Bpad;                   // slot of a token whose confidence is still pending (-1: none)
     float *wsm = reinterpret_cast<float *>(s_pend + Bpad);
@@ -216,34 +308,51 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
     // LSTM weights arrive "unit-major" (row = unit*4 + gate, engine.cu), so this CTA's rows
     // [u0*4, u1*4) are one contiguous block: W_hh always lives in shared memory, W_ih of the
     // upper layers too when it fits (else it is streamed from L2).
-    const float *w_hh[PK_MAX_LSTM], *w_ih[PK_MAX_LSTM];
+    // Shared-memory weights are stored pre-split for the tensor-core path: row = [hi: K+4][lo: K+4] bf16
+    // (= K+4 floats per row).
+    auto stage_rows = [&](bf16 *dst, const float *src, int rows, int K) {
+        const int KP = K + 4, RS = 2 * KP;
+        for (int idx = tid; idx < rows * K; idx += blockDim.x) {
+            const int r = idx / K, k = idx - r * K;
+            const float v = src[idx];
+            const bf16 h = __float2bfloat16_rn(v);
+            dst[(size_t)r * RS + k] = h;
+            dst[(size_t)r * RS + KP + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    };
+    const int RSP = 2 * (P + 4), RSJ = 2 * (J + 4);          // smem row strides (bf16) for K = P / K = J
+    const bf16 *w_hh[PK_MAX_LSTM], *w_ih_s[PK_MAX_LSTM];
+    const float *w_ih_g[PK_MAX_LSTM];
+    bf16 *wbf = reinterpret_cast<bf16 *>(wsm);
     {
-        float *cur = wsm;
+        bf16 *cur = wbf;
         for (int l = 0; l < L; ++l) {
-            for (int idx = tid; idx < nU * 4 * P; idx += blockDim.x) cur[idx] = p.Whh[l][(size_t)u0 * 4 * P + idx];
+            stage_rows(cur, p.Whh[l] + (size_t)u0 * 4 * P, nU * 4, P);
             w_hh[l] = cur;
-            cur += (size_t)UPC * 4 * P;
-            w_ih[l] = nullptr;
+            cur += (size_t)UPC * 4 * RSP;
+            w_ih_s[l] = nullptr;
+            w_ih_g[l] = nullptr;
             if (l > 0) {
                 if (p.wih_in_smem) {
-                    for (int idx = tid; idx < nU * 4 * P; idx += blockDim.x) cur[idx] = p.Wih[l][(size_t)u0 * 4 * P + idx];
-                    w_ih[l] = cur;
-                    cur += (size_t)UPC * 4 * P;
+                    stage_rows(cur, p.Wih[l] + (size_t)u0 * 4 * P, nU * 4, P);
+                    w_ih_s[l] = cur;
+                    cur += (size_t)UPC * 4 * RSP;
                 } else {
-                    w_ih[l] = p.Wih[l] + (size_t)u0 * 4 * P;
+                    w_ih_g[l] = p.Wih[l] + (size_t)u0 * 4 * P;
                 }
             }
         }
     }
-    float *w_p = wsm + (size_t)p.smem_lstm_floats;          // [JPC][P]
-    for (int idx = tid; idx < (j1 - j0) * P; idx += blockDim.x) w_p[idx] = p.Wp[(size_t)j0 * P + idx];
-    const float *w_o;                                        // [OPC][J], shared if it fits
+    bf16 *w_p = wbf + 2 * (size_t)p.smem_lstm_floats;        // [JPC] rows, K = P
+    stage_rows(w_p, p.Wp + (size_t)j0 * P, j1 - j0, P);
+    const bf16 *w_o_s = nullptr;                             // [OPC] rows, K = J: shared if it fits
+    const float *w_o_g = nullptr;
     if (p.out_in_smem) {
-        float *w_os = w_p + (size_t)JPC * P;
-        for (int idx = tid; idx < (o1 - o0) * J; idx += blockDim.x) w_os[idx] = p.Wout[(size_t)o0 * J + idx];
-        w_o = w_os;
+        bf16 *w_os = w_p + (size_t)JPC * RSP;
+        stage_rows(w_os, p.Wout + (size_t)o0 * J, o1 - o0, J);
+        w_o_s = w_os;
     } else {
-        w_o = p.Wout + (size_t)o0 * J;
+        w_o_g = p.Wout + (size_t)o0 * J;
     }
     for (int b = tid; b < Bpad; b += blockDim.x) {           // initial state (tdt.cpp:49-59)
         s_cur[b] = 0;
@@ -304,15 +413,15 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
             for (int bc = 0; bc < Bpad; bc += BCH) {
                 const int R = nU * 4;
                 if (R > 0) {
-                    rows_times_batch<true>(
+                    rows_times_batch_s(
                         w_hh[l], R, P, Bpad, bc,
                         [&](int b) { return h_rd + ((size_t)(l * 2 + s_cur[b])) * HS + (size_t)b * P; }, xs, red,
                         [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v; });
                     if (l > 0) {  // input part: W_ih . h'_{l-1}(new)
                         auto xh = [&](int b) { return h_rd + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; };
                         auto fa = [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] += v; };
-                        if (p.wih_in_smem) rows_times_batch<true>(w_ih[l], R, P, Bpad, bc, xh, xs, red, fa);
-                        else rows_times_batch<false>(w_ih[l], R, P, Bpad, bc, xh, xs, red, fa);
+                        if (p.wih_in_smem) rows_times_batch_s(w_ih_s[l], R, P, Bpad, bc, xh, xs, red, fa);
+                        else rows_times_batch<false>(w_ih_g[l], R, P, Bpad, bc, xh, xs, red, fa);
                     }
                     __syncthreads();
                     for (int idx = tid; idx < nU * BCH; idx += blockDim.x) {
@@ -351,8 +460,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
         for (int bc = 0; bc < Bpad; bc += BCH)
             for (int rg = j0; rg < j1; rg += RMAX) {
                 const int R = min(RMAX, j1 - rg);
-                rows_times_batch<true>(
-                    w_p + (size_t)(rg - j0) * P, R, P, Bpad, bc,
+                rows_times_batch_s(
+                    w_p + (size_t)(rg - j0) * RSP, R, P, Bpad, bc,
                     [&](int b) { return h_rd + ((size_t)((L - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; }, xs, red,
                     [&](int r, int b, float v) {
                         float e = 0.f;
@@ -377,9 +486,9 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                 auto xz = [&](int b) { return z_rd + (size_t)b * J; };
                 auto fl = [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v + p.bout[rg + r]; };
                 if (p.out_in_smem)
-                    rows_times_batch<true>(w_o + (size_t)(rg - o0) * J, R, J, Bpad, bc, xz, xs, red, fl);
+                    rows_times_batch_s(w_o_s + (size_t)(rg - o0) * RSJ, R, J, Bpad, bc, xz, xs, red, fl);
                 else
-                    rows_times_batch<false>(w_o + (size_t)(rg - o0) * J, R, J, Bpad, bc, xz, xs, red, fl);
+                    rows_times_batch<false>(w_o_g + (size_t)(rg - o0) * J, R, J, Bpad, bc, xz, xs, red, fl);
                 __syncthreads();
                 if (tid < BCH) {
                     for (int r = 0; r < R; ++r) {
@@ -483,9 +592,10 @@ __global__ void tdt_init_kernel(TdtParams p) {
 size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, bool *wih_in_smem, int *lstm_floats) {
     const int UPC = (p.P + grid - 1) / grid, JPC = (p.J + grid - 1) / grid, OPC = (p.V + p.D + grid - 1) / grid;
     const size_t budget = 225 * 1024 / sizeof(float);
-    size_t fixed = (size_t)NWARP * RMAX * BCH + RMAX * BCH + (size_t)NST * BCH * XLD + 6 * (size_t)p.Bpad;
-    const size_t hh = (size_t)p.L * UPC * 4 * p.P, ih = (size_t)(p.L - 1) * UPC * 4 * p.P;
-    const size_t wp = (size_t)JPC * p.P, wo = (size_t)OPC * p.J;
+    size_t fixed = (size_t)NWARP * RMAX * BCH + RMAX * BCH + (size_t)NST * BCH * XLDM + 6 * (size_t)p.Bpad;
+    // shared-memory weight rows are bf16 hi/lo with a 4-element pad each: K + 4 floats per row
+    const size_t hh = (size_t)p.L * UPC * 4 * (p.P + 4), ih = (size_t)(p.L - 1) * UPC * 4 * (p.P + 4);
+    const size_t wp = (size_t)JPC * (p.P + 4), wo = (size_t)OPC * (p.J + 4);
     size_t total = fixed + hh + wp;                 // always resident
     *wih_in_smem = (ih == 0) || (total + ih <= budget);
     if (*wih_in_smem) total += ih;
@@ -493,12 +603,6 @@ size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, bool *wih
     *out_in_smem = total + wo <= budget;
     if (*out_in_smem) total += wo;
     return total * sizeof(float);
-}
-
-void tdt_debug_fetch(long long *out8) {
-    cudaMemcpyFromSymbol(out8, g_tdt_dbg, sizeof(long long) * 8);
-    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaMemcpyToSymbol(g_tdt_dbg, z, sizeof(z));
 }
 
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st) {
