@@ -857,6 +857,7 @@ pk_status pk_engine::run_tdt() {
     p.pl_max = pl_max; p.pl_sum = pl_sum;
     p.key_lab = tdt_keys; p.key_dur = tdt_keys + 3 * (size_t)Bpad;
     p.dbg = reinterpret_cast<long long *>(tdt_keys + 6 * (size_t)Bpad);
+    p.dbg_variant = getenv("PK_TDT_DBG") ? atoi(getenv("PK_TDT_DBG")) : 0;
     p.tok = tok; p.t_start = t_start; p.t_end = t_end; p.t_conf = t_conf;
     // initial state: zero LSTM state, token = blank (SOS), t = 0 (tdt.cpp:49-59)
     const size_t HS = (size_t)p.P * bp;

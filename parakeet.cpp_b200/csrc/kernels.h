@@ -94,6 +94,7 @@ struct TdtParams {
     unsigned long long *key_lab, *key_dur;    // [3][Bpad] packed (value, index) arg-max keys
     unsigned int *bar;                        // grid barrier counter
     long long *dbg;                           // [8] optional: CTA-0 cycles per phase, steps
+    int dbg_variant;                          // 0: {P1,B1,P2,B2,P3,B3,P4}; 1: {P1 products, P1 cell, conf, P2, rest}
     int32_t *tok;                             // [n_utt][1+cap]
     int32_t *t_start, *t_end;                 // [n_utt][cap]
     float *t_conf;

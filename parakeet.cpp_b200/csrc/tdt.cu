@@ -38,7 +38,7 @@ constexpr int NWARP = 8;
 constexpr int BCH = 64;    // utterances per pass (2 per lane)
 
 constexpr int KC = NWARP * 4;   // k-values staged per chunk (4 per warp)
-constexpr int NST = 4;          // cp.async ring depth
+constexpr int NST = 8;          // cp.async ring depth
 constexpr int XLD = KC + 4;     // staged row stride (floats), CUDA-core path: 16 B aligned, conflict-free float4 reads
 constexpr int XLDM = KC + 8;    // staged row stride, tensor-core path: conflict-free float2 A-fragment reads
 constexpr int RPAD = 24;        // RMAX rounded up to whole 8-row MMA n-blocks
@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                         w_hh[l], R, P, Bpad, bc,
                         [&](int b) { return h_rd + ((size_t)(l * 2 + s_cur[b])) * HS + (size_t)b * P; }, xs, red,
                         [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] = v; });
+                    if (p.dbg_variant == 1) tick(0);
                     if (l > 0) {  // input part: W_ih . h'_{l-1}(new)
                         auto xh = [&](int b) { return h_rd + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; };
                         auto fa = [&](int r, int b, float v) { gsm[r * BCH + (b - bc)] += v; };
@@ -448,14 +449,15 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                     __syncthreads();
                 }
             }
-            tick(0);
+            tick(p.dbg_variant == 1 ? 1 : 0);
             grid_barrier(p.bar, G * (++nbar));
-            tick(1);
+            tick(p.dbg_variant == 1 ? 4 : 1);
         }
         // confidences of the tokens emitted in the previous step (partials are complete now)
         if (step > 0) finalize_conf((step - 1) % 3);
         __syncthreads();
         for (int b = tid; b < Bpad; b += blockDim.x) s_pend[b] = -1;
+        if (p.dbg_variant == 1) tick(2);
         // ================= P2: joint hidden z = relu(EP[t] + Wp . h') =================
         for (int bc = 0; bc < Bpad; bc += BCH)
             for (int rg = j0; rg < j1; rg += RMAX) {
@@ -474,9 +476,9 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                         for (int rr = 0; rr < TDT_NREP; ++rr) p.z[(size_t)rr * ZREP + (size_t)b * J + rg + r] = zv;
                     });
             }
-        tick(2);
+        tick(p.dbg_variant == 1 ? 3 : 2);
         grid_barrier(p.bar, G * (++nbar));
-        tick(3);
+        tick(p.dbg_variant == 1 ? 4 : 3);
         // ================= P3: logits -> per-CTA partials + global arg-max keys =================
         for (int bc = 0; bc < Bpad; bc += BCH) {
             float lmax = -INFINITY, lsum = 0.f, dmax = -INFINITY;
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
         }
         tick(4);
         grid_barrier(p.bar, G * (++nbar));
-        tick(5);
+        tick(p.dbg_variant == 1 ? 4 : 5);
         // ================= P4 (replicated in every CTA): state update =================
         int any = 0;
         for (int b = tid; b < p.n_utt; b += blockDim.x) {
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
             any |= act ? 1 : 0;
         }
         any = __syncthreads_or(any);
-        tick(6);
+        tick(p.dbg_variant == 1 ? 4 : 6);
         if (!any || step + 1 >= p.max_steps) break;
     }
     if (p.dbg && g == 0 && tid == 0) {
