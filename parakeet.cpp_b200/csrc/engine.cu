@@ -105,6 +105,7 @@ struct pk_engine {
     float *Whh[PK_MAX_LSTM] = {}, *Wih[PK_MAX_LSTM] = {}, *bih[PK_MAX_LSTM] = {};
     float *Whh_um[PK_MAX_LSTM] = {}, *Wih_um[PK_MAX_LSTM] = {};   // unit-major copies (decode kernel)
     float *Wp = nullptr, *Wout = nullptr, *bout = nullptr;
+    bf16 *Whh_s[PK_MAX_LSTM] = {}, *Wih_s[PK_MAX_LSTM] = {}, *Wp_s = nullptr, *Wout_s = nullptr;   // pre-split rows (tdt.cu)
 
     // ---- workspace
     float *d_pcm = nullptr;
@@ -506,6 +507,18 @@ pk_status pk_engine::load(const char *path) {
         launch_gemm_simt(embed, P, wih0, P, V, 4 * P, P, ep, stream);
         ++launches;
     }
+    {   // decode-kernel weights, split once into bf16 hi/lo rows
+        auto split = [&](const float *src, int rows, int K, bf16 **out) {
+            *out = dalloc<bf16>((size_t)rows * 2 * (K + 4));
+            if (*out) launch_tdt_split_rows(src, rows, K, *out, stream);
+            ++launches;
+            return *out != nullptr;
+        };
+        bool ok = split(Wp, J, P, &Wp_s) && split(Wout, V + D, J, &Wout_s);
+        for (int l = 0; l < c.lstm_layers && ok; ++l)
+            ok = split(Whh_um[l], 4 * P, P, &Whh_s[l]) && split(Wih_um[l], 4 * P, P, &Wih_s[l]);
+        if (!ok) return fail(PK_ERR_CUDA, "cudaMalloc failed (TDT split weights)");
+    }
     PK_CUDA(cudaStreamSynchronize(stream));
     PK_CUDA(cudaGetLastError());
     return PK_OK;
@@ -555,9 +568,8 @@ pk_status pk_engine::alloc_workspace() {
     t_conf = dalloc<float>(B * (size_t)cap);
     Bpad = ((Bmax + 31) / 32) * 32;
     const size_t HS = (size_t)c.pred_hidden * Bpad;
-    hbuf = dalloc<float>(HS * 2 * c.lstm_layers * TDT_NREP);
-    cbuf = dalloc<float>(HS * 2 * c.lstm_layers);
-    zbuf = dalloc<float>((size_t)c.joint_hidden * Bpad * TDT_NREP);
+    hbuf = dalloc<float>(HS * 2 * c.lstm_layers);                  // bf16 hi + lo planes
+    zbuf = dalloc<float>((size_t)c.joint_hidden * Bpad);           // bf16 hi + lo planes
     tdt_ints = dalloc<int32_t>((size_t)Bpad + 4);
     tdt_keys = dalloc<unsigned long long>((size_t)6 * Bpad + 8);
     const size_t PG = (size_t)3 * num_sms * Bpad;
@@ -850,19 +862,17 @@ pk_status pk_engine::run_tdt() {
     p.max_steps = maxT + cap + 2;
     for (int i = 0; i < 8; ++i) p.durations[i] = c.durations[i];
     p.EP = EP; p.row_off = d_row_off; p.G0 = G0;
-    for (int l = 0; l < c.lstm_layers; ++l) { p.Whh[l] = Whh_um[l]; p.Wih[l] = Wih_um[l]; p.bih[l] = bih[l]; }
-    p.Wp = Wp; p.Wout = Wout; p.bout = bout;
-    p.hbuf = hbuf; p.cbuf = cbuf; p.z = zbuf;
+    for (int l = 0; l < c.lstm_layers; ++l) { p.Whh[l] = Whh_s[l]; p.Wih[l] = Wih_s[l]; p.bih[l] = bih[l]; }
+    p.Wp = Wp_s; p.Wout = Wout_s; p.bout = bout;
+    p.hbuf = hbuf; p.z = zbuf;
     p.overflow = tdt_ints; p.bar = reinterpret_cast<unsigned int *>(tdt_ints + Bpad);
     p.pl_max = pl_max; p.pl_sum = pl_sum;
     p.key_lab = tdt_keys; p.key_dur = tdt_keys + 3 * (size_t)Bpad;
     p.dbg = reinterpret_cast<long long *>(tdt_keys + 6 * (size_t)Bpad);
-    p.dbg_variant = getenv("PK_TDT_DBG") ? atoi(getenv("PK_TDT_DBG")) : 0;
     p.tok = tok; p.t_start = t_start; p.t_end = t_end; p.t_conf = t_conf;
     // initial state: zero LSTM state, token = blank (SOS), t = 0 (tdt.cpp:49-59)
     const size_t HS = (size_t)p.P * bp;
-    PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * TDT_NREP * sizeof(float), stream));
-    PK_CUDA(cudaMemsetAsync(cbuf, 0, HS * 2 * p.L * sizeof(float), stream));
+    PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * sizeof(float), stream));
     cudaError_t ce;
     {
         Scope sc(this, CAT_TDT);

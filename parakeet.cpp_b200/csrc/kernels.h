@@ -5,7 +5,6 @@
 #include "pk_common.cuh"
 
 #define PK_MAX_LSTM 4
-#define TDT_NREP 8   // replicas of the TDT h / z vectors (see tdt.cu)
 
 namespace pk {
 
@@ -80,25 +79,26 @@ struct TdtParams {
     const float *EP;                          // [M][J] enc_proj(enc) + bias
     const int32_t *row_off;                   // [n_utt+1]
     const float *G0;                          // [V][4P] W_ih0 . E[token] + b0
-    const float *Whh[PK_MAX_LSTM];            // [P*4][P] unit-major: row = unit*4 + gate(i,f,g,o)
-    const float *Wih[PK_MAX_LSTM];            // [P*4][P] unit-major (layers >= 1)
+    // weights pre-split for the tensor-core products (launch_tdt_split_rows): row = [hi: K+4][lo: K+4] bf16
+    const bf16 *Whh[PK_MAX_LSTM];             // [P*4] rows, K = P, unit-major: row = unit*4 + gate(i,f,g,o)
+    const bf16 *Wih[PK_MAX_LSTM];             // [P*4] rows, K = P, unit-major (layers >= 1)
     const float *bih[PK_MAX_LSTM];            // [4P]    (layers >= 1)
-    const float *Wp;                          // [J][P]
-    const float *Wout;                        // [V+D][J]
+    const bf16 *Wp;                           // [J] rows, K = P
+    const bf16 *Wout;                         // [V+D] rows, K = J
     const float *bout;                        // [V+D]
-    float *hbuf;                              // [NREP][L][2][Bpad][P] LSTM h (two planes per utterance)
-    float *cbuf;                              // [L][2][Bpad][P]       LSTM c
-    float *z;                                 // [NREP][Bpad][J]       joint hidden
+    float *hbuf;                              // bf16 [hi|lo][L][2][Bpad][P] LSTM h (two state planes per utterance), zeroed
+    float *z;                                 // bf16 [hi|lo][Bpad][J]       joint hidden
     int32_t *overflow;                        // [Bpad]
     float *pl_max, *pl_sum;                   // [3][grid][Bpad] per-CTA (max, sum-exp) partials
     unsigned long long *key_lab, *key_dur;    // [3][Bpad] packed (value, index) arg-max keys
     unsigned int *bar;                        // grid barrier counter
     long long *dbg;                           // [8] optional: CTA-0 cycles per phase, steps
-    int dbg_variant;                          // 0: {P1,B1,P2,B2,P3,B3,P4}; 1: {P1 products, P1 cell, conf, P2, rest}
     int32_t *tok;                             // [n_utt][1+cap]
     int32_t *t_start, *t_end;                 // [n_utt][cap]
     float *t_conf;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
+// fp32 [rows][K] -> [rows][2 * (K + 4)] bf16 = [hi: K+4][lo: K+4]
+void launch_tdt_split_rows(const float *src, int rows, int K, bf16 *dst, cudaStream_t st);
 
 }  // namespace pk
