@@ -82,6 +82,12 @@ struct pk_engine {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_h2d = nullptr;              // recorded after the staging copies of a batch
+    // Host PCM arrives in H2D_CHUNKS utterance groups on `copy_stream`; the front end (mel, conv1+dw1)
+    // of group i runs on `stream` as soon as its samples have landed, i.e. under the DMA of group i+1.
+    static constexpr int H2D_CHUNKS = 8;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[H2D_CHUNKS] = {}, ev_front = nullptr;
+    bool front_done = false;                   // front end of the staged batch already launched (chunked path)
     std::string err;
     int64_t launches = 0;
     std::vector<void *> allocs;
@@ -211,7 +217,8 @@ struct pk_engine {
     pk_status upload_shapes();
     void gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiParams epi);
     pk_status gemm_err = PK_OK;
-    pk_status run_mel();
+    pk_status run_mel(int u0 = 0, int u1 = -1);
+    pk_status run_conv1(int u0 = 0, int u1 = -1);
     pk_status run_encoder(float *sub_out_host, float *layers_out_host);
     pk_status run_ctc(float *logprobs_dev_or_null);
     pk_status run_tdt();
@@ -657,10 +664,27 @@ void pk_engine::gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiPara
     ++launches;
 }
 
-pk_status pk_engine::run_mel() {
+// Front end of utterances [u0, u1): the offset arrays hold absolute positions in the packed
+// buffers, so a sub-range is just a shifted view of them.
+pk_status pk_engine::run_mel(int u0, int u1) {
+    if (u1 < 0) u1 = n_utt;
+    if (u1 <= u0) return PK_OK;
     Scope sc(this, CAT_MEL);
-    launch_mel(d_pcm, d_pcm_off, d_frame_off, n_utt, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
+    launch_mel(d_pcm, d_pcm_off + u0, d_frame_off + u0, u1 - u0, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
     launches += 2;
+    PK_CUDA(cudaGetLastError());
+    return PK_OK;
+}
+
+// conv1_ + ReLU + dw1_ of ConvSubsampling (encoder.cpp:219-241), first kernel of the encoder
+pk_status pk_engine::run_conv1(int u0, int u1) {
+    if (u1 < 0) u1 = n_utt;
+    if (u1 <= u0) return PK_OK;
+    const pk_config &c = cfg;
+    Scope sc(this, CAT_SUBSAMPLE);
+    launch_subsample_conv1_dw1(feats, d_frame_off + u0, d_s2_off + u0, u1 - u0, maxT2, c.mel_bins, c.sub_channels, c1_w, c1_b,
+                               dw1_w, dw1_b, sub1, stream);
+    ++launches;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -674,13 +698,7 @@ pk_status pk_engine::run_mel() {
 pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
     const pk_config &c = cfg;
     const int C = c.sub_channels, d = c.d_model, H = c.n_heads, hd = d / H;
-    // ---- ConvSubsampling (encoder.cpp:219-241)
-    {
-        Scope sc(this, CAT_SUBSAMPLE);
-        launch_subsample_conv1_dw1(feats, d_frame_off, d_s2_off, n_utt, maxT2, c.mel_bins, C, c1_w, c1_b, dw1_w, dw1_b,
-                                   sub1, stream);
-    }
-    ++launches;
+    // ---- ConvSubsampling (encoder.cpp:219-241); conv1_/dw1_ already ran (run_conv1)
     {
         EpiParams ep;
         ep.kind = EPI_BIAS_RELU_F32;
@@ -971,8 +989,13 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
         g_create_err = "cudaStreamCreate failed";
         return PK_ERR_CUDA;
     }
-    if (cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming) != cudaSuccess) {
-        g_create_err = "cudaEventCreate failed";
+    bool ev_ok = cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_front, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < pk_engine::H2D_CHUNKS && ev_ok; ++i)
+        ev_ok = cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok) {
+        g_create_err = "cudaEventCreate / cudaStreamCreate failed";
         return PK_ERR_CUDA;
     }
     e->Bmax = c.max_batch;
@@ -1009,6 +1032,10 @@ void pk_engine_destroy(pk_engine *e) {
     if (e->h_te) cudaFreeHost(e->h_te);
     if (e->h_tc) cudaFreeHost(e->h_tc);
     if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
+    if (e->ev_front) cudaEventDestroy(e->ev_front);
+    for (int i = 0; i < pk_engine::H2D_CHUNKS; ++i)
+        if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1180,25 +1207,57 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
     const bool pinned = cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();   // an unregistered host pointer is not an error for us
     cudaError_t ce = cudaSuccess;
+    e->front_done = false;
     if (pinned && packed) {
-        ce = cudaMemcpyAsync(e->d_pcm, pcm + offsets[0], total * sizeof(float), cudaMemcpyHostToDevice, e->stream);
-    } else {
-        // pageable -> pinned staging -> device, utterance by utterance so the DMA of utterance i
-        // overlaps the host copy of utterance i+1; utterances are re-packed back to back
-        for (int i = 0; i < n_utt && ce == cudaSuccess; ++i) {
-            const size_t ns = (size_t)(offsets[i + 1] - offsets[i]);
-            memcpy(e->h_pcm + e->pcm_off[i], pcm + offsets[i], ns * sizeof(float));
-            ce = cudaMemcpyAsync(e->d_pcm + e->pcm_off[i], e->h_pcm + e->pcm_off[i], ns * sizeof(float),
-                                 cudaMemcpyHostToDevice, e->stream);
+        // DMA in utterance groups on the copy stream; mel + conv1/dw1 of a group start as soon as it has
+        // landed, under the DMA of the next group (the copy of 64 x 10 s is ~0.8 ms of PCIe time).
+        if ((s = e->upload_shapes())) return s;
+        ce = cudaEventRecord(e->ev_front, e->stream);                  // d_pcm of the previous batch is free
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->copy_stream, e->ev_front, 0);
+        const int nch = std::min<int>(pk_engine::H2D_CHUNKS, n_utt);
+        int u0 = 0;
+        for (int i = 0; i < nch && ce == cudaSuccess; ++i) {
+            // group boundaries balanced by samples
+            int u1 = (i == nch - 1) ? n_utt : u0 + 1;
+            while (i < nch - 1 && u1 < n_utt - (nch - 1 - i) && (size_t)e->pcm_off[u1] < total * (size_t)(i + 1) / nch) ++u1;
+            const size_t o0 = (size_t)e->pcm_off[u0], o1 = (size_t)e->pcm_off[u1];
+            ce = cudaMemcpyAsync(e->d_pcm + o0, pcm + offsets[0] + o0, (o1 - o0) * sizeof(float), cudaMemcpyHostToDevice,
+                                 e->copy_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_chunk[i], e->copy_stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->stream, e->ev_chunk[i], 0);
+            if (ce != cudaSuccess) break;
+            if ((s = e->run_mel(u0, u1))) return s;
+            if ((s = e->run_conv1(u0, u1))) return s;
+            u0 = u1;
         }
+        if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D pcm: ") + cudaGetErrorString(ce));
+        e->front_done = true;
+        return PK_OK;
+    }
+    // pageable -> pinned staging -> device, utterance by utterance so the DMA of utterance i
+    // overlaps the host copy of utterance i+1; utterances are re-packed back to back
+    for (int i = 0; i < n_utt && ce == cudaSuccess; ++i) {
+        const size_t ns = (size_t)(offsets[i + 1] - offsets[i]);
+        memcpy(e->h_pcm + e->pcm_off[i], pcm + offsets[i], ns * sizeof(float));
+        ce = cudaMemcpyAsync(e->d_pcm + e->pcm_off[i], e->h_pcm + e->pcm_off[i], ns * sizeof(float),
+                             cudaMemcpyHostToDevice, e->stream);
     }
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D pcm: ") + cudaGetErrorString(ce));
     return e->upload_shapes();
 }
 
-static pk_status run_pipeline(pk_engine *e, pk_decoder dec) {
+// Front end (mel + conv1/dw1; 3 launches, always plain launches) unless pk_stage_pcm already ran it
+// group by group under the H2D copy.
+static pk_status run_front(pk_engine *e) {
+    if (e->front_done) return PK_OK;
     pk_status s;
     if ((s = e->run_mel())) return s;
+    if ((s = e->run_conv1())) return s;
+    e->front_done = true;
+    return PK_OK;
+}
+static pk_status run_pipeline(pk_engine *e, pk_decoder dec) {   // everything after the front end
+    pk_status s;
     if ((s = e->run_encoder(nullptr, nullptr))) return s;
     return dec == PK_DECODER_CTC ? e->run_ctc(nullptr) : e->run_tdt();
 }
@@ -1209,6 +1268,11 @@ pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
     if (!e || e->n_utt <= 0) return PK_ERR_INVALID;
     cudaSetDevice(e->device);
     if (e->gemm_err) return e->gemm_err;
+    {
+        pk_status fs = run_front(e);
+        e->front_done = false;      // a second pk_run_staged of the same staged batch re-runs the front end
+        if (fs) return fs;
+    }
     if (!e->use_graphs || e->prof_on) return run_pipeline(e, dec);
     std::string key(1, dec == PK_DECODER_CTC ? 'c' : 't');
     key.append(reinterpret_cast<const char *>(e->frame_off.data()), e->frame_off.size() * sizeof(int32_t));
@@ -1282,7 +1346,8 @@ pk_status pk_mel(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t
                  int32_t *n_frames_out) {
     pk_status s;
     if ((s = pk_stage_pcm(e, pcm, offsets, n_utt))) return s;
-    if ((s = e->run_mel())) return s;
+    if (!e->front_done && (s = e->run_mel())) return s;     // (a pinned caller buffer: already run group by group)
+    e->front_done = false;
     const size_t n = (size_t)e->frame_off[n_utt] * e->cfg.mel_bins;
     cudaError_t ce = cudaMemcpyAsync(feats_out, e->feats, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
@@ -1302,6 +1367,7 @@ pk_status pk_encode(pk_engine *e, const float *feats, const int32_t *n_frames, i
     const size_t nf = (size_t)e->frame_off[n_utt] * e->cfg.mel_bins;
     cudaError_t ce = cudaMemcpyAsync(e->feats, feats, nf * sizeof(float), cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D feats: ") + cudaGetErrorString(ce));
+    if ((s = e->run_conv1())) return s;
     if ((s = e->run_encoder(sub_out, layers_out))) return s;
     ce = cudaMemcpyAsync(enc_out, e->x, (size_t)e->M * e->cfg.d_model * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);

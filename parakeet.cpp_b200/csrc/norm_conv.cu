@@ -82,7 +82,7 @@ layernorm_kernel(const float *__restrict__ x, int M, int d, const float *__restr
 // SiLU (reference src/encoder.cpp:59-75).  A thread owns 4 channels and DW_TT consecutive frames and
 // slides the KS-tap window down the column: DW_TT + KS - 1 float4 loads and one read of its 4 x KS
 // taps for DW_TT x 4 outputs (the previous one-frame-per-thread version re-read both 9x).
-constexpr int DW_TT = 16;
+constexpr int DW_TT = 8;
 template <int KS>
 __global__ void __launch_bounds__(128)
 dwconv_bn_silu_kernel(const float *__restrict__ g, const int32_t *__restrict__ row_off, int d,
