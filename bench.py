@@ -280,9 +280,18 @@ def main():
     math_name = {0: "bf16x3", 1: "bf16", 2: "f32"}[int(cfg.math)]
     # fp32 CUDA-core GEMM is bounded by the fp32 FMA pipe, not by tcgen05: report against the
     # tensor roofline anyway (the bar the north star sets) and say so.
-    roofline = {"bound": "tensor", "kernel": "gemm (all GEMM launches of one step)",
+    # DRAM bytes of one launch of the dominant GEMM, from the committed ncu --set full capture
+    # (bench.py cannot run ncu on itself; profiles/r01_traffic.json says which launch and how it was taken)
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_note = tj["dram_bytes_per_launch"], f'{tj["kernel"]}; {tj["source"]}'
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05; all GEMM launches of one step)",
                 "achieved": gemm_tflops, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["bf16_sus"], "traffic": None,
+                "frac": gemm_tflops / pk["bf16_sus"], "traffic": traffic, "traffic_of": traffic_note,
                 "mma_frac": (3.0 if int(cfg.math) == 0 else 1.0) * gemm_tflops / pk["bf16_sus"] if int(cfg.math) != 2 else None,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9, "launches_per_step": gemm_n // PSTEPS,

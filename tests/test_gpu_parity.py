@@ -121,6 +121,23 @@ def test_encoder_ragged_batch_equals_singles(eng_tiny, O, synth, tiny):
         assert _rel(b, O.encoder_forward(tiny.W, f, tiny.ocfg)) < ENC_TOL
 
 
+def test_encoder_long_utterance(pkg, O, synth, tiny, math_mode):
+    """An 11 s utterance (T' = 138: three 64-key tiles, three 64-query tiles in the attention kernel)
+    next to a short one."""
+    import dataclasses
+    cfg = dataclasses.replace(tiny.cfg, math=MATH[math_mode], max_samples=200000, max_batch=4)
+    e = pkg.Engine(cfg, tiny.weights_path, 0)
+    try:
+        pcms = [synth.make_audio(n, 300 + i) for i, n in enumerate([176000, 30000])]
+        feats = [O.preprocess_audio(p) for p in pcms]
+        got = e.encode(feats)
+        assert got[0].shape[0] == 138
+        for f, b in zip(feats, got):
+            assert _rel(b, O.encoder_forward(tiny.W, f, tiny.ocfg)) < ENC_TOL
+    finally:
+        e.close()
+
+
 def test_encoder_110m_matches_reference_golden(eng110, O, m110, synth, golden):
     k = "m110.c0."
     n, aseed = (int(v) for v in golden[k + "n_samples"])
