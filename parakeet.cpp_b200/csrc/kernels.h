@@ -79,7 +79,7 @@ struct TdtParams {
     const float *EP;                          // [M][J] enc_proj(enc) + bias
     const int32_t *row_off;                   // [n_utt+1]
     const float *G0;                          // [V][4P] W_ih0 . E[token] + b0
-    // weights pre-split for the tensor-core products (launch_tdt_split_rows): row = [hi: K+4][lo: K+4] bf16
+    // weights pre-split for the tensor-core products (launch_tdt_split_rows): row = [hi: K][lo: K] bf16
     const bf16 *Whh[PK_MAX_LSTM];             // [P*4] rows, K = P, unit-major: row = unit*4 + gate(i,f,g,o)
     const bf16 *Wih[PK_MAX_LSTM];             // [P*4] rows, K = P, unit-major (layers >= 1)
     const float *bih[PK_MAX_LSTM];            // [4P]    (layers >= 1)
@@ -98,7 +98,7 @@ struct TdtParams {
     float *t_conf;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
-// fp32 [rows][K] -> [rows][2 * (K + 4)] bf16 = [hi: K+4][lo: K+4]
+// fp32 [rows][K] -> [rows][2 K] bf16 = [hi: K][lo: K]
 void launch_tdt_split_rows(const float *src, int rows, int K, bf16 *dst, cudaStream_t st);
 
 }  // namespace pk

@@ -17,50 +17,55 @@
 // symbols the inner loop is simply re-entered on the same frame with the same state), so it
 // is not modelled; a token capacity bounds the loop instead (reference would livelock).
 //
-// Design (weights-stationary): the grid is one CTA per SM; every CTA keeps its slice of
-// W_hh / W_ih / pred_proj / label+duration rows in shared memory for the whole decode and
-// only the per-utterance vectors (h, z) travel through L2 between the phases of a step:
+// Design (weights-stationary, 2-D decomposition): the grid is one CTA per SM, grouped in thread-block
+// CLUSTERS of CL = 4 (or 2) CTAs.  A cluster owns a block of weight ROWS (LSTM units, joint-hidden
+// rows, label/duration rows); inside the cluster, CTA rank q owns the K-SLICE [q K/CL, (q+1) K/CL) of
+// those rows, resident in shared memory for the whole decode.  Per phase a CTA therefore streams only
+// its k-slice of the per-utterance vectors (h, z) from L2 -- 1/CL of the bytes a row-only split needs
+// (that stream, LSU-bound at ~20 B/clk/SM, was the largest part of a step) -- multiplies it with its
+// weight slice on tensor cores, and the CL partial sums of a row meet through distributed shared
+// memory: after one cluster barrier each CTA adds the partials of the rows it finalises, reading its
+// peers' buffers with ld.shared::cluster in a fixed order (deterministic).
 //   P1 LSTM gates + cell (per layer) | P2 joint hidden | P3 logits -> per-CTA (max, sum-exp)
 //   partials + atomicMax of packed (value, index) keys | P4 state update, replicated in every
 //   CTA from the keys (no barrier before the next P1; confidences are finalised one phase later
 //   from the partials, in a fixed order, by the CTA that owns the utterance, while it waits at a
 //   grid barrier).
-// Three monotonic-counter grid barriers per step (cooperative launch guarantees co-residency).
+// Three monotonic-counter grid barriers per step (cooperative launch guarantees co-residency);
+// they also order the reuse of the partial-sum buffers between phases.
 // enc_proj(enc)+bias for all frames and the layer-0 input table W_ih.E[token]+b for all
 // tokens are precomputed by GEMMs (engine.cu).
 //
-// Every product  out[r][b] = sum_k W[r][k] x_b[k]  (weight rows r of this CTA, all utterances b) runs
-// on mma.sync.m16n8k16 with the bf16 hi/lo operand split of the encoder GEMMs
-// (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, fp32 accumulate: ~16 mantissa bits):
-//   * weights are split once at load (engine.cu): row r = [hi: K+4 bf16][lo: K+4 bf16];
-//   * the PRODUCER of a vector (LSTM cell, joint hidden) stores it already split, as bf16 hi / lo
-//     planes [utterance][k], so consumers only copy: 64 utterances x 64 k per cp.async chunk,
-//     A fragments by ldmatrix, no conversion in the inner loop;
-//   * operands of the phase epilogues (G0[token], EP[t], biases) are fetched BEFORE the product
-//     so their L2 latency overlaps the streaming; the LSTM cell state never leaves shared memory.
+// Every product runs on mma.sync.m16n8k16 with the bf16 hi/lo operand split of the encoder GEMMs
+// (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, fp32 accumulate: ~16 mantissa bits): weights are split once
+// at load (engine.cu: row = [hi: K][lo: K] bf16); the PRODUCER of a vector (LSTM cell, joint hidden)
+// stores it already split, as bf16 hi / lo planes [utterance][k], so consumers only copy (cp.async)
+// and read A fragments with ldmatrix.  Operands of the phase epilogues (G0[token], EP[t], biases)
+// are fetched BEFORE the product so their L2 latency overlaps it; the LSTM cell state never leaves
+// shared memory.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace pk {
 namespace {
 
-constexpr int RMAX = 20;        // weight rows per pass (5 LSTM units x 4 gates)
-constexpr int RPAD = 24;        // RMAX rounded up to whole 8-row MMA n-blocks
 constexpr int NWARP = 8;
+constexpr int NTHR = NWARP * 32;
 constexpr int BCH = 64;         // utterances per pass (4 MMA m-blocks)
-constexpr int KC = 64;          // k-values staged per chunk (2 k-steps per warp half)
-constexpr int NST = 4;          // cp.async ring depth
-constexpr int XLD = KC + 8;     // staged row stride (bf16): 144 B, conflict-free ldmatrix
-constexpr int RLD = BCH + 4;    // row stride of the partial-sum buffer (floats)
-constexpr int STAGE_ELEMS = 2 * BCH * XLD;   // one ring stage: hi plane + lo plane (bf16 elements)
+constexpr int RG = 80;          // weight rows per pass of a cluster (10 MMA n-blocks = 20 LSTM units)
+constexpr int RLD = BCH + 4;    // row stride of the partial-sum buffer (floats): conflict-free fragment stores
+constexpr int MYMAX = 40;       // rows one CTA finalises per pass (RG / CL, whole LSTM units: 10 units at CL = 2)
+constexpr int NPV = MYMAX * BCH / NTHR;   // epilogue items per thread
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -84,103 +89,159 @@ __device__ __forceinline__ void store_split(bf16 *hi, bf16 *lo, size_t idx, floa
     hi[idx] = h;
     lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
+// ---- thread-block cluster primitives
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_a, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
 
-// out(r, b) = sum_k W[r][k] * x_b[k] for r < R (R <= NB*8), b in [bc, bc+64).
-//   W     : pre-split rows, row r at W + r * 2*(K+4): [hi K+4][lo K+4] (shared memory when WS, else global/L2)
-//   xsrc  : b -> pointer to the K bf16 "hi" values of utterance b (global; lives in L2); lo = hi + lo_off
-//   pre   : (r, b) -> float, called BEFORE the product for the outputs this thread will finalise
-//   fin   : (r, b, sum, pre value)
-// M = utterances (4 blocks of 16), N = weight rows (NB blocks of 8).  Warp w owns utterance block
-// (w & 3) and k-half (w >> 2) of every 64-wide chunk; the two halves are added in `red` in a fixed order.
-template <int NB, bool WS, typename XSrc, typename Pre, typename Fin>
-__device__ __forceinline__ void rows_times_batch_mma(const bf16 *W, int R, int K, int Bpad, int bc, XSrc xsrc,
-                                                     size_t lo_off, bf16 *xs, float *red, Pre pre, Fin fin) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
-    const int mb = warp & 3, kh = warp >> 2;
-    const int KP = K + 4, RS = 2 * KP;
-    const int nchunks = K / KC;
-    // this thread copies 16-byte pieces q and q+4 (hi and lo) of staged row `row`
-    const int row = threadIdx.x >> 2, q = threadIdx.x & 3;
-    const bool vrow = (bc + row) < Bpad;
-    const bf16 *xsrc_hi = xsrc(vrow ? bc + row : 0) + q * 8;
+// Stage this CTA's k-slice of the 64 utterance vectors: xs[plane][utterance][KS + 8] bf16.
+//   xsrc(b) -> pointer to the first element of the slice of utterance b's hi row; lo = hi + lo_off
+template <typename XSrc>
+__device__ __forceinline__ void stage_x(XSrc xsrc, size_t lo_off, int KS, int Bpad, int bc, bf16 *xs) {
+    const int XLD = KS + 8, pieces = KS / 8;          // 16-byte pieces per row
     const uint32_t xs_s = smem_addr(xs);
-    const uint32_t dst0 = xs_s + (uint32_t)(row * XLD + q * 8) * 2u;
-    auto issue = [&](int c) {
-        if (c < nchunks && vrow) {
-            const uint32_t dst = dst0 + (uint32_t)((c % NST) * STAGE_ELEMS) * 2u;
-            const bf16 *s = xsrc_hi + c * KC;
-            cp_async16(dst, s);
-            cp_async16(dst + 64u, s + 32);
-            cp_async16(dst + (uint32_t)(BCH * XLD) * 2u, s + lo_off);
-            cp_async16(dst + (uint32_t)(BCH * XLD) * 2u + 64u, s + lo_off + 32);
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int c = 0; c < NST - 1; ++c) issue(c);
-
-    // operands of the epilogue: in flight while the product streams
-    constexpr int NIT = NB * 8 * BCH / (NWARP * 32);
-    float pv[NIT];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-        const int idx = threadIdx.x + i * NWARP * 32, r = idx / BCH, b2 = idx % BCH;
-        pv[i] = (r < R && bc + b2 < Bpad) ? pre(r, bc + b2) : 0.f;
+    for (int idx = threadIdx.x; idx < BCH * pieces; idx += NTHR) {
+        const int row = idx / pieces, pc = idx - row * pieces;
+        if (bc + row >= Bpad) continue;               // rows past the batch: stale data, results discarded
+        const bf16 *s = xsrc(bc + row) + pc * 8;
+        const uint32_t dst = xs_s + (uint32_t)(row * XLD + pc * 8) * 2u;
+        cp_async16(dst, s);
+        cp_async16(dst + (uint32_t)(BCH * XLD) * 2u, s + lo_off);
     }
-
-    float acc[NB][4];
-    const bf16 *wrow[NB];
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-        acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
-        wrow[nb] = W + (size_t)min(nb * 8 + g, R - 1) * RS + kh * 32 + 2 * cq;   // rows >= R: clamped, discarded
-    }
-    // ldmatrix lane address inside a stage: A tile rows mb*16.., columns kh*32 + ks*16
-    const uint32_t a_off = (uint32_t)((mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XLD + kh * 32 + ((lane >> 4) & 1) * 8) * 2u;
-    for (int c = 0; c < nchunks; ++c) {
-        cp_async_wait<NST - 2>();
-        __syncthreads();                       // chunk c landed for everyone; chunk c-1 fully consumed
-        issue(c + NST - 1);
-        const uint32_t st = xs_s + (uint32_t)((c % NST) * STAGE_ELEMS) * 2u + a_off;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            uint32_t ah[4], al[4];
-            ldsm_x4(ah, st + ks * 32u);
-            ldsm_x4(al, st + (uint32_t)(BCH * XLD) * 2u + ks * 32u);
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                const bf16 *wp = wrow[nb] + c * KC + ks * 16;
-                const uint32_t b0h = ldw32<WS>(wp), b1h = ldw32<WS>(wp + 8), b0l = ldw32<WS>(wp + KP), b1l = ldw32<WS>(wp + KP + 8);
-                mma_bf16(acc[nb], ah, b0h, b1h);
-                mma_bf16(acc[nb], ah, b0l, b1l);
-                mma_bf16(acc[nb], al, b0h, b1h);
-            }
-        }
-    }
-    cp_async_wait<0>();
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-        const int n = nb * 8 + 2 * cq, u = mb * 16 + g;
-        red[(kh * RPAD + n) * RLD + u] = acc[nb][0];
-        red[(kh * RPAD + n + 1) * RLD + u] = acc[nb][1];
-        red[(kh * RPAD + n) * RLD + u + 8] = acc[nb][2];
-        red[(kh * RPAD + n + 1) * RLD + u + 8] = acc[nb][3];
-    }
+    cp_async_commit_wait_all();
     __syncthreads();
+}
+
+// acc[nb] += W[rows of n-block nb][k-slice] . xs   for the NBH n-blocks of this warp
+//   W: row r at W + r * RS (bf16 elements): [hi ...][lo ...] with lo at +LO; k index 0 = first k of the slice
+//   warp w: utterance block (w & 3), n-blocks [ (w >> 2) * NBH, +NBH )
+template <int NBH, bool WS>
+__device__ __forceinline__ void mma_slice(float (&acc)[NBH][4], const bf16 *W, int RS, int LO, int R, int KS, const bf16 *xs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
+    const int mb = warp & 3, nh = warp >> 2;
+    const int XLD = KS + 8;
+    const uint32_t a_base = smem_addr(xs) + (uint32_t)((mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XLD + ((lane >> 4) & 1) * 8) * 2u;
+    const uint32_t lo_plane = (uint32_t)(BCH * XLD) * 2u;
+    const bf16 *wrow[NBH];
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-        const int idx = threadIdx.x + i * NWARP * 32, r = idx / BCH, b2 = idx % BCH;
-        if (r < R && bc + b2 < Bpad) fin(r, bc + b2, red[r * RLD + b2] + red[(RPAD + r) * RLD + b2], pv[i]);
+    for (int nb = 0; nb < NBH; ++nb)
+        wrow[nb] = W + (size_t)min((nh * NBH + nb) * 8 + g, R - 1) * RS + 2 * cq;   // rows >= R: clamped, discarded
+    for (int ks = 0; ks < KS / 16; ++ks) {
+        uint32_t ah[4], al[4];
+        ldsm_x4(ah, a_base + ks * 32u);
+        ldsm_x4(al, a_base + lo_plane + ks * 32u);
+#pragma unroll
+        for (int nb = 0; nb < NBH; ++nb) {
+            const bf16 *wp = wrow[nb] + ks * 16;
+            const uint32_t b0h = ldw32<WS>(wp), b1h = ldw32<WS>(wp + 8), b0l = ldw32<WS>(wp + LO), b1l = ldw32<WS>(wp + LO + 8);
+            mma_bf16(acc[nb], ah, b0h, b1h);
+            mma_bf16(acc[nb], ah, b0l, b1l);
+            mma_bf16(acc[nb], al, b0h, b1h);
+        }
+    }
+}
+template <int NBH>
+__device__ __forceinline__ void store_partials(const float (&acc)[NBH][4], float *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
+    const int mb = warp & 3, nh = warp >> 2;
+#pragma unroll
+    for (int nb = 0; nb < NBH; ++nb) {
+        const int n = (nh * NBH + nb) * 8 + 2 * cq, u = mb * 16 + g;
+        red[n * RLD + u] = acc[nb][0];
+        red[(n + 1) * RLD + u] = acc[nb][1];
+        red[n * RLD + u + 8] = acc[nb][2];
+        red[(n + 1) * RLD + u + 8] = acc[nb][3];
+    }
+}
+
+// One pass over R <= RG weight rows of the cluster: up to two products accumulated together
+// (W1 . x1 [+ W2 . x2]), partial sums exchanged through DSMEM, rows finalised by their owner CTA.
+//   myrow(i) -> row (0..R-1) of the i-th row this CTA finalises, i < nmy (nmy <= MYMAX)
+//   pre(r, b) -> float operand of the epilogue, fetched before the products;  fin(i, r, b, sum, pre)
+template <int CL, int NBH, bool WS1, bool WS2, typename X1, typename X2, typename MyRow, typename Pre, typename Fin>
+__device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X1 x1, const bf16 *W2, int RS2, int LO2, X2 x2,
+                                             size_t lo_off, int R, int KS, int Bpad, int bc, bf16 *xs, float *red, int nmy,
+                                             MyRow myrow, Pre pre, Fin fin) {
+    float acc[NBH][4];
+#pragma unroll
+    for (int nb = 0; nb < NBH; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+    // stage x1 (async) and fetch the epilogue operands while it is in flight
+    float pv[NPV];
+    {
+        const int XLD = KS + 8, pieces = KS / 8;
+        const uint32_t xs_s = smem_addr(xs);
+        for (int idx = threadIdx.x; idx < BCH * pieces; idx += NTHR) {
+            const int row = idx / pieces, pc = idx - row * pieces;
+            if (bc + row >= Bpad) continue;
+            const bf16 *s = x1(bc + row) + pc * 8;
+            const uint32_t dst = xs_s + (uint32_t)(row * XLD + pc * 8) * 2u;
+            cp_async16(dst, s);
+            cp_async16(dst + (uint32_t)(BCH * XLD) * 2u, s + lo_off);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < NPV; ++j) {
+        const int idx = threadIdx.x + j * NTHR, i = idx / BCH, b2 = idx % BCH;
+        pv[j] = (i < nmy && bc + b2 < Bpad) ? pre(myrow(i), bc + b2) : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    mma_slice<NBH, WS1>(acc, W1, RS1, LO1, R, KS, xs);
+    if (W2 != nullptr) {
+        __syncthreads();                              // everyone is done reading x1
+        stage_x(x2, lo_off, KS, Bpad, bc, xs);
+        mma_slice<NBH, WS2>(acc, W2, RS2, LO2, R, KS, xs);
+    }
+    store_partials<NBH>(acc, red);
+    cluster_sync_all();                               // all CL partial buffers complete and visible
+    uint32_t peer[CL];
+#pragma unroll
+    for (int q = 0; q < CL; ++q) peer[q] = mapa_rank(smem_addr(red), (uint32_t)q);
+#pragma unroll
+    for (int j = 0; j < NPV; ++j) {
+        const int idx = threadIdx.x + j * NTHR, i = idx / BCH, b2 = idx % BCH;
+        if (i < nmy && bc + b2 < Bpad) {
+            const int r = myrow(i);
+            const uint32_t off = (uint32_t)(r * RLD + b2) * 4u;
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < CL; ++q) s += ld_cluster_f32(peer[q] + off);
+            fin(i, r, bc + b2, s, pv[j]);
+        }
     }
     __syncthreads();
 }
 
-template <bool WS, typename XSrc, typename Pre, typename Fin>
-__device__ __forceinline__ void rows_times_batch(const bf16 *W, int R, int K, int Bpad, int bc, XSrc xsrc, size_t lo_off,
-                                                 bf16 *xs, float *red, Pre pre, Fin fin) {
-    if (R <= 8) rows_times_batch_mma<1, WS>(W, R, K, Bpad, bc, xsrc, lo_off, xs, red, pre, fin);
-    else if (R <= 16) rows_times_batch_mma<2, WS>(W, R, K, Bpad, bc, xsrc, lo_off, xs, red, pre, fin);
-    else rows_times_batch_mma<3, WS>(W, R, K, Bpad, bc, xsrc, lo_off, xs, red, pre, fin);
+template <int CL, bool WS1, bool WS2, typename X1, typename X2, typename MyRow, typename Pre, typename Fin>
+__device__ __forceinline__ void cluster_pass_n(const bf16 *W1, int RS1, int LO1, X1 x1, const bf16 *W2, int RS2, int LO2, X2 x2,
+                                               size_t lo_off, int R, int KS, int Bpad, int bc, bf16 *xs, float *red, int nmy,
+                                               MyRow myrow, Pre pre, Fin fin) {
+    if (R <= 16) cluster_pass<CL, 1, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
+    else if (R <= 32) cluster_pass<CL, 2, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
+    else if (R <= 48) cluster_pass<CL, 3, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
+    else cluster_pass<CL, 5, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
 }
 
 // Monotonic-counter grid barrier (all CTAs are co-resident: cooperative launch), split into
@@ -219,68 +280,94 @@ __device__ __forceinline__ void unpack_key(unsigned long long k, float &v, int &
     idx = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFu));
 }
 
-__global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) {
+struct TdtGeom {            // per-cluster row blocks and per-CTA shared-memory sizes (host and device agree)
+    int UPC, JPC, OPC;      // LSTM units / joint rows / output rows per CLUSTER
+    int KSP, KSJ;           // k-slice widths for K = P and K = J
+    int MU;                 // LSTM units one CTA finalises (ceil(UPC / CL))
+};
+__host__ __device__ inline TdtGeom tdt_geom(int P, int J, int NO, int n_clusters, int CL) {
+    TdtGeom q;
+    q.UPC = (P + n_clusters - 1) / n_clusters;
+    q.JPC = (J + n_clusters - 1) / n_clusters;
+    q.OPC = (NO + n_clusters - 1) / n_clusters;
+    q.KSP = P / CL;
+    q.KSJ = J / CL;
+    q.MU = (q.UPC + CL - 1) / CL;
+    return q;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
     extern __shared__ __align__(16) float sm[];
     const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
+    const int NC = G / CL;                                   // clusters
+    const int cid = (int)cluster_id_x(), rank = (int)cluster_ctarank();
     const int P = p.P, J = p.J, V = p.V, D = p.D, L = p.L, Bpad = p.Bpad;
     const int NO = V + D;
-    const int UPC = (P + G - 1) / G;            // LSTM units per CTA
-    const int u0 = min(g * UPC, P), u1 = min(u0 + UPC, P);
-    const int JPC = (J + G - 1) / G;
-    const int j0 = min(g * JPC, J), j1 = min(j0 + JPC, J);
-    const int OPC = (NO + G - 1) / G;
-    const int o0 = min(g * OPC, NO), o1 = min(o0 + OPC, NO);
-    const int nU = u1 - u0;
+    const TdtGeom ge = tdt_geom(P, J, NO, NC, CL);
+    const int u0 = min(cid * ge.UPC, P), u1 = min(u0 + ge.UPC, P), nU = u1 - u0;        // this cluster's LSTM units
+    const int j0 = min(cid * ge.JPC, J), j1 = min(j0 + ge.JPC, J);
+    const int o0 = min(cid * ge.OPC, NO), o1 = min(o0 + ge.OPC, NO);
+    const int KSP = ge.KSP, KSJ = ge.KSJ;
+    const int kP0 = rank * KSP, kJ0 = rank * KSJ;                                       // this CTA's k-slices
+    const int RSP = 2 * (KSP + 4), RSJ = 2 * (KSJ + 4);      // smem weight row strides (bf16): [hi KS+4][lo KS+4]
 
-    // ---- shared memory carve-up: [red][gates][ring][cell state][decode state][weights...]
-    float *red = sm;                               // [2][RPAD][RLD] k-half partial sums
-    float *gsm = red + 2 * RPAD * RLD;             // [RMAX][BCH] gate pre-activations / logits
-    bf16 *xs = reinterpret_cast<bf16 *>(gsm + RMAX * BCH);                 // [NST][2][BCH][XLD] cp.async ring
-    float *csm = reinterpret_cast<float *>(xs + (size_t)NST * STAGE_ELEMS); // [L][2][UPC][Bpad] LSTM cell state
-    int *s_cur = reinterpret_cast<int *>(csm + (size_t)L * 2 * UPC * Bpad); // replicated decode state, [Bpad] each
+    // ---- shared memory carve-up: [partials][gates][x slice][cell state][decode state][weights...]
+    float *red = sm;                                          // [RG][RLD] this CTA's k-slice partial sums
+    float *gsm = red + RG * RLD;                              // [MYMAX][BCH] gate pre-activations / logits of my rows
+    bf16 *xs = reinterpret_cast<bf16 *>(gsm + MYMAX * BCH);   // [2][BCH][KSmax + 8]
+    const int KSmax = max(KSP, KSJ);
+    float *csm = reinterpret_cast<float *>(xs + (size_t)2 * BCH * (KSmax + 8));  // [L][2][MU][Bpad] LSTM cell state
+    int *s_cur = reinterpret_cast<int *>(csm + (size_t)L * 2 * ge.MU * Bpad);    // replicated decode state, [Bpad] each
     int *s_token = s_cur + Bpad, *s_tpos = s_token + Bpad, *s_active = s_tpos + Bpad, *s_ntok = s_active + Bpad;
     int *s_pend = s_ntok + Bpad;                   // slot of a token whose confidence is still pending (-1: none)
     bf16 *wbf = reinterpret_cast<bf16 *>(s_pend + Bpad);
-    // LSTM weights arrive "unit-major" (row = unit*4 + gate, engine.cu), so this CTA's rows
+    // Weight rows in global memory are [hi: K][lo: K]; a CTA keeps columns [k0, k0 + KS) of its cluster's rows.
+    auto stage_rows = [&](bf16 *dst, const bf16 *src, int rows, int K, int k0, int KS) {
+        const int RS = 2 * (KS + 4), n8 = KS / 4;            // 8-byte pieces per half row
+        for (int i = tid; i < rows * n8; i += blockDim.x) {
+            const int r = i / n8, pc = i - r * n8;
+            const uint2 *s = reinterpret_cast<const uint2 *>(src + (size_t)r * 2 * K + k0) + pc;
+            uint2 *d = reinterpret_cast<uint2 *>(dst + (size_t)r * RS) + pc;
+            *d = *s;
+            *reinterpret_cast<uint2 *>(reinterpret_cast<bf16 *>(d) + KS + 4) = *reinterpret_cast<const uint2 *>(reinterpret_cast<const bf16 *>(s) + K);
+        }
+    };
+    // LSTM weights arrive "unit-major" (row = unit*4 + gate, engine.cu), so the cluster's rows
     // [u0*4, u1*4) are one contiguous block: W_hh always lives in shared memory, W_ih of the
     // upper layers too when it fits (else its fragments are read from L2).
-    const int RSP = 2 * (P + 4), RSJ = 2 * (J + 4);          // row strides (bf16) for K = P / K = J
-    auto stage_rows = [&](bf16 *dst, const bf16 *src, int rows, int RS) {   // 16-byte copies (RS * 2 B is a multiple of 16)
-        const int n16 = rows * RS / 8;
-        for (int i = tid; i < n16; i += blockDim.x)
-            reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
-    };
     const bf16 *w_hh[PK_MAX_LSTM], *w_ih[PK_MAX_LSTM];
     {
         bf16 *cur = wbf;
         for (int l = 0; l < L; ++l) {
-            stage_rows(cur, p.Whh[l] + (size_t)u0 * 4 * RSP, nU * 4, RSP);
+            stage_rows(cur, p.Whh[l] + (size_t)u0 * 4 * 2 * P, nU * 4, P, kP0, KSP);
             w_hh[l] = cur;
-            cur += (size_t)UPC * 4 * RSP;
+            cur += (size_t)ge.UPC * 4 * RSP;
             w_ih[l] = nullptr;
             if (l > 0) {
                 if (p.wih_in_smem) {
-                    stage_rows(cur, p.Wih[l] + (size_t)u0 * 4 * RSP, nU * 4, RSP);
+                    stage_rows(cur, p.Wih[l] + (size_t)u0 * 4 * 2 * P, nU * 4, P, kP0, KSP);
                     w_ih[l] = cur;
-                    cur += (size_t)UPC * 4 * RSP;
+                    cur += (size_t)ge.UPC * 4 * RSP;
                 } else {
-                    w_ih[l] = p.Wih[l] + (size_t)u0 * 4 * RSP;
+                    w_ih[l] = p.Wih[l] + (size_t)u0 * 4 * 2 * P + kP0;     // global: row stride 2P, lo at +P
                 }
             }
         }
     }
-    bf16 *w_p = wbf + 2 * (size_t)p.smem_lstm_floats;        // [JPC] rows, K = P
-    stage_rows(w_p, p.Wp + (size_t)j0 * RSP, j1 - j0, RSP);
-    const bf16 *w_o;                                         // [OPC] rows, K = J: shared if it fits
+    bf16 *w_p = wbf + 2 * (size_t)p.smem_lstm_floats;        // [JPC] rows, K-slice of P
+    stage_rows(w_p, p.Wp + (size_t)j0 * 2 * P, j1 - j0, P, kP0, KSP);
+    const bf16 *w_o;                                         // [OPC] rows, K-slice of J: shared if it fits
     if (p.out_in_smem) {
-        bf16 *w_os = w_p + (size_t)JPC * RSP;
-        stage_rows(w_os, p.Wout + (size_t)o0 * RSJ, o1 - o0, RSJ);
+        bf16 *w_os = w_p + (size_t)ge.JPC * RSP;
+        stage_rows(w_os, p.Wout + (size_t)o0 * 2 * J, o1 - o0, J, kJ0, KSJ);
         w_o = w_os;
     } else {
-        w_o = p.Wout + (size_t)o0 * RSJ;
+        w_o = p.Wout + (size_t)o0 * 2 * J + kJ0;              // global: row stride 2J, lo at +J
     }
-    for (int i = tid; i < L * 2 * UPC * Bpad; i += blockDim.x) csm[i] = 0.f;   // zero cell state (tdt.cpp:49-59)
-    for (int b = tid; b < Bpad; b += blockDim.x) {                             // initial decode state
+    const int RSO = p.out_in_smem ? RSJ : 2 * J, LOO = p.out_in_smem ? KSJ + 4 : J;
+    for (int i = tid; i < L * 2 * ge.MU * Bpad; i += blockDim.x) csm[i] = 0.f;   // zero cell state (tdt.cpp:49-59)
+    for (int b = tid; b < Bpad; b += blockDim.x) {                               // initial decode state
         s_cur[b] = 0;
         s_token[b] = V - 1;
         s_tpos[b] = 0;
@@ -315,6 +402,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
             if (lane == 0) p.t_conf[(size_t)b * p.cap + slot] = 1.0f / s;
         }
     };
+    auto nox = [&](int) { return static_cast<const bf16 *>(nullptr); };
 
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int slot) {   // phase timing of CTA 0 (debug aid, p.dbg may be null)
@@ -332,38 +420,48 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
             }
         // ================= P1: LSTM layers =================
         for (int l = 0; l < L; ++l) {
-            for (int bc = 0; bc < Bpad; bc += BCH) {
-                const int R = nU * 4;
-                if (R > 0) {
-                    // gate pre-activations: W_hh . h_prev + (W_ih0 . E[token] + b0 | b_l)   [+ W_ih . h'_{l-1}]
+            for (int bc = 0; bc < Bpad; bc += BCH)
+                for (int ug = 0; ug < nU; ug += RG / 4) {               // passes of <= 20 units (one for the 110m)
+                    const int nu = min(RG / 4, nU - ug), R = nu * 4;
+                    const int myu = (nu - rank + CL - 1) / CL;          // units ug + rank, ug + rank + CL, ...
+                    // rows I finalise: unit-local index ul = rank + CL * (i >> 2), gate i & 3
+                    auto myrow = [&](int i) { return ((rank + CL * (i >> 2)) << 2) | (i & 3); };
                     auto pre_g = [&](int r, int b) {
-                        const int u = u0 + (r >> 2), gt = r & 3;
+                        const int u = u0 + ug + (r >> 2), gt = r & 3;
                         return (l == 0) ? p.G0[(size_t)s_token[b] * 4 * P + gt * P + u] : p.bih[l][gt * P + u];
                     };
-                    auto xprev = [&](int b) { return hb + ((size_t)(l * 2 + s_cur[b])) * HS + (size_t)b * P; };
-                    rows_times_batch<true>(w_hh[l], R, P, Bpad, bc, xprev, h_lo, xs, red, pre_g,
-                                           [&](int r, int b, float v, float e) { gsm[r * BCH + (b - bc)] = v + e; });
-                    if (l > 0) {  // input part: W_ih . h'_{l-1}(new)
-                        auto xh = [&](int b) { return hb + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; };
-                        auto nopre = [&](int, int) { return 0.f; };
-                        auto fa = [&](int r, int b, float v, float) { gsm[r * BCH + (b - bc)] += v; };
-                        if (p.wih_in_smem) rows_times_batch<true>(w_ih[l], R, P, Bpad, bc, xh, h_lo, xs, red, nopre, fa);
-                        else rows_times_batch<false>(w_ih[l], R, P, Bpad, bc, xh, h_lo, xs, red, nopre, fa);
+                    auto fin_g = [&](int i, int, int b, float v, float e) { gsm[i * BCH + (b - bc)] = v + e; };
+                    auto xprev = [&](int b) { return hb + ((size_t)(l * 2 + s_cur[b])) * HS + (size_t)b * P + kP0; };
+                    const bf16 *W1 = w_hh[l] + (size_t)ug * 4 * RSP;
+                    if (l == 0) {
+                        cluster_pass_n<CL, true, true>(W1, RSP, KSP + 4, xprev, nullptr, 0, 0, nox, h_lo, R, KSP, Bpad, bc, xs, red,
+                                                       myu * 4, myrow, pre_g, fin_g);
+                    } else {   // + input part W_ih . h'_{l-1}(new), accumulated into the same partial sums
+                        auto xh = [&](int b) { return hb + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P + kP0; };
+                        if (p.wih_in_smem)
+                            cluster_pass_n<CL, true, true>(W1, RSP, KSP + 4, xprev, w_ih[l] + (size_t)ug * 4 * RSP, RSP, KSP + 4, xh, h_lo, R,
+                                                           KSP, Bpad, bc, xs, red, myu * 4, myrow, pre_g, fin_g);
+                        else
+                            cluster_pass_n<CL, true, false>(W1, RSP, KSP + 4, xprev, w_ih[l] + (size_t)ug * 4 * 2 * P, 2 * P, P, xh, h_lo, R,
+                                                            KSP, Bpad, bc, xs, red, myu * 4, myrow, pre_g, fin_g);
                     }
-                    for (int idx = tid; idx < nU * BCH; idx += blockDim.x) {
-                        const int ul = idx / BCH, bb = idx % BCH, b = bc + bb;
+                    // cell update of my units (tdt/lstm.cpp:11-29); state index = (pass, my unit slot)
+                    for (int idx = tid; idx < myu * BCH; idx += blockDim.x) {
+                        const int mi = idx / BCH, bb = idx % BCH, b = bc + bb;
                         if (b >= Bpad) continue;
-                        const float gi = gsm[(ul * 4 + 0) * BCH + bb], gf = gsm[(ul * 4 + 1) * BCH + bb];
-                        const float gg = gsm[(ul * 4 + 2) * BCH + bb], go = gsm[(ul * 4 + 3) * BCH + bb];
+                        const int u = u0 + ug + rank + CL * mi;
+                        const int cslot = ug / CL + mi;                // < MU
+                        const float gi = gsm[(mi * 4 + 0) * BCH + bb], gf = gsm[(mi * 4 + 1) * BCH + bb];
+                        const float gg = gsm[(mi * 4 + 2) * BCH + bb], go = gsm[(mi * 4 + 3) * BCH + bb];
                         const int cu = s_cur[b];
-                        const float c_old = csm[((size_t)(l * 2 + cu) * UPC + ul) * Bpad + b];
+                        const float c_old = csm[((size_t)(l * 2 + cu) * ge.MU + cslot) * Bpad + b];
                         const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
                         const float h_new = sigmoidf_(go) * tanhf(c_new);
-                        csm[((size_t)(l * 2 + 1 - cu) * UPC + ul) * Bpad + b] = c_new;
-                        store_split(hb, hb + h_lo, ((size_t)(l * 2 + 1 - cu)) * HS + (size_t)b * P + u0 + ul, h_new);
+                        csm[((size_t)(l * 2 + 1 - cu) * ge.MU + cslot) * Bpad + b] = c_new;
+                        store_split(hb, hb + h_lo, ((size_t)(l * 2 + 1 - cu)) * HS + (size_t)b * P + u, h_new);
                     }
+                    if (ug + RG / 4 < nU) cluster_sync_all();           // partial buffers are reused by the next pass
                 }
-            }
             tick(0);
             grid_arrive(p.bar);
             if (l == L - 1) {
@@ -378,18 +476,21 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
         }
         // ================= P2: joint hidden z = relu(EP[t] + Wp . h') =================
         for (int bc = 0; bc < Bpad; bc += BCH)
-            for (int rg = j0; rg < j1; rg += RMAX) {
-                const int R = min(RMAX, j1 - rg);
-                rows_times_batch<true>(
-                    w_p + (size_t)(rg - j0) * RSP, R, P, Bpad, bc,
-                    [&](int b) { return hb + ((size_t)((L - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P; }, h_lo, xs, red,
+            for (int rg = j0; rg < j1; rg += RG) {
+                const int R = min(RG, j1 - rg);
+                const int nmy = (R - rank + CL - 1) / CL;               // rows rank, rank + CL, ...
+                cluster_pass_n<CL, true, true>(
+                    w_p + (size_t)(rg - j0) * RSP, RSP, KSP + 4,
+                    [&](int b) { return hb + ((size_t)((L - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P + kP0; }, nullptr, 0, 0, nox,
+                    h_lo, R, KSP, Bpad, bc, xs, red, nmy, [&](int i) { return rank + CL * i; },
                     [&](int r, int b) {
                         if (b >= p.n_utt) return 0.f;
                         const int T = p.row_off[b + 1] - p.row_off[b];
                         const int t = min(s_tpos[b], T - 1);
                         return p.EP[(size_t)(p.row_off[b] + t) * J + rg + r];
                     },
-                    [&](int r, int b, float v, float e) { store_split(zb, zb + z_lo, (size_t)b * J + rg + r, fmaxf(v + e, 0.f)); });
+                    [&](int, int r, int b, float v, float e) { store_split(zb, zb + z_lo, (size_t)b * J + rg + r, fmaxf(v + e, 0.f)); });
+                if (rg + RG < j1) cluster_sync_all();
             }
         tick(2);
         grid_arrive(p.bar);
@@ -399,19 +500,23 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
         for (int bc = 0; bc < Bpad; bc += BCH) {
             float lmax = -INFINITY, lsum = 0.f, dmax = -INFINITY;
             int lidx = 0x7fffffff, didx = 0x7fffffff;
-            for (int rg = o0; rg < o1; rg += RMAX) {
-                const int R = min(RMAX, o1 - rg);
-                auto xz = [&](int b) { return zb + (size_t)b * J; };
+            for (int rg = o0; rg < o1; rg += RG) {
+                const int R = min(RG, o1 - rg);
+                const int nmy = (R - rank + CL - 1) / CL;
+                auto xz = [&](int b) { return zb + (size_t)b * J + kJ0; };
+                auto myrow = [&](int i) { return rank + CL * i; };
                 auto pb = [&](int r, int) { return p.bout[rg + r]; };
-                auto fl = [&](int r, int b, float v, float e) { gsm[r * BCH + (b - bc)] = v + e; };
+                auto fl = [&](int i, int, int b, float v, float e) { gsm[i * BCH + (b - bc)] = v + e; };
                 if (p.out_in_smem)
-                    rows_times_batch<true>(w_o + (size_t)(rg - o0) * RSJ, R, J, Bpad, bc, xz, z_lo, xs, red, pb, fl);
+                    cluster_pass_n<CL, true, true>(w_o + (size_t)(rg - o0) * RSO, RSO, LOO, xz, nullptr, 0, 0, nox, z_lo, R, KSJ, Bpad, bc, xs,
+                                                   red, nmy, myrow, pb, fl);
                 else
-                    rows_times_batch<false>(w_o + (size_t)(rg - o0) * RSJ, R, J, Bpad, bc, xz, z_lo, xs, red, pb, fl);
+                    cluster_pass_n<CL, false, true>(w_o + (size_t)(rg - o0) * RSO, RSO, LOO, xz, nullptr, 0, 0, nox, z_lo, R, KSJ, Bpad, bc, xs,
+                                                    red, nmy, myrow, pb, fl);
                 if (tid < BCH) {
-                    for (int r = 0; r < R; ++r) {
-                        const float v = gsm[r * BCH + tid];
-                        const int n = rg + r;
+                    for (int i = 0; i < nmy; ++i) {
+                        const float v = gsm[i * BCH + tid];
+                        const int n = rg + rank + CL * i;
                         if (n < V) {
                             if (v > lmax) {
                                 lsum = lsum * expf(lmax - v) + 1.f;
@@ -427,6 +532,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
                     }
                 }
                 __syncthreads();
+                if (rg + RG < o1) cluster_sync_all();
             }
             if (tid < BCH && bc + tid < Bpad) {
                 const int b = bc + tid;
@@ -490,6 +596,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) tdt_decode_kernel(TdtParams p) 
     }
     // confidences of the last step's tokens (all partials were visible at that step's last barrier)
     finalize_conf(step % 3);
+    cluster_sync_all();              // nobody leaves while a peer may still read its partial sums
 }
 
 __global__ void tdt_init_kernel(TdtParams p) {
@@ -505,34 +612,29 @@ __global__ void tdt_init_kernel(TdtParams p) {
     }
 }
 
-// fp32 rows [rows][K] -> pre-split rows [rows][2 * (K + 4)] = [hi: K+4][lo: K+4] bf16 (pads zero)
+// fp32 rows [rows][K] -> pre-split rows [rows][2 K] = [hi: K][lo: K] bf16
 __global__ void tdt_split_rows_kernel(const float *__restrict__ src, int rows, int K, bf16 *__restrict__ dst) {
-    const int KP = K + 4;
-    const size_t n = (size_t)rows * KP;
+    const size_t n = (size_t)rows * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / KP;
-        const int k = (int)(i - r * KP);
-        const float v = k < K ? src[r * K + k] : 0.f;
+        const size_t r = i / K;
+        const int k = (int)(i - r * K);
+        const float v = src[i];
         const bf16 h = __float2bfloat16_rn(v);
-        dst[r * 2 * KP + k] = h;
-        dst[r * 2 * KP + KP + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        dst[r * 2 * K + k] = h;
+        dst[r * 2 * K + K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
 }
 
-}  // namespace
-
-void launch_tdt_split_rows(const float *src, int rows, int K, bf16 *dst, cudaStream_t st) {
-    tdt_split_rows_kernel<<<256, 256, 0, st>>>(src, rows, K, dst);
-}
-
-size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, bool *wih_in_smem, int *lstm_floats) {
-    const int UPC = (p.P + grid - 1) / grid, JPC = (p.J + grid - 1) / grid, OPC = (p.V + p.D + grid - 1) / grid;
+// Shared memory of one CTA (bytes) for `n_clusters` clusters of CL; decides what stays in shared memory.
+size_t tdt_smem_bytes(const TdtParams &p, int n_clusters, int CL, bool *out_in_smem, bool *wih_in_smem, int *lstm_floats) {
+    const TdtGeom ge = tdt_geom(p.P, p.J, p.V + p.D, n_clusters, CL);
     const size_t budget = 225 * 1024 / sizeof(float);
-    size_t fixed = (size_t)2 * RPAD * RLD + RMAX * BCH + (size_t)NST * STAGE_ELEMS / 2 + (size_t)p.L * 2 * UPC * p.Bpad +
+    const int KSmax = ge.KSP > ge.KSJ ? ge.KSP : ge.KSJ;
+    size_t fixed = (size_t)RG * RLD + (size_t)MYMAX * BCH + (size_t)2 * BCH * (KSmax + 8) / 2 + (size_t)p.L * 2 * ge.MU * p.Bpad +
                    6 * (size_t)p.Bpad;
-    // weight rows are bf16 hi/lo with a 4-element pad each: K + 4 floats per row
-    const size_t hh = (size_t)p.L * UPC * 4 * (p.P + 4), ih = (size_t)(p.L - 1) * UPC * 4 * (p.P + 4);
-    const size_t wp = (size_t)JPC * (p.P + 4), wo = (size_t)OPC * (p.J + 4);
+    // a staged weight row = [hi KS+4][lo KS+4] bf16 = KS + 4 floats
+    const size_t hh = (size_t)p.L * ge.UPC * 4 * (ge.KSP + 4), ih = (size_t)(p.L - 1) * ge.UPC * 4 * (ge.KSP + 4);
+    const size_t wp = (size_t)ge.JPC * (ge.KSP + 4), wo = (size_t)ge.OPC * (ge.KSJ + 4);
     size_t total = fixed + hh + wp;                 // always resident
     *wih_in_smem = (ih == 0) || (total + ih <= budget);
     if (*wih_in_smem) total += ih;
@@ -542,26 +644,79 @@ size_t tdt_smem_bytes(const TdtParams &p, int grid, bool *out_in_smem, bool *wih
     return total * sizeof(float);
 }
 
+template <int CL>
+cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
+    *fits = false;
+    if (p.P % (16 * CL) || p.J % (16 * CL)) return cudaSuccess;
+    // upper bound on clusters; the occupancy query below says how many can be co-resident
+    int nc = num_sms / CL;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.blockDim = dim3(NTHR);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t err = cudaFuncSetAttribute(tdt_decode_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    (void)err;
+    cudaGetLastError();
+    for (int iter = 0; iter < 2; ++iter) {
+        const TdtGeom ge = tdt_geom(p.P, p.J, p.V + p.D, nc, CL);
+        bool out_in_smem, wih_in_smem;
+        int lstm_floats;
+        const size_t smem = tdt_smem_bytes(p, nc, CL, &out_in_smem, &wih_in_smem, &lstm_floats);
+        if (smem > 227 * 1024) return cudaSuccess;
+        err = cudaFuncSetAttribute(tdt_decode_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
+        cfg.gridDim = dim3(nc * CL);
+        cfg.dynamicSmemBytes = smem;
+        int max_clusters = 0;
+        err = cudaOccupancyMaxActiveClusters(&max_clusters, tdt_decode_kernel<CL>, &cfg);
+        if (err != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
+        if (max_clusters >= nc) {
+            p.out_in_smem = out_in_smem ? 1 : 0;
+            p.wih_in_smem = wih_in_smem ? 1 : 0;
+            p.smem_lstm_floats = lstm_floats;
+            *fits = true;
+            tdt_init_kernel<<<(3 * p.Bpad + 127) / 128, 128, 0, st>>>(p);
+            return cudaLaunchKernelEx(&cfg, tdt_decode_kernel<CL>, p);
+        }
+        if (max_clusters < 1) return cudaSuccess;
+        nc = max_clusters;                           // retry with what fits (geometry and smem change with nc)
+    }
+    return cudaSuccess;
+}
+
+// Co-resident cluster counts are a property of the device and the kernel's footprint: decide once
+// which cluster size to use (prefer 4 when it keeps >= 3/4 of the SMs busy).
+int g_tdt_cl = 0;
+
+}  // namespace
+
+void launch_tdt_split_rows(const float *src, int rows, int K, bf16 *dst, cudaStream_t st) {
+    tdt_split_rows_kernel<<<256, 256, 0, st>>>(src, rows, K, dst);
+}
+
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st) {
-    if (p.P % KC || p.J % KC) return cudaErrorInvalidValue;
-    int grid = num_sms;
-    // every CTA must own <= 5 LSTM units (RMAX = 20 gate rows)
-    if ((p.P + grid - 1) / grid * 4 > RMAX) return cudaErrorInvalidConfiguration;
-    bool out_in_smem, wih_in_smem;
-    int lstm_floats;
-    size_t smem = tdt_smem_bytes(p, grid, &out_in_smem, &wih_in_smem, &lstm_floats);
-    p.out_in_smem = out_in_smem ? 1 : 0;
-    p.wih_in_smem = wih_in_smem ? 1 : 0;
-    p.smem_lstm_floats = lstm_floats;
-    cudaError_t err = cudaFuncSetAttribute(tdt_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    int occ = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tdt_decode_kernel, NWARP * 32, smem);
-    if (err != cudaSuccess) return err;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
-    tdt_init_kernel<<<(3 * p.Bpad + 127) / 128, 128, 0, st>>>(p);
-    void *args[] = {&p};
-    return cudaLaunchCooperativeKernel((void *)tdt_decode_kernel, dim3(grid), dim3(NWARP * 32), args, smem, st);
+    bool fits = false;
+    cudaError_t err;
+    if (g_tdt_cl == 0) {
+        g_tdt_cl = 4;
+        if (const char *ev = getenv("PK_TDT_CLUSTER")) g_tdt_cl = atoi(ev) == 2 ? 2 : 4;
+    }
+    if (g_tdt_cl == 4) {
+        err = launch_cl<4>(p, num_sms, st, &fits);
+        if (fits) return err;
+        g_tdt_cl = 2;
+    }
+    err = launch_cl<2>(p, num_sms, st, &fits);
+    if (fits) return err;
+    return cudaErrorLaunchOutOfResources;
 }
 
 }  // namespace pk
