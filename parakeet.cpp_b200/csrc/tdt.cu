@@ -390,14 +390,23 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
         for (int b = g + warp * G; b < p.n_utt; b += G * NWARP) {   // utterances owned by this CTA (b % G == g)
             const int slot = s_pend[b];
             if (slot < 0) continue;
+            // all partials of this lane first (one L2 round trip), then max and sum (fixed order: q ascending per lane)
+            constexpr int QMAX = 8;                                  // grids up to 256 CTAs
+            float m[QMAX], sv[QMAX];
+#pragma unroll
+            for (int i = 0; i < QMAX; ++i) {
+                const int q = lane + 32 * i;
+                m[i] = q < G ? p.pl_max[buf * PB + (size_t)q * Bpad + b] : -INFINITY;
+                sv[i] = q < G ? p.pl_sum[buf * PB + (size_t)q * Bpad + b] : 0.f;
+            }
             float gmax = -INFINITY;
-            for (int q = lane; q < G; q += 32) gmax = fmaxf(gmax, p.pl_max[buf * PB + (size_t)q * Bpad + b]);
+#pragma unroll
+            for (int i = 0; i < QMAX; ++i) gmax = fmaxf(gmax, m[i]);
             gmax = warp_max(gmax);
             float s = 0.f;
-            for (int q = lane; q < G; q += 32) {
-                const float m = p.pl_max[buf * PB + (size_t)q * Bpad + b];
-                if (m > -INFINITY) s += p.pl_sum[buf * PB + (size_t)q * Bpad + b] * expf(m - gmax);
-            }
+#pragma unroll
+            for (int i = 0; i < QMAX; ++i)
+                if (m[i] > -INFINITY) s += sv[i] * expf(m[i] - gmax);
             s = warp_sum(s);
             if (lane == 0) p.t_conf[(size_t)b * p.cap + slot] = 1.0f / s;
         }
@@ -650,6 +659,7 @@ cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
     if (p.P % (16 * CL) || p.J % (16 * CL)) return cudaSuccess;
     // upper bound on clusters; the occupancy query below says how many can be co-resident
     int nc = num_sms / CL;
+    if (nc * CL > 256) nc = 256 / CL;                // finalize_conf reads <= 8 partials per lane
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
