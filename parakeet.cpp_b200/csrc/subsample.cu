@@ -19,7 +19,7 @@ namespace {
 
 constexpr int TT2 = 4;  // t2 rows per block
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 subsample_conv1_dw1_kernel(const float *__restrict__ feats, const int32_t *__restrict__ frame_off,
                            const int32_t *__restrict__ s2_off, int mel, int C,
                            const float *__restrict__ w1, const float *__restrict__ b1,
@@ -32,76 +32,77 @@ subsample_conv1_dw1_kernel(const float *__restrict__ feats, const int32_t *__res
     const int r0 = blockIdx.x * TT2;
     if (r0 >= t2n) return;
     const int stride = mel + 4;
-    const int nrows = 4 * TT2 + 3;
-    const int row_base = 4 * r0 - 3;  // feature row of S[0]
+    constexpr int NROWS = 4 * TT2 + 3;      // feature rows 4*r0-3 .. 4*r0+4*TT2-1
+    constexpr int NQ = 2 * TT2 + 1;         // conv1 rows 2*r0-1 .. 2*r0+2*TT2-1, shared by the TT2 outputs
+    const int row_base = 4 * r0 - 3;        // feature row of S[0]
     const float *src = feats + (size_t)frame_off[b] * mel;
-    for (int i = threadIdx.x; i < nrows * stride; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NROWS * stride; i += blockDim.x) {
         const int rr = i / stride, cc = i - rr * stride - 2;
         const int fr = row_base + rr;
         S[i] = (fr >= 0 && fr < F && cc >= 0 && cc < mel) ? src[(size_t)fr * mel + cc] : 0.f;
     }
     __syncthreads();
-    const int c = threadIdx.x;
-    if (c >= C) return;
-    float W1[9], WD[9];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float W1[9], WD[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        W1[i] = w1[c * 9 + i];
-        WD[i] = wd[c * 9 + i];
-    }
-    const float B1 = b1[c], BD = bd[c];
-
-    for (int tt = 0; tt < TT2; ++tt) {
-        const int t2 = r0 + tt;
-        if (t2 >= t2n) break;
-        bool rv[3];  // conv1 row validity (zero padding of dw1's input)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int t1 = 2 * t2 - 1 + i;
-            rv[i] = (t1 >= 0 && t1 < t1n);
+        for (int i = 0; i < 9; ++i) {
+            W1[i] = w1[c * 9 + i];
+            WD[i] = wd[c * 9 + i];
         }
-        // S rows for this t2: feature rows 4*t2-3 .. 4*t2+3  ->  local 4*tt .. 4*tt+6
-        const float *Srow = S + (4 * tt) * stride;
-        float colprev[7];
+        const float B1 = b1[c], BD = bd[c];
+        bool rv[NQ];  // conv1 row validity (zero padding of dw1's input)
 #pragma unroll
-        for (int r = 0; r < 7; ++r) colprev[r] = Srow[r * stride + 1];  // col -1 (zero pad)
-        float p2[3], p1[3] = {0.f, 0.f, 0.f}, cur[3];
-        p2[0] = p2[1] = p2[2] = 0.f;
-        const size_t orow = ((size_t)s2_off[b] + (size_t)t2) * f2n;
+        for (int q = 0; q < NQ; ++q) {
+            const int t1 = 2 * r0 - 1 + q;
+            rv[q] = (t1 >= 0 && t1 < t1n);
+        }
+        // walk along the frequency axis; conv1 values of the NQ rows at column f1 are computed once and
+        // feed every output row that needs them (a t2-outer loop computes each shared row twice)
+        float colprev[NROWS];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) colprev[r] = S[r * stride + 1];  // col -1 (zero pad)
+        float p2[NQ], p1[NQ], cur[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) p2[q] = p1[q] = 0.f;
         for (int f1 = 0; f1 < 2 * f2n; ++f1) {
-            float2 nw[7];
+            float2 nw[NROWS];
 #pragma unroll
-            for (int r = 0; r < 7; ++r)
-                nw[r] = *reinterpret_cast<const float2 *>(Srow + r * stride + 2 * f1 + 2);
+            for (int r = 0; r < NROWS; ++r) nw[r] = *reinterpret_cast<const float2 *>(S + r * stride + 2 * f1 + 2);
             const bool fv = f1 < f1n;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int q = 0; q < NQ; ++q) {
                 float v = B1;
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    v = fmaf(W1[p * 3 + 0], colprev[2 * i + p], v);
-                    v = fmaf(W1[p * 3 + 1], nw[2 * i + p].x, v);
-                    v = fmaf(W1[p * 3 + 2], nw[2 * i + p].y, v);
+                for (int pp = 0; pp < 3; ++pp) {
+                    v = fmaf(W1[pp * 3 + 0], colprev[2 * q + pp], v);
+                    v = fmaf(W1[pp * 3 + 1], nw[2 * q + pp].x, v);
+                    v = fmaf(W1[pp * 3 + 2], nw[2 * q + pp].y, v);
                 }
-                cur[i] = (rv[i] && fv) ? fmaxf(v, 0.f) : 0.f;
+                cur[q] = (rv[q] && fv) ? fmaxf(v, 0.f) : 0.f;
             }
             if (f1 & 1) {
-                float acc = BD;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    acc = fmaf(WD[i * 3 + 0], p2[i], acc);
-                    acc = fmaf(WD[i * 3 + 1], p1[i], acc);
-                    acc = fmaf(WD[i * 3 + 2], cur[i], acc);
+                for (int tt = 0; tt < TT2; ++tt) {
+                    const int t2 = r0 + tt;
+                    if (t2 < t2n) {
+                        float acc = BD;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            acc = fmaf(WD[i * 3 + 0], p2[2 * tt + i], acc);
+                            acc = fmaf(WD[i * 3 + 1], p1[2 * tt + i], acc);
+                            acc = fmaf(WD[i * 3 + 2], cur[2 * tt + i], acc);
+                        }
+                        store_act(out, (((size_t)s2_off[b] + (size_t)t2) * f2n + (f1 >> 1)) * C + c, acc);
+                    }
                 }
-                store_act(out, (orow + (f1 >> 1)) * C + c, acc);
             }
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                p2[i] = p1[i];
-                p1[i] = cur[i];
+            for (int q = 0; q < NQ; ++q) {
+                p2[q] = p1[q];
+                p1[q] = cur[q];
             }
 #pragma unroll
-            for (int r = 0; r < 7; ++r) colprev[r] = nw[r].y;
+            for (int r = 0; r < NROWS; ++r) colprev[r] = nw[r].y;
         }
     }
 }
@@ -158,6 +159,7 @@ void launch_subsample_conv1_dw1(const float *feats, const int32_t *frame_off, co
                                 const float *wd, const float *bd, ActBuf out, cudaStream_t st) {
     dim3 grid((max_t2 + TT2 - 1) / TT2, n_utt);
     int threads = ((C + 31) / 32) * 32;
+    if (threads > 256) threads = 256;            // the kernel strides over channels
     size_t smem = sizeof(float) * (4 * TT2 + 3) * (mel + 4);
     subsample_conv1_dw1_kernel<<<grid, threads, smem, st>>>(feats, frame_off, s2_off, mel, C, w1, b1, wd, bd,
                                                             out);
