@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                         csm[((size_t)(l * 2 + 1 - cu) * ge.MU + cslot) * Bpad + b] = c_new;
                         store_split(hb, hb + h_lo, ((size_t)(l * 2 + 1 - cu)) * HS + (size_t)b * P + u, h_new);
                     }
-                    if (ug + RG / 4 < nU) cluster_sync_all();           // partial buffers are reused by the next pass
+                    if (ug + RG / 4 < nU || bc + BCH < Bpad) cluster_sync_all();   // partial buffers are reused by the next pass
                 }
             tick(0);
             grid_arrive(p.bar);
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                         return p.EP[(size_t)(p.row_off[b] + t) * J + rg + r];
                     },
                     [&](int, int r, int b, float v, float e) { store_split(zb, zb + z_lo, (size_t)b * J + rg + r, fmaxf(v + e, 0.f)); });
-                if (rg + RG < j1) cluster_sync_all();
+                if (rg + RG < j1 || bc + BCH < Bpad) cluster_sync_all();
             }
         tick(2);
         grid_arrive(p.bar);
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                     }
                 }
                 __syncthreads();
-                if (rg + RG < o1) cluster_sync_all();
+                if (rg + RG < o1 || bc + BCH < Bpad) cluster_sync_all();
             }
             if (tid < BCH && bc + tid < Bpad) {
                 const int b = bc + tid;
@@ -672,11 +672,8 @@ cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    cudaError_t err = cudaFuncSetAttribute(tdt_decode_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
-    (void)err;
-    cudaGetLastError();
+    cudaError_t err;
     for (int iter = 0; iter < 2; ++iter) {
-        const TdtGeom ge = tdt_geom(p.P, p.J, p.V + p.D, nc, CL);
         bool out_in_smem, wih_in_smem;
         int lstm_floats;
         const size_t smem = tdt_smem_bytes(p, nc, CL, &out_in_smem, &wih_in_smem, &lstm_floats);

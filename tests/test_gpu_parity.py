@@ -205,6 +205,27 @@ def test_tdt_batch_lockstep_equals_singles(eng_tiny, O, tiny):
         assert np.allclose([t.confidence for t in g], [w[3] for w in want], rtol=1e-3)
 
 
+def test_tdt_more_than_64_utterances(pkg, O, tiny, math_mode):
+    """> 64 utterances: the decode kernel walks the batch in passes of 64 (cluster partial-sum buffers are
+    reused between passes); every utterance must still equal its batch-of-1 decode and the oracle."""
+    import dataclasses
+    cfg = dataclasses.replace(tiny.cfg, math=MATH[math_mode], max_batch=96, max_samples=40000)
+    e = pkg.Engine(cfg, tiny.weights_path, 0)
+    try:
+        rng = np.random.default_rng(5)
+        encs = [rng.standard_normal((int(T), tiny.ocfg.d_model)).astype(np.float32) for T in rng.integers(1, 30, size=75)]
+        got = e.decode(encs, 1)
+        for i in (0, 31, 63, 64, 70, 74):
+            assert _tt(got[i]) == _tt(e.decode([encs[i]], 1)[0])
+            try:
+                want = O.tdt_greedy_decode(tiny.W, encs[i], tiny.ocfg, with_timestamps=True, max_steps=4000)
+            except RuntimeError:
+                continue
+            assert _tt(got[i]) == [w[:3] for w in want]
+    finally:
+        e.close()
+
+
 # ------------------------------------------------------------------ whole path through the public API
 def test_transcriber_api_matches_reference_golden(pkg, tiny, synth, golden, math_mode):
     import dataclasses
