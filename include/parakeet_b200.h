@@ -134,6 +134,14 @@ pk_status pk_transcribe_batch(pk_engine *e, const float *pcm, const int64_t *off
 
 /* Device-resident variant for throughput measurement: stage PCM once ... */
 pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt);
+/* Serving pipeline (no reference counterpart: the reference is synchronous and batch-1).  Starts the
+ * host-to-device copy of the NEXT batch into the engine's second PCM buffer on a copy stream and
+ * returns at once, so the copy runs under the current batch's kernels:
+ *     pk_prefetch_pcm(b0); loop { pk_stage_pcm(b_i); pk_run_staged(); pk_prefetch_pcm(b_{i+1}); pk_fetch_tokens(); }
+ * pk_stage_pcm / pk_transcribe_batch with the same (pcm, offsets, n_utt) then adopt the prefetched buffer
+ * instead of copying.  The samples are read when this call is made; the buffer must be page-locked and
+ * packed back to back (PK_ERR_INVALID otherwise) and must stay valid until the adopting call returns. */
+pk_status pk_prefetch_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt);
 /* ... then run the path on the staged batch; tokens stay on the device until
  * pk_fetch_tokens.  Asynchronous on the engine stream. */
 pk_status pk_run_staged(pk_engine *e, pk_decoder dec);

@@ -115,6 +115,10 @@ struct pk_engine {
 
     // ---- workspace
     float *d_pcm = nullptr;
+    float *d_pcm_alt = nullptr;               // second PCM buffer (pk_prefetch_pcm); swapped with d_pcm on adoption
+    cudaEvent_t ev_pcm_free[2] = {}, ev_prefetch = nullptr;   // [k]: last front end reading buffer k has run; prefetch copy done
+    int pcm_cur = 0;                           // which physical buffer d_pcm currently is
+    struct { const float *pcm = nullptr; int32_t n = 0; std::vector<int64_t> off; bool valid = false; } pref;
     int64_t *d_pcm_off = nullptr;
     int32_t *d_frame_off = nullptr, *d_s2_off = nullptr, *d_row_off = nullptr, *d_t2_rows = nullptr;
     float *logmel = nullptr, *feats = nullptr;
@@ -540,6 +544,7 @@ pk_status pk_engine::alloc_workspace() {
     const int t1 = conv_len(Fmax), t2 = conv_len(t1);
     const size_t rows2 = B * t2 * f2n, rows3 = B * (size_t)Tmax * f3n, Mx = B * (size_t)Tmax;
     d_pcm = dalloc<float>(B * (size_t)c.max_samples + 8);
+    d_pcm_alt = dalloc<float>(B * (size_t)c.max_samples + 8);
     d_pcm_off = dalloc<int64_t>(B + 1);
     d_frame_off = dalloc<int32_t>(B + 1);
     d_s2_off = dalloc<int32_t>(B + 1);
@@ -994,6 +999,9 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
                  cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < pk_engine::H2D_CHUNKS && ev_ok; ++i)
         ev_ok = cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&e->ev_prefetch, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_pcm_free[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_pcm_free[1], cudaEventDisableTiming) == cudaSuccess;
     if (!ev_ok) {
         g_create_err = "cudaEventCreate / cudaStreamCreate failed";
         return PK_ERR_CUDA;
@@ -1035,6 +1043,9 @@ void pk_engine_destroy(pk_engine *e) {
     if (e->ev_front) cudaEventDestroy(e->ev_front);
     for (int i = 0; i < pk_engine::H2D_CHUNKS; ++i)
         if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
+    if (e->ev_prefetch) cudaEventDestroy(e->ev_prefetch);
+    for (int i = 0; i < 2; ++i)
+        if (e->ev_pcm_free[i]) cudaEventDestroy(e->ev_pcm_free[i]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1208,6 +1219,23 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
     cudaGetLastError();   // an unregistered host pointer is not an error for us
     cudaError_t ce = cudaSuccess;
     e->front_done = false;
+    if (e->pref.valid) {
+        const bool same = e->pref.pcm == pcm && e->pref.n == n_utt &&
+                          std::equal(e->pref.off.begin(), e->pref.off.end(), offsets);
+        e->pref.valid = false;
+        if (same) {      // the samples are already on their way into the second buffer: adopt it
+            if ((s = e->upload_shapes())) return s;
+            std::swap(e->d_pcm, e->d_pcm_alt);
+            e->pcm_cur ^= 1;
+            ce = cudaStreamWaitEvent(e->stream, e->ev_prefetch, 0);
+            if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("prefetch wait: ") + cudaGetErrorString(ce));
+            if ((s = e->run_mel())) return s;
+            if ((s = e->run_conv1())) return s;
+            cudaEventRecord(e->ev_pcm_free[e->pcm_cur], e->stream);
+            e->front_done = true;
+            return PK_OK;
+        }
+    }
     if (pinned && packed) {
         // DMA in utterance groups on the copy stream; mel + conv1/dw1 of a group start as soon as it has
         // landed, under the DMA of the next group (the copy of 64 x 10 s is ~0.8 ms of PCIe time).
@@ -1231,6 +1259,7 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
             u0 = u1;
         }
         if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D pcm: ") + cudaGetErrorString(ce));
+        cudaEventRecord(e->ev_pcm_free[e->pcm_cur], e->stream);
         e->front_done = true;
         return PK_OK;
     }
@@ -1246,6 +1275,33 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
     return e->upload_shapes();
 }
 
+pk_status pk_prefetch_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt) {
+    if (!e || !pcm || !offsets) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    if (n_utt <= 0 || n_utt > e->Bmax) return e->fail(PK_ERR_CAPACITY, "bad batch size");
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, pcm) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const int64_t total = offsets[n_utt] - offsets[0];
+    bool ok = pinned && total > 0;
+    for (int i = 0; i < n_utt && ok; ++i) {
+        const int64_t ns = offsets[i + 1] - offsets[i];
+        ok = ns >= 400 && ns <= e->cfg.max_samples;
+    }
+    if (!ok) return e->fail(PK_ERR_INVALID, "pk_prefetch_pcm needs a page-locked, packed buffer of valid utterances");
+    // the second buffer was last read by the front end of the batch before the current one
+    cudaError_t ce = cudaStreamWaitEvent(e->copy_stream, e->ev_pcm_free[e->pcm_cur ^ 1], 0);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(e->d_pcm_alt, pcm + offsets[0], (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_prefetch, e->copy_stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_prefetch_pcm: ") + cudaGetErrorString(ce));
+    e->pref.pcm = pcm;
+    e->pref.n = n_utt;
+    e->pref.off.assign(offsets, offsets + n_utt + 1);
+    e->pref.valid = true;
+    return PK_OK;
+}
+
 // Front end (mel + conv1/dw1; 3 launches, always plain launches) unless pk_stage_pcm already ran it
 // group by group under the H2D copy.
 static pk_status run_front(pk_engine *e) {
@@ -1253,6 +1309,7 @@ static pk_status run_front(pk_engine *e) {
     pk_status s;
     if ((s = e->run_mel())) return s;
     if ((s = e->run_conv1())) return s;
+    cudaEventRecord(e->ev_pcm_free[e->pcm_cur], e->stream);
     e->front_done = true;
     return PK_OK;
 }

@@ -42,7 +42,7 @@ class _PkTokens(C.Structure):
 
 EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engine_destroy", "pk_last_error",
            "pk_mel_frames", "pk_encoder_frames", "pk_mel", "pk_encode", "pk_decode", "pk_ctc_logprobs",
-           "pk_transcribe_batch", "pk_stage_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
+           "pk_transcribe_batch", "pk_stage_pcm", "pk_prefetch_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
            "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
            "pk_detokenize", "pk_group_words"]
@@ -75,6 +75,7 @@ def load_library():
     L.pk_ctc_logprobs.argtypes = [vp, f32p, C.c_int32, f32p]
     L.pk_transcribe_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int, C.POINTER(_PkTokens)]
     L.pk_stage_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
+    L.pk_prefetch_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
     L.pk_run_staged.argtypes = [vp, C.c_int]
     L.pk_fetch_tokens.argtypes = [vp, C.POINTER(_PkTokens)]
     L.pk_sync.argtypes = [vp]
@@ -374,6 +375,17 @@ class Engine:
     # -- device-resident variant (bench)
     def stage(self, buf: np.ndarray, off: np.ndarray):
         self._check(self.L.pk_stage_pcm(self.h, _f32p(buf), _i64p(off), len(off) - 1), "pk_stage_pcm")
+
+    def prefetch(self, buf: np.ndarray, off: np.ndarray):
+        """Start the H2D copy of the NEXT batch (page-locked packed buffer) under the current batch's kernels;
+        the following stage() / transcribe_packed() with the same arguments adopts it."""
+        self._check(self.L.pk_prefetch_pcm(self.h, _f32p(buf), _i64p(off), len(off) - 1), "pk_prefetch_pcm")
+
+    def fetch_into(self, out):
+        """pk_fetch_tokens into preallocated arrays (see _tokens)."""
+        t, arrs = out
+        self._check(self.L.pk_fetch_tokens(self.h, C.byref(t)), "pk_fetch_tokens")
+        return arrs
 
     def run_staged(self, decoder: Decoder):
         self._check(self.L.pk_run_staged(self.h, int(decoder)), "pk_run_staged")

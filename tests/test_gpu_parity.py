@@ -226,6 +226,41 @@ def test_tdt_more_than_64_utterances(pkg, O, tiny, math_mode):
         e.close()
 
 
+def test_prefetch_pipeline_equals_blocking_call(pkg, tiny, synth, math_mode):
+    """pk_prefetch_pcm double buffering: the H2D copy of the next batch is started while the current one runs;
+    every batch must give exactly the tokens of the blocking pk_transcribe_batch, also when batches alternate."""
+    import dataclasses
+    import torch
+    e = pkg.Engine(dataclasses.replace(tiny.cfg, math=MATH[math_mode]), tiny.weights_path, 0)
+    try:
+        batches = []
+        for k, lens in enumerate(([32000, 20000, 8000], [16000, 400, 31000, 12345])):
+            pcms = [synth.make_audio(n, 500 + 10 * k + i) for i, n in enumerate(lens)]
+            buf = torch.from_numpy(np.concatenate(pcms)).pin_memory().numpy()
+            off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            arrs = e.transcribe_packed(buf, off, pkg.Decoder.TDT)
+            want = [arrs["ids"][b, :arrs["len"][b]].tolist() for b in range(len(lens))]
+            assert sum(len(w) for w in want) > 0
+            batches.append((buf, off, want))
+        e.prefetch(batches[0][0], batches[0][1])
+        for it in range(5):
+            buf, off, want = batches[it % 2]
+            nbuf, noff, _ = batches[(it + 1) % 2]
+            e.stage(buf, off)
+            e.run_staged(pkg.Decoder.TDT)
+            e.prefetch(nbuf, noff)
+            arrs = e.fetch_into(e._tokens(len(off) - 1))
+            assert [arrs["ids"][b, :arrs["len"][b]].tolist() for b in range(len(off) - 1)] == want
+        # a stage() that does not match the outstanding prefetch falls back to a normal copy
+        buf, off, want = batches[1]
+        e.stage(buf, off)
+        e.run_staged(pkg.Decoder.TDT)
+        arrs = e.fetch_into(e._tokens(len(off) - 1))
+        assert [arrs["ids"][b, :arrs["len"][b]].tolist() for b in range(len(off) - 1)] == want
+    finally:
+        e.close()
+
+
 # ------------------------------------------------------------------ whole path through the public API
 def test_transcriber_api_matches_reference_golden(pkg, tiny, synth, golden, math_mode):
     import dataclasses
