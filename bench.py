@@ -98,6 +98,26 @@ def make_checkpoint(tmpdir):
     return pkg, synth, cfg, wp
 
 
+def omp_threads():
+    """CPUs the reference's OpenMP team can really run on: the affinity mask capped by the cgroup CPU quota
+    (the GPU boxes show 128 CPUs but grant 16 CPUs of time; 128 spinning threads made the reference 4.6x slower).
+    The team size is applied with omp_set_num_threads on the OpenMP runtime libpkref.so uses."""
+    import ctypes
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU path (Transcriber::transcribe, transcribe.hpp:99-179)."""
     if rank != 0:
@@ -107,8 +127,7 @@ def run_reference(args, rank, world):
     if not R.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpkref.so not built"}))
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = omp_threads()
     pkg, synth, cfg, wp = make_checkpoint(args.tmp)
     m = R.RefModel(wp, "", 0)
     clips = [synth.make_audio(CLIP_SAMPLES, 1000 + i) for i in range(2)]
@@ -129,7 +148,7 @@ def run_reference(args, rank, world):
             "config": {"workload": "tdt-ctc-110m TDT decode, 10 s 16 kHz synthetic clips", "clips_per_step": 1,
                        "note": "bounded sample: 1 clip per step of the 64-clip batch"},
             "cpu_baseline": {"value": val, "unit": "x real-time", "cores": cores, "kind": "reference",
-                             "sample": f"{args.steps} x one 10 s clip, TDT, OMP_NUM_THREADS={os.environ['OMP_NUM_THREADS']}",
+                             "sample": f"{args.steps} x one 10 s clip, TDT, OpenMP team = {cores} threads (affinity mask capped by the cgroup CPU quota)",
                              "stage_ms_per_clip": {"mel": stage[0] / args.steps, "encoder": stage[1] / args.steps,
                                                    "decode": stage[2] / args.steps}},
             "e2e": {"value": val, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -344,15 +363,14 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import refbind as R
         if R.available():
-            cores = os.cpu_count() or 1
-            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            cores = omp_threads()
             m = R.RefModel(wp, "", 0)
             m.transcribe(pcms[0][:32000], args.decoder)                 # touch the weights
             t0 = time.perf_counter()
             ids, stage = m.transcribe(pcms[0], args.decoder)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": CLIP_SECONDS / dt, "unit": "x real-time", "cores": cores, "kind": "reference",
-                                    "sample": "1 x 10 s clip of the batch (clip 0), all host threads",
+                                    "sample": f"1 x 10 s clip of the batch (clip 0), OpenMP team = {cores} threads (cgroup CPU quota)",
                                     "stage_ms": {"mel": stage[0], "encoder": stage[1], "decode": stage[2]},
                                     "tokens_match_gpu": ids == [t.token_id for t in ref_tokens[0]]}
             m.close()
