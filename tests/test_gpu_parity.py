@@ -7,6 +7,8 @@ Tolerances: tokens / frames / argmax are bit-exact; floating point uses the nort
 bound "encoder activations within 1e-3 rel fp32" (max-abs error / max-abs reference), and
 tighter where the arithmetic is exact fp32.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -294,6 +296,30 @@ def test_transcribe_110m_whole_path_tokens(pkg, m110, synth, golden, math_mode):
     assert r.text == bytes(golden[k + "ctc_text"]).decode()
     r = t.transcribe(pcm, pkg.Decoder.TDT, True)
     assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == golden[k + "tdt_tok"].tolist()
+    t.engine.close()
+
+
+def test_transcribe_110m_more_clips_tokens_match_reference(pkg, m110, synth, math_mode):
+    """Twenty more full-size clips decoded by the compiled reference (tests/golden/make_golden.py 110m_extra:
+    four of 3 ... 10 s plus the first 16 clips of bench.py's batch): CTC and TDT tokens + frames bit-exact,
+    confidences to 1e-3, as ONE ragged batch.  The closest CTC argmax decision in these clips has a top-2
+    log-prob gap of 0.0006."""
+    import dataclasses
+    gx = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_110m_extra_v1.npz"))
+    n_clips = int(gx["n_clips"][0])
+    assert n_clips >= 4
+    t = pkg.Transcriber(m110.weights_path, m110.vocab_path, dataclasses.replace(m110.cfg, math=MATH[math_mode]))
+    pcms = []
+    for ci in range(n_clips):
+        n, aseed = (int(v) for v in gx[f"x110.c{ci}.n_samples"])
+        pcms.append(synth.make_audio(n, aseed))
+    for dec, tag in ((pkg.Decoder.CTC, "ctc"), (pkg.Decoder.TDT, "tdt")):
+        rs = t.transcribe_batch(pcms, dec, True)
+        for ci, r in enumerate(rs):
+            k = f"x110.c{ci}."
+            assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == gx[k + tag + "_tok"].tolist(), (tag, ci)
+            assert np.allclose([x.confidence for x in r.timestamped_tokens], gx[k + tag + "_conf"], rtol=1e-3, atol=1e-6)
+            assert r.text == bytes(gx[k + tag + "_text"]).decode()
     t.engine.close()
 
 
