@@ -154,8 +154,46 @@ def main_110m_extra():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def main_600m_extra():
+    """Three more tdt-600m clips (tokens, frames, confidences, text only)."""
+    out = {}
+    ocfg = O.make_tdt_600m_config()
+    clips = [(40000, 2001), (72000, 2002), (56000, 2003)]
+    with tempfile.TemporaryDirectory() as td:
+        W = synth.make_weights(ocfg, seed=0)
+        wp = os.path.join(td, "m600.safetensors")
+        synth.save_safetensors(wp, W)
+        pieces = synth.make_vocab(ocfg.vocab - 1, seed=0)
+        vp = os.path.join(td, "m600.vocab.txt")
+        synth.save_vocab(vp, pieces)
+        m = R.RefModel(wp, vp, 1)
+        kept = 0
+        for n, aseed in clips:
+            pcm = synth.make_audio(n, aseed)
+            feats = R.mel(pcm, ocfg.mel_bins)
+            enc = m.encode(feats, ocfg.d_model)
+            try:
+                tdt = m.tdt_greedy(enc, True)
+            except Exception as ex:
+                print("skip", n, aseed, type(ex).__name__, ex)
+                continue
+            k = f"x600.c{kept}."
+            kept += 1
+            out[k + "n_samples"] = np.array([n, aseed], np.int64)
+            out[k + "tdt_tok"], out[k + "tdt_conf"] = toks_arr(tdt)
+            out[k + "tdt_text"] = np.frombuffer(m.detok([t[0] for t in tdt]).encode(), np.uint8)
+            print("x600", kept - 1, n, aseed, "tdt", len(tdt))
+        m.close()
+    out["n_clips"] = np.array([kept], np.int64)
+    path = os.path.join(ROOT, "tests", "golden", "golden_600m_extra_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "110m_extra":
+    if len(sys.argv) > 1 and sys.argv[1] == "600m_extra":
+        main_600m_extra()
+    elif len(sys.argv) > 1 and sys.argv[1] == "110m_extra":
         main_110m_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "600m":
         main_600m()

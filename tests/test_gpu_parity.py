@@ -435,5 +435,16 @@ def test_tdt_600m_preset_matches_reference_golden(pkg, O, synth, m600):
     assert r.text == bytes(g[k + "tdt_text"]).decode()
     rs = t.transcribe_batch([pcm[:40000], pcm, pcm[:16000]], pkg.Decoder.TDT)
     assert rs[1].token_ids == r.token_ids
+    # three more clips decoded by the compiled reference (make_golden.py 600m_extra), as one ragged batch
+    gx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_600m_extra_v1.npz"))
+    pcms = []
+    for ci in range(int(gx["n_clips"][0])):
+        n2, seed2 = (int(v) for v in gx[f"x600.c{ci}.n_samples"])
+        pcms.append(synth.make_audio(n2, seed2))
+    for ci, r2 in enumerate(t.transcribe_batch(pcms, pkg.Decoder.TDT, True)):
+        kx = f"x600.c{ci}."
+        assert [[x.token_id, x.start_frame, x.end_frame] for x in r2.timestamped_tokens] == gx[kx + "tdt_tok"].tolist(), ci
+        assert np.allclose([x.confidence for x in r2.timestamped_tokens], gx[kx + "tdt_conf"], rtol=1e-3, atol=1e-6)
+        assert r2.text == bytes(gx[kx + "tdt_text"]).decode()
     e.close()
     t.engine.close()
