@@ -12,8 +12,11 @@ rank owns its own 64 clips, the only exchange is one all-gather of the token buf
 
   value  : whole-job audio-seconds per second with the PCM already resident in HBM
            (pk_stage_pcm once, then pk_run_staged per step on the engine stream).
-  e2e    : same metric through the public API call pk_transcribe_batch with HOST buffers,
-           H2D of the PCM and D2H of the tokens inside the timed region.
+  e2e    : same metric through the public C-ABI with HOST buffers: every step copies its 41 MB of PCM from
+           page-locked memory and reads its tokens back inside the timed region, driven as a serving loop
+           (pk_stage_pcm + pk_run_staged + pk_prefetch_pcm(next batch) + pk_fetch_tokens: the H2D copy of
+           batch i+1 runs under the kernels of batch i); e2e.sync_call = the single blocking call
+           pk_transcribe_batch per batch.
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section "Measurement".
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/libpkref.so,
