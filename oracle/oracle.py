@@ -51,6 +51,10 @@ class Config:
     has_ctc: bool = True
     joint_prefix: str = "tdt_joint_."   # ParakeetTDTCTC (tdt_ctc.cpp:5-9)
     name: str = "tdt-ctc-110m"
+    # streaming encoder only (StreamingEncoderConfig, streaming_encoder.hpp:18-24)
+    att_context_left: int = 70
+    att_context_right: int = 0
+    xscaling: bool = False
 
 
 def make_110m_config() -> Config:          # config.hpp:77-95
@@ -61,6 +65,17 @@ def make_tdt_600m_config() -> Config:      # config.hpp:98-116, tdt.cpp:28-32
     return Config(mel_bins=128, d_model=1024, n_layers=24, n_heads=8, ff=4096,
                   vocab=8193, lstm_layers=2, has_ctc=False, joint_prefix="joint_.",
                   name="tdt-600m")
+
+
+def make_eou_120m_config() -> Config:      # eou.hpp:32-55 (streaming; ParakeetEOU registers "joint_", eou.cpp:9-13)
+    return Config(has_ctc=False, joint_prefix="joint_.", att_context_left=70, att_context_right=1, name="eou-120m")
+
+
+def make_tiny_stream_config() -> Config:
+    """Not a reference preset: a small streaming shape for fast unit tests only."""
+    return Config(mel_bins=80, sub_channels=64, d_model=128, n_layers=2, n_heads=2, ff=256, vocab=33, pred_hidden=64,
+                  joint_hidden=64, has_ctc=False, joint_prefix="joint_.", att_context_left=12, att_context_right=1,
+                  name="tiny-stream")
 
 
 def make_tiny_config() -> Config:
@@ -471,6 +486,212 @@ def tdt_greedy_decode(W, enc, cfg: Config, max_symbols=10, with_timestamps=False
                 t += skip
                 break
     return out
+
+
+# ----------------------------------------------------------------------------
+# Streaming path (eou-120m)         src/audio.cpp:170-259, src/streaming_encoder.cpp, src/eou.cpp
+# ----------------------------------------------------------------------------
+class StreamingPreprocessor:
+    """StreamingAudioPreprocessor (audio.cpp:172-259): carried pre-emphasis sample, overlap buffer of the
+    samples past the last complete frame, center=False STFT (no reflect padding), log-mel WITHOUT
+    normalisation (the running statistics of the header are never used)."""
+
+    def __init__(self, n_mels: int = 80):
+        self.n_mels = n_mels
+        self.last = F32(0.0)
+        self.overlap = np.zeros(0, F32)
+
+    def process_chunk(self, samples):
+        n_fft, win_len, hop = 512, 400, 160
+        x = np.asarray(samples, F32)
+        pre = np.empty_like(x)                                    # :206-213
+        prev = self.last
+        if len(x):
+            pre[0] = x[0] - F32(0.97) * prev
+            pre[1:] = x[1:] - F32(0.97) * x[:-1]
+            self.last = x[-1]
+        buf = np.concatenate([self.overlap, pre]).astype(F32)      # :216-221
+        total = len(buf)
+        if total < win_len:                                        # :225-229
+            self.overlap = buf
+            return None
+        n_frames = (total - win_len) // hop + 1                    # :231-236
+        consumed = (n_frames - 1) * hop + win_len                  # :239-240
+        self.overlap = buf[consumed:].copy()
+        sig = buf[:consumed]
+        # fft::stft(center=False) frames are n_fft = 512 long while `consumed` was sized with win_length = 400,
+        # so the STFT returns one frame fewer than n_frames (13-14 per 2560-sample chunk) and the overlap
+        # buffer holds only the samples past `consumed` -- both quirks kept (SURVEY section 8f row 2).
+        frames = stft_frames_no_center(sig, n_fft, win_len, hop)
+        spec = np.fft.rfft(frames.astype(F32), n=n_fft, axis=1).astype(np.complex64)
+        mag = np.abs(spec).astype(F32)
+        power = (mag * mag).T
+        fb = mel_filterbank(n_fft // 2 + 1, self.n_mels)
+        mel = fb.T.astype(F32) @ power
+        return np.ascontiguousarray(np.log(mel + F32(5.96046448e-8)).astype(F32).T)   # (n_frames, n_mels)
+
+
+def stft_frames_no_center(sig, n_fft, win_len, hop):
+    """Frames of fft::stft(center=False) (fft.cpp:1478-1605): frame count (len - n_fft)//hop + 1 over the
+    signal as given, each frame n_fft samples times the centre-padded window."""
+    win = np.zeros(n_fft, dtype=F32)
+    lp = (n_fft - win_len) // 2
+    win[lp:lp + win_len] = hann_window(win_len)
+    if len(sig) < n_fft:                       # fft.cpp:1516-1521: the reference throws here
+        raise ValueError("stft: signal length (%d) is less than n_fft (%d)" % (len(sig), n_fft))
+    n_frames = (len(sig) - n_fft) // hop + 1
+    idx = np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]
+    return sig[idx] * win[None, :]
+
+
+class StreamEncoderCache:
+    """EncoderCache / BlockCache (streaming_encoder.hpp:28-44)."""
+
+    def __init__(self, n_layers):
+        self.sub = None                                   # leftover mel frames (n, mel)
+        self.conv = [None] * n_layers                     # (d, k-1) GLU outputs
+        self.k = [None] * n_layers                        # (H, n, hd)
+        self.v = [None] * n_layers
+        self.frames_seen = 0
+
+
+def stream_subsample_cached(W, feats, cache: StreamEncoderCache, cfg: Config):
+    """CausalConvSubsampling::forward_cached (streaming_encoder.cpp:339-378): prepend the leftover frames,
+    run the ordinary (zero-padded) subsampling on the largest multiple of 8 frames, keep the rest."""
+    mel_in = feats if cache.sub is None else np.concatenate([cache.sub, feats], axis=0)
+    total = mel_in.shape[0]
+    consumable = (total // 8) * 8
+    if consumable == 0:
+        cache.sub = np.ascontiguousarray(mel_in)
+        return None
+    cache.sub = np.ascontiguousarray(mel_in[consumable:]) if total > consumable else None
+    return conv_subsampling(W, mel_in[:consumable], cfg)          # ReLU variant (eou preset default)
+
+
+def stream_attention_cached(W, p, x, pos_emb, cache: StreamEncoderCache, li, cfg: Config, apply_context_mask=False):
+    """StreamingConformerAttention::forward_cached (streaming_encoder.cpp:160-272): K/V of the chunk appended to
+    the cache (trimmed to att_context_left AFTER use as this chunk's keys), position scores WITHOUT rel_shift
+    (right-most kv_len columns), then the bounded-context mask -- which has NO EFFECT on the reference's CPU
+    path: the mask is built as a float32 tensor of 1.0 / 0.0 (:246-258) and axiom's CPU masked_fill reads the
+    first BYTE of every mask element (cpu_operations.cpp:2699-2701, :2719-2721); the low byte of 1.0f
+    (0x3F800000, little endian) is 0, so nothing is ever filled.  The compiled reference therefore attends to
+    every cached key and to the whole chunk.  apply_context_mask=True gives the intended behaviour."""
+    C, d = x.shape
+    H = cfg.n_heads
+    hd = d // H
+    h = layer_norm(x, W[p + "norm_.weight"], W[p + "norm_.bias"])
+    q = linear(h, W[p + "mha_.q_proj.weight"], W[p + "mha_.q_proj.bias"]).reshape(C, H, hd).transpose(1, 0, 2)
+    k = linear(h, W[p + "mha_.k_proj.weight"], W[p + "mha_.k_proj.bias"]).reshape(C, H, hd).transpose(1, 0, 2)
+    v = linear(h, W[p + "mha_.v_proj.weight"], W[p + "mha_.v_proj.bias"]).reshape(C, H, hd).transpose(1, 0, 2)
+    if cache.k[li] is not None:                                           # :185-189
+        k = np.concatenate([cache.k[li], k], axis=1)
+        v = np.concatenate([cache.v[li], v], axis=1)
+    kv = k.shape[1]
+    L, Rr = cfg.att_context_left, cfg.att_context_right
+    if kv > L:                                                            # :193-208
+        cache.k[li], cache.v[li] = k[:, kv - L:].copy(), v[:, kv - L:].copy()
+    else:
+        cache.k[li], cache.v[li] = k.copy(), v.copy()
+    u = W[p + "pos_bias_u_"].reshape(H, 1, hd)
+    vb = W[p + "pos_bias_v_"].reshape(H, 1, hd)
+    ac = (q + u) @ k.transpose(0, 2, 1)                                   # (H, C, kv)
+    P = pos_emb.shape[0]
+    pp = linear(pos_emb, W[p + "pos_proj_.weight"]).reshape(P, H, hd).transpose(1, 0, 2)
+    ps = (q + vb) @ pp.transpose(0, 2, 1)                                 # (H, C, P), no rel_shift
+    if P > kv:                                                            # :224-232
+        ps = ps[:, :, P - kv:]
+    scores = ((ac + ps) * F32(1.0 / math.sqrt(hd))).astype(F32)
+    if apply_context_mask and (L >= 0 or Rr >= 0):                        # :239-262 (see docstring)
+        qi = np.arange(C)[:, None] + (kv - C)
+        dist = qi - np.arange(kv)[None, :]
+        masked = (dist > L) | (-dist > Rr)
+        scores = np.where(masked[None, :, :], F32(-1e9), scores).astype(F32)
+    a = softmax(scores, axis=-1)
+    o = (a @ v).transpose(1, 0, 2).reshape(C, d)
+    o = linear(o, W[p + "mha_.out_proj.weight"], W[p + "mha_.out_proj.bias"])
+    return (x + o).astype(F32)
+
+
+def stream_conv_cached(W, p, x, cache: StreamEncoderCache, li, cfg: Config):
+    """CausalConformerConvModule::forward_cached (streaming_encoder.cpp:41-80): the k-1 previous GLU outputs
+    (zeros for the first chunk) are prepended, the depthwise conv runs without padding."""
+    d = x.shape[1]
+    h = layer_norm(x, W[p + "norm_.weight"], W[p + "norm_.bias"])
+    h = linear(h, W[p + "pointwise_conv1_.weight"][:, :, 0], W[p + "pointwise_conv1_.bias"])
+    h = (h[:, :d] * sigmoid(h[:, d:])).astype(F32).T                      # (d, C)
+    cl = cfg.conv_k - 1
+    left = cache.conv[li] if cache.conv[li] is not None else np.zeros((d, cl), F32)
+    h = np.concatenate([left, h], axis=1)
+    cache.conv[li] = np.ascontiguousarray(h[:, h.shape[1] - cl:])
+    h = depthwise_conv1d(h, W[p + "depthwise_conv_.weight"], W[p + "depthwise_conv_.bias"], 0).T   # (C, d)
+    mean, var = W[p + "batch_norm_.running_mean"], W[p + "batch_norm_.running_var"]
+    h = ((h - mean) / np.sqrt(var + F32(1e-5)) * W[p + "batch_norm_.weight"] + W[p + "batch_norm_.bias"]).astype(F32)
+    h = silu(h)
+    h = linear(h, W[p + "pointwise_conv2_.weight"][:, :, 0], W[p + "pointwise_conv2_.bias"])
+    return (x + h).astype(F32)
+
+
+def stream_encoder_chunk(W, feats, cache: StreamEncoderCache, cfg: Config):
+    """StreamingFastConformerEncoder::forward_chunk (streaming_encoder.cpp:425-472). feats (n, mel) -> (C, d) | None."""
+    x = stream_subsample_cached(W, feats, cache, cfg)
+    if x is None:
+        return None
+    if cfg.xscaling:
+        x = (x * F32(math.sqrt(cfg.d_model))).astype(F32)
+    C = x.shape[0]
+    pos = sinusoidal_position_embedding(cfg.att_context_left + C, cfg.d_model)      # :451-452
+    for i in range(cfg.n_layers):
+        p = f"encoder_.layers_.{i}."
+        x = feed_forward(W, p + "ffn1_.", x)
+        x = stream_attention_cached(W, p + "attn_.", x, pos, cache, i, cfg)
+        x = stream_conv_cached(W, p + "conv_.", x, cache, i, cfg)
+        x = feed_forward(W, p + "ffn2_.", x)
+        x = layer_norm(x, W[p + "final_norm_.weight"], W[p + "final_norm_.bias"])
+    cache.frames_seen += C
+    return x
+
+
+class StreamDecodeState:
+    """StreamingDecodeState (eou.hpp:80-87)."""
+
+    def __init__(self, cfg: Config):
+        H = cfg.pred_hidden
+        self.states = [(np.zeros(H, F32), np.zeros(H, F32)) for _ in range(cfg.lstm_layers)]
+        self.token = cfg.vocab - 1
+        self.frame_offset = 0
+        self.tokens = []
+
+
+def stream_decode_chunk(W, enc, st: StreamDecodeState, cfg: Config, max_symbols=10, max_steps=100000):
+    """rnnt_streaming_decode_chunk (eou.cpp:17-98): the offline TDT loop per chunk with carried LSTM state and
+    absolute frame numbers; end frame is NOT clamped to the chunk; same no-forced-advance quirk."""
+    C = enc.shape[0]
+    blank = cfg.vocab - 1
+    new, t, steps = [], 0, 0
+    base = st.frame_offset
+    while t < C:
+        for _sym in range(max_symbols):
+            steps += 1
+            if steps > max_steps:
+                raise RuntimeError("stream_decode_chunk: livelock")
+            saved = st.states
+            pred, st.states = prediction_step(W, st.token, st.states, cfg)
+            lab, dur = tdt_joint(W, enc[t], pred, cfg)
+            tok = first_argmax(lab)
+            di = first_argmax(dur)
+            skip = cfg.durations[di] if di < len(cfg.durations) else 1
+            if tok == blank:
+                st.states = saved
+                t += max(skip, 1)
+                break
+            new.append((tok, base + t, base + t + max(skip, 1) - 1, float(np.exp(F32(lab[tok])))))
+            st.tokens.append(tok)
+            st.token = tok
+            if skip > 0:
+                t += skip
+                break
+    st.frame_offset += C
+    return new
 
 
 # ----------------------------------------------------------------------------

@@ -153,3 +153,44 @@ class RefModel:
         ids = np.zeros(cap, np.int32); ms = np.zeros(3, np.float64)
         n = _check(lib().pkref_transcribe(self.h, pcm, len(pcm), 0 if decoder == "ctc" else 1, cap, ids, ms))
         return [int(x) for x in ids[:n]], ms.tolist()
+
+
+class RefStream:
+    """One stream through the compiled reference's STREAMING path (oracle/ref_harness_stream.cpp):
+    StreamingAudioPreprocessor -> StreamingFastConformerEncoder::forward_chunk -> rnnt_streaming_decode_chunk."""
+
+    def __init__(self, weights_path, cfg):
+        L = lib()
+        L.pkref_stream_new.restype = C.c_void_p
+        L.pkref_stream_new.argtypes = [C.c_char_p] + [C.c_int] * 12
+        L.pkref_stream_last_error.restype = C.c_char_p
+        L.pkref_stream_free.argtypes = [C.c_void_p]
+        L.pkref_stream_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self.L, self.cfg = L, cfg
+        self.h = L.pkref_stream_new(weights_path.encode(), cfg.mel_bins, cfg.sub_channels, cfg.d_model, cfg.n_layers, cfg.n_heads,
+                                    cfg.ff, cfg.vocab, cfg.pred_hidden, cfg.lstm_layers, cfg.joint_hidden, cfg.att_context_left,
+                                    cfg.att_context_right)
+        if not self.h:
+            raise RuntimeError("pkref_stream_new: " + L.pkref_stream_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.pkref_stream_free(self.h)
+            self.h = None
+
+    def chunk(self, pcm):
+        """-> (feats (n, mel) | None, enc (C, d) | None, [(id, start, end, conf), ...])"""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        cap_f, cap_e, cap_t = 4 + len(pcm) // 160, 2 + len(pcm) // 1280 + 2, 4096
+        feats = np.zeros((cap_f, self.cfg.mel_bins), np.float32)
+        enc = np.zeros((cap_e, self.cfg.d_model), np.float32)
+        tok = np.zeros((cap_t, 3), np.int32)
+        conf = np.zeros(cap_t, np.float32)
+        nf, ne, nt = C.c_int(), C.c_int(), C.c_int()
+        rc = self.L.pkref_stream_chunk(self.h, pcm.ctypes.data, len(pcm), feats.ctypes.data, cap_f, C.byref(nf), enc.ctypes.data,
+                                       cap_e, C.byref(ne), tok.ctypes.data, conf.ctypes.data, cap_t, C.byref(nt))
+        if rc != 0:
+            raise RuntimeError("pkref_stream_chunk: " + self.L.pkref_stream_last_error().decode())
+        toks = [(int(tok[i, 0]), int(tok[i, 1]), int(tok[i, 2]), float(conf[i])) for i in range(nt.value)]
+        return (feats[:nf.value].copy() if nf.value else None, enc[:ne.value].copy() if ne.value else None, toks)

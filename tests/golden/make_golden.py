@@ -190,8 +190,50 @@ def main_600m_extra():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+STREAM_SCHEDULE = [2560, 2560, 2560, 1000, 4000, 2560, 2560, 2560, 2560, 5000, 2560, 2560, 2560, 2560, 2560, 2560, 2560]
+
+
+def main_stream():
+    """Streaming path (eou-120m) through the compiled reference, chunk by chunk:
+    StreamingAudioPreprocessor -> forward_chunk -> rnnt_streaming_decode_chunk (oracle/ref_harness_stream.cpp).
+    The oracle is run FIRST on every model: the reference would hang on a livelocking decode."""
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        for tag, ocfg, wseed, aseed, sched in (("tstream", O.make_tiny_stream_config(), 3, 77, STREAM_SCHEDULE),
+                                               ("eou120", O.make_eou_120m_config(), 0, 1200, [2560] * 14)):
+            W = synth.make_weights(ocfg, seed=wseed)
+            pcm = synth.make_audio(sum(sched), aseed)
+            pre, cache, st = O.StreamingPreprocessor(ocfg.mel_bins), O.StreamEncoderCache(ocfg.n_layers), O.StreamDecodeState(ocfg)
+            pos = 0
+            for n in sched:                                   # raises RuntimeError on a livelock
+                f = pre.process_chunk(pcm[pos:pos + n]); pos += n
+                e = O.stream_encoder_chunk(W, f, cache, ocfg) if f is not None else None
+                if e is not None:
+                    O.stream_decode_chunk(W, e, st, ocfg, max_steps=5000)
+            wp = os.path.join(td, tag + ".safetensors")
+            synth.save_safetensors(wp, W)
+            rs = R.RefStream(wp, ocfg)
+            pos, ntok = 0, 0
+            out[tag + ".schedule"] = np.array(sched, np.int64)
+            out[tag + ".seeds"] = np.array([wseed, aseed], np.int64)
+            for ci, n in enumerate(sched):
+                f, e, toks = rs.chunk(pcm[pos:pos + n]); pos += n
+                k = f"{tag}.k{ci}."
+                out[k + "feats"] = f if f is not None else np.zeros((0, ocfg.mel_bins), np.float32)
+                out[k + "enc"] = e if e is not None else np.zeros((0, ocfg.d_model), np.float32)
+                out[k + "tok"], out[k + "conf"] = toks_arr(toks)
+                ntok += len(toks)
+            rs.close()
+            print(tag, "chunks", len(sched), "tokens", ntok)
+    path = os.path.join(ROOT, "tests", "golden", "golden_stream_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "600m_extra":
+    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+        main_stream()
+    elif len(sys.argv) > 1 and sys.argv[1] == "600m_extra":
         main_600m_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "110m_extra":
         main_110m_extra()

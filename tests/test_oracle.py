@@ -6,8 +6,12 @@
       (tests/golden/golden_v1.npz <- tests/golden/make_golden.py),
   (3) when oracle/_ref/libpkref.so is present, the live compiled reference.
 """
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _lp_from_pattern(pattern, V=1025):
@@ -193,3 +197,98 @@ def test_golden_600m_decode(O, synth):
     tdt = O.tdt_greedy_decode({k: W[k] for k in rng_needed}, g["m600.c0.enc"], ocfg, with_timestamps=True)
     assert [[t[0], t[1], t[2]] for t in tdt] == g["m600.c0.tdt_tok"].tolist()
     assert np.allclose([t[3] for t in tdt], g["m600.c0.tdt_conf"], rtol=1e-4)
+
+
+# ------------------------------------------------------------------ streaming path (eou-120m)
+def _run_stream_oracle(O, synth, W, ocfg, pcm, sched):
+    pre, cache, st = O.StreamingPreprocessor(ocfg.mel_bins), O.StreamEncoderCache(ocfg.n_layers), O.StreamDecodeState(ocfg)
+    pos, out = 0, []
+    for n in sched:
+        f = pre.process_chunk(pcm[pos:pos + n])
+        pos += n
+        e = O.stream_encoder_chunk(W, f, cache, ocfg) if f is not None else None
+        t = O.stream_decode_chunk(W, e, st, ocfg, max_steps=5000) if e is not None else []
+        out.append((f, e, t))
+    return out
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-9))
+
+
+@pytest.mark.parametrize("tag", ["tstream", "eou120"])
+def test_golden_streaming_chunks(O, synth, tag):
+    """The streaming restatement (StreamingPreprocessor, stream_encoder_chunk, stream_decode_chunk) against the
+    compiled reference's chunk-by-chunk outputs (tests/golden/make_golden.py stream): frame-count quirk (13/14
+    frames per 2560 samples), leftover-frame cache, K/V and conv caches, un-shifted position scores, the
+    ineffective CPU context mask, carried LSTM state, absolute frame numbers."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_stream_v1.npz"))
+    ocfg = O.make_tiny_stream_config() if tag == "tstream" else O.make_eou_120m_config()
+    wseed, aseed = (int(v) for v in g[tag + ".seeds"])
+    sched = [int(v) for v in g[tag + ".schedule"]]
+    W = synth.make_weights(ocfg, seed=wseed)
+    pcm = synth.make_audio(sum(sched), aseed)
+    n_tok = 0
+    for ci, (f, e, t) in enumerate(_run_stream_oracle(O, synth, W, ocfg, pcm, sched)):
+        k = f"{tag}.k{ci}."
+        gf, ge_, gt, gc = g[k + "feats"], g[k + "enc"], g[k + "tok"], g[k + "conf"]
+        assert (0 if f is None else f.shape[0]) == gf.shape[0]
+        if gf.shape[0]:
+            assert _rel(f, gf) < 1e-4
+        assert (0 if e is None else e.shape[0]) == ge_.shape[0]
+        if ge_.shape[0]:
+            assert _rel(e, ge_) < 1e-4
+        assert [list(x[:3]) for x in t] == gt.tolist()
+        assert np.allclose([x[3] for x in t], gc, rtol=1e-3)
+        n_tok += len(t)
+    assert n_tok > 5
+
+
+def test_streaming_context_mask_is_inert_in_the_reference(O, synth):
+    """Documented reference quirk: on CPU the bounded-context mask of forward_cached never fills anything
+    (float mask read bytewise), so the golden encoder output matches the oracle WITHOUT the mask and differs
+    from the intended masked attention once a chunk has 3 frames."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_stream_v1.npz"))
+    ocfg = O.make_tiny_stream_config()
+    wseed, aseed = (int(v) for v in g["tstream.seeds"])
+    sched = [int(v) for v in g["tstream.schedule"]]
+    W = synth.make_weights(ocfg, seed=wseed)
+    pcm = synth.make_audio(sum(sched), aseed)
+    pre, cache = O.StreamingPreprocessor(ocfg.mel_bins), O.StreamEncoderCache(ocfg.n_layers)
+    real = O.stream_attention_cached
+    try:
+        O.stream_attention_cached = lambda *a, **kw: real(*a, apply_context_mask=True, **kw)
+        pos, worst = 0, 0.0
+        for ci, n in enumerate(sched):
+            f = pre.process_chunk(pcm[pos:pos + n])
+            pos += n
+            e = O.stream_encoder_chunk(W, f, cache, ocfg) if f is not None else None
+            if e is not None:
+                worst = max(worst, _rel(e, g[f"tstream.k{ci}.enc"]))
+    finally:
+        O.stream_attention_cached = real
+    assert worst > 1e-3
+
+
+def test_live_reference_streaming(O, synth, refbind, tmp_path):
+    if refbind is None:
+        pytest.skip("oracle/_ref/libpkref.so not built")
+    ocfg = O.make_tiny_stream_config()
+    W = synth.make_weights(ocfg, seed=9)
+    wp = str(tmp_path / "ts9.safetensors")
+    synth.save_safetensors(wp, W)
+    sched = [2560, 3000, 800, 2560, 6000, 2560, 2560]
+    pcm = synth.make_audio(sum(sched), 91)
+    want = _run_stream_oracle(O, synth, W, ocfg, pcm, sched)      # oracle first: the reference would hang on a livelock
+    rs = refbind.RefStream(wp, ocfg)
+    pos = 0
+    for n, (f, e, t) in zip(sched, want):
+        rf, re_, rt = rs.chunk(pcm[pos:pos + n])
+        pos += n
+        assert (rf is None) == (f is None) and (re_ is None) == (e is None)
+        if f is not None:
+            assert _rel(f, rf) < 1e-4
+        if e is not None:
+            assert _rel(e, re_) < 1e-4
+        assert [x[:3] for x in rt] == [x[:3] for x in t]
+    rs.close()
