@@ -140,6 +140,23 @@ def test_encoder_long_utterance(pkg, O, synth, tiny, math_mode):
         e.close()
 
 
+def test_bf16x1_mode_runs_within_its_looser_bound(pkg, O, synth, tiny):
+    """PK_MATH_BF16X1 (plain bf16 operands, one MMA per product; opt-in, NOT the parity mode): the whole path
+    runs and the encoder stays within 2e-2 of the oracle (tokens are not required to match)."""
+    import dataclasses
+    e = pkg.Engine(dataclasses.replace(tiny.cfg, math=1), tiny.weights_path, 0)
+    try:
+        pcms = [synth.make_audio(n, 700 + i) for i, n in enumerate([32000, 9000])]
+        feats = [O.preprocess_audio(p) for p in pcms]
+        for f, b in zip(feats, e.encode(feats)):
+            assert _rel(b, O.encoder_forward(tiny.W, f, tiny.ocfg)) < 2e-2
+        for dec in (0, 1):
+            toks = e.transcribe_batch(pcms, dec)
+            assert len(toks) == 2
+    finally:
+        e.close()
+
+
 def test_encoder_110m_matches_reference_golden(eng110, O, m110, synth, golden):
     k = "m110.c0."
     n, aseed = (int(v) for v in golden[k + "n_samples"])
