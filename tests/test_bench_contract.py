@@ -1,0 +1,50 @@
+"""The bench.py output contract, checked on the committed bench lines (profiles/): every key the driver and the
+judge read must be there with the right type.  (The lines themselves are produced on the GPU box.)"""
+import glob
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_l_bench_n*.json")))
+
+
+def _line(path):
+    return json.loads(open(path).read().strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("path", LINES, ids=[os.path.basename(p) for p in LINES])
+def test_bench_line_has_the_contract_keys(path):
+    d = _line(path)
+    for k, t in (("metric", str), ("value", float), ("unit", str), ("n_gpus", int), ("steps", int), ("warmup", int),
+                 ("ms_per_step", float), ("higher_is_better", bool), ("scaling", str), ("dtype", str), ("data", str),
+                 ("config", dict), ("e2e", dict), ("gpu_launches", int), ("clocks", dict), ("roofline", dict)):
+        assert isinstance(d[k], t), (k, type(d[k]))
+    assert "vs_baseline" in d and d["vs_baseline"] is None          # BASELINE.md has no published number for B200
+    assert d["warmup"] >= 3 and d["scaling"] == "weak" and d["higher_is_better"] is True
+    assert "workload" in d["config"] and "l2" in d["config"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 160000 * 4 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] <= d["value"] * 1.02                           # end to end cannot beat the device-resident number
+    assert e["sync_call"]["value"] <= e["value"] * 1.02
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not any("slowdown" in x for x in c["reasons"])
+    assert d["gpu_launches"] > 0
+    if d["n_gpus"] == 1:
+        b = d["cpu_baseline"]
+        assert b["kind"] in ("reference", "port") and b["cores"] >= 1 and b["value"] > 0 and b["sample"]
+        assert b.get("tokens_match_gpu", True) is True
+
+
+def test_reference_arm_line():
+    p = os.path.join(ROOT, "profiles", "r01_l_bench_reference_arm.json")
+    d = _line(p)
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "reference"
+    ours = _line(os.path.join(ROOT, "profiles", "r01_l_bench_n1.json"))
+    assert d["metric"] == ours["metric"] and d["unit"] == ours["unit"]
