@@ -695,6 +695,133 @@ def stream_decode_chunk(W, enc, st: StreamDecodeState, cfg: Config, max_symbols=
 
 
 # ----------------------------------------------------------------------------
+# Phrase-boosted decode                                    src/phrase_boost.cpp
+# ----------------------------------------------------------------------------
+class ContextTrie:
+    """ContextTrie (phrase_boost.cpp:9-66): node 0 = root; active-state sets always contain the root."""
+
+    def __init__(self, phrases=()):
+        self.children = [{}]
+        self.is_end = [False]
+        for ids in phrases:
+            self.insert(ids)
+
+    def insert(self, ids):                                     # :11-27
+        if not len(ids):
+            return
+        node = 0
+        for t in ids:
+            t = int(t)
+            nxt = self.children[node].get(t)
+            if nxt is None:
+                nxt = len(self.children)
+                self.children[node][t] = nxt
+                self.children.append({})
+                self.is_end.append(False)
+            node = nxt
+        self.is_end[node] = True
+
+    def boosted(self, active):                                 # get_boosted_tokens :40-51
+        out = set()
+        for st in active:
+            if 0 <= st < len(self.children):
+                out.update(self.children[st].keys())
+        return out
+
+    def advance(self, active, token):                          # :53-66
+        nxt = {0}
+        for st in active:
+            if 0 <= st < len(self.children) and token in self.children[st]:
+                nxt.add(self.children[st][token])
+        return nxt
+
+
+def _boosted_argmax(row, boosted, boost):
+    """argmax_v(row[v] + boost * [v in boosted]), first maximum (strict '>' scan, phrase_boost.cpp:94-102)."""
+    v = np.asarray(row, F32).copy()
+    if boosted:
+        idx = np.fromiter(boosted, dtype=np.int64)
+        idx = idx[idx < len(v)]
+        v[idx] = v[idx] + F32(boost)
+    return int(np.argmax(v))
+
+
+def ctc_greedy_decode_with_timestamps_boosted(lp, trie: ContextTrie, boost=5.0, blank=1024):
+    """ctc_greedy_decode_with_timestamps_boosted (phrase_boost.cpp:122-176): the plain CTC loop with the boosted
+    argmax; the trie advances on every emission; confidence = exp of the UNboosted log-prob."""
+    T = lp.shape[0]
+    out, prev, active = [], -1, {0}
+    for t in range(T):
+        best = _boosted_argmax(lp[t], trie.boosted(active), boost)
+        if best != prev:
+            if prev != -1 and prev != blank and out:
+                out[-1] = (out[-1][0], out[-1][1], t - 1, out[-1][3])
+            if best != blank:
+                out.append((best, t, t, float(np.exp(F32(lp[t, best])))))
+                active = trie.advance(active, best)
+        prev = best
+    if out:
+        out[-1] = (out[-1][0], out[-1][1], T - 1, out[-1][3])
+    return out
+
+
+def tdt_greedy_decode_with_timestamps_boosted(W, enc, cfg: Config, trie: ContextTrie, boost=5.0, max_symbols=10,
+                                              max_steps=100000):
+    """tdt_greedy_decode_with_timestamps_boosted (phrase_boost.cpp:266-352): tdt_greedy_decode with the boosted
+    label argmax (durations are not boosted), raw log-prob confidence, end frame clamped to T-1."""
+    T = enc.shape[0]
+    blank = cfg.vocab - 1
+    H = cfg.pred_hidden
+    states = [(np.zeros(H, F32), np.zeros(H, F32)) for _ in range(cfg.lstm_layers)]
+    token, t, out, steps, active = blank, 0, [], 0, {0}
+    while t < T:
+        for _sym in range(max_symbols):
+            steps += 1
+            if steps > max_steps:
+                raise RuntimeError("tdt_greedy_decode_boosted: livelock")
+            saved = states
+            pred, states = prediction_step(W, token, states, cfg)
+            lab, dur = tdt_joint(W, enc[t], pred, cfg)
+            tok = _boosted_argmax(lab, trie.boosted(active), boost)
+            di = first_argmax(dur)
+            skip = cfg.durations[di] if di < len(cfg.durations) else 1
+            if tok == blank:
+                states = saved
+                t += max(skip, 1)
+                break
+            out.append((tok, t, min(t + max(skip, 1) - 1, T - 1), float(np.exp(F32(lab[tok])))))
+            active = trie.advance(active, tok)
+            token = tok
+            if skip > 0:
+                t += skip
+                break
+    return out
+
+
+def tokenizer_encode(text, pieces):
+    """Tokenizer::encode (vocab.cpp:76-117): prepend U+2581, spaces -> U+2581, greedy longest match over the
+    pieces on BYTES, unknown bytes skipped."""
+    if not pieces or not text:
+        return []
+    table = {}
+    for i, pc in enumerate(pieces):
+        table[pc.encode("utf-8")] = i                # later duplicates overwrite, like operator[] (vocab.cpp:70)
+    max_len = max(len(k) for k in table)
+    data = (SP_MARK + text.replace(" ", SP_MARK)).encode("utf-8")
+    out, pos = [], 0
+    while pos < len(data):
+        for ln in range(min(max_len, len(data) - pos), 0, -1):
+            tid = table.get(data[pos:pos + ln])
+            if tid is not None:
+                out.append(tid)
+                pos += ln
+                break
+        else:
+            pos += 1
+    return out
+
+
+# ----------------------------------------------------------------------------
 # Tokenizer + word timestamps (host-side)    src/vocab.cpp src/timestamp.cpp
 # ----------------------------------------------------------------------------
 SP_MARK = "▁"

@@ -12,6 +12,7 @@
 //   ctc_greedy_decode(_with_timestamps)  src/ctc.cpp:40-127
 //   tdt_greedy_decode(_with_timestamps)  src/tdt.cpp:36-201
 //   Tokenizer / group_timestamps         src/vocab.cpp, src/timestamp.cpp
+//   ContextTrie, *_decode_boosted        src/phrase_boost.cpp (next-row groundwork)
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may load this library.
 
@@ -28,6 +29,7 @@
 #include "parakeet/config.hpp"
 #include "parakeet/ctc.hpp"
 #include "parakeet/encoder.hpp"
+#include "parakeet/phrase_boost.hpp"
 #include "parakeet/tdt.hpp"
 #include "parakeet/tdt_ctc.hpp"
 #include "parakeet/timestamp.hpp"
@@ -342,6 +344,73 @@ int pkref_transcribe(void *h, const float *pcm, int64_t n, int decoder, int cap,
         int k = (int)toks[0].size();
         for (int i = 0; i < k && i < cap; ++i) ids[i] = toks[0][i];
         return k;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// ---- phrase-boosted decode (src/phrase_boost.cpp).  Phrases arrive as token-id sequences:
+// ids = concatenation, phrase p = ids[off[p] .. off[p+1]); ContextTrie::insert is the reference's own.
+static ContextTrie make_trie(const int *ids, const int *off, int n_phrases) {
+    ContextTrie trie;
+    for (int p = 0; p < n_phrases; ++p) trie.insert(std::vector<int>(ids + off[p], ids + off[p + 1]));
+    return trie;
+}
+
+// lp (T, V) -> boosted CTC greedy with timestamps; returns the token count (<= T).
+int pkref_ctc_greedy_boosted(const float *lp, int T, int V, int blank, const int *ph_ids, const int *ph_off, int n_phrases,
+                             float boost, int *ids, int *start, int *end, float *conf) {
+    try {
+        auto t = Tensor::from_data(lp, Shape{1, (size_t)T, (size_t)V}, true);
+        auto trie = make_trie(ph_ids, ph_off, n_phrases);
+        auto r = ctc_greedy_decode_with_timestamps_boosted(t, trie, boost, blank);
+        auto r2 = ctc_greedy_decode_boosted(t, trie, boost, blank);
+        if (r2[0].size() != r[0].size()) { g_err = "boosted CTC: id-only and timestamped variants disagree"; return -1; }
+        for (size_t i = 0; i < r[0].size(); ++i) {
+            if (r2[0][i] != r[0][i].token_id) { g_err = "boosted CTC: id-only and timestamped variants disagree"; return -1; }
+            ids[i] = r[0][i].token_id;
+            start[i] = r[0][i].start_frame;
+            end[i] = r[0][i].end_frame;
+            conf[i] = r[0][i].confidence;
+        }
+        return (int)r[0].size();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// enc (T, d) -> boosted TDT greedy with timestamps; returns the token count (only cap are written) or -1.
+int pkref_tdt_greedy_boosted(void *h, const float *enc, int T, int d, const int *ph_ids, const int *ph_off, int n_phrases,
+                             float boost, int cap, int *ids, int *start, int *end, float *conf) {
+    try {
+        auto *m = static_cast<RefModel *>(h);
+        auto e = Tensor::from_data(enc, Shape{1, (size_t)T, (size_t)d}, true);
+        auto trie = make_trie(ph_ids, ph_off, n_phrases);
+        auto r = tdt_greedy_decode_with_timestamps_boosted(m->prediction(), m->joint(), e, m->durations(), trie, boost,
+                                                           m->blank());
+        int n = (int)r[0].size();
+        for (int i = 0; i < n && i < cap; ++i) {
+            ids[i] = r[0][i].token_id;
+            start[i] = r[0][i].start_frame;
+            end[i] = r[0][i].end_frame;
+            conf[i] = r[0][i].confidence;
+        }
+        return n;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// Tokenizer::encode (src/vocab.cpp:76-117) with the model's vocabulary; returns the id count.
+int pkref_tok_encode(void *h, const char *text, int cap, int *ids) {
+    try {
+        auto *m = static_cast<RefModel *>(h);
+        auto r = m->tok.encode(text);
+        for (size_t i = 0; i < r.size() && (int)i < cap; ++i) ids[i] = r[i];
+        return (int)r.size();
     } catch (const std::exception &e) {
         g_err = e.what();
         return -1;

@@ -194,3 +194,53 @@ class RefStream:
             raise RuntimeError("pkref_stream_chunk: " + self.L.pkref_stream_last_error().decode())
         toks = [(int(tok[i, 0]), int(tok[i, 1]), int(tok[i, 2]), float(conf[i])) for i in range(nt.value)]
         return (feats[:nf.value].copy() if nf.value else None, enc[:ne.value].copy() if ne.value else None, toks)
+
+
+def _phrases(phrases):
+    ids = np.array([t for ph in phrases for t in ph], np.int32)
+    off = np.zeros(len(phrases) + 1, np.int32)
+    off[1:] = np.cumsum([len(ph) for ph in phrases])
+    return np.ascontiguousarray(ids if len(ids) else np.zeros(1, np.int32)), off
+
+
+def ctc_greedy_boosted(lp, blank, phrases, boost=5.0):
+    """ctc_greedy_decode_with_timestamps_boosted (src/phrase_boost.cpp:122-176) on one utterance."""
+    L = lib()
+    lp = np.ascontiguousarray(lp, np.float32)
+    T, V = lp.shape
+    ids, off = _phrases(phrases)
+    o = [np.zeros(T, np.int32) for _ in range(3)]
+    conf = np.zeros(T, np.float32)
+    L.pkref_ctc_greedy_boosted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.pkref_ctc_greedy_boosted(lp.ctypes.data, T, V, blank, ids.ctypes.data, off.ctypes.data, len(phrases), boost,
+                                   o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data, conf.ctypes.data)
+    if n < 0:
+        raise RuntimeError("pkref_ctc_greedy_boosted: " + L.pkref_last_error().decode())
+    return [(int(o[0][i]), int(o[1][i]), int(o[2][i]), float(conf[i])) for i in range(n)]
+
+
+def tdt_greedy_boosted(model, enc, phrases, boost=5.0, cap=8192):
+    """tdt_greedy_decode_with_timestamps_boosted (src/phrase_boost.cpp:266-352) with a RefModel."""
+    L = lib()
+    enc = np.ascontiguousarray(enc, np.float32)
+    ids, off = _phrases(phrases)
+    o = [np.zeros(cap, np.int32) for _ in range(3)]
+    conf = np.zeros(cap, np.float32)
+    L.pkref_tdt_greedy_boosted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.pkref_tdt_greedy_boosted(model.h, enc.ctypes.data, enc.shape[0], enc.shape[1], ids.ctypes.data, off.ctypes.data,
+                                   len(phrases), boost, cap, o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data, conf.ctypes.data)
+    if n < 0:
+        raise RuntimeError("pkref_tdt_greedy_boosted: " + L.pkref_last_error().decode())
+    return [(int(o[0][i]), int(o[1][i]), int(o[2][i]), float(conf[i])) for i in range(min(n, cap))]
+
+
+def tok_encode(model, text, cap=4096):
+    L = lib()
+    ids = np.zeros(cap, np.int32)
+    L.pkref_tok_encode.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+    n = L.pkref_tok_encode(model.h, text.encode("utf-8"), cap, ids.ctypes.data)
+    if n < 0:
+        raise RuntimeError("pkref_tok_encode: " + L.pkref_last_error().decode())
+    return ids[:n].tolist()

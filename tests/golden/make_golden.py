@@ -230,8 +230,71 @@ def main_stream():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def boost_cases(vocab, base_ctc, rng):
+    """Phrase sets for the boosted-decode fixtures: random short phrases plus one that continues a prefix of the
+    unboosted output (so that deeper trie states are visited)."""
+    phrases = [rng.integers(0, vocab - 1, size=int(rng.integers(1, 4))).tolist() for _ in range(6)]
+    if len(base_ctc) > 4:
+        k = int(rng.integers(0, len(base_ctc) - 3))
+        phrases.append([int(v) for v in base_ctc[k:k + 2]] + [int(rng.integers(0, vocab - 1))])
+    return phrases, float(rng.choice([2.0, 5.0, 9.0]))
+
+
+def main_boost():
+    """Phrase-boosted CTC / TDT decode (src/phrase_boost.cpp) through the compiled reference,
+    on the tiny model's golden encoder outputs.  TDT cases on which the ORACLE detects the livelock are recorded as
+    such and never sent to the reference (it would hang)."""
+    out = {}
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    ocfg = O.make_tiny_config()
+    with tempfile.TemporaryDirectory() as td:
+        W = synth.make_weights(ocfg, seed=3)
+        wp = os.path.join(td, "tiny.safetensors")
+        synth.save_safetensors(wp, W)
+        pieces = synth.make_vocab(ocfg.vocab - 1, seed=3)
+        vp = os.path.join(td, "tiny.vocab.txt")
+        synth.save_vocab(vp, pieces)
+        m = R.RefModel(wp, vp, 0, cfg=ocfg)
+        rng = np.random.default_rng(11)
+        n = 0
+        for ci in (0, 1, 3):
+            enc = g[f"tiny.c{ci}.enc"]
+            lp = m.ctc_logprobs(enc, ocfg.vocab)
+            base = [t[0] for t in R.ctc_greedy(lp, ocfg.vocab - 1, True)[0]]
+            for _ in range(4):
+                phrases, boost = boost_cases(ocfg.vocab, base, rng)
+                k = f"boost.k{n}."
+                n += 1
+                out[k + "clip"] = np.array([ci], np.int64)
+                out[k + "boost"] = np.array([boost], np.float32)
+                out[k + "ph_ids"] = np.array([t for ph in phrases for t in ph], np.int32)
+                out[k + "ph_len"] = np.array([len(ph) for ph in phrases], np.int32)
+                out[k + "ctc_tok"], out[k + "ctc_conf"] = toks_arr(R.ctc_greedy_boosted(lp, ocfg.vocab - 1, phrases, boost))
+                try:
+                    O.tdt_greedy_decode_with_timestamps_boosted(W, enc, ocfg, O.ContextTrie(phrases), boost, max_steps=3000)
+                    tdt, live = R.tdt_greedy_boosted(m, enc, phrases, boost), 0
+                except RuntimeError:
+                    tdt, live = [], 1
+                out[k + "tdt_tok"], out[k + "tdt_conf"] = toks_arr(tdt)
+                out[k + "tdt_livelock"] = np.array([live], np.int64)
+                print(k, "boost", boost, "ctc", len(out[k + "ctc_tok"]), "tdt", len(tdt), "livelock" if live else "")
+        out["n_cases"] = np.array([n], np.int64)
+        # Tokenizer::encode known answers on the synthetic vocabulary
+        texts = [" ".join(p.replace(O.SP_MARK, " ").strip() for p in pieces[3:9]), "zz " + pieces[5].replace(O.SP_MARK, ""), ""]
+        for i, tx in enumerate(texts):
+            out[f"enc.k{i}.text"] = np.frombuffer(tx.encode(), np.uint8)
+            out[f"enc.k{i}.ids"] = np.array(R.tok_encode(m, tx) if tx else [], np.int32)
+        out["n_texts"] = np.array([len(texts)], np.int64)
+        m.close()
+    path = os.path.join(ROOT, "tests", "golden", "golden_boost_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "stream":
+    if len(sys.argv) > 1 and sys.argv[1] == "boost":
+        main_boost()
+    elif len(sys.argv) > 1 and sys.argv[1] == "stream":
         main_stream()
     elif len(sys.argv) > 1 and sys.argv[1] == "600m_extra":
         main_600m_extra()

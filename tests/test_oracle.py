@@ -292,3 +292,75 @@ def test_live_reference_streaming(O, synth, refbind, tmp_path):
             assert _rel(e, re_) < 1e-4
         assert [x[:3] for x in rt] == [x[:3] for x in t]
     rs.close()
+
+
+# ------------------------------------------------------------------ phrase-boosted decode
+def _boost_case(g, k):
+    lens = g[k + "ph_len"].tolist()
+    ids = g[k + "ph_ids"].tolist()
+    phrases, p = [], 0
+    for n in lens:
+        phrases.append(ids[p:p + n])
+        p += n
+    return phrases, float(g[k + "boost"][0]), int(g[k + "clip"][0])
+
+
+def test_context_trie_semantics(O):
+    """ContextTrie (phrase_boost.cpp:9-66): shared prefixes share nodes, the root is always active, the boosted
+    set is the union of the children of the active states."""
+    t = O.ContextTrie([[1, 2, 3], [1, 2, 4], [5]])
+    assert len(t.children) == 6                                   # root, 1, 1-2, 1-2-3, 1-2-4, 5
+    assert t.boosted({0}) == {1, 5}
+    a = t.advance({0}, 1)
+    assert 0 in a and len(a) == 2 and t.boosted(a) == {1, 5, 2}
+    a = t.advance(a, 2)
+    assert t.boosted(a) == {1, 5, 3, 4}
+    assert t.advance(a, 9) == {0}
+    empty = O.ContextTrie([[]])
+    assert len(empty.children) == 1 and empty.boosted({0}) == set()
+
+
+def test_golden_boosted_decode(O, synth, golden):
+    """ctc_/tdt_greedy_decode_with_timestamps_boosted restated in the oracle against the compiled reference
+    (tests/golden/make_golden.py boost): boosted first-max argmax, trie advance on emission, raw-log-prob confidence."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_boost_v1.npz"))
+    ocfg = O.make_tiny_config()
+    W = synth.make_weights(ocfg, seed=3)
+    changed = 0
+    for n in range(int(g["n_cases"][0])):
+        k = f"boost.k{n}."
+        phrases, boost, ci = _boost_case(g, k)
+        enc = golden[f"tiny.c{ci}.enc"]
+        lp = O.ctc_log_probs(W, enc)
+        trie = O.ContextTrie(phrases)
+        got = O.ctc_greedy_decode_with_timestamps_boosted(lp, trie, boost, ocfg.vocab - 1)
+        assert [list(x[:3]) for x in got] == g[k + "ctc_tok"].tolist()
+        assert np.allclose([x[3] for x in got], g[k + "ctc_conf"], rtol=1e-3)
+        changed += [x[0] for x in got] != [x[0] for x in O.ctc_greedy_decode_with_timestamps(lp, ocfg.vocab - 1)]
+        if int(g[k + "tdt_livelock"][0]):
+            with pytest.raises(RuntimeError):
+                O.tdt_greedy_decode_with_timestamps_boosted(W, enc, ocfg, trie, boost, max_steps=3000)
+        else:
+            got = O.tdt_greedy_decode_with_timestamps_boosted(W, enc, ocfg, trie, boost, max_steps=3000)
+            assert [list(x[:3]) for x in got] == g[k + "tdt_tok"].tolist()
+            assert np.allclose([x[3] for x in got], g[k + "tdt_conf"], rtol=1e-3)
+    assert changed >= 6                                           # the boosts really alter the decode
+    pieces = synth.make_vocab(ocfg.vocab - 1, seed=3)
+    for i in range(int(g["n_texts"][0])):                         # Tokenizer::encode (vocab.cpp:76-117)
+        text = bytes(g[f"enc.k{i}.text"]).decode()
+        assert O.tokenizer_encode(text, pieces) == g[f"enc.k{i}.ids"].tolist()
+    assert len(g["enc.k0.ids"]) >= 4
+
+
+def test_live_reference_boosted_ctc(O, synth, refbind, golden):
+    if refbind is None:
+        pytest.skip("oracle/_ref/libpkref.so not built")
+    ocfg = O.make_tiny_config()
+    W = synth.make_weights(ocfg, seed=3)
+    lp = O.ctc_log_probs(W, golden["tiny.c1.enc"])
+    rng = np.random.default_rng(23)
+    for _ in range(5):
+        phrases = [rng.integers(0, ocfg.vocab - 1, size=int(rng.integers(1, 5))).tolist() for _ in range(8)]
+        want = refbind.ctc_greedy_boosted(lp, ocfg.vocab - 1, phrases, 4.0)
+        got = O.ctc_greedy_decode_with_timestamps_boosted(lp, O.ContextTrie(phrases), 4.0, ocfg.vocab - 1)
+        assert [x[:3] for x in got] == [x[:3] for x in want]
