@@ -105,6 +105,12 @@ class Tokenizer {
         buf.resize(n < 0 ? 0 : std::min<size_t>((size_t)n, buf.size() - 1));
         return buf;
     }
+    // Tokenizer::encode (vocab.cpp:76-117)
+    std::vector<int> encode(const std::string &text) const {
+        std::vector<int32_t> a(2 * text.size() + 8);
+        int n = pk_tokenize(v_, text.c_str(), a.data(), (int32_t)a.size());
+        return std::vector<int>(a.begin(), a.begin() + (n < 0 ? 0 : n));
+    }
     std::vector<WordTimestamp> group(const std::vector<TimestampedToken> &t) const {
         const int n = (int)t.size();
         std::vector<int32_t> id(n), st(n), en(n);
@@ -124,6 +130,47 @@ class Tokenizer {
   private:
     pk_vocab *v_ = nullptr;
 };
+
+// ─── phrase boosting (phrase_boost.hpp:22-66, CTC variants :70-176), host side ──
+class ContextTrie {
+  public:
+    void insert(const std::vector<int> &token_ids) {
+        if (token_ids.empty()) return;
+        ids_.insert(ids_.end(), token_ids.begin(), token_ids.end());
+        off_.push_back((int32_t)ids_.size());
+    }
+    void build(const std::vector<std::string> &phrases, const Tokenizer &tokenizer) {
+        for (const auto &p : phrases) insert(tokenizer.encode(p));
+    }
+    bool empty() const { return off_.size() <= 1; }
+    const std::vector<int32_t> &ids() const { return ids_; }
+    const std::vector<int32_t> &offsets() const { return off_; }
+  private:
+    std::vector<int32_t> ids_, off_{0};
+};
+
+// log_probs: one utterance, (n_frames, vocab) row-major (e.g. from pk_ctc_logprobs)
+inline std::vector<TimestampedToken> ctc_greedy_decode_with_timestamps_boosted(const float *log_probs, int n_frames, int vocab,
+                                                                               const ContextTrie &trie, float boost_score = 5.0f,
+                                                                               int blank_id = 1024) {
+    std::vector<int32_t> id(n_frames + 1), st(n_frames + 1), en(n_frames + 1);
+    std::vector<float> cf(n_frames + 1);
+    static const int32_t none = 0;
+    const int n = pk_ctc_decode_boosted(log_probs, n_frames, vocab, blank_id, trie.ids().empty() ? &none : trie.ids().data(),
+                                        trie.offsets().data(), (int32_t)trie.offsets().size() - 1, boost_score, id.data(),
+                                        st.data(), en.data(), cf.data(), n_frames + 1);
+    if (n < 0) throw std::runtime_error("ctc_greedy_decode_boosted: invalid arguments");
+    std::vector<TimestampedToken> out;
+    for (int i = 0; i < n; ++i) out.push_back({id[i], st[i], en[i], cf[i]});
+    return out;
+}
+inline std::vector<int> ctc_greedy_decode_boosted(const float *log_probs, int n_frames, int vocab, const ContextTrie &trie,
+                                                  float boost_score = 5.0f, int blank_id = 1024) {
+    std::vector<int> ids;
+    for (const auto &t : ctc_greedy_decode_with_timestamps_boosted(log_probs, n_frames, vocab, trie, boost_score, blank_id))
+        ids.push_back(t.token_id);
+    return ids;
+}
 
 // ─── minimal read_audio (audio_io.hpp): 16 kHz mono PCM16 / float32 WAV ──────
 inline std::vector<float> read_audio(const std::string &path) {

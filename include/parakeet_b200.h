@@ -190,6 +190,21 @@ int32_t pk_group_words(const pk_vocab *v, const int32_t *ids, const int32_t *sta
                        const int32_t *end, const float *conf, int32_t n, char *buf, int32_t cap,
                        float *w_start, float *w_end, float *w_conf);
 
+/* Tokenizer::encode (src/vocab.cpp:76-117): U+2581-prefixed, spaces -> U+2581, greedy longest piece match on
+ * bytes, unknown bytes skipped.  Writes at most cap ids; returns the full count. */
+int32_t pk_tokenize(const pk_vocab *v, const char *text, int32_t *ids, int32_t cap);
+
+/* Phrase-boosted CTC greedy decode of ONE utterance on the host (widening row: SURVEY.md section 8f(3)), replacing
+ * ctc_greedy_decode_boosted / ctc_greedy_decode_with_timestamps_boosted (src/phrase_boost.cpp:70-176) and the
+ * ContextTrie they use (:9-66).  logprobs = (n_frames, vocab) row-major as returned by pk_ctc_logprobs; the
+ * phrases are token-id sequences (pk_tokenize), phrase p = phrase_ids[phrase_off[p] .. phrase_off[p+1]).
+ * Every frame takes argmax_v(logprob[v] + boost * [v continues an active phrase]) (first maximum), the trie
+ * advances on emissions, confidences are exp of the UNboosted log-prob.  start / end / conf may be NULL.
+ * Returns the number of tokens (at most `cap` are written) or -1 on invalid arguments. */
+int32_t pk_ctc_decode_boosted(const float *logprobs, int32_t n_frames, int32_t vocab, int32_t blank,
+                              const int32_t *phrase_ids, const int32_t *phrase_off, int32_t n_phrases, float boost,
+                              int32_t *ids, int32_t *start, int32_t *end, float *conf, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,10 +8,14 @@
 //   group_timestamps  src/timestamp.cpp:24-75 (Words mode) a piece starting with U+2581
 //                                            opens a new word; word conf = min token conf;
 //                                            seconds = frame * 0.08f (timestamp.hpp:31-35).
+//   Tokenizer::encode src/vocab.cpp:76-117  greedy longest piece match on bytes (pk_tokenize).
+//   ContextTrie + ctc_greedy_decode(_with_timestamps)_boosted  src/phrase_boost.cpp:9-176 (pk_ctc_decode_boosted).
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <cmath>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/parakeet_b200.h"
@@ -119,6 +123,117 @@ int32_t pk_group_words(const pk_vocab *v, const int32_t *ids, const int32_t *sta
     if (!word.empty()) flush();
     emit(all, buf, cap);
     return n_words;
+}
+
+int32_t pk_tokenize(const pk_vocab *v, const char *text, int32_t *ids, int32_t cap) {
+    if (!v || !text || v->pieces.empty() || !text[0]) return 0;
+    std::unordered_map<std::string, int32_t> table;             // later duplicates win, like operator[] in the reference
+    size_t max_len = 0;
+    for (size_t i = 0; i < v->pieces.size(); ++i) {
+        table[v->pieces[i]] = (int32_t)i;
+        max_len = std::max(max_len, v->pieces[i].size());
+    }
+    std::string input = kMark;
+    for (const char *c = text; *c; ++c) {
+        if (*c == ' ') input += kMark;
+        else input += *c;
+    }
+    int32_t n = 0;
+    size_t pos = 0;
+    while (pos < input.size()) {
+        size_t len = std::min(max_len, input.size() - pos);
+        int32_t id = -1;
+        for (; len >= 1; --len) {
+            auto it = table.find(input.substr(pos, len));
+            if (it != table.end()) {
+                id = it->second;
+                break;
+            }
+        }
+        if (id >= 0) {
+            if (ids && n < cap) ids[n] = id;
+            ++n;
+            pos += len;
+        } else {
+            ++pos;                                               // unknown byte: skipped
+        }
+    }
+    return n;
+}
+
+namespace {
+// ContextTrie (phrase_boost.cpp:9-66): node 0 = root; the active set always contains the root.
+struct Trie {
+    std::vector<std::unordered_map<int32_t, int32_t>> children{1};
+    void insert(const int32_t *ids, int32_t n) {
+        int32_t node = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            auto it = children[node].find(ids[i]);
+            if (it == children[node].end()) {
+                const int32_t next = (int32_t)children.size();
+                children[node][ids[i]] = next;
+                children.emplace_back();
+                node = next;
+            } else {
+                node = it->second;
+            }
+        }
+    }
+};
+}  // namespace
+
+int32_t pk_ctc_decode_boosted(const float *lp, int32_t T, int32_t V, int32_t blank, const int32_t *ph_ids,
+                              const int32_t *ph_off, int32_t n_phrases, float boost, int32_t *ids, int32_t *start,
+                              int32_t *end, float *conf, int32_t cap) {
+    if (!lp || T < 0 || V <= 0 || n_phrases < 0 || (n_phrases > 0 && (!ph_ids || !ph_off)) || !ids || cap < 0) return -1;
+    Trie trie;
+    for (int32_t p = 0; p < n_phrases; ++p) trie.insert(ph_ids + ph_off[p], ph_off[p + 1] - ph_off[p]);
+    std::vector<int32_t> active{0}, next;
+    std::vector<uint8_t> boosted((size_t)V, 0);
+    std::vector<int32_t> marked;
+    int32_t n = 0, prev = -1, last = -1;                         // last = slot of the most recent token (for end frames)
+    for (int32_t t = 0; t < T; ++t) {
+        const float *row = lp + (size_t)t * V;
+        for (int32_t m : marked) boosted[m] = 0;
+        marked.clear();
+        for (int32_t st : active)
+            for (const auto &kv : trie.children[st])
+                if (kv.first >= 0 && kv.first < V && !boosted[kv.first]) {
+                    boosted[kv.first] = 1;
+                    marked.push_back(kv.first);
+                }
+        int32_t best = 0;
+        float best_val = row[0] + (boosted[0] ? boost : 0.0f);
+        for (int32_t v2 = 1; v2 < V; ++v2) {                     // strict '>': the first maximum wins
+            const float val = row[v2] + (boosted[v2] ? boost : 0.0f);
+            if (val > best_val) {
+                best_val = val;
+                best = v2;
+            }
+        }
+        if (best != prev) {
+            if (prev != -1 && prev != blank && last >= 0 && end && last < cap) end[last] = t - 1;
+            if (best != blank) {
+                if (n < cap) {
+                    ids[n] = best;
+                    if (start) start[n] = t;
+                    if (end) end[n] = t;
+                    if (conf) conf[n] = std::exp(row[best]);     // raw (unboosted) log-prob
+                }
+                last = n++;
+                next.assign(1, 0);                               // advance: the root plus every continued phrase
+                for (int32_t st : active) {
+                    auto it = trie.children[st].find(best);
+                    if (it != trie.children[st].end() && std::find(next.begin(), next.end(), it->second) == next.end())
+                        next.push_back(it->second);
+                }
+                active.swap(next);
+            }
+        }
+        prev = best;
+    }
+    if (last >= 0 && end && last < cap) end[last] = T - 1;
+    return n;
 }
 
 }  // extern "C"

@@ -45,7 +45,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_transcribe_batch", "pk_stage_pcm", "pk_prefetch_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
            "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
-           "pk_detokenize", "pk_group_words"]
+           "pk_detokenize", "pk_group_words", "pk_tokenize", "pk_ctc_decode_boosted"]
 
 _lib = None
 
@@ -75,6 +75,11 @@ def load_library():
     L.pk_ctc_logprobs.argtypes = [vp, f32p, C.c_int32, f32p]
     L.pk_transcribe_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int, C.POINTER(_PkTokens)]
     L.pk_stage_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
+    L.pk_tokenize.argtypes = [vp, C.c_char_p, i32p, C.c_int32]
+    L.pk_tokenize.restype = C.c_int32
+    L.pk_ctc_decode_boosted.argtypes = [f32p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, C.c_int32, C.c_float, i32p, i32p, i32p,
+                                        f32p, C.c_int32]
+    L.pk_ctc_decode_boosted.restype = C.c_int32
     L.pk_prefetch_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
     L.pk_run_staged.argtypes = [vp, C.c_int]
     L.pk_fetch_tokens.argtypes = [vp, C.POINTER(_PkTokens)]
@@ -451,6 +456,13 @@ class Tokenizer:
         self.L.pk_detokenize(self.h, _i32p(a), len(a), buf, len(buf))
         return buf.value.decode("utf-8")
 
+    def encode(self, text: str) -> List[int]:
+        """Tokenizer::encode (src/vocab.cpp:76-117)."""
+        raw = text.encode("utf-8")
+        ids = np.zeros(2 * len(raw) + 8, np.int32)
+        n = self.L.pk_tokenize(self.h, raw, _i32p(ids), len(ids))
+        return ids[:n].tolist()
+
     def group_words(self, toks: Sequence[TimestampedToken]) -> List[WordTimestamp]:
         n = len(toks)
         ids = np.array([t.token_id for t in toks], np.int32)
@@ -463,6 +475,26 @@ class Tokenizer:
                                   _f32p(we), _f32p(wc))
         words = buf.value.decode("utf-8").split("\n")[:k]
         return [WordTimestamp(words[i], float(ws[i]), float(we[i]), float(wc[i])) for i in range(k)]
+
+
+def ctc_greedy_decode_boosted(logprobs: np.ndarray, phrases: Sequence[Sequence[int]], boost_score: float = 5.0,
+                              blank_id: Optional[int] = None) -> List[TimestampedToken]:
+    """ctc_greedy_decode_with_timestamps_boosted (src/phrase_boost.cpp:122-176) on one utterance's log-probs
+    (Engine.ctc_logprobs); phrases are token-id sequences (Tokenizer.encode).  Host code behind pk_ctc_decode_boosted."""
+    L = load_library()
+    lp = np.ascontiguousarray(logprobs, np.float32)
+    T, V = lp.shape
+    blank = V - 1 if blank_id is None else blank_id
+    flat = np.array([t for ph in phrases for t in ph] or [0], np.int32)
+    off = np.zeros(len(phrases) + 1, np.int32)
+    off[1:] = np.cumsum([len(ph) for ph in phrases])
+    ids, st, en = (np.zeros(max(T, 1), np.int32) for _ in range(3))
+    cf = np.zeros(max(T, 1), np.float32)
+    n = L.pk_ctc_decode_boosted(_f32p(lp), T, V, blank, _i32p(flat), _i32p(off), len(phrases), float(boost_score), _i32p(ids),
+                                _i32p(st), _i32p(en), _f32p(cf), len(ids))
+    if n < 0:
+        raise ValueError("pk_ctc_decode_boosted: invalid arguments")
+    return [TimestampedToken(int(ids[i]), int(st[i]), int(en[i]), float(cf[i])) for i in range(n)]
 
 
 class Transcriber:

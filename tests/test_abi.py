@@ -71,6 +71,40 @@ def test_text_helpers_match_oracle(pkg, O, tiny):
         assert np.allclose([[w.start, w.end, w.confidence] for w in got], [[w[1], w[2], w[3]] for w in want], rtol=1e-6) or not want
 
 
+def test_tokenize_and_boosted_ctc_match_reference_goldens(pkg, O, synth, tiny, golden):
+    """Host code behind pk_tokenize / pk_ctc_decode_boosted (no device needed) against the compiled reference's
+    fixtures (tests/golden/make_golden.py boost) and the oracle: Tokenizer::encode, ContextTrie, boosted CTC greedy."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_boost_v1.npz"))
+    tok = pkg.engine.Tokenizer(tiny.vocab_path)
+    for i in range(int(g["n_texts"][0])):
+        text = bytes(g[f"enc.k{i}.text"]).decode()
+        assert tok.encode(text) == g[f"enc.k{i}.ids"].tolist()
+        assert tok.encode(text) == O.tokenizer_encode(text, tiny.pieces)
+    assert tok.decode(tok.encode("")) == ""
+    for n in range(int(g["n_cases"][0])):
+        k = f"boost.k{n}."
+        lens, ids, p, phrases = g[k + "ph_len"].tolist(), g[k + "ph_ids"].tolist(), 0, []
+        for ln in lens:
+            phrases.append(ids[p:p + ln])
+            p += ln
+        lp = O.ctc_log_probs(tiny.W, golden[f"tiny.c{int(g[k + 'clip'][0])}.enc"])
+        got = pkg.engine.ctc_greedy_decode_boosted(lp, phrases, float(g[k + "boost"][0]))
+        assert [[t.token_id, t.start_frame, t.end_frame] for t in got] == g[k + "ctc_tok"].tolist()
+        assert np.allclose([t.confidence for t in got], g[k + "ctc_conf"], rtol=1e-3)
+    # no phrases == plain greedy (ctc.cpp:79-127); random phrase sets == oracle
+    lp = O.ctc_log_probs(tiny.W, golden["tiny.c0.enc"])
+    plain = O.ctc_greedy_decode_with_timestamps(lp, tiny.ocfg.vocab - 1)
+    assert [(t.token_id, t.start_frame, t.end_frame) for t in pkg.engine.ctc_greedy_decode_boosted(lp, [])] == [x[:3] for x in plain]
+    rng = np.random.default_rng(31)
+    for _ in range(10):
+        phrases = [rng.integers(0, tiny.ocfg.vocab - 1, size=int(rng.integers(1, 5))).tolist() for _ in range(int(rng.integers(1, 9)))]
+        boost = float(rng.uniform(0.5, 12.0))
+        want = O.ctc_greedy_decode_with_timestamps_boosted(lp, O.ContextTrie(phrases), boost, tiny.ocfg.vocab - 1)
+        got = pkg.engine.ctc_greedy_decode_boosted(lp, phrases, boost)
+        assert [(t.token_id, t.start_frame, t.end_frame) for t in got] == [x[:3] for x in want]
+
+
 def test_vocab_missing_file_raises(pkg):
     with pytest.raises(RuntimeError):
         pkg.engine.Tokenizer("/nonexistent/vocab.txt")

@@ -364,3 +364,39 @@ def test_live_reference_boosted_ctc(O, synth, refbind, golden):
         want = refbind.ctc_greedy_boosted(lp, ocfg.vocab - 1, phrases, 4.0)
         got = O.ctc_greedy_decode_with_timestamps_boosted(lp, O.ContextTrie(phrases), 4.0, ocfg.vocab - 1)
         assert [x[:3] for x in got] == [x[:3] for x in want]
+
+
+def _boost_lp(pattern_or_none):
+    V = 1025
+    if pattern_or_none is not None:                      # BoostedCTCDecode.*EmptyTrie* (test_all.cpp:1369-1388, :1428-1452)
+        return _lp_from_pattern(pattern_or_none, V)
+    lp = np.full((3, V), -10.0, np.float32)              # BoostedCTCDecode.BoostFlipsDecision (test_all.cpp:1390-1426)
+    lp[0, 42], lp[0, 43], lp[0, 1024] = -0.1, -0.2, -5.0
+    lp[1, 1024] = lp[2, 1024] = 0.0
+    return lp
+
+
+def test_reference_known_answers_boosted_ctc_and_trie(O, pkg):
+    """The reference's own phrase-boost tests (tests/test_all.cpp:1278-1452) on the oracle AND on the host C-ABI."""
+    # ContextTrie.{EmptyTrie, InsertAndSize, GetBoostedTokens, Advance, AdvanceNonMatchingToken, MultiplePhrases}
+    t = O.ContextTrie()
+    assert len(t.children) == 1 and t.boosted({0}) == set()
+    t.insert([10, 20, 30])
+    assert len(t.children) == 4
+    t.insert([10, 25])
+    assert t.boosted({0}) == {10}
+    nxt = t.advance({0}, 10)
+    assert 0 in nxt and 20 in t.boosted(nxt)
+    assert t.advance({0}, 999) == {0}
+    m = O.ContextTrie([[10, 20], [10, 30], [40, 50]])
+    assert m.boosted({0}) == {10, 40}
+    assert {20, 30, 10, 40} <= m.boosted(m.advance({0}, 10))
+    # BoostedCTCDecode.*
+    for decode in (lambda lp, ph: [x[:2] for x in O.ctc_greedy_decode_with_timestamps_boosted(lp, O.ContextTrie(ph), 5.0, 1024)],
+                   lambda lp, ph: [(x.token_id, x.start_frame) for x in pkg.engine.ctc_greedy_decode_boosted(lp, ph, 5.0, 1024)]):
+        lp = _boost_lp([5, 5, 1024, 8, 8, 8])
+        plain = [x[:2] for x in O.ctc_greedy_decode_with_timestamps(lp, 1024)]
+        assert decode(lp, []) == plain == [(5, 0), (8, 3)]
+        flip = _boost_lp(None)
+        assert [x[0] for x in decode(flip, [])] == [42]
+        assert [x[0] for x in decode(flip, [[43]])] == [43]
