@@ -105,6 +105,28 @@ def test_tokenize_and_boosted_ctc_match_reference_goldens(pkg, O, synth, tiny, g
         assert [(t.token_id, t.start_frame, t.end_frame) for t in got] == [x[:3] for x in want]
 
 
+def test_cpp_shim_host_functions(pkg, O, tiny, tmp_path):
+    """The C++ shim's host-only pieces (Tokenizer::encode, ContextTrie, boosted CTC decode) compiled with g++ and
+    run without a device; answers = the reference's BoostedCTCDecode tests and the oracle's encode."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "parakeet.cpp_b200")
+    exe = str(tmp_path / "cpp_host_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp_host_check.cpp"),
+                    "-L", libdir, "-lparakeet_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    text = " ".join(p.replace(O.SP_MARK, " ").strip() for p in tiny.pieces[3:7])
+    out = subprocess.run([exe, tiny.vocab_path, text], check=True, capture_output=True, text=True).stdout.splitlines()
+    want = O.tokenizer_encode(text, tiny.pieces)
+    assert out[0].split()[1:] == [str(i) for i in want] and len(want) >= 3
+    assert out[1] == "decode " + O.detokenize(want, tiny.pieces)
+    assert out[2] == "plain 42 n=1"
+    assert out[3] == "boosted 43 start=0 end=2 n=1 empty=1/0"
+    assert out[4] == "built %d" % len(want)
+
+
 def test_vocab_missing_file_raises(pkg):
     with pytest.raises(RuntimeError):
         pkg.engine.Tokenizer("/nonexistent/vocab.txt")
