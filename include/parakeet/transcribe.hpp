@@ -196,7 +196,6 @@ inline std::vector<float> read_audio(const std::string &path) {
         pos += 8 + sz + (sz & 1);
     }
     if (!pcm || !ch) throw std::runtime_error("malformed WAV: " + path);
-    if (sr != 16000) throw std::runtime_error("Sample rate mismatch: audio=" + std::to_string(sr) + " expected=16000");
     std::vector<float> mono;
     if (tag == 1 && bits == 16) {
         const size_t n = pcm_bytes / 2 / ch;
@@ -217,7 +216,19 @@ inline std::vector<float> read_audio(const std::string &path) {
     } else {
         throw std::runtime_error("unsupported WAV encoding: " + path);
     }
+    if (sr != 16000) {   // read_audio resamples to the target rate (audio_io.cpp:123-195, :227-232)
+        std::vector<float> r((size_t)std::max<int64_t>(pk_resample_len((int64_t)mono.size(), (int32_t)sr, 16000), 0));
+        pk_resample(mono.data(), (int64_t)mono.size(), (int32_t)sr, 16000, r.data(), (int64_t)r.size());
+        return r;
+    }
     return mono;
+}
+
+// parakeet::resample (audio_io.hpp:41)
+inline std::vector<float> resample(const std::vector<float> &samples, int src_rate, int dst_rate) {
+    std::vector<float> r((size_t)std::max<int64_t>(pk_resample_len((int64_t)samples.size(), src_rate, dst_rate), 0));
+    pk_resample(samples.data(), (int64_t)samples.size(), src_rate, dst_rate, r.data(), (int64_t)r.size());
+    return r;
 }
 
 namespace detail {

@@ -205,6 +205,13 @@ int32_t pk_ctc_decode_boosted(const float *logprobs, int32_t n_frames, int32_t v
                               const int32_t *phrase_ids, const int32_t *phrase_off, int32_t n_phrases, float boost,
                               int32_t *ids, int32_t *start, int32_t *end, float *conf, int32_t cap);
 
+/* Sample-rate conversion on the host (widening row: SURVEY.md section 8f(4)), replacing parakeet::resample /
+ * sinc_resample (src/audio_io.cpp:123-195, :238-251): 32-tap Kaiser (beta 7.857) windowed sinc evaluated in double,
+ * output length ceil(n * dst / src).  pk_resample_len gives that length; pk_resample writes at most `cap` samples and
+ * returns the full length (or -1 on invalid arguments).  src_rate == dst_rate copies. */
+int64_t pk_resample_len(int64_t n, int32_t src_rate, int32_t dst_rate);
+int64_t pk_resample(const float *in, int64_t n, int32_t src_rate, int32_t dst_rate, float *out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,6 +163,55 @@ def preprocess_audio(pcm: np.ndarray, n_mels: int = 80) -> np.ndarray:
     return np.ascontiguousarray(feat.T.astype(F32))          # :156
 
 
+def sinc_resample(x, src_rate: int, dst_rate: int):
+    """sinc_resample (audio_io.cpp:123-195), in double like the reference: output length ceil(n*up/down); per
+    output a 32-tap Kaiser(beta 7.857)-windowed sinc around floor(i * src/dst), cutoff min(1, dst/src), the window
+    (not the tap range) widened by src/dst when downsampling, weights renormalised by their sum."""
+    x = np.asarray(x, F32)
+    if src_rate == dst_rate:
+        return x.copy()
+    g = math.gcd(src_rate, dst_rate)
+    up, down = dst_rate // g, src_rate // g
+    n = len(x)
+    m = (n * up + down - 1) // down
+    HW, BETA = 16, 7.857
+    ratio = src_rate / dst_rate
+    cutoff = min(1.0, 1.0 / max(ratio, 1.0))
+    sample_ratio = dst_rate / src_rate
+    width = max(1.0, ratio)
+
+    def i0(v):                                                  # bessel_i0 :101-111 (series with the same stopping rule)
+        v = np.asarray(v, np.float64)
+        s = np.ones_like(v)
+        term = np.ones_like(v)
+        done = np.zeros(v.shape, bool)
+        for k in range(1, 30):
+            term = np.where(done, term, term * (v * v) / (4.0 * k * k))
+            s = np.where(done, s, s + term)
+            done |= term < 1e-12 * s
+        return s
+
+    i = np.arange(m, dtype=np.float64)
+    src_pos = i / sample_ratio
+    center = np.floor(src_pos).astype(np.int64)
+    j = center[:, None] + np.arange(-HW + 1, HW + 1)[None, :]              # taps center-15 .. center+16
+    valid = (j >= 0) & (j < n)
+    dist = src_pos[:, None] - j
+    wpos = dist / width
+    valid &= np.abs(wpos) <= HW
+    arg = 2.0 * (wpos + HW) / (2.0 * HW) - 1.0                             # kaiser_window :114-121
+    val = np.maximum(1.0 - arg * arg, 0.0)
+    w = i0(BETA * np.sqrt(val)) / i0(np.float64(BETA))
+    xx = dist * cutoff * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sinc = np.where(np.abs(xx) < 1e-10, 1.0, np.sin(xx) / xx)
+    weight = np.where(valid, sinc * w * cutoff, 0.0)
+    xs = x.astype(np.float64)[np.clip(j, 0, max(n - 1, 0))]
+    ssum = (xs * weight).sum(axis=1)
+    wsum = weight.sum(axis=1)
+    return np.where(wsum > 1e-10, ssum / np.where(wsum == 0, 1, wsum), 0.0).astype(F32)
+
+
 # ----------------------------------------------------------------------------
 # axiom primitives                       third_party/axiom/src/tensor/operations.cpp
 # ----------------------------------------------------------------------------

@@ -26,6 +26,7 @@
 #include <axiom/io/safetensors.hpp>
 
 #include "parakeet/audio.hpp"
+#include "parakeet/audio_io.hpp"
 #include "parakeet/config.hpp"
 #include "parakeet/ctc.hpp"
 #include "parakeet/encoder.hpp"
@@ -398,6 +399,20 @@ int pkref_tdt_greedy_boosted(void *h, const float *enc, int T, int d, const int 
             conf[i] = r[0][i].confidence;
         }
         return n;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// parakeet::resample (src/audio_io.cpp:238-251 -> sinc_resample :123-195); returns the output length.
+int pkref_resample(const float *in, int n, int src_rate, int dst_rate, float *out, int cap) {
+    try {
+        auto t = Tensor::from_data(in, Shape{(size_t)n}, true);
+        auto r = resample(t, src_rate, dst_rate).ascontiguousarray();
+        const int m = (int)r.shape()[0];
+        std::memcpy(out, r.typed_data<float>(), sizeof(float) * (size_t)std::min(m, cap));
+        return m;
     } catch (const std::exception &e) {
         g_err = e.what();
         return -1;

@@ -244,3 +244,16 @@ def tok_encode(model, text, cap=4096):
     if n < 0:
         raise RuntimeError("pkref_tok_encode: " + L.pkref_last_error().decode())
     return ids[:n].tolist()
+
+
+def resample(x, src_rate, dst_rate):
+    """parakeet::resample (src/audio_io.cpp:238-251)."""
+    L = lib()
+    x = np.ascontiguousarray(x, np.float32)
+    cap = int(len(x) * dst_rate / src_rate) + 16
+    out = np.zeros(cap, np.float32)
+    L.pkref_resample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    m = L.pkref_resample(x.ctypes.data, len(x), src_rate, dst_rate, out.ctypes.data, cap)
+    if m < 0:
+        raise RuntimeError("pkref_resample: " + L.pkref_last_error().decode())
+    return out[:m].copy()

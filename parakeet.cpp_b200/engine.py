@@ -45,7 +45,8 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_transcribe_batch", "pk_stage_pcm", "pk_prefetch_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
            "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
-           "pk_detokenize", "pk_group_words", "pk_tokenize", "pk_ctc_decode_boosted"]
+           "pk_detokenize", "pk_group_words", "pk_tokenize", "pk_ctc_decode_boosted",
+           "pk_resample_len", "pk_resample"]
 
 _lib = None
 
@@ -75,6 +76,10 @@ def load_library():
     L.pk_ctc_logprobs.argtypes = [vp, f32p, C.c_int32, f32p]
     L.pk_transcribe_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int, C.POINTER(_PkTokens)]
     L.pk_stage_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
+    L.pk_resample_len.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    L.pk_resample_len.restype = C.c_int64
+    L.pk_resample.argtypes = [f32p, C.c_int64, C.c_int32, C.c_int32, f32p, C.c_int64]
+    L.pk_resample.restype = C.c_int64
     L.pk_tokenize.argtypes = [vp, C.c_char_p, i32p, C.c_int32]
     L.pk_tokenize.restype = C.c_int32
     L.pk_ctc_decode_boosted.argtypes = [f32p, C.c_int32, C.c_int32, C.c_int32, i32p, i32p, C.c_int32, C.c_float, i32p, i32p, i32p,
@@ -475,6 +480,18 @@ class Tokenizer:
                                   _f32p(we), _f32p(wc))
         words = buf.value.decode("utf-8").split("\n")[:k]
         return [WordTimestamp(words[i], float(ws[i]), float(we[i]), float(wc[i])) for i in range(k)]
+
+
+def resample(samples: np.ndarray, src_rate: int, dst_rate: int = 16000) -> np.ndarray:
+    """parakeet::resample (src/audio_io.cpp:238-251): Kaiser-windowed sinc, host code behind pk_resample."""
+    L = load_library()
+    x = np.ascontiguousarray(samples, np.float32)
+    m = L.pk_resample_len(len(x), src_rate, dst_rate)
+    if m < 0:
+        raise ValueError("pk_resample: invalid arguments")
+    out = np.zeros(max(m, 1), np.float32)
+    L.pk_resample(_f32p(x if len(x) else np.zeros(1, np.float32)), len(x), src_rate, dst_rate, _f32p(out), m)
+    return out[:m]
 
 
 def ctc_greedy_decode_boosted(logprobs: np.ndarray, phrases: Sequence[Sequence[int]], boost_score: float = 5.0,

@@ -31,5 +31,11 @@ int main(int argc, char **argv) {
     parakeet::ContextTrie built;
     built.build({text}, tok);
     std::printf("built %zu\n", built.ids().size());
+    if (argc > 3) {   // read_audio on a WAV that is not 16 kHz: resampled like the reference's read_audio
+        auto pcm = parakeet::read_audio(argv[3]);
+        double acc = 0.0;
+        for (size_t i = 0; i < pcm.size(); ++i) acc += (double)pcm[i] * (double)((i % 7) + 1);
+        std::printf("wav %zu %.9e %.9e\n", pcm.size(), pcm.empty() ? 0.0 : (double)pcm[pcm.size() / 2], acc);
+    }
     return 0;
 }

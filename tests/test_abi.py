@@ -118,13 +118,47 @@ def test_cpp_shim_host_functions(pkg, O, tiny, tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp_host_check.cpp"),
                     "-L", libdir, "-lparakeet_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
     text = " ".join(p.replace(O.SP_MARK, " ").strip() for p in tiny.pieces[3:7])
-    out = subprocess.run([exe, tiny.vocab_path, text], check=True, capture_output=True, text=True).stdout.splitlines()
+    import struct
+    rng = np.random.default_rng(8)
+    pcm16 = (rng.standard_normal(5000) * 6000).astype(np.int16)
+    wav = str(tmp_path / "a22k.wav")
+    with open(wav, "wb") as f:                                    # mono PCM16 at 22.05 kHz
+        f.write(b"RIFF" + struct.pack("<I", 36 + 2 * len(pcm16)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 22050, 44100, 2, 16))
+        f.write(b"data" + struct.pack("<I", 2 * len(pcm16)) + pcm16.tobytes())
+    out = subprocess.run([exe, tiny.vocab_path, text, wav], check=True, capture_output=True, text=True).stdout.splitlines()
     want = O.tokenizer_encode(text, tiny.pieces)
     assert out[0].split()[1:] == [str(i) for i in want] and len(want) >= 3
     assert out[1] == "decode " + O.detokenize(want, tiny.pieces)
     assert out[2] == "plain 42 n=1"
     assert out[3] == "boosted 43 start=0 end=2 n=1 empty=1/0"
     assert out[4] == "built %d" % len(want)
+    res = O.sinc_resample(pcm16.astype(np.float32) / np.float32(32768.0), 22050, 16000)      # audio_io.cpp: PCM16 / 32768, then resample
+    n_s, mid_s, acc_s = out[5].split()[1:]
+    assert int(n_s) == len(res)
+    assert abs(float(mid_s) - float(res[len(res) // 2])) <= 1e-7 * max(1.0, abs(float(res[len(res) // 2])))
+    acc = float(np.sum(res.astype(np.float64) * ((np.arange(len(res)) % 7) + 1)))
+    assert abs(float(acc_s) - acc) <= 1e-6 * max(1.0, abs(acc))
+
+
+def test_resample_matches_oracle_and_reference(pkg, O, refbind):
+    """pk_resample (host) == the oracle's sinc_resample == the compiled reference's parakeet::resample, bit for bit
+    (double arithmetic in the same order), for down- and up-sampling, integer and fractional ratios, tiny inputs."""
+    rng = np.random.default_rng(4)
+    for sr, dr, n in [(44100, 16000, 9000), (48000, 16000, 5001), (8000, 16000, 2500), (22050, 16000, 3000), (24000, 16000, 999),
+                      (96000, 16000, 6000), (16000, 16000, 50), (11025, 16000, 3), (16000, 8000, 1000), (44100, 16000, 0)]:
+        x = (rng.standard_normal(n) * 0.3).astype(np.float32)
+        got = pkg.engine.resample(x, sr, dr)
+        want = O.sinc_resample(x, sr, dr)
+        assert got.shape == want.shape == (pkg.engine.load_library().pk_resample_len(n, sr, dr),)
+        assert np.array_equal(got, want), (sr, dr, n, float(np.abs(got - want).max()))
+        if refbind is not None and n > 0:
+            assert np.array_equal(got, refbind.resample(x, sr, dr)), (sr, dr, n)
+    assert pkg.engine.load_library().pk_resample_len(-1, 16000, 16000) == -1
+    # a resampled 1 kHz tone keeps its frequency
+    t = np.arange(44100, dtype=np.float64) / 44100.0
+    y = pkg.engine.resample(np.sin(2 * np.pi * 1000.0 * t).astype(np.float32), 44100, 16000)
+    spec = np.abs(np.fft.rfft(y[1000:1000 + 8000]))
+    assert abs(int(spec.argmax()) * 16000 / 8000 - 1000.0) <= 2.0
 
 
 def test_vocab_missing_file_raises(pkg):
