@@ -3,12 +3,14 @@
 
     audio-seconds / second (RTFx), tdt-ctc-110m, 10 s clips, 1/2/4/8 x B200
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 110m-64x10s|600m-16x30s]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path (PCM -> log-mel -> FastConformer -> TDT greedy) over
-one batch of 64 synthetic 10 s clips per GPU (BASELINE.json configs[1]); weak scaling: every
-rank owns its own 64 clips, the only exchange is one all-gather of the token buffers.
+one batch of 64 synthetic 10 s clips per GPU (BASELINE.json configs[1]; --config 600m-16x30s:
+configs[2]).  The K timed steps form one JOB of K x 64 DISTINCT clips per GPU (weak scaling); the
+only exchange is ONE all-gather of the job's token rows after the last step, issued behind the
+C-ABI (pk_allgather_tokens) inside the timed region: K=16 on 8 GPUs is BASELINE configs[4].
 
   value  : whole-job audio-seconds per second with the PCM already resident in HBM
            (pk_stage_pcm once, then pk_run_staged per step on the engine stream).
@@ -39,11 +41,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
-CLIP_SAMPLES = 160000
-CLIP_SECONDS = 10.0
-BATCH = 64
-ENC_GFLOP_PER_CLIP = 28.23      # SURVEY.md section 8d, excl. the input-independent pos_proj
 METRIC = "audio-seconds/sec (RTFx) tdt-ctc-110m 10s clips"
+
+# BASELINE.json configs[1] (the configuration the metric is quoted on) and configs[2]; SURVEY.md section 8d for the
+# algorithmic encoder work per clip (excl. the input-independent pos_proj).
+CONFIGS = {
+    "110m-64x10s": dict(model="tdt-ctc-110m", preset=0, batch=64, clip_samples=160000, enc_gflop=28.23, metric=METRIC,
+                        cpu_sample_samples=160000),
+    "600m-16x30s": dict(model="tdt-600m", preset=1, batch=16, clip_samples=480000, enc_gflop=470.9,
+                        metric="audio-seconds/sec (RTFx) tdt-600m 30s clips", cpu_sample_samples=16000),
+}
 
 
 def peaks():
@@ -89,11 +96,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_checkpoint(tmpdir):
+def make_checkpoint(tmpdir, conf=None):
+    conf = conf or CONFIGS["110m-64x10s"]
     pkg = ge.load_package()
     from parakeet_cpp_b200 import synth
-    cfg = pkg.make_110m_config(max_batch=BATCH, max_samples=CLIP_SAMPLES)
-    wp = os.path.join(tmpdir, "pk110m_seed0.safetensors")
+    mk = pkg.make_110m_config if conf["preset"] == 0 else pkg.make_tdt_600m_config
+    cfg = mk(max_batch=conf["batch"], max_samples=conf["clip_samples"])
+    wp = os.path.join(tmpdir, "pk110m_seed0.safetensors" if conf["preset"] == 0 else "pk600m_seed0.safetensors")
     if not os.path.exists(wp):
         W = synth.make_weights(cfg, seed=0)
         synth.save_safetensors(wp + ".tmp", W)
@@ -121,7 +130,7 @@ def omp_threads():
     return n
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, conf):
     """The reference's own CPU path (Transcriber::transcribe, transcribe.hpp:99-179)."""
     if rank != 0:
         return
@@ -131,27 +140,29 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpkref.so not built"}))
         return
     cores = omp_threads()
-    pkg, synth, cfg, wp = make_checkpoint(args.tmp)
-    m = R.RefModel(wp, "", 0)
-    clips = [synth.make_audio(CLIP_SAMPLES, 1000 + i) for i in range(2)]
+    pkg, synth, cfg, wp = make_checkpoint(args.tmp, conf)
+    m = R.RefModel(wp, "", conf["preset"])
+    n = conf["cpu_sample_samples"]
+    secs = n / 16000.0
+    clips = [synth.make_audio(n, 1000 + i) for i in range(2)]
     for i in range(args.warmup):
         m.transcribe(clips[i % 2], "tdt")
         if i == 0 and args.warmup > 1:
-            break                                  # one warm-up pass is enough for a 10 s CPU step
+            break                                  # one warm-up pass is enough for a CPU step of seconds
     t0 = time.perf_counter()
     stage = np.zeros(3)
     for i in range(args.steps):
         _, ms = m.transcribe(clips[i % 2], "tdt")
         stage += ms
     dt = time.perf_counter() - t0
-    val = args.steps * CLIP_SECONDS / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "x real-time", "n_gpus": args.gpus,
+    val = args.steps * secs / dt
+    line = {"impl": "reference", "metric": conf["metric"], "value": val, "unit": "x real-time", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "tdt-ctc-110m TDT decode, 10 s 16 kHz synthetic clips", "clips_per_step": 1,
-                       "note": "bounded sample: 1 clip per step of the 64-clip batch"},
+            "config": {"workload": f"{conf['model']} TDT decode, {secs:g} s 16 kHz synthetic clips", "clips_per_step": 1,
+                       "note": f"bounded sample: 1 clip of {secs:g} s per step of the {conf['batch']}-clip batch"},
             "cpu_baseline": {"value": val, "unit": "x real-time", "cores": cores, "kind": "reference",
-                             "sample": f"{args.steps} x one 10 s clip, TDT, OpenMP team = {cores} threads (affinity mask capped by the cgroup CPU quota)",
+                             "sample": f"{args.steps} x one {secs:g} s clip, TDT, OpenMP team = {cores} threads (affinity mask capped by the cgroup CPU quota)",
                              "stage_ms_per_clip": {"mel": stage[0] / args.steps, "encoder": stage[1] / args.steps,
                                                    "decode": stage[2] / args.steps}},
             "e2e": {"value": val, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -164,18 +175,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="110m-64x10s", choices=sorted(CONFIGS))
     ap.add_argument("--decoder", default="tdt", choices=["tdt", "ctc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tmp", default=os.environ.get("PK_BENCH_TMP", "/tmp/pk_bench"))
     args = ap.parse_args()
     os.makedirs(args.tmp, exist_ok=True)
+    conf = CONFIGS[args.config]
+    BATCH, CLIP_SAMPLES = conf["batch"], conf["clip_samples"]
+    CLIP_SECONDS = CLIP_SAMPLES / 16000.0
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, conf)
         return
 
     import torch
@@ -186,32 +201,38 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
-        pkg, synth, cfg, wp = make_checkpoint(args.tmp)
+        pkg, synth, cfg, wp = make_checkpoint(args.tmp, conf)
     if world > 1:
         dist.barrier()
-    pkg, synth, cfg, wp = make_checkpoint(args.tmp)
+    pkg, synth, cfg, wp = make_checkpoint(args.tmp, conf)
     eng = pkg.Engine(cfg, wp, local)
     dec = pkg.Decoder.TDT if args.decoder == "tdt" else pkg.Decoder.CTC
+    if dec == pkg.Decoder.CTC and not cfg.has_ctc:
+        raise SystemExit("bench.py: this model has no CTC head")
+    K = args.steps
+    NJ = max(K, args.warmup)                       # micro-batches held by the job buffers
 
-    # this rank's 64 clips (weak scaling): seeds 1000 + global clip index
-    pcms = [synth.make_audio(CLIP_SAMPLES, 1000 + rank * BATCH + i) for i in range(BATCH)]
-    # the step's host input: one packed fp32 buffer in PAGE-LOCKED host memory
-    buf = torch.from_numpy(np.concatenate(pcms)).pin_memory().numpy()
-    off = np.arange(BATCH + 1, dtype=np.int64) * CLIP_SAMPLES
-
-    # single cross-GPU exchange: all-gather of the int32 token buffers
-    gather = None
+    # The multi-GPU exchange lives behind the C-ABI: the engine owns an NCCL communicator (rank 0 creates the
+    # unique id, torch.distributed only carries its 128 bytes) and pk_allgather_tokens issues the one collective.
     if world > 1:
-        ptr, rows, ints = eng.token_buffer()
+        uid = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init_rank(uid[0], rank, world)
 
-        class _Buf:
-            __cuda_array_interface__ = {"shape": (BATCH, ints), "typestr": "<i4", "data": (ptr, False), "version": 3}
-        tok_local = torch.as_tensor(_Buf(), device=f"cuda:{local}")
-        tok_all = torch.empty((world * BATCH, ints), dtype=torch.int32, device=f"cuda:{local}")
+    # This rank's job: K micro-batches of BATCH DISTINCT clips (weak scaling).  Micro-batch 0 holds the seeded clips
+    # 1000 + rank * BATCH + i (the ones the golden fixtures pin); micro-batch k holds clip (i + k) % BATCH of that
+    # set rotated by 997 k samples: different samples, mel frames and tokens in every step, at memcpy cost.
+    base = [synth.make_audio(CLIP_SAMPLES, 1000 + rank * BATCH + i) for i in range(BATCH)]
+    big = torch.empty(NJ * BATCH * CLIP_SAMPLES, dtype=torch.float32).pin_memory().numpy()   # PAGE-LOCKED host input
+    for k in range(NJ):
+        for i in range(BATCH):
+            o = (k * BATCH + i) * CLIP_SAMPLES
+            big[o:o + CLIP_SAMPLES] = np.roll(base[(i + k) % BATCH], 997 * k) if k else base[i]
+    off = np.arange(BATCH + 1, dtype=np.int64) * CLIP_SAMPLES          # offsets of one micro-batch
+    off_all = np.arange(NJ * BATCH + 1, dtype=np.int64) * CLIP_SAMPLES
 
-        def gather():
-            eng.sync()
-            dist.all_gather_into_tensor(tok_all, tok_local)
+    def mb(k):                                                         # host view of micro-batch k
+        return big[k * BATCH * CLIP_SAMPLES:(k + 1) * BATCH * CLIP_SAMPLES]
 
     def barrier():
         eng.sync()
@@ -222,14 +243,13 @@ def main():
 
     stream = torch.cuda.ExternalStream(eng.stream(), device=local)   # events must be recorded on the engine stream
 
-    def timed(fn, steps):
-        """K steps bracketed by barrier+sync; device time via events on the ENGINE stream."""
+    def timed(fn):
+        """fn() runs the K steps; bracketed by barrier+sync; device time via events on the ENGINE stream."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(steps):
-            fn()
+        fn()
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - w0
@@ -240,78 +260,114 @@ def main():
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall
 
-    # ---- device-resident throughput ("value")
-    eng.stage(buf, off)
+    # ---- device-resident throughput ("value"): the whole job's PCM is staged in HBM once; a step selects its
+    # micro-batch (no copy), runs the path and appends its token rows to the device job buffer; ONE all-gather
+    # after the last step (inside the timed region).  No host synchronisation anywhere in the loop.
+    eng.job_stage(big, off_all)
+    eng.job_begin(NJ * BATCH, world)               # size the job buffers once, outside every timed region
 
-    def step_resident():
-        eng.flush_l2()
-        eng.run_staged(dec)
-        if gather:
-            gather()
+    def job_resident(steps):
+        eng.job_begin(steps * BATCH, world)
+        for k in range(steps):
+            eng.flush_l2()
+            eng.job_select(k * BATCH, BATCH)
+            eng.run_staged(dec)
+            eng.job_append()
+        if world > 1:
+            eng.allgather_tokens()
 
-    for _ in range(args.warmup):
-        step_resident()
+    job_resident(args.warmup)
+    job_resident(args.warmup)       # (second pass: CUDA graph replay of the batch shape)
     l0 = eng.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    ms, wall = timed(step_resident, args.steps)
+    ms, wall = timed(lambda: job_resident(K))
     clocks = sampler.stop()
     launches = eng.launch_count() - l0
-    ref_tokens = eng.fetch(BATCH)
-    audio_s = args.steps * BATCH * CLIP_SECONDS * world
+    rows_all = eng.job_fetch(world * K * BATCH, gathered=True) if world > 1 else eng.job_fetch(K * BATCH)
+    mine = rows_all[rank * K * BATCH:(rank + 1) * K * BATCH]
+    assert int((rows_all[:, 0] > 0).sum()) == rows_all.shape[0], "bench: an utterance of the job decoded to nothing"
+    eng.job_select(0, BATCH)
+    eng.run_staged(dec)
+    ref_tokens = eng.fetch(BATCH)                                  # micro-batch 0 again, through the plain token path
+    assert [r[1:1 + r[0]].tolist() for r in mine[:BATCH]] == [[t.token_id for t in u] for u in ref_tokens]
+    distinct = len({r[1:1 + r[0]].tobytes() for r in rows_all})
+    audio_s = K * BATCH * CLIP_SECONDS * world
     value = audio_s / (max(ms, 1e-9) / 1e3)
 
-    # ---- end-to-end through the public API with host buffers ("e2e"): every step copies its 41 MB of PCM
-    # from page-locked host memory and reads its tokens back.  Two ways a caller can drive it:
-    #   sync     : pk_transcribe_batch (one blocking call per batch, like the reference's transcribe())
-    #   pipelined: pk_stage_pcm + pk_run_staged + pk_prefetch_pcm(next batch) + pk_fetch_tokens -- the H2D
-    #              copy of batch i+1 runs under the kernels of batch i (double-buffered PCM on the device)
+    # ---- the former per-step variant, for the scaling curve's history: every step all-gathers its own 64 rows
+    per_step = None
+    if world > 1:
+        def steps_with_gather():
+            for k in range(K):
+                eng.flush_l2()
+                eng.job_begin(BATCH, world)
+                eng.job_select(k * BATCH, BATCH)
+                eng.run_staged(dec)
+                eng.job_append()
+                eng.allgather_tokens()
+        steps_with_gather()
+        ms_ps, _ = timed(steps_with_gather)
+        per_step = {"value": audio_s / (ms_ps / 1e3), "ms_per_step": ms_ps / K,
+                    "note": "one pk_allgather_tokens per step on the engine stream (no host sync)"}
+
+    # ---- end-to-end through the public API with host buffers ("e2e"): every step copies its PCM from page-locked
+    # host memory and reads its tokens back; the job's rows are all-gathered once and read back at the end.
+    #   sync     : pk_transcribe_batch (one blocking call per micro-batch, like the reference's transcribe())
+    #   pipelined: pk_stage_pcm + pk_run_staged + pk_prefetch_pcm(next micro-batch) + pk_fetch_tokens -- the H2D
+    #              copy of micro-batch k+1 runs under the kernels of micro-batch k (double-buffered PCM on the device)
     tok_out = eng._tokens(BATCH)
 
-    def step_sync():
-        eng.flush_l2()
-        arrs = eng.transcribe_packed(buf, off, dec, tok_out)     # H2D of buf + D2H of the token arrays inside
-        if gather:
-            gather()
-        return arrs
+    def job_sync(steps):
+        eng.job_begin(steps * BATCH, world)
+        for k in range(steps):
+            eng.flush_l2()
+            arrs = eng.transcribe_packed(mb(k), off, dec, tok_out)     # H2D of the PCM + D2H of the token arrays inside
+            eng.job_append()
+        if world > 1:
+            eng.allgather_tokens()
+        return eng.job_fetch(world * steps * BATCH if world > 1 else steps * BATCH, gathered=world > 1), arrs
 
-    def step_pipelined():
-        eng.flush_l2()
-        eng.stage(buf, off)              # adopts the copy started by the previous step's prefetch
-        eng.run_staged(dec)
-        eng.prefetch(buf, off)           # this is the NEXT step's input: its H2D is inside the timed region too
-        arrs = eng.fetch_into(tok_out)   # D2H of this step's tokens
-        if gather:
-            gather()
-        return arrs
+    def job_pipelined(steps):
+        eng.job_begin(steps * BATCH, world)
+        eng.prefetch(mb(0), off)                                       # H2D of micro-batch 0: inside the timed region
+        for k in range(steps):
+            eng.flush_l2()
+            eng.stage(mb(k), off)            # adopts the copy started by the previous step's prefetch
+            eng.run_staged(dec)
+            eng.job_append()
+            if k + 1 < steps:
+                eng.prefetch(mb(k + 1), off)
+            arrs = eng.fetch_into(tok_out)   # D2H of this step's tokens
+        if world > 1:
+            eng.allgather_tokens()
+        return eng.job_fetch(world * steps * BATCH if world > 1 else steps * BATCH, gathered=world > 1), arrs
 
-    def time_e2e(step_fn):
-        for _ in range(2):
-            o = step_fn()
-        assert [o["ids"][b, :o["len"][b]].tolist() for b in range(BATCH)] == [[t.token_id for t in u] for u in ref_tokens]
+    def time_e2e(job_fn):
+        job_fn(2)
         barrier()
         w0 = time.perf_counter()
-        for _ in range(args.steps):
-            o = step_fn()
+        rows, o = job_fn(K)
         barrier()
         wall_ = time.perf_counter() - w0
+        assert np.array_equal(rows, rows_all), "bench: e2e job rows differ from the device-resident job"
         if world > 1:
             t = torch.tensor([wall_], device=f"cuda:{local}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall_ = float(t[0])
         return wall_, o
 
-    sync_wall, out = time_e2e(step_sync)
-    eng.prefetch(buf, off)               # prime the pipeline (outside the timed region; every timed step issues its own)
-    e2e_wall, out = time_e2e(step_pipelined)
-    eng.stage(buf, off)                  # drain the last prefetch
-    eng.sync()
+    sync_wall, out = time_e2e(job_sync)
+    e2e_wall, out = time_e2e(job_pipelined)
     e2e_value = audio_s / e2e_wall
-    n_tok = int(out["len"].sum())
-    d2h = BATCH * (1 + eng.cap) * 4 + 3 * BATCH * eng.cap * 4      # token rows + start/end/conf as copied by fetch
+    n_tok = int(mine[:, 0].sum())
+    W = 1 + eng.cap
+    # per step: token rows + start/end/conf (pk_fetch_tokens) + this step's share of the job rows read back at the end
+    d2h = BATCH * W * 4 + 3 * BATCH * eng.cap * 4 + world * BATCH * W * 4
 
     # ---- per-kernel-class device time (separate profiled pass; not the timed value)
+    eng.job_select(0, BATCH)
     eng.profile_begin()
     PSTEPS = 3
     for _ in range(PSTEPS):
@@ -323,59 +379,71 @@ def main():
     gemm_tflops = gemm_fl / max(gemm_ms, 1e-9) / 1e9
     enc_ms = sum(prof[k][0] for k in ("subsample", "gemm", "layernorm", "attention", "dwconv")) / PSTEPS
     math_name = {0: "bf16x3", 1: "bf16", 2: "f32"}[int(cfg.math)]
-    # fp32 CUDA-core GEMM is bounded by the fp32 FMA pipe, not by tcgen05: report against the
-    # tensor roofline anyway (the bar the north star sets) and say so.
-    # DRAM bytes of one launch of the dominant GEMM, from the committed ncu --set full capture
-    # (bench.py cannot run ncu on itself; profiles/r01_traffic.json says which launch and how it was taken)
+    # The timed region is seconds long at ~1 kW: the sustained bf16 peak is the denominator; the burst figure is
+    # reported beside it (frac_of_burst) because short runs keep the boost clock.
+    # DRAM bytes of one launch of the dominant GEMM come from the committed ncu --set full capture
+    # (bench.py cannot run ncu on itself; profiles/*_traffic.json says which launch and how it was taken)
     traffic, traffic_note = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        traffic, traffic_note = tj["dram_bytes_per_launch"], f'{tj["kernel"]}; {tj["source"]}'
-    except (OSError, KeyError, ValueError):
-        pass
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05; all GEMM launches of one step)",
+    for tf in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                tj = json.load(f)
+            traffic, traffic_note = tj["dram_bytes_per_launch"], f'{tj["kernel"]}; {tj["source"]}'
+            break
+        except (OSError, KeyError, ValueError):
+            continue
+    enc_gflop = conf["enc_gflop"]
+    roofline = {"bound": "tensor", "kernel": "gemm_tc kernels (tcgen05; all GEMM launches of one step)",
                 "achieved": gemm_tflops, "peak": pk["bf16_sus"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["bf16_sus"], "traffic": traffic, "traffic_of": traffic_note,
+                "frac": gemm_tflops / pk["bf16_sus"], "frac_of_burst": gemm_tflops / pk["bf16"],
+                "traffic": traffic if args.config == "110m-64x10s" else None, "traffic_of": traffic_note,
                 "mma_frac": (3.0 if int(cfg.math) == 0 else 1.0) * gemm_tflops / pk["bf16_sus"] if int(cfg.math) != 2 else None,
                 "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9, "launches_per_step": gemm_n // PSTEPS,
                 "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "encoder": {"ms_per_clip": enc_ms / BATCH, "ms_per_batch": enc_ms,
-                            "algorithmic_tflops": ENC_GFLOP_PER_CLIP * BATCH / max(enc_ms, 1e-9),
-                            "frac_of_bf16_peak": ENC_GFLOP_PER_CLIP * BATCH / max(enc_ms, 1e-9) / pk["bf16_sus"]},
+                            "algorithmic_tflops": enc_gflop * BATCH / max(enc_ms, 1e-9),
+                            "frac_of_bf16_peak": enc_gflop * BATCH / max(enc_ms, 1e-9) / pk["bf16_sus"]},
                 "per_class_ms_per_step": {k: v[0] / PSTEPS for k, v in prof.items()}}
 
-    line = {"metric": METRIC, "value": value, "unit": "x real-time", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    line = {"metric": conf["metric"], "value": value, "unit": "x real-time", "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": math_name, "data": "synthetic",
-            "config": {"workload": f"tdt-ctc-110m {args.decoder.upper()} decode, batch=64x10s synthetic clips per GPU",
-                       "clips_per_gpu_per_step": BATCH, "global_clips_per_step": BATCH * world,
-                       "parallelism": f"utterance-sharded dp{world}, one all-gather of token buffers",
+            "config": {"workload": f"{conf['model']} {args.decoder.upper()} decode, batch={BATCH}x{CLIP_SECONDS:g}s synthetic clips per GPU per step; "
+                                   f"a job = {K} steps of DISTINCT clips per GPU ({K * BATCH * world} clips in all), token rows appended on the device, "
+                                   "ONE all-gather at the end (K=16, N=8 is BASELINE configs[4]: 8192 clips)",
+                       "clips_per_gpu_per_step": BATCH, "global_clips_per_step": BATCH * world, "job_clips": K * BATCH * world,
+                       "distinct_hypotheses_in_job": distinct,
+                       "parallelism": f"utterance-sharded dp{world}; pk_allgather_tokens: one ncclAllGather of the job's token rows on the engine stream",
                        "l2": "256 MiB scratch written between steps (inside the timed region)",
-                       "tokens_per_step_rank0": n_tok},
-            "e2e": {"value": e2e_value, "unit": "x real-time", "h2d_bytes_per_step": int(buf.nbytes) * 1,
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_wall / args.steps,
-                    "api": "pk_stage_pcm + pk_run_staged + pk_prefetch_pcm(next batch) + pk_fetch_tokens: pinned host PCM in, "
-                           "host token arrays out, H2D of batch i+1 under the kernels of batch i",
-                    "sync_call": {"value": audio_s / sync_wall, "ms_per_step": 1e3 * sync_wall / args.steps,
-                                  "api": "pk_transcribe_batch (one blocking call per batch)"}},
+                       "tokens_in_job_this_rank": n_tok},
+            "e2e": {"value": e2e_value, "unit": "x real-time", "h2d_bytes_per_step": int(mb(0).nbytes),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_wall / K,
+                    "api": "pk_stage_pcm + pk_run_staged + pk_job_append + pk_prefetch_pcm(next micro-batch) + pk_fetch_tokens per step, then "
+                           "pk_allgather_tokens + pk_job_fetch once: pinned host PCM in, host token arrays out, H2D of micro-batch k+1 under the "
+                           "kernels of micro-batch k",
+                    "sync_call": {"value": audio_s / sync_wall, "ms_per_step": 1e3 * sync_wall / K,
+                                  "api": "pk_transcribe_batch (one blocking call per micro-batch) + pk_job_append"}},
             "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks, "roofline": roofline}
+    if per_step:
+        line["per_step_allgather"] = per_step
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import refbind as R
         if R.available():
             cores = omp_threads()
-            m = R.RefModel(wp, "", 0)
-            m.transcribe(pcms[0][:32000], args.decoder)                 # touch the weights
+            m = R.RefModel(wp, "", conf["preset"])
+            ns = conf["cpu_sample_samples"]
+            m.transcribe(base[0][:min(ns, 32000)], args.decoder)                 # touch the weights
             t0 = time.perf_counter()
-            ids, stage = m.transcribe(pcms[0], args.decoder)
+            ids, stage = m.transcribe(base[0][:ns], args.decoder)
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": CLIP_SECONDS / dt, "unit": "x real-time", "cores": cores, "kind": "reference",
-                                    "sample": f"1 x 10 s clip of the batch (clip 0), OpenMP team = {cores} threads (cgroup CPU quota)",
-                                    "stage_ms": {"mel": stage[0], "encoder": stage[1], "decode": stage[2]},
-                                    "tokens_match_gpu": ids == [t.token_id for t in ref_tokens[0]]}
+            line["cpu_baseline"] = {"value": (ns / 16000.0) / dt, "unit": "x real-time", "cores": cores, "kind": "reference",
+                                    "sample": f"the first {ns / 16000.0:g} s of clip 0 of the batch, OpenMP team = {cores} threads (cgroup CPU quota)",
+                                    "stage_ms": {"mel": stage[0], "encoder": stage[1], "decode": stage[2]}}
+            if ns == CLIP_SAMPLES:
+                line["cpu_baseline"]["tokens_match_gpu"] = ids == [t.token_id for t in ref_tokens[0]]
             m.close()
         else:
             line["cpu_baseline"] = {"value": None, "unit": "x real-time", "cores": 0, "kind": "reference",

@@ -132,7 +132,11 @@ pk_status pk_ctc_logprobs(pk_engine *e, const float *enc, int32_t total_frames, 
 pk_status pk_transcribe_batch(pk_engine *e, const float *pcm, const int64_t *offsets,
                               int32_t n_utt, pk_decoder dec, pk_tokens *out);
 
-/* Device-resident variant for throughput measurement: stage PCM once ... */
+/* Device-resident variant for throughput measurement: stage PCM once ...
+ * Buffer lifetime: when `pcm` is page-locked, the engine DMAs straight from it and pk_stage_pcm returns while
+ * the copy may still be in flight -- the buffer must stay valid AND unmodified until the next pk_fetch_tokens /
+ * pk_sync on this engine returns (the same holds for a buffer handed to pk_prefetch_pcm).  Pageable buffers are
+ * copied before the call returns. */
 pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt);
 /* Serving pipeline (no reference counterpart: the reference is synchronous and batch-1).  Starts the
  * host-to-device copy of the NEXT batch into the engine's second PCM buffer on a copy stream and
@@ -152,6 +156,36 @@ pk_status pk_sync(pk_engine *e);
  * int32 rows [n_utt][1 + cap] = (len, ids...).  The caller (torch.distributed /
  * NCCL) all-gathers this buffer; see INTEGRATION.md. */
 pk_status pk_token_buffer(pk_engine *e, void **dev_ptr, int32_t *rows, int32_t *row_ints);
+
+/* ---- Jobs and the single cross-GPU exchange (BASELINE configs[4]: 8192 clips over 8 GPUs).
+ * The reference is single-device and batch-1 (transcribe.hpp:170-171); this is what a sharded host adds around
+ * Transcriber::transcribe.  A rank owns a contiguous block of clips and runs it in micro-batches of at most
+ * pk_config.max_batch; after every pk_run_staged, pk_job_append copies that micro-batch's token rows
+ * (int32 [1 + cap] = len, ids...) into a device-resident job buffer of rows_local rows (asynchronous, engine
+ * stream).  pk_allgather_tokens then issues ONE ncclAllGather of the job buffer on the engine stream (no host
+ * synchronisation; rows a rank did not fill have len = 0), and pk_job_fetch copies local (gathered = 0) or
+ * gathered (gathered = 1: rank-major [world][rows_local]) rows to the host.
+ *
+ * NCCL is resolved at run time (dlopen "libnccl.so.2": the copy the process already uses); without it these
+ * calls return PK_ERR_NCCL.  Either pass the host's own ncclComm_t to pk_allgather_tokens, or let the engine
+ * own one: rank 0 calls pk_nccl_unique_id, the host broadcasts the 128 bytes, every rank calls pk_comm_init_rank. */
+#define PK_NCCL_UNIQUE_ID_BYTES 128
+pk_status pk_job_begin(pk_engine *e, int64_t rows_local, int32_t world);
+pk_status pk_job_append(pk_engine *e);
+pk_status pk_nccl_unique_id(void *id128);
+pk_status pk_comm_init_rank(pk_engine *e, const void *id128, int32_t rank, int32_t world);
+pk_status pk_allgather_tokens(pk_engine *e, void *nccl_comm /* ncclComm_t, or NULL: the engine's communicator */);
+pk_status pk_job_fetch(pk_engine *e, int32_t gathered, int32_t *rows_out, int64_t n_rows, int32_t *row_ints);
+/* Device-resident job input for throughput measurement: copy the PCM of a whole job (any number of utterances,
+ * host buffer, packed or not) to the device once, then make micro-batch [first, first + n_utt) the staged batch
+ * without a copy (pk_run_staged / pk_job_append follow as usual). */
+pk_status pk_job_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt);
+pk_status pk_job_select(pk_engine *e, int32_t first, int32_t n_utt);
+
+/* Number of utterances of the last pk_fetch_tokens whose TDT hypothesis was cut at the engine's token capacity
+ * (2 T'max + 8 per utterance; only reachable on inputs that livelock the reference's tdt_greedy_decode, which
+ * never forces an advance after max_symbols_per_step, src/tdt.cpp:66-104). */
+int32_t pk_truncated_count(const pk_engine *e);
 
 /* CUDA stream of the engine (cudaStream_t as void*), for event timing. */
 void *pk_stream(pk_engine *e);

@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-diag-suppress", "550"]
 CU = ["mel.cu", "subsample.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "norm_conv.cu", "ctc.cu",
       "tdt.cu", "engine.cu"]
-CPP = ["safetensors.cpp", "text.cpp"]
+CPP = ["safetensors.cpp", "text.cpp", "nccl_dl.cpp"]
 
 
 def _newer(src_list, out):
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if log.strip():
                 print(log, file=sys.stderr)
     if force or _newer(objs, LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

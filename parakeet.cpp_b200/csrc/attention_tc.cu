@@ -1,4 +1,4 @@
-// attention_tc.cu -- K7 on tensor cores (head_dim 64): the relative-position attention of
+// attention_tc.cu -- K7 on tensor cores (head_dim 64 and 128): the relative-position attention of
 // reference src/encoder.cpp:111-178 (rel_shift :85-109)
 //     S[i,j] = ((q_i + u).k_j + (q_i + v).PP[i-j]) / sqrt(hd),  ctx_i = softmax_j(S[i,:]) V
 // with every product on mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) using the same hi/lo
@@ -13,8 +13,11 @@
 // K / V / PP-window tiles are cp.async'ed (16 B) into shared memory, Q fragments are read straight
 // from global memory into registers, all fragments come from ldmatrix (V through .trans).
 //
-// One CTA = (64-query tile, head, utterance), 4 warps x 16 query rows; 93 KB smem -> 2 CTAs per SM
-// (one CTA's tile loads overlap the other's MMAs).  Per 64-key tile a warp does
+// One CTA = (64-query tile, head, utterance), 4 warps x 16 query rows.  head_dim 64 (tdt-ctc-110m):
+// Q fragments live in registers, 93 KB smem -> 2 CTAs per SM (one CTA's tile loads overlap the other's
+// MMAs).  head_dim 128 (tdt-600m, config.hpp:98-116): the Qu / Qv tiles are staged in shared memory once
+// and read through ldmatrix (128 fragment registers would spill), and the G patch aliases the K tile
+// (dead after AC), 209 KB smem -> 1 CTA per SM.  Per 64-key tile a warp does
 //   AC  = Qu . K^T                  16 x 64   (8 n-blocks x 4 k-steps x 3 MMAs)
 //   G   = Qv . PPwin^T              16 x 80   window of relative positions i-j (10 x 4 x 3 MMAs)
 //   S   = AC + skew(G)              G goes through a per-warp smem patch: S[r][jj] += G[r][r+63-jj]
@@ -25,17 +28,22 @@
 namespace pk {
 namespace {
 
-constexpr int HD = 64, BQ = 64, BKV = 64, LDS_ = 72;   // LDS_: smem row stride in bf16 (144 B: conflict-free ldmatrix)
+constexpr int BQ = 64, BKV = 64;
 constexpr int NPW = 128;                               // relative-position window rows per (q-tile, k-tile)
 constexpr int LDG_ = 84;                               // G patch row stride (floats)
 constexpr int TCA_THREADS = 128;
 
+// LDS_: smem row stride in bf16 (HD + 8: 144 B / 272 B rows, conflict-free ldmatrix)
+template <int HD, bool QS>
 struct __align__(16) AttnSmem {
-    bf16 k_hi[BKV * LDS_], k_lo[BKV * LDS_];
+    static constexpr int LDS_ = HD + 8;
+    bf16 k_hi[BKV * LDS_], k_lo[BKV * LDS_];          // QS: the per-warp G patches alias this tile (dead after AC)
     bf16 v_hi[BKV * LDS_], v_lo[BKV * LDS_];          // [key][dim]; PV reads it through ldmatrix.trans
     bf16 pp_hi[NPW * LDS_], pp_lo[NPW * LDS_];
-    float g[4][16 * LDG_];
+    float g[QS ? 1 : 4][QS ? 4 : 16 * LDG_];          // QS = false: own G patches
+    bf16 q[QS ? 4 : 1][QS ? BQ * LDS_ : 8];           // QS = true: Qu_hi, Qu_lo, Qv_hi, Qv_lo tiles
 };
+static_assert(sizeof(float) * 4 * 16 * LDG_ <= sizeof(bf16) * 2 * BKV * (128 + 8), "G patches must fit in the K tile");
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -71,21 +79,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // B fragments of two adjacent 8-row n-blocks (rows n0..n0+15 of a row-major [n][LDS_] tile) for the
 // 16-wide k-step at k0: r[0], r[1] = (b0, b1) of block n0; r[2], r[3] = (b0, b1) of block n0 + 8.
+template <int LDS_>
 __device__ __forceinline__ uint32_t bfrag_addr(const bf16 *base, int n0, int k0, int lane) {
     return smem_addr(base + (n0 + ((lane >> 4) << 3) + (lane & 7)) * LDS_ + k0 + (((lane >> 3) & 1) << 3));
 }
+// A fragment (a0..a3 of m16n8k16) of rows m0..m0+15, k-step at k0 of a row-major [m][LDS_] tile.
+template <int LDS_>
+__device__ __forceinline__ uint32_t afrag_addr(const bf16 *base, int m0, int k0, int lane) {
+    return smem_addr(base + (m0 + (lane & 7) + (((lane >> 3) & 1) << 3)) * LDS_ + k0 + ((lane >> 4) << 3));
+}
 // Same for B[k][n] = src[k0 + k][n0 + n] (src row-major [k][LDS_]) through ldmatrix.trans:
 // r[0], r[1] = (b0, b1) of columns n0..n0+7; r[2], r[3] of columns n0+8..n0+15.
+template <int LDS_>
 __device__ __forceinline__ uint32_t bfrag_t_addr(const bf16 *base, int k0, int n0, int lane) {
     return smem_addr(base + (k0 + (((lane >> 3) & 1) << 3) + (lane & 7)) * LDS_ + n0 + ((lane >> 4) << 3));
 }
 
-__global__ void __launch_bounds__(TCA_THREADS, 2)
+template <int HD, bool QS>
+__global__ void __launch_bounds__(TCA_THREADS, QS ? 1 : 2)
 relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restrict__ qkv_lo, int ld_qkv,
                            const int32_t *__restrict__ row_off, const bf16 *__restrict__ pp_hi,
                            const bf16 *__restrict__ pp_lo, int tmax, int d_model, ActBuf out) {
     extern __shared__ __align__(16) uint8_t smraw[];
-    AttnSmem &sm = *reinterpret_cast<AttnSmem *>(smraw);
+    using SM = AttnSmem<HD, QS>;
+    constexpr int LDS_ = SM::LDS_, KS = HD / 16, NBO = HD / 8, CH = HD / 8;   // k-steps, output n-blocks, 16 B chunks per row
+    SM &sm = *reinterpret_cast<SM *>(smraw);
     const int b = blockIdx.z, h = blockIdx.y;
     const int r0 = row_off[b], T = row_off[b + 1] - r0;
     const int i0 = blockIdx.x * BQ;
@@ -93,13 +111,14 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
     const int wrow = warp * 16;          // this warp's first query row inside the tile
 
-    // ---- Q fragments (A operand, rows wrow+g / wrow+g+8, 4 k-steps), straight from the planes
-    uint32_t qu_h[4][4], qu_l[4][4], qv_h[4][4], qv_l[4][4];
-    {
+    // ---- Q fragments (A operand, rows wrow+g / wrow+g+8, KS k-steps): registers straight from the planes
+    // (head_dim 64) or the Qu / Qv tiles staged in shared memory (head_dim 128)
+    uint32_t qu_h[QS ? 1 : KS][4], qu_l[QS ? 1 : KS][4], qv_h[QS ? 1 : KS][4], qv_l[QS ? 1 : KS][4];
+    if (!QS) {
         const int ia = i0 + wrow + g, ib = ia + 8;
         const size_t oa = (size_t)(r0 + ia) * ld_qkv + h * HD + 2 * c, ob = (size_t)(r0 + ib) * ld_qkv + h * HD + 2 * c;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+        for (int ks = 0; ks < (QS ? 1 : KS); ++ks)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const bool okr = ((e & 1) ? ib : ia) < T;
@@ -109,23 +128,37 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
                 qv_h[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_hi + o + d_model) : 0u;
                 qv_l[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_lo + o + d_model) : 0u;
             }
+    } else {
+        // joins the first key tile's cp.async group (waited for before the first MMA)
+        const uint32_t sq0 = smem_addr(sm.q[0]), sq1 = smem_addr(sm.q[1]), sq2 = smem_addr(sm.q[2]), sq3 = smem_addr(sm.q[3]);
+        for (int idx = tid; idx < BQ * CH; idx += TCA_THREADS) {
+            const int i = idx / CH, ch = idx % CH;
+            const bool ok = (i0 + i < T);
+            const size_t o = (size_t)(r0 + (ok ? i0 + i : 0)) * ld_qkv + h * HD + ch * 8;
+            const uint32_t so = (uint32_t)(i * LDS_ + ch * 8) * 2u;
+            const int nb = ok ? 16 : 0;
+            cp_async16(sq0 + so, qkv_hi + o, nb);
+            cp_async16(sq1 + so, qkv_lo + o, nb);
+            cp_async16(sq2 + so, qkv_hi + o + d_model, nb);
+            cp_async16(sq3 + so, qkv_lo + o + d_model, nb);
+        }
     }
 
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    float oacc[8][4];
+    float oacc[NBO][4];
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
+    for (int nb = 0; nb < NBO; ++nb)
 #pragma unroll
         for (int e = 0; e < 4; ++e) oacc[nb][e] = 0.f;
-    float *gs = sm.g[warp];
+    float *gs = QS ? reinterpret_cast<float *>(sm.k_hi) + warp * 16 * LDG_ : sm.g[QS ? 0 : warp];
     const uint32_t sk_hi = smem_addr(sm.k_hi), sk_lo = smem_addr(sm.k_lo), sv_hi = smem_addr(sm.v_hi), sv_lo = smem_addr(sm.v_lo);
     const uint32_t sp_hi = smem_addr(sm.pp_hi), sp_lo = smem_addr(sm.pp_lo);
 
     for (int j0 = 0; j0 < T; j0 += BKV) {
         __syncthreads();                 // previous key tile fully consumed
         // ---- K, V rows j0..j0+63 and the PP window, 16 B per cp.async
-        for (int idx = tid; idx < BKV * 8; idx += TCA_THREADS) {
-            const int j = idx >> 3, ch = idx & 7;
+        for (int idx = tid; idx < BKV * CH; idx += TCA_THREADS) {
+            const int j = idx / CH, ch = idx % CH;
             const bool ok = (j0 + j < T);
             const size_t o = (size_t)(r0 + (ok ? j0 + j : 0)) * ld_qkv + 2 * d_model + h * HD + ch * 8;
             const uint32_t so = (uint32_t)(j * LDS_ + ch * 8) * 2u;
@@ -136,8 +169,8 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
             cp_async16(sv_lo + so, qkv_lo + o + d_model, nb);
         }
         const int pmin = i0 - (j0 + BKV - 1);
-        for (int idx = tid; idx < NPW * 8; idx += TCA_THREADS) {
-            const int w = idx >> 3, ch = idx & 7;
+        for (int idx = tid; idx < NPW * CH; idx += TCA_THREADS) {
+            const int w = idx / CH, ch = idx % CH;
             const int prow = pmin + w + tmax - 1;
             const bool ok = (prow >= 0 && prow < 2 * tmax - 1);
             const size_t o = (size_t)(ok ? prow : 0) * d_model + h * HD + ch * 8;
@@ -157,18 +190,25 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
 #pragma unroll
             for (int e = 0; e < 4; ++e) sacc[nb][e] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t ah_[4], al_[4];
+            if (QS) {
+                ldsm_x4(ah_, afrag_addr<LDS_>(sm.q[0], wrow, ks * 16, lane));
+                ldsm_x4(al_, afrag_addr<LDS_>(sm.q[QS ? 1 : 0], wrow, ks * 16, lane));
+            }
+            const uint32_t (&ah)[4] = QS ? ah_ : qu_h[QS ? 0 : ks];
+            const uint32_t (&al)[4] = QS ? al_ : qu_l[QS ? 0 : ks];
 #pragma unroll
             for (int np = 0; np < 4; ++np) {
                 uint32_t bh[4], bl[4];
-                ldsm_x4(bh, bfrag_addr(sm.k_hi, np * 16, ks * 16, lane));
-                ldsm_x4(bl, bfrag_addr(sm.k_lo, np * 16, ks * 16, lane));
-                mma_bf16(sacc[2 * np], qu_h[ks], bh[0], bh[1]);
-                mma_bf16(sacc[2 * np + 1], qu_h[ks], bh[2], bh[3]);
-                mma_bf16(sacc[2 * np], qu_h[ks], bl[0], bl[1]);
-                mma_bf16(sacc[2 * np + 1], qu_h[ks], bl[2], bl[3]);
-                mma_bf16(sacc[2 * np], qu_l[ks], bh[0], bh[1]);
-                mma_bf16(sacc[2 * np + 1], qu_l[ks], bh[2], bh[3]);
+                ldsm_x4(bh, bfrag_addr<LDS_>(sm.k_hi, np * 16, ks * 16, lane));
+                ldsm_x4(bl, bfrag_addr<LDS_>(sm.k_lo, np * 16, ks * 16, lane));
+                mma_bf16(sacc[2 * np], ah, bh[0], bh[1]);
+                mma_bf16(sacc[2 * np + 1], ah, bh[2], bh[3]);
+                mma_bf16(sacc[2 * np], ah, bl[0], bl[1]);
+                mma_bf16(sacc[2 * np + 1], ah, bl[2], bl[3]);
+                mma_bf16(sacc[2 * np], al, bh[0], bh[1]);
+                mma_bf16(sacc[2 * np + 1], al, bh[2], bh[3]);
             }
         }
         // ---- G = Qv PPwin^T (16 x 80: window rows wrow .. wrow+79), through the smem patch, skewed into S
@@ -179,20 +219,28 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
 #pragma unroll
                 for (int e = 0; e < 4; ++e) gacc[nb][e] = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t ah_[4], al_[4];
+                if (QS) {
+                    ldsm_x4(ah_, afrag_addr<LDS_>(sm.q[QS ? 2 : 0], wrow, ks * 16, lane));
+                    ldsm_x4(al_, afrag_addr<LDS_>(sm.q[QS ? 3 : 0], wrow, ks * 16, lane));
+                }
+                const uint32_t (&ah)[4] = QS ? ah_ : qv_h[QS ? 0 : ks];
+                const uint32_t (&al)[4] = QS ? al_ : qv_l[QS ? 0 : ks];
 #pragma unroll
                 for (int np = 0; np < 5; ++np) {
                     uint32_t bh[4], bl[4];
-                    ldsm_x4(bh, bfrag_addr(sm.pp_hi, wrow + np * 16, ks * 16, lane));
-                    ldsm_x4(bl, bfrag_addr(sm.pp_lo, wrow + np * 16, ks * 16, lane));
-                    mma_bf16(gacc[2 * np], qv_h[ks], bh[0], bh[1]);
-                    mma_bf16(gacc[2 * np + 1], qv_h[ks], bh[2], bh[3]);
-                    mma_bf16(gacc[2 * np], qv_h[ks], bl[0], bl[1]);
-                    mma_bf16(gacc[2 * np + 1], qv_h[ks], bl[2], bl[3]);
-                    mma_bf16(gacc[2 * np], qv_l[ks], bh[0], bh[1]);
-                    mma_bf16(gacc[2 * np + 1], qv_l[ks], bh[2], bh[3]);
+                    ldsm_x4(bh, bfrag_addr<LDS_>(sm.pp_hi, wrow + np * 16, ks * 16, lane));
+                    ldsm_x4(bl, bfrag_addr<LDS_>(sm.pp_lo, wrow + np * 16, ks * 16, lane));
+                    mma_bf16(gacc[2 * np], ah, bh[0], bh[1]);
+                    mma_bf16(gacc[2 * np + 1], ah, bh[2], bh[3]);
+                    mma_bf16(gacc[2 * np], ah, bl[0], bl[1]);
+                    mma_bf16(gacc[2 * np + 1], ah, bl[2], bl[3]);
+                    mma_bf16(gacc[2 * np], al, bh[0], bh[1]);
+                    mma_bf16(gacc[2 * np + 1], al, bh[2], bh[3]);
                 }
             }
+            if (QS) __syncthreads();      // every warp has finished AC: the K tile may now hold the G patches
 #pragma unroll
             for (int nb = 0; nb < 10; ++nb) {
                 *reinterpret_cast<float2 *>(gs + g * LDG_ + nb * 8 + 2 * c) = make_float2(gacc[nb][0], gacc[nb][1]);
@@ -211,7 +259,8 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
             __syncwarp();
         }
         // ---- scale (1/sqrt(64), folded with log2 e), mask, online softmax in base 2 (rows g and g+8)
-        constexpr float kScale = 0.125f * 1.4426950408889634f;
+        constexpr float kScale = (HD == 64 ? 0.125f : 0.08838834764831845f) * 1.4426950408889634f;
+        static_assert(HD == 64 || HD == 128, "head_dim");
         float alpha[2];
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -245,7 +294,7 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
             m_run[hrow] = m_new;
         }
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+        for (int nb = 0; nb < NBO; ++nb) {
             oacc[nb][0] *= alpha[0];
             oacc[nb][1] *= alpha[0];
             oacc[nb][2] *= alpha[1];
@@ -260,10 +309,10 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
             split2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);
             split2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);
 #pragma unroll
-            for (int np = 0; np < 4; ++np) {
+            for (int np = 0; np < HD / 16; ++np) {
                 uint32_t bh[4], bl[4];
-                ldsm_x4_t(bh, bfrag_t_addr(sm.v_hi, kk * 16, np * 16, lane));
-                ldsm_x4_t(bl, bfrag_t_addr(sm.v_lo, kk * 16, np * 16, lane));
+                ldsm_x4_t(bh, bfrag_t_addr<LDS_>(sm.v_hi, kk * 16, np * 16, lane));
+                ldsm_x4_t(bl, bfrag_t_addr<LDS_>(sm.v_lo, kk * 16, np * 16, lane));
                 mma_bf16(oacc[2 * np], ph, bh[0], bh[1]);
                 mma_bf16(oacc[2 * np + 1], ph, bh[2], bh[3]);
                 mma_bf16(oacc[2 * np], ph, bl[0], bl[1]);
@@ -280,7 +329,7 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
         if (i >= T) continue;
         const float inv = 1.0f / l_run[hrow];
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+        for (int nb = 0; nb < NBO; ++nb) {
             const size_t idx = (size_t)(r0 + i) * d_model + h * HD + nb * 8 + 2 * c;
             const float x = oacc[nb][hrow * 2] * inv, y = oacc[nb][hrow * 2 + 1] * inv;
             if (out.f32) *reinterpret_cast<float2 *>(out.f32 + idx) = make_float2(x, y);
@@ -296,21 +345,32 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
 
 }  // namespace
 
-bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt,
-                                int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
-                                int d_model, ActBuf out, cudaStream_t st) {
-    if (head_dim != HD || !qkv_hi || !qkv_lo || !pp_hi || !pp_lo) return false;
+template <int HD, bool QS>
+static bool launch_attn_t(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt, int max_T,
+                          int n_heads, const bf16 *pp_hi, const bf16 *pp_lo, int tmax, int d_model, ActBuf out, cudaStream_t st) {
+    using SM = AttnSmem<HD, QS>;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(relpos_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(AttnSmem)) != cudaSuccess)
+        if (cudaFuncSetAttribute(relpos_attention_tc_kernel<HD, QS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SM)) != cudaSuccess)
             return false;
         attr = true;
     }
     dim3 grid((max_T + BQ - 1) / BQ, n_heads, n_utt);
-    relpos_attention_tc_kernel<<<grid, TCA_THREADS, sizeof(AttnSmem), st>>>(qkv_hi, qkv_lo, ld_qkv, row_off, pp_hi, pp_lo,
-                                                                          tmax, d_model, out);
+    relpos_attention_tc_kernel<HD, QS><<<grid, TCA_THREADS, sizeof(SM), st>>>(qkv_hi, qkv_lo, ld_qkv, row_off, pp_hi, pp_lo,
+                                                                              tmax, d_model, out);
     return true;
+}
+
+bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt,
+                                int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
+                                int d_model, ActBuf out, cudaStream_t st) {
+    if (!qkv_hi || !qkv_lo || !pp_hi || !pp_lo) return false;
+    if (head_dim == 64)
+        return launch_attn_t<64, false>(qkv_hi, qkv_lo, ld_qkv, row_off, n_utt, max_T, n_heads, pp_hi, pp_lo, tmax, d_model, out, st);
+    if (head_dim == 128)
+        return launch_attn_t<128, true>(qkv_hi, qkv_lo, ld_qkv, row_off, n_utt, max_T, n_heads, pp_hi, pp_lo, tmax, d_model, out, st);
+    return false;
 }
 
 }  // namespace pk

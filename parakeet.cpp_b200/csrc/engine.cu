@@ -27,6 +27,7 @@
 
 #include "../../include/parakeet_b200.h"
 #include "kernels.h"
+#include "nccl_dl.h"
 #include "safetensors.h"
 
 using namespace pk;
@@ -144,13 +145,28 @@ struct pk_engine {
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;
-    bool attn_tc = true;                       // mma.sync attention for head_dim 64 (PK_ATTN_TC=0: fp32 kernel)
+    bool attn_tc = true;                       // mma.sync attention for head_dim 64 / 128 (PK_ATTN_TC=0: fp32 kernel)
 
     // ---- the staged batch
     int n_utt = 0;
     std::vector<int64_t> pcm_off;
     std::vector<int32_t> frame_off, s2_off, row_off, t2_rows;
     int maxF = 0, maxT2 = 0, maxT = 0, M = 0, M2 = 0;
+
+    // ---- a JOB: many micro-batches on this GPU, ONE exchange at the end (BASELINE configs[4])
+    int32_t *job_tok = nullptr, *job_all = nullptr;   // [job_cap_rows][1 + cap] local rows; [job_world * job_cap_rows][1 + cap] gathered
+    int64_t job_cap_rows = 0, job_rows = 0, job_alloc_rows = 0;   // rows per rank of this job / appended so far / allocated (x world)
+    int job_world = 1;
+    int32_t *h_job = nullptr;                          // pinned staging of the gathered rows
+    size_t h_job_ints = 0;
+    float *job_pcm = nullptr;                          // device-resident PCM of a whole job (pk_job_stage_pcm)
+    size_t job_pcm_cap = 0;
+    std::vector<int64_t> job_off;
+    const float *pcm_src = nullptr;                    // front end reads this instead of d_pcm (a slice of job_pcm)
+    void *nccl_comm = nullptr;                         // ncclComm_t (pk_comm_init_rank) -- owned
+    int nccl_rank = 0, nccl_world = 1;
+    bool last_tdt = false;                             // the token buffer holds a TDT decode (overflow flags are valid)
+    int32_t truncated = 0;                             // utterances of the last fetch whose TDT hypothesis hit the token capacity
 
     // ---- optional per-kernel-class timing (CUDA events on the engine stream)
     enum { CAT_MEL, CAT_SUBSAMPLE, CAT_GEMM, CAT_LAYERNORM, CAT_ATTENTION, CAT_DWCONV, CAT_CTC, CAT_TDT, CAT_N };
@@ -415,7 +431,7 @@ pk_status pk_engine::load(const char *path) {
             ep.ldo = d;
             launch_gemm_simt(d_emb, d, wpos, d, NP, d, d, ep, stream);
             ++launches;
-            if (cfg.math != PK_MATH_FP32 && hd == 64) {
+            if (cfg.math != PK_MATH_FP32 && (hd == 64 || hd == 128)) {
                 L.pp_hi = dalloc<bf16>((size_t)NP * d);
                 L.pp_lo = dalloc<bf16>((size_t)NP * d);
                 if (!L.pp_hi || !L.pp_lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (pp planes)");
@@ -561,7 +577,7 @@ pk_status pk_engine::alloc_workspace() {
     ln = act_alloc(Mx, d);
     ffh = act_alloc(Mx, c.ff);
     qkv = dalloc<float>(Mx * 3 * d);
-    if (cfg.math != PK_MATH_FP32 && c.d_model / c.n_heads == 64) {
+    if (cfg.math != PK_MATH_FP32 && (c.d_model / c.n_heads == 64 || c.d_model / c.n_heads == 128)) {
         qkvp_hi = dalloc<bf16>(Mx * 4 * d);
         qkvp_lo = dalloc<bf16>(Mx * 4 * d);
         if (!qkvp_hi || !qkvp_lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (qkv planes)");
@@ -675,7 +691,7 @@ pk_status pk_engine::run_mel(int u0, int u1) {
     if (u1 < 0) u1 = n_utt;
     if (u1 <= u0) return PK_OK;
     Scope sc(this, CAT_MEL);
-    launch_mel(d_pcm, d_pcm_off + u0, d_frame_off + u0, u1 - u0, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
+    launch_mel(pcm_src ? pcm_src : d_pcm, d_pcm_off + u0, d_frame_off + u0, u1 - u0, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
     launches += 2;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
@@ -865,6 +881,7 @@ pk_status pk_engine::run_ctc(float *logprobs_dev) {
         launch_ctc_collapse(best, bconf, d_row_off, n_utt, c.vocab - 1, cap, tok, t_start, t_end, t_conf, stream);
     }
     launches += 2;
+    last_tdt = false;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }
@@ -902,6 +919,7 @@ pk_status pk_engine::run_tdt() {
         ce = launch_tdt_decode(p, num_sms, stream);
     }
     launches += 2;
+    last_tdt = true;
     if (ce != cudaSuccess) return fail(PK_ERR_CUDA, std::string("tdt_decode launch: ") + cudaGetErrorString(ce));
     PK_CUDA(cudaGetLastError());
     return PK_OK;
@@ -914,7 +932,12 @@ pk_status pk_engine::fetch(pk_tokens *out) {
     if (out->start) PK_CUDA(cudaMemcpyAsync(h_ts, t_start, n * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     if (out->end) PK_CUDA(cudaMemcpyAsync(h_te, t_end, n * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     if (out->conf) PK_CUDA(cudaMemcpyAsync(h_tc, t_conf, n * cap * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    int32_t *h_ovf = h_meta + 6 * (Bmax + 1);      // (upload_shapes uses the first 6 (n+1) ints)
+    if (last_tdt) PK_CUDA(cudaMemcpyAsync(h_ovf, tdt_ints, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     PK_CUDA(cudaStreamSynchronize(stream));
+    truncated = 0;
+    if (last_tdt)
+        for (size_t b = 0; b < n; ++b) truncated += h_ovf[b] != 0;
     for (size_t b = 0; b < n; ++b) {
         const int32_t len = h_tok[b * (1 + cap)];
         if (len > out->cap) return fail(PK_ERR_CAPACITY, "pk_tokens.cap too small for utterance " + std::to_string(b));
@@ -1033,6 +1056,8 @@ void pk_engine_destroy(pk_engine *e) {
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->nccl_comm && nccl_api().ok) nccl_api().CommDestroy(e->nccl_comm);
+    if (e->h_job) cudaFreeHost(e->h_job);
     if (e->h_pcm) cudaFreeHost(e->h_pcm);
     if (e->h_meta) cudaFreeHost(e->h_meta);
     if (e->h_tok) cudaFreeHost(e->h_tok);
@@ -1209,6 +1234,7 @@ pk_status pk_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, i
     cudaSetDevice(e->device);
     pk_status s = e->set_batch_shapes(nullptr, offsets, n_utt);
     if (s) return s;
+    e->pcm_src = nullptr;
     const size_t total = (size_t)e->pcm_off[n_utt];
     cudaEventSynchronize(e->ev_h2d);  // previous batch's staging copies have left the pinned buffers
     // Is the caller's buffer already page-locked and packed back to back?  Then DMA straight from it.
@@ -1333,6 +1359,16 @@ pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
     if (!e->use_graphs || e->prof_on) return run_pipeline(e, dec);
     std::string key(1, dec == PK_DECODER_CTC ? 'c' : 't');
     key.append(reinterpret_cast<const char *>(e->frame_off.data()), e->frame_off.size() * sizeof(int32_t));
+    if (e->graphs.size() >= 32 && e->graphs.find(key) == e->graphs.end()) {
+        // Bound the cache at INSERTION: with variable-length audio nearly every batch shape is new.  Drop the
+        // entries that never got a graph first; if the instantiated graphs alone fill it, drop those too.
+        for (auto it = e->graphs.begin(); it != e->graphs.end();)
+            it = it->second.exec ? std::next(it) : e->graphs.erase(it);
+        if (e->graphs.size() >= 24) {
+            for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+            e->graphs.clear();
+        }
+    }
     auto &g = e->graphs[key];
     if (g.exec) {
         cudaError_t ce = cudaGraphLaunch(g.exec, e->stream);
@@ -1341,14 +1377,7 @@ pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
         return PK_OK;
     }
     if (g.seen++ == 0) return run_pipeline(e, dec);
-    if (e->graphs.size() > 16) {   // bound the cache: drop everything but this entry
-        for (auto &kv : e->graphs)
-            if (kv.second.exec && &kv.second != &g) cudaGraphExecDestroy(kv.second.exec);
-        pk_engine::GraphEntry keep = g;
-        e->graphs.clear();
-        e->graphs[key] = keep;
-    }
-    auto &gg = e->graphs[key];
+    auto &gg = g;
     const int64_t l0 = e->launches;
     cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce));
@@ -1398,6 +1427,144 @@ pk_status pk_token_buffer(pk_engine *e, void **dev_ptr, int32_t *rows, int32_t *
     if (row_ints) *row_ints = 1 + e->cap;
     return PK_OK;
 }
+
+// ===================================================================== jobs and the single exchange step
+// SURVEY.md section 8e / BASELINE configs[4]: a rank transcribes its block of clips in micro-batches; the token
+// rows (len, ids...) of every micro-batch are appended to a device-resident job buffer; ONE ncclAllGather of that
+// buffer (on the engine stream, no host synchronisation) assembles the result of all ranks.
+
+pk_status pk_job_begin(pk_engine *e, int64_t rows_local, int32_t world) {
+    if (!e || rows_local < 1 || world < 1) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    const size_t W = 1 + (size_t)e->cap;
+    if (rows_local * world > e->job_alloc_rows || !e->job_tok) {     // (grow-only; freed with the engine)
+        cudaStreamSynchronize(e->stream);
+        e->job_tok = e->dalloc<int32_t>((size_t)rows_local * W);
+        e->job_all = e->dalloc<int32_t>((size_t)world * rows_local * W);
+        if (!e->job_tok || !e->job_all) return e->fail(PK_ERR_CUDA, "cudaMalloc failed (job buffers)");
+        if (e->h_job) cudaFreeHost(e->h_job);
+        e->h_job_ints = (size_t)world * rows_local * W;
+        if (cudaMallocHost(&e->h_job, e->h_job_ints * sizeof(int32_t)) != cudaSuccess) return e->fail(PK_ERR_CUDA, "cudaMallocHost failed (job rows)");
+        e->job_alloc_rows = rows_local * world;
+    }
+    e->job_cap_rows = rows_local;
+    e->job_world = world;
+    e->job_rows = 0;
+    // rows a rank does not fill (a short last block) stay (len = 0)
+    cudaError_t ce = cudaMemsetAsync(e->job_tok, 0, (size_t)rows_local * W * sizeof(int32_t), e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_job_begin: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+pk_status pk_job_append(pk_engine *e) {
+    if (!e || !e->job_tok || e->n_utt <= 0) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    if (e->job_rows + e->n_utt > e->job_cap_rows) return e->fail(PK_ERR_CAPACITY, "pk_job_append: job buffer full");
+    const size_t W = 1 + (size_t)e->cap;
+    cudaError_t ce = cudaMemcpyAsync(e->job_tok + (size_t)e->job_rows * W, e->tok, (size_t)e->n_utt * W * sizeof(int32_t),
+                                     cudaMemcpyDeviceToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_job_append: ") + cudaGetErrorString(ce));
+    e->job_rows += e->n_utt;
+    return PK_OK;
+}
+
+pk_status pk_job_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt) {
+    if (!e || !pcm || !offsets || n_utt < 1) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    const int64_t total = offsets[n_utt] - offsets[0];
+    if (total <= 0) return e->fail(PK_ERR_INVALID, "pk_job_stage_pcm: empty job");
+    if ((size_t)total + 8 > e->job_pcm_cap) {
+        cudaStreamSynchronize(e->stream);
+        e->job_pcm = e->dalloc<float>((size_t)total + 8);
+        if (!e->job_pcm) return e->fail(PK_ERR_CUDA, "cudaMalloc failed (job PCM)");
+        e->job_pcm_cap = (size_t)total + 8;
+    }
+    e->job_off.assign(n_utt + 1, 0);
+    for (int i = 0; i <= n_utt; ++i) e->job_off[i] = offsets[i] - offsets[0];
+    cudaError_t ce = cudaMemcpyAsync(e->job_pcm, pcm + offsets[0], (size_t)total * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_job_stage_pcm: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+pk_status pk_job_select(pk_engine *e, int32_t first, int32_t n_utt) {
+    if (!e) return PK_ERR_INVALID;
+    if (e->job_off.empty() || first < 0 || n_utt < 1 || (size_t)first + (size_t)n_utt > e->job_off.size() - 1)
+        return e->fail(PK_ERR_INVALID, "pk_job_select: range outside the staged job");
+    cudaSetDevice(e->device);
+    pk_status s = e->set_batch_shapes(nullptr, e->job_off.data() + first, n_utt);
+    if (s) return s;
+    if ((s = e->upload_shapes())) return s;
+    e->pcm_src = e->job_pcm + e->job_off[first];
+    e->front_done = false;
+    return PK_OK;
+}
+
+pk_status pk_nccl_unique_id(void *id128) {
+    if (!id128) return PK_ERR_INVALID;
+    const NcclApi &n = nccl_api();
+    if (!n.ok) {
+        g_create_err = n.why;
+        return PK_ERR_NCCL;
+    }
+    NcclApi::UniqueId id;
+    if (n.GetUniqueId(&id) != 0) {
+        g_create_err = "ncclGetUniqueId failed";
+        return PK_ERR_NCCL;
+    }
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return PK_OK;
+}
+
+pk_status pk_comm_init_rank(pk_engine *e, const void *id128, int32_t rank, int32_t world) {
+    if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return PK_ERR_INVALID;
+    const NcclApi &n = nccl_api();
+    if (!n.ok) return e->fail(PK_ERR_NCCL, n.why);
+    cudaSetDevice(e->device);
+    if (e->nccl_comm) {
+        n.CommDestroy(e->nccl_comm);
+        e->nccl_comm = nullptr;
+    }
+    NcclApi::UniqueId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    const int rc = n.CommInitRank(&e->nccl_comm, world, id, rank);
+    if (rc != 0) return e->fail(PK_ERR_NCCL, std::string("ncclCommInitRank: ") + n.GetErrorString(rc));
+    e->nccl_rank = rank;
+    e->nccl_world = world;
+    return PK_OK;
+}
+
+pk_status pk_allgather_tokens(pk_engine *e, void *nccl_comm) {
+    if (!e || !e->job_tok) return PK_ERR_INVALID;
+    const NcclApi &n = nccl_api();
+    if (!n.ok) return e->fail(PK_ERR_NCCL, n.why);
+    void *comm = nccl_comm ? nccl_comm : e->nccl_comm;
+    if (!comm) return e->fail(PK_ERR_NCCL, "pk_allgather_tokens: no communicator (pk_comm_init_rank or pass an ncclComm_t)");
+    cudaSetDevice(e->device);
+    const size_t cnt = (size_t)e->job_cap_rows * (1 + (size_t)e->cap);
+    const int rc = n.AllGather(e->job_tok, e->job_all, cnt, /*ncclInt32*/ 2, comm, e->stream);
+    if (rc != 0) return e->fail(PK_ERR_NCCL, std::string("ncclAllGather: ") + n.GetErrorString(rc));
+    ++e->launches;
+    return PK_OK;
+}
+
+pk_status pk_job_fetch(pk_engine *e, int32_t gathered, int32_t *rows_out, int64_t n_rows, int32_t *row_ints) {
+    if (!e || !e->job_tok) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    const size_t W = 1 + (size_t)e->cap;
+    if (row_ints) *row_ints = (int32_t)W;
+    if (!rows_out) return PK_OK;
+    const int64_t have = gathered ? e->job_world * e->job_cap_rows : e->job_cap_rows;
+    if (n_rows < 0 || n_rows > have) return e->fail(PK_ERR_CAPACITY, "pk_job_fetch: more rows than the job holds");
+    cudaError_t ce = cudaMemcpyAsync(e->h_job, gathered ? e->job_all : e->job_tok, (size_t)n_rows * W * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_job_fetch: ") + cudaGetErrorString(ce));
+    memcpy(rows_out, e->h_job, (size_t)n_rows * W * sizeof(int32_t));
+    return PK_OK;
+}
+
+int32_t pk_truncated_count(const pk_engine *e) { return e ? e->truncated : 0; }
 
 pk_status pk_mel(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, float *feats_out,
                  int32_t *n_frames_out) {

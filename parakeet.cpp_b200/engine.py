@@ -46,7 +46,9 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
            "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
            "pk_detokenize", "pk_group_words", "pk_tokenize", "pk_ctc_decode_boosted",
-           "pk_resample_len", "pk_resample"]
+           "pk_resample_len", "pk_resample",
+           "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
+           "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count"]
 
 _lib = None
 
@@ -105,6 +107,15 @@ def load_library():
     L.pk_vocab_size.argtypes = [vp]
     L.pk_detokenize.argtypes = [vp, i32p, C.c_int32, C.c_char_p, C.c_int32]
     L.pk_group_words.argtypes = [vp, i32p, i32p, i32p, f32p, C.c_int32, C.c_char_p, C.c_int32, f32p, f32p, f32p]
+    L.pk_job_begin.argtypes = [vp, C.c_int64, C.c_int32]
+    L.pk_job_append.argtypes = [vp]
+    L.pk_nccl_unique_id.argtypes = [C.c_char_p]
+    L.pk_comm_init_rank.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    L.pk_allgather_tokens.argtypes = [vp, vp]
+    L.pk_job_fetch.argtypes = [vp, C.c_int32, i32p, C.c_int64, i32p]
+    L.pk_job_stage_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
+    L.pk_job_select.argtypes = [vp, C.c_int32, C.c_int32]
+    L.pk_truncated_count.argtypes = [vp]
     _lib = L
     return L
 
@@ -432,6 +443,42 @@ class Engine:
 
     def stream(self) -> int:
         return int(self.L.pk_stream(self.h) or 0)
+
+    # -- jobs: many micro-batches, one exchange
+    def job_begin(self, rows_local: int, world: int = 1):
+        self._check(self.L.pk_job_begin(self.h, rows_local, world), "pk_job_begin")
+
+    def job_append(self):
+        self._check(self.L.pk_job_append(self.h), "pk_job_append")
+
+    def job_stage(self, buf: np.ndarray, off: np.ndarray):
+        self._check(self.L.pk_job_stage_pcm(self.h, _f32p(buf), _i64p(off), len(off) - 1), "pk_job_stage_pcm")
+
+    def job_select(self, first: int, n: int):
+        self._check(self.L.pk_job_select(self.h, first, n), "pk_job_select")
+
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.L.pk_nccl_unique_id(buf) != 0:
+            raise RuntimeError("pk_nccl_unique_id failed: " + self.L.pk_last_error(None).decode())
+        return buf.raw
+
+    def comm_init_rank(self, uid: bytes, rank: int, world: int):
+        self._check(self.L.pk_comm_init_rank(self.h, uid, rank, world), "pk_comm_init_rank")
+
+    def allgather_tokens(self, comm=None):
+        self._check(self.L.pk_allgather_tokens(self.h, comm), "pk_allgather_tokens")
+
+    def job_fetch(self, n_rows: int, gathered: bool = False) -> np.ndarray:
+        """-> int32 [n_rows, 1 + cap] rows (len, ids...) of this rank's job (or of all ranks, rank-major)."""
+        out = np.zeros((n_rows, 1 + self.cap), np.int32)
+        w = C.c_int32()
+        self._check(self.L.pk_job_fetch(self.h, int(gathered), _i32p(out), n_rows, C.byref(w)), "pk_job_fetch")
+        assert w.value == 1 + self.cap
+        return out
+
+    def truncated_count(self) -> int:
+        return int(self.L.pk_truncated_count(self.h))
 
     def token_buffer(self):
         p, rows, ints = C.c_void_p(), C.c_int32(), C.c_int32()

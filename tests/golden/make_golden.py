@@ -190,6 +190,48 @@ def main_600m_extra():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def main_600m_long():
+    """BASELINE config 3 (tdt-600m, 30 s clips, T' = 376) through the compiled reference: one full 30 s clip
+    (mel statistics, every 4th encoder row, TDT tokens + frames + confidences, text) and one 21 s clip (tokens only)
+    so that the GPU test can run a RAGGED batch at the configuration's full size.  The CPU reference needs
+    several minutes per clip."""
+    out = {}
+    ocfg = O.make_tdt_600m_config()
+    clips = [(480000, 1000), (336000, 3001)]      # clip 0 = clip 0 of bench.py's 16 x 30 s batch (seed 1000 + i)
+    with tempfile.TemporaryDirectory() as td:
+        W = synth.make_weights(ocfg, seed=0)
+        wp = os.path.join(td, "m600.safetensors")
+        synth.save_safetensors(wp, W)
+        pieces = synth.make_vocab(ocfg.vocab - 1, seed=0)
+        vp = os.path.join(td, "m600.vocab.txt")
+        synth.save_vocab(vp, pieces)
+        m = R.RefModel(wp, vp, 1)
+        kept = 0
+        for n, aseed in clips:
+            pcm = synth.make_audio(n, aseed)
+            feats = R.mel(pcm, ocfg.mel_bins)
+            enc = m.encode(feats, ocfg.d_model)
+            try:
+                tdt = m.tdt_greedy(enc, True)
+            except Exception as ex:
+                print("skip", n, aseed, type(ex).__name__, ex)
+                continue
+            k = f"l600.c{kept}."
+            kept += 1
+            out[k + "n_samples"] = np.array([n, aseed], np.int64)
+            out[k + "mel_stats"] = np.array([feats.mean(), feats.std(), np.abs(feats).max(), feats[::7, ::3].sum()], np.float64)
+            out[k + "enc_rows4"] = enc[::4].copy()
+            out[k + "enc_T"] = np.array([enc.shape[0]], np.int64)
+            out[k + "tdt_tok"], out[k + "tdt_conf"] = toks_arr(tdt)
+            out[k + "tdt_text"] = np.frombuffer(m.detok([t[0] for t in tdt]).encode(), np.uint8)
+            print("l600", kept - 1, n, aseed, "T", enc.shape[0], "tdt", len(tdt), flush=True)
+        m.close()
+    out["n_clips"] = np.array([kept], np.int64)
+    path = os.path.join(ROOT, "tests", "golden", "golden_600m_long_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 STREAM_SCHEDULE = [2560, 2560, 2560, 1000, 4000, 2560, 2560, 2560, 2560, 5000, 2560, 2560, 2560, 2560, 2560, 2560, 2560]
 
 
@@ -300,6 +342,8 @@ if __name__ == "__main__":
         main_600m_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "110m_extra":
         main_110m_extra()
+    elif len(sys.argv) > 1 and sys.argv[1] == "600m_long":
+        main_600m_long()
     elif len(sys.argv) > 1 and sys.argv[1] == "600m":
         main_600m()
     else:

@@ -465,3 +465,89 @@ def test_tdt_600m_preset_matches_reference_golden(pkg, O, synth, m600):
         assert r2.text == bytes(gx[kx + "tdt_text"]).decode()
     e.close()
     t.engine.close()
+
+
+def test_tdt_600m_config3_full_size_ragged_batch(pkg, O, synth, m600):
+    """BASELINE configs[2] at its full size: tdt-600m, 30 s clips (T' = 376: 6 x 6 attention tiles of the head_dim-128
+    tensor-core kernel, 3 GEMM row tiles per utterance), as a RAGGED 16-utterance batch.  Two clips were decoded by the
+    compiled reference (make_golden.py 600m_long: a 30 s and a 21 s clip; ~25 CPU-minutes each); the other rows are
+    shorter cuts whose results must equal single-utterance runs (batch invariance)."""
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_600m_long_v1.npz")
+    g = np.load(p)
+    nclips = int(g["n_clips"][0])
+    pcms = []
+    for ci in range(nclips):
+        n, aseed = (int(v) for v in g[f"l600.c{ci}.n_samples"])
+        pcms.append(synth.make_audio(n, aseed))
+    cfg = pkg.make_tdt_600m_config(max_batch=16, max_samples=480000)
+    e = pkg.Engine(cfg, m600["weights_path"], 0)
+    # encoder activations of the 30 s clip (every 4th row is in the fixture)
+    feats = e.mel([pcms[0]])[0]
+    ms = g["l600.c0.mel_stats"]
+    assert abs(float(feats.mean()) - ms[0]) < 1e-4 and abs(float(feats.std()) - ms[1]) < 1e-3
+    enc = e.encode([feats])[0]
+    assert enc.shape[0] == int(g["l600.c0.enc_T"][0]) == 376
+    assert _rel(enc[::4], g["l600.c0.enc_rows4"]) < ENC_TOL
+    # the ragged 16-utterance batch through the whole path
+    batch = list(pcms) + [pcms[0][:n] for n in (400, 16000, 80000, 160000, 240000, 333333, 479999)] + \
+        [pcms[-1][:n] for n in (48000, 123456, 300000)] + [synth.make_audio(480000, 1001 + i) for i in range(16 - nclips - 10)]
+    assert len(batch) == 16
+    got = e.transcribe_batch(batch, pkg.Decoder.TDT)
+    assert e.truncated_count() in range(0, 15)      # (a cut may hit the reference's livelock; the golden rows may not)
+    for ci in range(nclips):
+        assert len(got[ci]) < e.cap
+        k = f"l600.c{ci}."
+        assert [list(t) for t in _tt(got[ci])] == g[k + "tdt_tok"].tolist(), ci
+        assert np.allclose([t.confidence for t in got[ci]], g[k + "tdt_conf"], rtol=1e-3, atol=1e-6)
+    for i in (nclips + 3, nclips + 5, nclips + 8):          # batch invariance on three of the cuts
+        alone = e.transcribe_batch([batch[i]], pkg.Decoder.TDT)[0]
+        assert _tt(alone) == _tt(got[i]), i
+    e.close()
+
+
+def test_attention_hd128_tensor_core_equals_fp32_kernel(pkg, O, synth, m600, monkeypatch):
+    """head_dim 128: the mma.sync bf16x3 attention (Q tiles in shared memory) against the fp32 SIMT attention
+    (PK_ATTN_TC=0) on the same engine configuration, 9 s clip (T' = 113, two key tiles)."""
+    pcm = synth.make_audio(144000, 4242)
+    cfg = pkg.make_tdt_600m_config(max_batch=2, max_samples=160000)
+    feats = O.preprocess_audio(pcm, 128)
+    e = pkg.Engine(cfg, m600["weights_path"], 0)
+    enc_tc = e.encode([feats, feats[:500]])
+    e.close()
+    monkeypatch.setenv("PK_ATTN_TC", "0")
+    e = pkg.Engine(cfg, m600["weights_path"], 0)
+    enc_f32 = e.encode([feats, feats[:500]])
+    e.close()
+    for a, b in zip(enc_tc, enc_f32):
+        assert _rel(a, b) < 2e-4
+
+
+def test_job_api_appends_microbatches_and_allgathers(pkg, tiny, synth, math_mode):
+    """SURVEY section 8e behind the C-ABI: micro-batches appended to the device job buffer, ONE ncclAllGather
+    (world size 1 here: NCCL resolved with dlopen, communicator owned by the engine), rows read back; and the
+    device-resident job input (pk_job_stage_pcm / pk_job_select) against the host-buffer path."""
+    import dataclasses
+    e = pkg.Engine(dataclasses.replace(tiny.cfg, math=MATH[math_mode]), tiny.weights_path, 0)
+    lens = [32000, 20000, 64000, 12345, 8000, 16001, 40000, 2000, 400, 25000, 31000]
+    pcms = [synth.make_audio(n, 700 + i) for i, n in enumerate(lens)]
+    want = e.transcribe_batch(pcms[:8], pkg.Decoder.TDT) + e.transcribe_batch(pcms[8:], pkg.Decoder.TDT)
+    from parakeet_cpp_b200.engine import _pack
+    buf, off = _pack(pcms)
+    e.job_stage(buf, off)
+    e.comm_init_rank(e.nccl_unique_id(), 0, 1)
+    for rnd in range(2):                                     # second round: buffers are reused, rows reset
+        e.job_begin(12, 1)
+        for first, n in ((0, 8), (8, 3)):
+            e.job_select(first, n)
+            e.run_staged(pkg.Decoder.TDT)
+            e.job_append()
+        e.allgather_tokens()
+        rows = e.job_fetch(12, gathered=True)
+        assert np.array_equal(rows, e.job_fetch(12, gathered=False))
+        assert rows[11, 0] == 0                              # the row nobody filled
+        for i, w in enumerate(want):
+            assert rows[i, 1:1 + rows[i, 0]].tolist() == [t.token_id for t in w], (rnd, i)
+    with pytest.raises(RuntimeError):                        # job buffer full
+        e.job_append(); e.job_append()
+    e.close()
