@@ -182,6 +182,31 @@ pk_status pk_job_fetch(pk_engine *e, int32_t gathered, int32_t *rows_out, int64_
 pk_status pk_job_stage_pcm(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt);
 pk_status pk_job_select(pk_engine *e, int32_t first, int32_t n_utt);
 
+/* ---- Streaming (BASELINE configs[3]: eou-120m, 160 ms chunks), replacing
+ * StreamingTranscriber::transcribe_chunk / reset (src/eou.cpp:111-149): StreamingAudioPreprocessor::process_chunk
+ * (src/audio.cpp:195-259), StreamingFastConformerEncoder::forward_chunk (src/streaming_encoder.cpp:425-472) and
+ * rnnt_streaming_decode_chunk (src/eou.cpp:17-98).  The reference advances ONE stream per call; here n_streams streams
+ * advance in lock step and share every weight read.  The engine must have been created with max_batch >= n_streams and
+ * max_samples large enough that its encoder-frame capacity is >= att_context_left + frames per chunk (6.4 s is plenty
+ * for the eou-120m preset: left context 70).  Per-stream state (sample overlap, leftover mel frames, K/V and conv caches,
+ * LSTM state, last token, frame offset) lives on the device.
+ *   pk_stream_open : allocate the state of n_streams streams (att_context_left / right of StreamingEncoderConfig,
+ *                    streaming_encoder.hpp:18-24; the right context / mask is inert in the reference's CPU path and is
+ *                    not applied).
+ *   pk_stream_step : stream s receives pcm[offsets[s] .. offsets[s+1]) (host fp32; an empty chunk is allowed); `out` rows
+ *                    (n = n_streams, may be NULL) receive the tokens emitted BY THIS STEP, start/end = absolute encoder
+ *                    frames (the end frame is not clamped to the chunk, eou.cpp:81-84).  Optional taps (may be NULL):
+ *                    mel_out packed (sum nf_s, mel_bins) new log-mel frames, n_mel[s] = nf_s; enc_out packed
+ *                    (sum C_s, d_model) encoder rows of this step, n_enc[s] = C_s.  A first chunk of 400..511 samples
+ *                    returns PK_ERR_INVALID where the reference's STFT throws (fft.cpp:1516-1521).
+ *   pk_stream_reset: StreamingTranscriber::reset for one stream (-1: all). */
+pk_status pk_stream_open(pk_engine *e, int32_t n_streams, int32_t max_chunk_samples, int32_t att_context_left,
+                         int32_t att_context_right);
+pk_status pk_stream_reset(pk_engine *e, int32_t stream);
+pk_status pk_stream_step(pk_engine *e, const float *pcm, const int64_t *offsets, pk_tokens *out, float *mel_out,
+                         int32_t *n_mel, float *enc_out, int32_t *n_enc);
+int32_t pk_stream_count(const pk_engine *e);
+
 /* Number of utterances of the last pk_fetch_tokens whose TDT hypothesis was cut at the engine's token capacity
  * (2 T'max + 8 per utterance; only reachable on inputs that livelock the reference's tdt_greedy_decode, which
  * never forces an advance after max_symbols_per_step, src/tdt.cpp:66-104). */

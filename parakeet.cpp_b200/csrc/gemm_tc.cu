@@ -66,6 +66,18 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// One elected lane of a fully active warp (the warp-specialised roles below run under it): unlike `lane == 0`, ptxas
+// then knows that exactly one thread executes the region and issues UTCHMMA / UTMALDG from uniform registers directly
+// instead of wrapping every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -160,7 +172,7 @@ __device__ __forceinline__ void epi_load(const EpiParams &epi, int rb, int gc, i
 // start refilling this accumulator buffer while the tail is still being stored.
 template <int NCOLS, int EK, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, int row0, int gcol0, int M, int N,
-                                              const EpiParams &epi_param, int lane, ReleaseFn release) {
+                                              const EpiParams &epi_param, int lane, ReleaseFn release, int dbg = 0) {
     // Register copy of the parameters for the fast path.  (The out-of-line edge path takes the
     // struct by reference; reading fields through that same object here makes every pointer a
     // generic-address reload after each store.)
@@ -184,6 +196,7 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
             tmem_ld16_issue(taddr + (uint32_t)(ch + 1) * 16u, vn);
             epi_load<EK>(epi, rb, gc0 + 16 + cc, M, vec_ok && gc0 + 32 <= N, on);
         }
+        if (!(dbg & 4)) {       // (measurement aid, bit 2: TMEM drain only)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             sts128(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, vc[4 * j], vc[4 * j + 1], vc[4 * j + 2], vc[4 * j + 3]);
@@ -194,13 +207,18 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
         if (interior) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) val[i] = epi_math<EK>(val[i], oc.b, oc.r[i], epi.alpha);
+            if (dbg & 8) {      // (measurement aid, bit 3: everything but the global stores)
+                if (val[0].x + val[1].y + val[2].z + val[3].w == 1.2345e-30f) epi_store<EK>(epi, rb, gc0 + cc, val[0], oc.bu, oc.bv);
+            } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (rb + i * 8 < M) epi_store<EK>(epi, rb + i * 8, gc0 + cc, val[i], oc.bu, oc.bv);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (rb + i * 8 < M) epilogue4(epi_param, rb + i * 8, gc0 + cc, N, val[i]);
+        }
         }
         __syncwarp();
         if (has_next) {
@@ -219,6 +237,14 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
             }
         }
     }
+}
+
+// measurement aid: SM cycles and nanoseconds CTA 0 spent in its epilogue loop (effective SM clock under this kernel)
+__device__ unsigned long long g_clk_probe[2];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 constexpr int EPI_WARPS = 8;                    // two per TMEM lane quarter, each half of the columns
@@ -244,7 +270,7 @@ template <int BN, int NPASS, int EK>
 __global__ void __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-               int K, const __grid_constant__ EpiParams epi) {
+               int K, const __grid_constant__ EpiParams epi, int dbg) {
     using C = TcCfg<BN, NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -280,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;   // global k-block counter across tiles
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
@@ -289,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
+                    if (dbg & 2) { mbar_arrive(&full[s]); continue; }      // measurement aid: MMAs on stale smem, no loads
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
                     tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
                     tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
@@ -301,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -339,18 +366,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int half = ew >> 2;                    // which half of the BN columns
         const uint32_t stg_s = smem_u32(staging + (size_t)ew * 32 * STG_LD);   // explicit .shared accesses
         uint32_t tcount = 0;
+        const bool probe = dbg && blockIdx.x == 0 && threadIdx.x == 64;
+        long long pc0 = 0;
+        unsigned long long pg0 = 0;
+        if (probe) { pc0 = clock64(); pg0 = globaltimer_ns(); }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+            if (dbg & 1) {                           // measurement aid: drain nothing, release at once
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                continue;
+            }
             epilogue_slab<BN / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN / 2), M, N, epi, lane, [&]() {
                 tcgen05_fence_before();              // last TMEM read of this tile has landed: release the buffer
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            });
+            }, dbg);
         }
+        if (probe) { g_clk_probe[0] = (unsigned long long)(clock64() - pc0); g_clk_probe[1] = globaltimer_ns() - pg0; }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -424,7 +462,7 @@ template <int NPASS, int EK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-                int K, const __grid_constant__ EpiParams epi) {
+                int K, const __grid_constant__ EpiParams epi, int dbg) {
     using C = Tc2Cfg<NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -463,7 +501,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int tile = pair; tile < num_tiles; tile += npairs) {
                 const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
@@ -474,6 +512,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
                     const uint32_t lbar = mapa_rank(smem_u32(&full[s]), 0);   // the leader's full barrier
+                    if (dbg & 2) { mbar_arrive_cluster(lbar); continue; }     // measurement aid: no loads
                     if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
                     else mbar_arrive_cluster(lbar);
                     tma_load_2d_2sm(st, &tmA_hi, lbar, kb * BK, m0);
@@ -487,7 +526,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
+        if (leader && elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2);
             uint32_t it = 0, tcount = 0;
             for (int tile = pair; tile < num_tiles; tile += npairs, ++tcount) {
@@ -532,11 +571,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + buf * BN2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN2 / 2));
+            if (dbg & 1) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);
+                continue;
+            }
             epilogue_slab<BN2 / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN2 / 2), M, N, epi, lane, [&]() {
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);   // leader's barrier counts both CTAs
-            });
+            }, dbg);
         }
     }
     tcgen05_fence_before();
@@ -545,6 +590,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
 }
+
+int g_dbg = 0;   // PK_GEMM_DBG (measurement aid, tc_set_debug): bit 0 = epilogue releases without draining, bit 1 = no TMA loads
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -580,7 +627,7 @@ cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K
     const int num_tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
     dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    gemm_tc_kernel<BN, NPASS, EK><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
+    gemm_tc_kernel<BN, NPASS, EK><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi, g_dbg);
     return cudaGetLastError();
 }
 
@@ -602,7 +649,7 @@ cudaError_t launch_k2(const TcOperand &A, const TcOperand &W, int M, int N, int 
     const int num_tiles = ((N + BN2 - 1) / BN2) * ((M + 2 * BM - 1) / (2 * BM));
     const int pairs = num_tiles < num_sms / 2 ? num_tiles : num_sms / 2;
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    gemm_tc2_kernel<NPASS, EK><<<dim3(2 * pairs), TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi);
+    gemm_tc2_kernel<NPASS, EK><<<dim3(2 * pairs), TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi, g_dbg);
     return cudaGetLastError();
 }
 
@@ -659,6 +706,12 @@ int tc_tile_n(int N) { return N <= 64 ? 64 : 128; }
 
 static bool g_use_2cta = false;   // measured on B200 (64x10 s): the pair kernel is not faster yet at M = 8064
 void tc_set_2cta(bool on) { g_use_2cta = on; }
+void tc_set_debug(int bits) { g_dbg = bits; }
+double tc_probe_mhz() {   // effective SM clock seen by CTA 0 of the last 1-CTA launch with a non-zero debug mask (bit 4 = probe only)
+    unsigned long long h[2] = {0, 0};
+    if (cudaMemcpyFromSymbol(h, g_clk_probe, sizeof(h)) != cudaSuccess || h[1] == 0) return 0.0;
+    return 1e3 * (double)h[0] / (double)h[1];
+}
 
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st) {

@@ -21,6 +21,41 @@ size_t mel_smem_bytes(const MelTables &tb);
 void launch_mel(const float *pcm, const int64_t *pcm_off, const int32_t *frame_off, int n_utt, int max_frames,
                 int n_mels, const MelTables &tb, float *logmel, float *feats, cudaStream_t st);
 
+// streaming variant (StreamingAudioPreprocessor::process_chunk, src/audio.cpp:195-259): `sig` holds, per stream, the
+// already pre-emphasised samples [overlap | chunk]; frame f = window . sig[f*160 .. f*160+512) (center = False, no
+// reflection), n_frames[b] frames, log-mel WITHOUT normalisation written to logmel rows out_row[b] + f.
+void launch_mel_stream(const float *sig, const int64_t *sig_off, const int32_t *n_frames, const int32_t *out_row, int n_streams,
+                       int max_frames, int n_mels, const MelTables &tb, float *logmel, cudaStream_t st);
+
+// ------------------------------------------------------------------ stream.cu (streaming eou path)
+constexpr int STREAM_OVL_CAP = 512;   // overlap buffer per stream (< 400 samples are ever kept, audio.cpp:225-240)
+struct StreamPlan {                   // one row per stream and step, computed on the host from the chunk sizes
+    int64_t chunk_off;                // offset of this stream's chunk in the packed chunk buffer
+    int64_t sig_off;                  // offset of [overlap | pre-emphasised chunk] in the signal scratch
+    int32_t chunk_len, ovl_len;       // samples in the chunk / carried overlap
+    int32_t consumed;                 // samples covered by the frames of this step (0: none; overlap = whole signal)
+    int32_t nf;                       // new mel frames (the reference's STFT yields one fewer than its own count)
+    int32_t left;                     // leftover mel frames from the previous steps (< 8)
+    int32_t min_off;                  // first row of [leftover | new] frames in mel_in
+    int32_t take;                     // frames consumed by the subsampling this step (multiple of 8)
+    int32_t feat_off;                 // first row in the packed encoder input (valid if take > 0)
+};
+struct StreamState {
+    float *ovl;                       // [S][STREAM_OVL_CAP]
+    float *last;                      // [S] pre-emphasis carry (audio.cpp:206-213)
+    float *melq;                      // [S][8][n_mels] leftover mel frames (streaming_encoder.cpp:348-385)
+};
+void launch_stream_prep(const float *chunk, const StreamPlan *plan, StreamState st, int n_streams, float *ssig, float *mel_in,
+                        int n_mels, cudaStream_t s);
+void launch_stream_post(const float *chunk, const StreamPlan *plan, StreamState st, int n_streams, const float *ssig,
+                        const float *mel_in, int n_mels, float *feats, cudaStream_t s);
+bool launch_stream_attention(const float *qkv, int ld_qkv, const int32_t *row_off, const int32_t *act_stream, int n_active,
+                             int max_C, const int32_t *cache_len, const int32_t *ring_start, float *kc, float *vc, int L,
+                             int n_heads, int hd, int d_model, const float *pp, int tmax, const float *bu, const float *bv,
+                             ActBuf out, cudaStream_t s);
+bool launch_stream_dwconv(const float *glu, const int32_t *row_off, const int32_t *act_stream, int n_active, float *cache, int d,
+                          int ks, const float *w, const float *bias, ActBuf out, cudaStream_t s);
+
 // ------------------------------------------------------------------ subsample.cu (K3, K4)
 void launch_subsample_conv1_dw1(const float *feats, const int32_t *frame_off, const int32_t *s2_off, int n_utt,
                                 int max_t2, int mel, int C, const float *w1, const float *b1, const float *wd,
@@ -43,6 +78,8 @@ struct TcOperand {
 bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t rows, uint64_t K, uint32_t box_rows);
 int tc_tile_n(int N);
 void tc_set_2cta(bool on);   // debug/measurement switch: use the cta_group::2 kernel for N >= 256 (default off; PK_GEMM_2CTA=1)   // N-tile (= box_rows of the weight operand) chosen for an [N][K] weight
+void tc_set_debug(int bits); // measurement aid (PK_GEMM_DBG): bit 0 = skip the epilogue's work, bit 1 = skip the TMA loads (results are garbage)
+double tc_probe_mhz();
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st);
 
@@ -96,6 +133,14 @@ struct TdtParams {
     int32_t *tok;                             // [n_utt][1+cap]
     int32_t *t_start, *t_end;                 // [n_utt][cap]
     float *t_conf;
+    // Carried decode state (rnnt_streaming_decode_chunk, src/eou.cpp:17-98): the LSTM state, the last token and the
+    // absolute frame number survive from chunk to chunk.  carry = 1: hbuf plane 0 holds the committed h on entry and on
+    // exit, c_state [L][Bpad][P] the committed cell state, tok_state [Bpad] the last emitted token; emitted frames are
+    // frame_base[b] + t and the end frame is NOT clamped to the chunk (eou.cpp:81-84); utterances with no frames idle.
+    int carry;
+    float *c_state;
+    int32_t *tok_state;
+    const int32_t *frame_base;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
 // fp32 [rows][K] -> [rows][2 K] bf16 = [hi: K][lo: K]

@@ -58,9 +58,13 @@ __device__ __forceinline__ float preemph_reflect(const float *__restrict__ x, in
     return v;
 }
 
+// STREAM = true: the streaming preprocessor's frames (audio.cpp:195-259): `pcm` is the pre-emphasised signal
+// [overlap | chunk] of stream b, frame f = window . sig[f*160 + j], j in [0, 512) (center = False: no reflection, no
+// half-window shift), n_frames from `n_frames_arr`, output row = frame_off[b] + f.
+template <bool STREAM>
 __global__ void __launch_bounds__(WARPS * 32)
 mel_logpower_kernel(const float *__restrict__ pcm, const int64_t *__restrict__ pcm_off,
-                    const int32_t *__restrict__ frame_off, int n_mels, MelTables tb,
+                    const int32_t *__restrict__ frame_off, const int32_t *__restrict__ n_frames_arr, int n_mels, MelTables tb,
                     float *__restrict__ logmel) {
     extern __shared__ float smem[];
     // layout: [window 400][tw256 512][tw512 514][fb weights nnz][per-warp: frame 512 | Z 512 | P 260]
@@ -72,7 +76,7 @@ mel_logpower_kernel(const float *__restrict__ pcm, const int64_t *__restrict__ p
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_frames = frame_off[b + 1] - frame_off[b];
+    const int n_frames = STREAM ? n_frames_arr[b] : frame_off[b + 1] - frame_off[b];
     const int f0 = blockIdx.x * (WARPS * 4);
     if (f0 >= n_frames) return;
 
@@ -94,14 +98,16 @@ mel_logpower_kernel(const float *__restrict__ pcm, const int64_t *__restrict__ p
         const int f = f0 + warp * 4 + fi;
         if (f >= n_frames) break;  // warp-uniform
         // frame j in [0,512) <-> sample index f*HOP - 256 + j; window is zero outside [56, 456)
-        const int64_t s0 = (int64_t)f * HOP - N_FFT / 2;
+        const int64_t s0 = (int64_t)f * HOP - (STREAM ? 0 : N_FFT / 2);
         const bool interior = (s0 + WIN_PAD - 1 >= 0) && (s0 + WIN_PAD + WIN <= n);
         for (int j = lane; j < N_FFT; j += 32) {
             float v = 0.f;
             if (j >= WIN_PAD && j < WIN_PAD + WIN) {
                 const int64_t i = s0 + j;
                 float y;
-                if (interior) {
+                if (STREAM) {
+                    y = x[i];
+                } else if (interior) {
                     y = x[i] - 0.97f * x[i - 1];  // coalesced; x[i-1] hits the same lines
                 } else {
                     y = preemph_reflect(x, i, n);
@@ -227,11 +233,18 @@ void launch_mel(const float *pcm, const int64_t *pcm_off, const int32_t *frame_o
                 int max_frames, int n_mels, const MelTables &tb, float *logmel, float *feats,
                 cudaStream_t st) {
     dim3 grid((max_frames + WARPS * 4 - 1) / (WARPS * 4), n_utt);
-    mel_logpower_kernel<<<grid, WARPS * 32, mel_smem_bytes(tb), st>>>(pcm, pcm_off, frame_off, n_mels, tb,
-                                                                      logmel);
+    mel_logpower_kernel<false><<<grid, WARPS * 32, mel_smem_bytes(tb), st>>>(pcm, pcm_off, frame_off, nullptr, n_mels, tb,
+                                                                             logmel);
     int groups = 640 / n_mels;  // 8 for 80 bins, 5 for 128
     mel_normalize_kernel<<<n_utt, groups * n_mels, sizeof(float) * groups * n_mels, st>>>(
         logmel, frame_off, n_mels, feats);
+}
+
+void launch_mel_stream(const float *sig, const int64_t *sig_off, const int32_t *n_frames, const int32_t *out_row, int n_streams,
+                       int max_frames, int n_mels, const MelTables &tb, float *logmel, cudaStream_t st) {
+    if (max_frames <= 0) return;
+    dim3 grid((max_frames + WARPS * 4 - 1) / (WARPS * 4), n_streams);
+    mel_logpower_kernel<true><<<grid, WARPS * 32, mel_smem_bytes(tb), st>>>(sig, sig_off, out_row, n_frames, n_mels, tb, logmel);
 }
 
 }  // namespace pk

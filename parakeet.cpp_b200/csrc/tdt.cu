@@ -369,13 +369,28 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
     for (int i = tid; i < L * 2 * ge.MU * Bpad; i += blockDim.x) csm[i] = 0.f;   // zero cell state (tdt.cpp:49-59)
     for (int b = tid; b < Bpad; b += blockDim.x) {                               // initial decode state
         s_cur[b] = 0;
-        s_token[b] = V - 1;
+        s_token[b] = (p.carry && b < p.n_utt) ? p.tok_state[b] : V - 1;
         s_tpos[b] = 0;
-        s_active[b] = b < p.n_utt ? 1 : 0;
+        s_active[b] = (b < p.n_utt && p.row_off[b + 1] > p.row_off[b]) ? 1 : 0;
         s_ntok[b] = 0;
         s_pend[b] = -1;
     }
     __syncthreads();
+    // Units this CTA finalises (same enumeration as the cell update in P1): pass ug, slot mi -> unit u, state slot cslot.
+    auto for_my_units = [&](auto fn) {
+        for (int ug = 0; ug < nU; ug += RG / 4) {
+            const int nu = min(RG / 4, nU - ug), myu = (nu - rank + CL - 1) / CL;
+            for (int mi = 0; mi < myu; ++mi) fn(u0 + ug + rank + CL * mi, ug / CL + mi);
+        }
+    };
+    if (p.carry) {   // committed cell state of the previous chunk -> plane 0 (eou.cpp:22-33 initialises it to zero once)
+        for (int l = 0; l < L; ++l)
+            for_my_units([&](int u, int cslot) {
+                for (int b = tid; b < Bpad; b += blockDim.x)
+                    csm[((size_t)(l * 2 + 0) * ge.MU + cslot) * Bpad + b] = p.c_state[((size_t)l * Bpad + b) * P + u];
+            });
+        __syncthreads();
+    }
 
     // h: bf16 planes [hi|lo][L][2][Bpad][P] (two state planes per utterance); z: [hi|lo][Bpad][J]
     const size_t HS = (size_t)P * Bpad;
@@ -495,6 +510,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                     [&](int r, int b) {
                         if (b >= p.n_utt) return 0.f;
                         const int T = p.row_off[b + 1] - p.row_off[b];
+                        if (T <= 0) return 0.f;           // (carried decode: a stream without frames this chunk)
                         const int t = min(s_tpos[b], T - 1);
                         return p.EP[(size_t)(p.row_off[b] + t) * J + rg + r];
                     },
@@ -576,8 +592,9 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                 if (n < p.cap && (b % G) == g) { // the owner CTA writes the token; confidence follows
                     int32_t *row = p.tok + (size_t)b * (1 + p.cap);
                     row[1 + n] = lidx;
-                    p.t_start[(size_t)b * p.cap + n] = t;
-                    p.t_end[(size_t)b * p.cap + n] = min(t + max(skip, 1) - 1, T - 1);
+                    const int base = p.carry ? p.frame_base[b] : 0;
+                    p.t_start[(size_t)b * p.cap + n] = base + t;
+                    p.t_end[(size_t)b * p.cap + n] = p.carry ? base + t + max(skip, 1) - 1 : min(t + max(skip, 1) - 1, T - 1);
                     row[0] = n + 1;
                 }
                 if (n < p.cap) s_pend[b] = n;
@@ -605,6 +622,23 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
     }
     // confidences of the last step's tokens (all partials were visible at that step's last barrier)
     finalize_conf(step % 3);
+    if (p.carry) {
+        // Hand the committed state to the next chunk: cell state of my units, h of my units into plane 0, last token.
+        // (Every CTA left the loop at the same step, after the step's last grid barrier: nobody reads h any more.)
+        for (int l = 0; l < L; ++l)
+            for_my_units([&](int u, int cslot) {
+                for (int b = tid; b < Bpad; b += blockDim.x) {
+                    const int cu = s_cur[b];
+                    p.c_state[((size_t)l * Bpad + b) * P + u] = csm[((size_t)(l * 2 + cu) * ge.MU + cslot) * Bpad + b];
+                    if (cu == 1) {
+                        const size_t src = ((size_t)(l * 2 + 1)) * HS + (size_t)b * P + u, dst = ((size_t)(l * 2 + 0)) * HS + (size_t)b * P + u;
+                        hb[dst] = hb[src];
+                        hb[h_lo + dst] = hb[h_lo + src];
+                    }
+                }
+            });
+        for (int b = g + tid * G; b < p.n_utt; b += G * blockDim.x) p.tok_state[b] = s_token[b];
+    }
     cluster_sync_all();              // nobody leaves while a peer may still read its partial sums
 }
 

@@ -48,7 +48,8 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_detokenize", "pk_group_words", "pk_tokenize", "pk_ctc_decode_boosted",
            "pk_resample_len", "pk_resample",
            "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
-           "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count"]
+           "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count",
+           "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count"]
 
 _lib = None
 
@@ -116,6 +117,10 @@ def load_library():
     L.pk_job_stage_pcm.argtypes = [vp, f32p, i64p, C.c_int32]
     L.pk_job_select.argtypes = [vp, C.c_int32, C.c_int32]
     L.pk_truncated_count.argtypes = [vp]
+    L.pk_stream_open.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.pk_stream_reset.argtypes = [vp, C.c_int32]
+    L.pk_stream_step.argtypes = [vp, f32p, i64p, C.POINTER(_PkTokens), f32p, i32p, f32p, i32p]
+    L.pk_stream_count.argtypes = [vp]
     _lib = L
     return L
 
@@ -145,6 +150,9 @@ class ModelConfig:
     has_ctc: bool = True
     joint_prefix: str = "tdt_joint_."
     name: str = "tdt-ctc-110m"
+    # streaming encoder only (StreamingEncoderConfig, streaming_encoder.hpp:18-24)
+    att_context_left: int = 70
+    att_context_right: int = 0
     # engine capacity
     max_batch: int = 64
     max_samples: int = 160000
@@ -172,6 +180,22 @@ def make_110m_config(**kw) -> ModelConfig:           # config.hpp:77-95
 def make_tdt_600m_config(**kw) -> ModelConfig:       # config.hpp:98-116
     base = dict(mel_bins=128, d_model=1024, n_layers=24, ff=4096, vocab=8193, lstm_layers=2, has_ctc=False,
                 joint_prefix="joint_.", name="tdt-600m", max_batch=16, max_samples=480000)
+    base.update(kw)
+    return ModelConfig(**base)
+
+
+def make_eou_120m_config(**kw) -> ModelConfig:       # eou.hpp:32-55 (streaming; ParakeetEOU registers "joint_", eou.cpp:9-13)
+    base = dict(has_ctc=False, joint_prefix="joint_.", name="eou-120m", att_context_left=70, att_context_right=1,
+                max_batch=64, max_samples=102400)
+    base.update(kw)
+    return ModelConfig(**base)
+
+
+def make_tiny_stream_config(**kw) -> ModelConfig:
+    """Small test-only streaming shape (mirrors oracle.make_tiny_stream_config; not a reference preset)."""
+    base = dict(sub_channels=64, d_model=128, n_layers=2, n_heads=2, ff=256, vocab=33, pred_hidden=64, joint_hidden=64,
+                has_ctc=False, joint_prefix="joint_.", name="tiny-stream", att_context_left=12, att_context_right=1,
+                max_batch=8, max_samples=102400)
     base.update(kw)
     return ModelConfig(**base)
 
@@ -476,6 +500,36 @@ class Engine:
         self._check(self.L.pk_job_fetch(self.h, int(gathered), _i32p(out), n_rows, C.byref(w)), "pk_job_fetch")
         assert w.value == 1 + self.cap
         return out
+
+    # -- streaming (eou path): n_streams streams advanced in lock step, one chunk per stream and step
+    def stream_open(self, n_streams: int, max_chunk_samples: int = 5120):
+        self._check(self.L.pk_stream_open(self.h, n_streams, max_chunk_samples, self.cfg.att_context_left,
+                                          self.cfg.att_context_right), "pk_stream_open")
+        self.n_streams = n_streams
+
+    def stream_reset(self, stream: int = -1):
+        self._check(self.L.pk_stream_reset(self.h, stream), "pk_stream_reset")
+
+    def stream_step(self, chunks: Sequence[np.ndarray], taps: bool = False, out=None, raw: bool = False):
+        """chunks[s] = the samples stream s receives in this step (may be empty).  Returns the tokens each stream emitted
+        in this step (absolute frames); with taps also the new log-mel frames and the encoder rows per stream."""
+        S = self.n_streams
+        assert len(chunks) == S
+        buf, off = _pack(chunks)
+        if out is None:
+            out = self._tokens(S)
+        t, arrs = out
+        if not taps:
+            self._check(self.L.pk_stream_step(self.h, _f32p(buf), _i64p(off), C.byref(t), None, None, None, None), "pk_stream_step")
+            return arrs if raw else self._unpack(arrs, S)
+        max_nf = 8 + max(len(c) for c in chunks) // 160 + 4
+        mel = np.zeros((S * max_nf, self.cfg.mel_bins), np.float32)
+        enc = np.zeros((S * (max_nf // 8 + 2), self.cfg.d_model), np.float32)
+        n_mel, n_enc = np.zeros(S, np.int32), np.zeros(S, np.int32)
+        self._check(self.L.pk_stream_step(self.h, _f32p(buf), _i64p(off), C.byref(t), _f32p(mel), _i32p(n_mel), _f32p(enc), _i32p(n_enc)),
+                    "pk_stream_step")
+        mo, eo = np.concatenate([[0], np.cumsum(n_mel)]), np.concatenate([[0], np.cumsum(n_enc)])
+        return self._unpack(arrs, S), [mel[mo[i]:mo[i + 1]].copy() for i in range(S)], [enc[eo[i]:eo[i + 1]].copy() for i in range(S)]
 
     def truncated_count(self) -> int:
         return int(self.L.pk_truncated_count(self.h))

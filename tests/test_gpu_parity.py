@@ -551,3 +551,83 @@ def test_job_api_appends_microbatches_and_allgathers(pkg, tiny, synth, math_mode
     with pytest.raises(RuntimeError):                        # job buffer full
         e.job_append(); e.job_append()
     e.close()
+
+
+# ------------------------------------------------------------------ streaming eou path (BASELINE config 4)
+def _stream_engine(pkg, O, synth, tag, S, tmpdir, math):
+    import dataclasses
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_stream_v1.npz"))
+    ocfg = O.make_tiny_stream_config() if tag == "tstream" else O.make_eou_120m_config()
+    cfg = pkg.make_tiny_stream_config(max_batch=max(S, 8)) if tag == "tstream" else pkg.make_eou_120m_config(max_batch=max(S, 8))
+    wseed, aseed = (int(v) for v in g[tag + ".seeds"])
+    sched = [int(v) for v in g[tag + ".schedule"]]
+    wp = os.path.join(str(tmpdir), tag + ".safetensors")
+    synth.save_safetensors(wp, synth.make_weights(ocfg, seed=wseed))
+    e = pkg.Engine(dataclasses.replace(cfg, math=MATH[math]), wp, 0)
+    e.stream_open(S, max(sched))
+    return e, g, sched, synth.make_audio(sum(sched), aseed)
+
+
+@pytest.mark.parametrize("tag", ["tstream", "eou120"])
+def test_streaming_chunks_match_reference_golden(pkg, O, synth, tmp_path, math_mode, tag):
+    """One stream, chunk by chunk, against the compiled reference (golden_stream_v1.npz): new log-mel frames (13/14 per
+    2560 samples: the reference's STFT quirk), encoder rows of the chunk (leftover-frame cache, K/V ring, conv cache,
+    un-shifted position scores), tokens with absolute frames and confidences (carried LSTM state)."""
+    e, g, sched, pcm = _stream_engine(pkg, O, synth, tag, 1, tmp_path, math_mode)
+    pos, n_tok = 0, 0
+    for ci, n in enumerate(sched):
+        toks, mel, enc = e.stream_step([pcm[pos:pos + n]], taps=True)
+        pos += n
+        k = f"{tag}.k{ci}."
+        gf, ge_, gt, gc = g[k + "feats"], g[k + "enc"], g[k + "tok"], g[k + "conf"]
+        assert mel[0].shape == gf.shape, ci
+        if gf.shape[0]:
+            assert np.abs(mel[0] - gf).max() < 2e-3 * max(1.0, float(np.abs(gf).max())), ci      # un-normalised log-mel (|x| up to ~17)
+        assert enc[0].shape == ge_.shape, ci
+        if ge_.shape[0]:
+            assert _rel(enc[0], ge_) < ENC_TOL, ci
+        assert [list(t) for t in _tt(toks[0])] == gt.tolist(), ci
+        assert np.allclose([t.confidence for t in toks[0]], gc, rtol=1e-3, atol=1e-6), ci
+        n_tok += len(toks[0])
+    assert n_tok > 5
+    # reset, then the same stream again: identical tokens (StreamingTranscriber::reset, eou.cpp:145-149)
+    e.stream_reset(0)
+    pos, again = 0, []
+    for n in sched:
+        again += [_tt(e.stream_step([pcm[pos:pos + n]])[0])]
+        pos += n
+    assert [[list(t) for t in a] for a in again] == [g[f"{tag}.k{ci}.tok"].tolist() for ci in range(len(sched))]
+    e.close()
+
+
+def test_streaming_many_streams_lockstep(pkg, O, synth, tmp_path, math_mode):
+    """S streams in lock step: copies of the golden stream started at different steps (so cache fill levels, ring
+    positions and leftover-frame counts differ between the rows of one step), an always-silent stream and a stream that
+    is reset half way.  Every copy must reproduce the reference's tokens of its own timeline."""
+    tag, S = "tstream", 6
+    e, g, sched, pcm = _stream_engine(pkg, O, synth, tag, S, tmp_path, math_mode)
+    want = [g[f"{tag}.k{ci}.tok"].tolist() for ci in range(len(sched))]
+    starts = [0, 1, 3, 4, None, 0]                   # stream 4 never gets samples; stream 5 is reset at step 8 and restarts
+    cuts = np.concatenate([[0], np.cumsum(sched)])
+    empty = np.zeros(0, np.float32)
+    got = [[] for _ in range(S)]
+    local = [0] * S                                  # next chunk index of each stream's own timeline
+    for step in range(len(sched) + 5):
+        if step == 8:
+            e.stream_reset(5)
+            local[5], got[5] = 0, []
+        chunks = []
+        for s in range(S):
+            active = starts[s] is not None and step >= starts[s] and local[s] < len(sched)
+            chunks.append(pcm[cuts[local[s]]:cuts[local[s] + 1]] if active else empty)
+        toks = e.stream_step(chunks)
+        for s in range(S):
+            if len(chunks[s]):
+                got[s].append([list(t) for t in _tt(toks[s])])
+                local[s] += 1
+            else:
+                assert toks[s] == []
+    for s in (0, 1, 2, 3):
+        assert got[s] == want, s
+    assert got[5] == want[:len(got[5])] and len(got[5]) >= 10
+    e.close()
