@@ -264,12 +264,22 @@ int32_t pk_ctc_decode_boosted(const float *logprobs, int32_t n_frames, int32_t v
                               const int32_t *phrase_ids, const int32_t *phrase_off, int32_t n_phrases, float boost,
                               int32_t *ids, int32_t *start, int32_t *end, float *conf, int32_t cap);
 
-/* Sample-rate conversion on the host (widening row: SURVEY.md section 8f(4)), replacing parakeet::resample /
- * sinc_resample (src/audio_io.cpp:123-195, :238-251): 32-tap Kaiser (beta 7.857) windowed sinc evaluated in double,
- * output length ceil(n * dst / src).  pk_resample_len gives that length; pk_resample writes at most `cap` samples and
- * returns the full length (or -1 on invalid arguments).  src_rate == dst_rate copies. */
+/* Sample-rate conversion (widening row: SURVEY.md section 8f(4)), replacing parakeet::resample / sinc_resample
+ * (src/audio_io.cpp:123-195, :238-251): 32-tap Kaiser (beta 7.857) windowed sinc in double, output length
+ * ceil(n * dst / src) (pk_resample_len), implemented as a POLYPHASE filter: the weights depend only on the phase
+ * (i * down) mod up, so they are tabulated once per rate pair (csrc/resample.cu).
+ *   pk_stage_pcm_rate : like pk_stage_pcm for a batch recorded at `src_rate`: the raw samples go to the device and are
+ *                       converted there straight into the staged 16 kHz batch (read_audio's resampling, audio_io.cpp:227-232,
+ *                       without a host pass).  Utterance lengths are checked at 16 kHz.
+ *   pk_resample_batch : device conversion of a batch between arbitrary rates, results back to the host
+ *                       (out_offsets = prefix sums of pk_resample_len per utterance).
+ *   pk_resample       : the same filter evaluated on the host for engine-less callers (parakeet::resample of the C++
+ *                       shim); writes at most `cap` samples, returns the full length or -1 on invalid arguments. */
 int64_t pk_resample_len(int64_t n, int32_t src_rate, int32_t dst_rate);
 int64_t pk_resample(const float *in, int64_t n, int32_t src_rate, int32_t dst_rate, float *out, int64_t cap);
+pk_status pk_stage_pcm_rate(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, int32_t src_rate);
+pk_status pk_resample_batch(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, int32_t src_rate,
+                            int32_t dst_rate, float *out, const int64_t *out_offsets);
 
 #ifdef __cplusplus
 }

@@ -976,6 +976,7 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
             fprintf(stderr, "gemm_tc M=%d N=%d K=%d epi=%d math=%d: %.1f us  %.1f TFLOP/s algorithmic (x%d MMA)  [probe %.0f MHz]\n", M, N, K,
                     epi_kind, math, us, tf, math == PK_MATH_BF16X3 ? 3 : 1, tc_probe_mhz());
             cudaEventDestroy(e0); cudaEventDestroy(e1);
+            if (getenv("PK_GEMM_DBG") && (atoi(getenv("PK_GEMM_DBG")) & 32)) tc_print_timeline(8);
         }
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = PK_ERR_CUDA;
@@ -1354,6 +1355,99 @@ pk_status pk_job_fetch(pk_engine *e, int32_t gathered, int32_t *rows_out, int64_
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_job_fetch: ") + cudaGetErrorString(ce));
     memcpy(rows_out, e->h_job, (size_t)n_rows * W * sizeof(int32_t));
+    return PK_OK;
+}
+
+// ===================================================================== non-16 kHz input
+// Raw samples at `src_rate` go to the device as they are; the polyphase kernel (resample.cu) writes the 16 kHz signal
+// straight into the staged PCM buffer, so the resampled audio never exists on the host.
+static pk_status stage_raw(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, std::vector<int64_t> &in_off) {
+    in_off.assign(n_utt + 1, 0);
+    for (int i = 0; i < n_utt; ++i) {
+        if (offsets[i + 1] < offsets[i]) return e->fail(PK_ERR_INVALID, "offsets must be non-decreasing");
+        in_off[i + 1] = in_off[i] + (offsets[i + 1] - offsets[i]);
+    }
+    const size_t total = (size_t)in_off[n_utt];
+    if (total + 8 > e->d_raw_cap) {
+        cudaStreamSynchronize(e->stream);
+        e->d_raw = e->dalloc<float>(total + 8);
+        if (!e->d_raw) return e->fail(PK_ERR_CUDA, "cudaMalloc failed (raw PCM)");
+        e->d_raw_cap = total + 8;
+    }
+    if (!e->d_raw_off) {
+        e->d_raw_off = e->dalloc<int64_t>(2 * ((size_t)e->Bmax + 1));
+        if (!e->d_raw_off) return e->fail(PK_ERR_CUDA, "cudaMalloc failed (raw offsets)");
+    }
+    cudaError_t ce = cudaSuccess;
+    for (int i = 0; i < n_utt && ce == cudaSuccess; ++i)      // (pageable or pinned; utterances need not be packed)
+        if (in_off[i + 1] > in_off[i])
+            ce = cudaMemcpyAsync(e->d_raw + in_off[i], pcm + offsets[i], (size_t)(in_off[i + 1] - in_off[i]) * sizeof(float),
+                                 cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(e->d_raw_off, in_off.data(), (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);   // in_off / pageable sources are the caller's
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("H2D raw pcm: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+pk_status pk_stage_pcm_rate(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, int32_t src_rate) {
+    if (!e || !pcm || !offsets || src_rate <= 0) return PK_ERR_INVALID;
+    if (src_rate == 16000) return pk_stage_pcm(e, pcm, offsets, n_utt);
+    cudaSetDevice(e->device);
+    if (n_utt < 1 || n_utt > e->Bmax) return e->fail(PK_ERR_CAPACITY, "bad batch size");
+    std::vector<int64_t> in_off, out_off(n_utt + 1, 0);
+    pk_status s = stage_raw(e, pcm, offsets, n_utt, in_off);
+    if (s) return s;
+    int64_t max_out = 0;
+    for (int i = 0; i < n_utt; ++i) {
+        const int64_t m = pk_resample_len(in_off[i + 1] - in_off[i], src_rate, 16000);
+        out_off[i + 1] = out_off[i] + m;
+        max_out = std::max(max_out, m);
+    }
+    if ((s = e->set_batch_shapes(nullptr, out_off.data(), n_utt))) return s;     // (length checks at 16 kHz)
+    e->pcm_src = nullptr;
+    e->pref.valid = false;
+    if ((s = e->upload_shapes())) return s;
+    if (!launch_resample(e->d_raw, e->d_raw_off, e->d_pcm_off, n_utt, max_out, src_rate, 16000, e->d_pcm, e->stream))
+        return e->fail(PK_ERR_CUDA, "resample launch failed");
+    ++e->launches;
+    e->front_done = false;
+    return PK_OK;
+}
+
+pk_status pk_resample_batch(pk_engine *e, const float *pcm, const int64_t *offsets, int32_t n_utt, int32_t src_rate,
+                            int32_t dst_rate, float *out, const int64_t *out_offsets) {
+    if (!e || !pcm || !offsets || !out || !out_offsets || src_rate <= 0 || dst_rate <= 0 || n_utt < 1) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    if (n_utt > e->Bmax) return e->fail(PK_ERR_CAPACITY, "bad batch size");
+    std::vector<int64_t> in_off, out_off(n_utt + 1, 0);
+    pk_status s = stage_raw(e, pcm, offsets, n_utt, in_off);
+    if (s) return s;
+    int64_t max_out = 0;
+    for (int i = 0; i < n_utt; ++i) {
+        const int64_t m = pk_resample_len(in_off[i + 1] - in_off[i], src_rate, dst_rate);
+        if (out_offsets[i + 1] - out_offsets[i] != m) return e->fail(PK_ERR_INVALID, "pk_resample_batch: out_offsets must be prefix sums of pk_resample_len");
+        out_off[i + 1] = out_off[i] + m;
+        max_out = std::max(max_out, m);
+    }
+    const size_t total = (size_t)out_off[n_utt];
+    if (total > (size_t)e->Bmax * (size_t)e->cfg.max_samples) return e->fail(PK_ERR_CAPACITY, "pk_resample_batch: output exceeds the PCM workspace");
+    cudaError_t ce = cudaMemcpyAsync(e->d_raw_off + e->Bmax + 1, out_off.data(), (size_t)(n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_resample_batch: ") + cudaGetErrorString(ce));
+    float *dst = e->d_pcm_alt;                       // (the second PCM buffer: the staged batch stays intact)
+    e->pref.valid = false;
+    if (src_rate == dst_rate) {
+        ce = cudaMemcpyAsync(dst, e->d_raw, total * sizeof(float), cudaMemcpyDeviceToDevice, e->stream);
+    } else if (!launch_resample(e->d_raw, e->d_raw_off, e->d_raw_off + e->Bmax + 1, n_utt, max_out, src_rate, dst_rate, dst, e->stream)) {
+        return e->fail(PK_ERR_CUDA, "resample launch failed");
+    }
+    ++e->launches;
+    for (int i = 0; i < n_utt && ce == cudaSuccess; ++i)
+        if (out_off[i + 1] > out_off[i])
+            ce = cudaMemcpyAsync(out + out_offsets[i], dst + out_off[i], (size_t)(out_off[i + 1] - out_off[i]) * sizeof(float),
+                                 cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_resample_batch: ") + cudaGetErrorString(ce));
     return PK_OK;
 }
 

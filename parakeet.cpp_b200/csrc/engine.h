@@ -151,6 +151,9 @@ struct pk_engine {
     size_t job_pcm_cap = 0;
     std::vector<int64_t> job_off;
     const float *pcm_src = nullptr;                    // front end reads this instead of d_pcm (a slice of job_pcm)
+    float *d_raw = nullptr;                            // input at its own sample rate (pk_stage_pcm_rate / pk_resample_batch)
+    size_t d_raw_cap = 0;
+    int64_t *d_raw_off = nullptr;                      // [Bmax + 1] offsets of the raw utterances
     void *nccl_comm = nullptr;                         // ncclComm_t (pk_comm_init_rank) -- owned
     int nccl_rank = 0, nccl_world = 1;
     bool last_tdt = false;                             // the token buffer holds a TDT decode (overflow flags are valid)

@@ -28,6 +28,8 @@
 // Every spin-wait is bounded and traps, so a protocol bug is an error, not a hung GPU.
 #include <cuda.h>
 
+#include <cstdio>
+
 #include "kernels.h"
 
 namespace pk {
@@ -241,6 +243,9 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
 
 // measurement aid: SM cycles and nanoseconds CTA 0 spent in its epilogue loop (effective SM clock under this kernel)
 __device__ unsigned long long g_clk_probe[2];
+// measurement aid (debug bit 5): per-tile timeline of CTA 0 -- [tile][0..3] = MMA thread: accumulator free, last MMA issued;
+// epilogue warp 2: accumulator full seen, tile stored.  (clock64 of SM 0's CTA)
+__device__ long long g_timeline[64][4];
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -335,6 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
+                if ((dbg & 32) && blockIdx.x == 0 && tcount < 64) g_timeline[tcount][0] = clock64();
                 const uint32_t tmem_d = tmem_base + buf * BN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % C::STAGES;
@@ -357,6 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     umma_commit(&empty[s]);          // frees the stage when these MMAs retire
                 }
                 umma_commit(&acc_full[buf]);         // accumulator of this tile complete
+                if ((dbg & 32) && blockIdx.x == 0 && tcount < 64) g_timeline[tcount][1] = clock64();
             }
         }
     } else {
@@ -375,6 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
+            if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][2] = clock64();
             const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
             if (dbg & 1) {                           // measurement aid: drain nothing, release at once
                 tcgen05_fence_before();
@@ -387,6 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }, dbg);
+            if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
         if (probe) { g_clk_probe[0] = (unsigned long long)(clock64() - pc0); g_clk_probe[1] = globaltimer_ns() - pg0; }
     }
@@ -707,6 +716,14 @@ int tc_tile_n(int N) { return N <= 64 ? 64 : 128; }
 static bool g_use_2cta = false;   // measured on B200 (64x10 s): the pair kernel is not faster yet at M = 8064
 void tc_set_2cta(bool on) { g_use_2cta = on; }
 void tc_set_debug(int bits) { g_dbg = bits; }
+void tc_print_timeline(int n_tiles) {   // after a 1-CTA launch with debug bit 5
+    long long h[64][4];
+    if (cudaMemcpyFromSymbol(h, g_timeline, sizeof(h)) != cudaSuccess) return;
+    const long long t0 = h[0][0];
+    for (int i = 0; i < n_tiles && i < 64; ++i)
+        fprintf(stderr, "    tile %2d: acc free %7lld  mma issued %7lld | acc full seen %7lld  stored %7lld   (epilogue %lld cyc)\n", i,
+                h[i][0] - t0, h[i][1] - t0, h[i][2] - t0, h[i][3] - t0, h[i][3] - h[i][2]);
+}
 double tc_probe_mhz() {   // effective SM clock seen by CTA 0 of the last 1-CTA launch with a non-zero debug mask (bit 4 = probe only)
     unsigned long long h[2] = {0, 0};
     if (cudaMemcpyFromSymbol(h, g_clk_probe, sizeof(h)) != cudaSuccess || h[1] == 0) return 0.0;

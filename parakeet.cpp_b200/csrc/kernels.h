@@ -56,6 +56,11 @@ bool launch_stream_attention(const float *qkv, int ld_qkv, const int32_t *row_of
 bool launch_stream_dwconv(const float *glu, const int32_t *row_off, const int32_t *act_stream, int n_active, float *cache, int d,
                           int ks, const float *w, const float *bias, ActBuf out, cudaStream_t s);
 
+// ------------------------------------------------------------------ resample.cu (front-of-path rate conversion)
+// utterance b: in[in_off[b] .. in_off[b+1]) at src_rate -> out[out_off[b] .. out_off[b+1]) at dst_rate (lengths = pk_resample_len)
+bool launch_resample(const float *in, const int64_t *in_off, const int64_t *out_off, int n_utt, int64_t max_out, int src_rate,
+                     int dst_rate, float *out, cudaStream_t st);
+
 // ------------------------------------------------------------------ subsample.cu (K3, K4)
 void launch_subsample_conv1_dw1(const float *feats, const int32_t *frame_off, const int32_t *s2_off, int n_utt,
                                 int max_t2, int mel, int C, const float *w1, const float *b1, const float *wd,
@@ -80,6 +85,7 @@ int tc_tile_n(int N);
 void tc_set_2cta(bool on);   // debug/measurement switch: use the cta_group::2 kernel for N >= 256 (default off; PK_GEMM_2CTA=1)   // N-tile (= box_rows of the weight operand) chosen for an [N][K] weight
 void tc_set_debug(int bits); // measurement aid (PK_GEMM_DBG): bit 0 = skip the epilogue's work, bit 1 = skip the TMA loads (results are garbage)
 double tc_probe_mhz();
+void tc_print_timeline(int n_tiles);
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st);
 

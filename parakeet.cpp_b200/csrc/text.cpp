@@ -238,65 +238,4 @@ int32_t pk_ctc_decode_boosted(const float *lp, int32_t T, int32_t V, int32_t bla
     return n;
 }
 
-namespace {
-double bessel_i0(double x) {                                   // audio_io.cpp:101-111
-    double sum = 1.0, term = 1.0;
-    for (int k = 1; k < 30; ++k) {
-        term *= (x * x) / (4.0 * k * k);
-        sum += term;
-        if (term < 1e-12 * sum) break;
-    }
-    return sum;
-}
-double kaiser_window(double n, double N, double beta) {        // audio_io.cpp:114-121
-    const double arg = 2.0 * n / N - 1.0;
-    double val = 1.0 - arg * arg;
-    if (val < 0.0) val = 0.0;
-    return bessel_i0(beta * std::sqrt(val)) / bessel_i0(beta);
-}
-}  // namespace
-
-int64_t pk_resample_len(int64_t n, int32_t src_rate, int32_t dst_rate) {
-    if (n < 0 || src_rate <= 0 || dst_rate <= 0) return -1;
-    if (src_rate == dst_rate) return n;
-    const int g = std::gcd(src_rate, dst_rate);
-    const int64_t up = dst_rate / g, down = src_rate / g;
-    return (n * up + down - 1) / down;
-}
-
-int64_t pk_resample(const float *in, int64_t n, int32_t src_rate, int32_t dst_rate, float *out, int64_t cap) {
-    const int64_t m = pk_resample_len(n, src_rate, dst_rate);
-    if (m < 0 || (n > 0 && !in) || (cap > 0 && !out)) return -1;
-    if (src_rate == dst_rate) {
-        if (n > 0) memcpy(out, in, sizeof(float) * (size_t)std::min(n, cap));
-        return m;
-    }
-    constexpr int HALF_WIDTH = 16;                              // 80 dB stop band, 16-tap half width
-    constexpr double BETA = 7.857;
-    const double ratio = (double)src_rate / dst_rate;
-    const double cutoff = std::min(1.0, 1.0 / std::max(ratio, 1.0));
-    const double filter_scale = cutoff;
-    const double sample_ratio = (double)dst_rate / src_rate;
-    const double width_factor = std::max(1.0, ratio);           // widens the WINDOW (not the tap range) when downsampling
-    for (int64_t i = 0; i < m && i < cap; ++i) {
-        const double src_pos = (double)i / sample_ratio;         // a true division: see oracle/Makefile on -freciprocal-math
-        const int center = (int)std::floor(src_pos);
-        double sum = 0.0, weight_sum = 0.0;
-        for (int j = center - HALF_WIDTH + 1; j <= center + HALF_WIDTH; ++j) {
-            if (j < 0 || j >= (int)n) continue;
-            const double dist = src_pos - j;
-            const double window_pos = dist / width_factor;
-            if (std::abs(window_pos) > HALF_WIDTH) continue;
-            const double w = kaiser_window(window_pos + HALF_WIDTH, 2.0 * HALF_WIDTH, BETA);
-            const double x = dist * cutoff * M_PI;
-            const double sinc_val = std::abs(x) < 1e-10 ? 1.0 : std::sin(x) / x;
-            const double weight = sinc_val * w * filter_scale;
-            sum += in[j] * weight;
-            weight_sum += weight;
-        }
-        out[i] = weight_sum > 1e-10 ? (float)(sum / weight_sum) : 0.0f;
-    }
-    return m;
-}
-
 }  // extern "C"

@@ -49,7 +49,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_resample_len", "pk_resample",
            "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
            "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count",
-           "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count"]
+           "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count", "pk_stage_pcm_rate", "pk_resample_batch"]
 
 _lib = None
 
@@ -121,6 +121,8 @@ def load_library():
     L.pk_stream_reset.argtypes = [vp, C.c_int32]
     L.pk_stream_step.argtypes = [vp, f32p, i64p, C.POINTER(_PkTokens), f32p, i32p, f32p, i32p]
     L.pk_stream_count.argtypes = [vp]
+    L.pk_stage_pcm_rate.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int32]
+    L.pk_resample_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int32, C.c_int32, f32p, i64p]
     _lib = L
     return L
 
@@ -467,6 +469,26 @@ class Engine:
 
     def stream(self) -> int:
         return int(self.L.pk_stream(self.h) or 0)
+
+    # -- non-16 kHz input: converted on the device
+    def stage_rate(self, pcms: Sequence[np.ndarray], src_rate: int):
+        buf, off = _pack(pcms)
+        self._check(self.L.pk_stage_pcm_rate(self.h, _f32p(buf), _i64p(off), len(pcms), src_rate), "pk_stage_pcm_rate")
+
+    def transcribe_batch_rate(self, pcms: Sequence[np.ndarray], src_rate: int, decoder: Decoder) -> List[List[TimestampedToken]]:
+        self.stage_rate(pcms, src_rate)
+        self.run_staged(decoder)
+        return self.fetch(len(pcms))
+
+    def resample_batch(self, pcms: Sequence[np.ndarray], src_rate: int, dst_rate: int) -> List[np.ndarray]:
+        buf, off = _pack(pcms)
+        lens = [int(self.L.pk_resample_len(len(p), src_rate, dst_rate)) for p in pcms]
+        ooff = np.zeros(len(pcms) + 1, np.int64)
+        ooff[1:] = np.cumsum(lens)
+        out = np.zeros(int(ooff[-1]), np.float32)
+        self._check(self.L.pk_resample_batch(self.h, _f32p(buf), _i64p(off), len(pcms), src_rate, dst_rate, _f32p(out), _i64p(ooff)),
+                    "pk_resample_batch")
+        return [out[ooff[i]:ooff[i + 1]].copy() for i in range(len(pcms))]
 
     # -- jobs: many micro-batches, one exchange
     def job_begin(self, rows_local: int, world: int = 1):
