@@ -252,6 +252,201 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide epilogue (interior tiles): one warp drains a 32-row x 64-column slab of the accumulator.
+// Measured on B200 (profiles/r02_gemm_timeline.txt): the 16-column epilogue above spent ~9000 cycles per 128 x 128
+// tile against ~7300 for the tile's MMAs -- 40 % of it in global stores that wrote 32-byte pieces of 8 different rows
+// per instruction (one L2 request per 32 B sector).  Here every global store (and residual load) instruction covers
+// four FULL 128-byte lines: a lane first finishes its own row in registers (tcgen05.ld 32x32b.x32 x 2 -> 64 columns,
+// bias / activation / bf16 split applied row-wise, bias fetched by warp-uniform broadcast loads), writes 128 B of it
+// into the warp's 4 KB staging tile (16-byte pieces XOR-swizzled by the row: conflict-free both ways), and the warp
+// reads the tile back transposed -- lane = (row it*4 + lane/8, piece lane%8) -- so 8 lanes cover one 128-byte line.
+// The accumulator buffer is released as soon as the two TMEM loads have landed, long before the stores.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+constexpr int STGW_BYTES = 4096;                // per-warp staging tile of the wide epilogue: 32 rows x 128 B
+
+// lane's 128-byte row segment (32 words) -> staging; then the warp stores the 32 x 128 B tile to global memory, rows
+// row0 .. row0+31 at `base + row * ld_bytes` (base already includes the column offset).  RESID: out = resid + value.
+__device__ int g_store_mode;    // measurement aid: 0 = st.global, 1 = st.global.cs (evict-first), 2 = st.global.wt
+__device__ __forceinline__ void stg128(void *p, const uint4 &v, int mode) {
+    if (mode == 1)
+        asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (mode == 2)
+        asm volatile("st.global.wt.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        *reinterpret_cast<uint4 *>(p) = v;
+}
+template <bool RESID>
+__device__ __forceinline__ void store_tile128(uint32_t stg_s, int lane, const uint32_t *r, uint8_t *base, const uint8_t *rbase,
+                                              size_t ld_bytes, int row0, int M) {
+    const int smode = g_store_mode;
+    uint4 rr[8];
+    if (RESID) {        // residual pieces in the transposed (coalesced) pattern, in flight while the tile is staged
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + (lane >> 3);
+            rr[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (row0 + row < M) rr[it] = *reinterpret_cast<const uint4 *>(rbase + (size_t)(row0 + row) * ld_bytes + ((lane & 7) << 4));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        sts128(stg_s + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3), c = lane & 7;
+        uint4 v = lds128u(stg_s + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)));
+        if (RESID) {
+            v.x = __float_as_uint(__uint_as_float(rr[it].x) + __uint_as_float(v.x));
+            v.y = __float_as_uint(__uint_as_float(rr[it].y) + __uint_as_float(v.y));
+            v.z = __float_as_uint(__uint_as_float(rr[it].z) + __uint_as_float(v.z));
+            v.w = __float_as_uint(__uint_as_float(rr[it].w) + __uint_as_float(v.w));
+        }
+        if (row0 + row < M) stg128(base + (size_t)(row0 + row) * ld_bytes + (c << 4), v, smode);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// Can the slab [gcol0, gcol0 + 64) of this launch take the wide path?  (warp-uniform)
+template <int EK>
+__device__ __forceinline__ bool wide_ok(const EpiParams &epi, int gcol0, int N) {
+    if (gcol0 + 64 > N) return false;
+    if (EK == EPI_BIAS_F32 || EK == EPI_BIAS_RELU_F32 || EK == EPI_RESID_F32) return (epi.ldo & 3) == 0;
+    if (EK == EPI_GLU_F32) return (epi.ldo & 3) == 0;
+    if (EK == EPI_QKV_ACT) return (epi.ldo & 7) == 0 && (epi.qcols & 63) == 0 && epi.act.hi != nullptr;
+    return (epi.ldo & 7) == 0 && epi.act.hi != nullptr;
+}
+
+template <int EK, typename ReleaseFn>
+__device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, int row0, int gcol0, int M, const EpiParams &epi_param,
+                                                int lane, ReleaseFn release, bool last_slab) {
+    const EpiParams epi = epi_param;
+    uint32_t a0[32], a1[32];
+    tmem_ld32_issue(taddr, a0);
+    tmem_ld32_issue(taddr + 32u, a1);
+    tmem_wait_ld();
+    if (last_slab) release();
+    // row-wise on 32 columns [c0, c0 + 32) of the slab: + bias (warp-uniform float4 loads), activation
+    auto rowmath = [&](const uint32_t (&a)[32], int c0, float (&v)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi.bias) b = __ldg(reinterpret_cast<const float4 *>(epi.bias + gcol0 + c0 + j));
+            v[j] = __uint_as_float(a[j]) + b.x;
+            v[j + 1] = __uint_as_float(a[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(a[j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(a[j + 3]) + b.w;
+        }
+        if (EK == EPI_BIAS_RELU_F32 || EK == EPI_BIAS_RELU_ACT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (EK == EPI_BIAS_SILU_ACT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+        } else if (EK == EPI_RESID_F32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= epi.alpha;
+        }
+    };
+    if (EK == EPI_BIAS_F32 || EK == EPI_BIAS_RELU_F32 || EK == EPI_RESID_F32) {
+        // fp32 rows: 256 B per lane -> two 128-byte passes
+        uint8_t *ob = reinterpret_cast<uint8_t *>(epi.out_f32 + gcol0);
+        const uint8_t *rb = reinterpret_cast<const uint8_t *>(epi.resid + gcol0);
+        const size_t ldb = (size_t)epi.ldo * 4;
+        {
+            float v[32];
+            rowmath(a0, 0, v);
+            uint32_t r[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+            store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob, rb, ldb, row0, M);
+        }
+        {
+            float v[32];
+            rowmath(a1, 32, v);
+            uint32_t r[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+            store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob + 128, rb + 128, ldb, row0, M);
+        }
+    } else if (EK == EPI_GLU_F32) {
+        uint32_t r[32];
+        {
+            float v[32];
+            rowmath(a0, 0, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] = __float_as_uint(v[2 * k] * fast_sigmoid(v[2 * k + 1]));
+        }
+        {
+            float v[32];
+            rowmath(a1, 32, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[16 + k] = __float_as_uint(v[2 * k] * fast_sigmoid(v[2 * k + 1]));
+        }
+        store_tile128<false>(stg_s, lane, r, reinterpret_cast<uint8_t *>(epi.out_f32 + (gcol0 >> 1)), nullptr, (size_t)epi.ldo * 4, row0, M);
+    } else {
+        // bf16 hi / lo planes: 64 columns = 128 B per lane and plane
+        const size_t ldb = (size_t)epi.ldo * 2;
+        const bool q_part = (EK == EPI_QKV_ACT) && gcol0 < epi.qcols;
+        const int dcol = (EK == EPI_QKV_ACT) ? (q_part ? gcol0 : gcol0 + epi.qcols) : gcol0;
+        const int nvar = q_part ? 2 : 1;
+#pragma unroll 1
+        for (int var = 0; var < nvar; ++var) {
+            uint32_t hi[32], lo[32];
+            const float *pb = var == 0 ? epi.bias_u : epi.bias_v;
+            {
+                float v[32];
+                rowmath(a0, 0, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q_part) b = __ldg(reinterpret_cast<const float4 *>(pb + gcol0 + j));
+                    split_pair(v[j] + b.x, v[j + 1] + b.y, hi[j >> 1], lo[j >> 1]);
+                    split_pair(v[j + 2] + b.z, v[j + 3] + b.w, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
+                }
+            }
+            {
+                float v[32];
+                rowmath(a1, 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q_part) b = __ldg(reinterpret_cast<const float4 *>(pb + gcol0 + 32 + j));
+                    split_pair(v[j] + b.x, v[j + 1] + b.y, hi[16 + (j >> 1)], lo[16 + (j >> 1)]);
+                    split_pair(v[j + 2] + b.z, v[j + 3] + b.w, hi[16 + (j >> 1) + 1], lo[16 + (j >> 1) + 1]);
+                }
+            }
+            const int col = dcol + var * epi.qcols;
+            store_tile128<false>(stg_s, lane, hi, reinterpret_cast<uint8_t *>(epi.act.hi + col), nullptr, ldb, row0, M);
+            if (epi.act.lo) store_tile128<false>(stg_s, lane, lo, reinterpret_cast<uint8_t *>(epi.act.lo + col), nullptr, ldb, row0, M);
+        }
+    }
+}
+
 constexpr int EPI_WARPS = 8;                    // two per TMEM lane quarter, each half of the columns
 constexpr int TC_THREADS_P = 64 + EPI_WARPS * 32;
 
@@ -261,11 +456,12 @@ struct TcCfg {
     static constexpr int W_BYTES = BN * BK * 2;
     static constexpr int PLANES = (NPASS == 3) ? 2 : 1;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
-    static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;   // epilogue transpose staging
-    static constexpr int AVAIL = 225 * 1024 - STG_BYTES - 1024 - 256;
+    static constexpr int STG_BYTES = EPI_WARPS * STGW_BYTES;    // epilogue staging: one 32 x 128 B tile per warp
+    static constexpr int AVAIL = 227 * 1024 - STG_BYTES - 1024 - 256;
     static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
+    static_assert(STG_BYTES >= EPI_WARPS * 32 * STG_LD * 4, "staging also serves the 16-column path");
 };
 
 // Persistent: grid = min(#tiles, #SMs); CTA c takes tiles c, c+grid, ...  (n-tile fastest so
@@ -371,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ew = warp - 2;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int half = ew >> 2;                    // which half of the BN columns
-        const uint32_t stg_s = smem_u32(staging + (size_t)ew * 32 * STG_LD);   // explicit .shared accesses
+        const uint32_t stg_s = smem_u32(staging) + (uint32_t)ew * STGW_BYTES;   // explicit .shared accesses
         uint32_t tcount = 0;
         const bool probe = dbg && blockIdx.x == 0 && threadIdx.x == 64;
         long long pc0 = 0;
@@ -390,11 +586,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 continue;
             }
-            epilogue_slab<BN / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN / 2), M, N, epi, lane, [&]() {
+            auto release = [&]() {
                 tcgen05_fence_before();              // last TMEM read of this tile has landed: release the buffer
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            }, dbg);
+            };
+            if (BN == 128 && !(dbg & 64) && wide_ok<EK>(epi, n0 + half * 64, N))
+                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, n0 + half * 64, M, epi, lane, release, true);
+            else
+                epilogue_slab<BN / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN / 2), M, N, epi, lane, release, dbg);
             if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
         if (probe) { g_clk_probe[0] = (unsigned long long)(clock64() - pc0); g_clk_probe[1] = globaltimer_ns() - pg0; }
@@ -460,8 +660,8 @@ struct Tc2Cfg {
     static constexpr int W_BYTES = (BN2 / 2) * BK * 2;          // this CTA's 128 rows of W, one plane
     static constexpr int PLANES = (NPASS == 3) ? 2 : 1;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
-    static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
-    static constexpr int AVAIL = 225 * 1024 - STG_BYTES - 1024 - 256;
+    static constexpr int STG_BYTES = EPI_WARPS * STGW_BYTES;
+    static constexpr int AVAIL = 227 * 1024 - STG_BYTES - 1024 - 256;
     static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 2 * BN2;                   // 512: double-buffered 256-column accumulator
@@ -542,6 +742,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);
                 tcgen05_fence_after();
+                if ((dbg & 32) && blockIdx.x == 0 && tcount < 64) g_timeline[tcount][0] = clock64();
                 const uint32_t tmem_d = tmem_base + buf * BN2;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % C::STAGES;
@@ -564,6 +765,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     umma_commit_2sm(&empty[s]);      // frees stage s in both CTAs
                 }
                 umma_commit_2sm(&acc_full[buf]);     // accumulator ready in both CTAs
+                if ((dbg & 32) && blockIdx.x == 0 && tcount < 64) g_timeline[tcount][1] = clock64();
             }
         }
     } else {
@@ -571,7 +773,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        const uint32_t stg_s = smem_u32(staging + (size_t)ew * 32 * STG_LD);   // explicit .shared accesses
+        const uint32_t stg_s = smem_u32(staging) + (uint32_t)ew * STGW_BYTES;   // explicit .shared accesses
         const uint32_t lempty0 = mapa_rank(smem_u32(&acc_empty[0]), 0), lempty1 = mapa_rank(smem_u32(&acc_empty[1]), 0);
         uint32_t tcount = 0;
         for (int tile = pair; tile < num_tiles; tile += npairs, ++tcount) {
@@ -579,6 +781,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
+            if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][2] = clock64();
             const uint32_t taddr = tmem_base + buf * BN2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN2 / 2));
             if (dbg & 1) {
                 tcgen05_fence_before();
@@ -586,11 +789,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);
                 continue;
             }
-            epilogue_slab<BN2 / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN2 / 2), M, N, epi, lane, [&]() {
+            auto release = [&]() {
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(buf ? lempty1 : lempty0);   // leader's barrier counts both CTAs
-            }, dbg);
+            };
+            const int gc = n0 + half * (BN2 / 2);
+            if (!(dbg & 64) && wide_ok<EK>(epi, gc, N) && wide_ok<EK>(epi, gc + 64, N)) {
+                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, gc, M, epi, lane, release, false);
+                epilogue_slab64<EK>(taddr + 64u, stg_s, m0 + q * 32, gc + 64, M, epi, lane, release, true);
+            } else {
+                epilogue_slab<BN2 / 2, EK>(taddr, stg_s, m0 + q * 32, gc, M, N, epi, lane, release, dbg);
+            }
+            if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
     }
     tcgen05_fence_before();
@@ -715,7 +926,11 @@ int tc_tile_n(int N) { return N <= 64 ? 64 : 128; }
 
 static bool g_use_2cta = false;   // measured on B200 (64x10 s): the pair kernel is not faster yet at M = 8064
 void tc_set_2cta(bool on) { g_use_2cta = on; }
-void tc_set_debug(int bits) { g_dbg = bits; }
+void tc_set_debug(int bits) {
+    g_dbg = bits & 0xff;
+    const int mode = (bits >> 8) & 3;
+    cudaMemcpyToSymbol(g_store_mode, &mode, sizeof(int));
+}
 void tc_print_timeline(int n_tiles) {   // after a 1-CTA launch with debug bit 5
     long long h[64][4];
     if (cudaMemcpyFromSymbol(h, g_timeline, sizeof(h)) != cudaSuccess) return;

@@ -631,3 +631,32 @@ def test_streaming_many_streams_lockstep(pkg, O, synth, tmp_path, math_mode):
         assert got[s] == want, s
     assert got[5] == want[:len(got[5])] and len(got[5]) >= 10
     e.close()
+
+
+# ------------------------------------------------------------------ front-of-path rate conversion
+def test_gpu_resampler_matches_oracle_and_feeds_the_path(pkg, O, synth, tiny, refbind):
+    """The polyphase kernel (csrc/resample.cu) against the oracle's sinc_resample (= the compiled reference's
+    parakeet::resample, pinned on the CPU in tests/test_abi.py): identical floats except where the reference's
+    per-output rounding of i / (dst/src) differs from the exact rational position (bound: 1 ulp, >= 99.9 % identical);
+    and a 22.05 kHz batch converted on the device (pk_stage_pcm_rate) gives the tokens of the host-converted batch."""
+    e = pkg.Engine(tiny.cfg, tiny.weights_path, 0)
+    rng = np.random.default_rng(9)
+    for sr, dr, lens in [(44100, 16000, [9000, 3, 20000]), (48000, 16000, [5001]), (8000, 16000, [2500, 1]), (22050, 16000, [30000, 12345]),
+                         (96000, 16000, [6000]), (16000, 8000, [1000]), (11025, 16000, [4097])]:
+        xs = [(rng.standard_normal(n) * 0.3).astype(np.float32) for n in lens]
+        got = e.resample_batch(xs, sr, dr)
+        for x, g in zip(xs, got):
+            want = O.sinc_resample(x, sr, dr)
+            assert g.shape == want.shape
+            same = float(np.mean(g == want)) if len(want) else 1.0
+            assert same >= 0.999, (sr, dr, len(x), same)
+            assert np.all(np.abs(g - want) <= np.spacing(np.abs(want).astype(np.float32)) + 1e-45), (sr, dr, len(x))
+            if refbind is not None and len(x) > 16:
+                assert float(np.mean(g == refbind.resample(x, sr, dr))) >= 0.999
+    # whole path from 22.05 kHz input
+    pcm22 = [synth.make_audio(44100, 31)[:n] for n in (44100, 30000)]      # (any signal; treated as 22.05 kHz samples)
+    host16 = [O.sinc_resample(p, 22050, 16000) for p in pcm22]
+    want = e.transcribe_batch(host16, pkg.Decoder.TDT)
+    got = e.transcribe_batch_rate(pcm22, 22050, pkg.Decoder.TDT)
+    assert [_tt(a) for a in got] == [_tt(b) for b in want]
+    e.close()
