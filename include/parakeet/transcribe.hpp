@@ -14,7 +14,7 @@
 //   * the model only ever lives on the CUDA device: to_gpu() is a checked no-op and there
 //     is no CPU fallback;
 //   * transcribe_batch() is an addition (the reference is batch-1, transcribe.hpp:170-171);
-//   * phrase boosting (TranscribeOptions::boost_phrases) is not on the GPU path and throws;
+//   * phrase boosting (TranscribeOptions::boost_phrases) runs on the device for both decoders (pk_set_boost);
 //   * TDTTranscriber passes blank = vocab-1 like the reference CLI (src/main.cpp:252), not
 //     the header's hard-coded 1024 (transcribe.hpp:256-261) which is wrong for 8193 tokens.
 // Link with libparakeet_b200.so.
@@ -100,7 +100,7 @@ class Tokenizer {
     size_t vocab_size() const { return loaded() ? (size_t)pk_vocab_size(v_) + 1 : 0; }   // +1 blank, like the reference
     std::string decode(const std::vector<int> &ids) const {
         std::vector<int32_t> a(ids.begin(), ids.end());
-        std::string buf(64 + 64 * a.size(), '\0');
+        std::string buf(2 + ((size_t)pk_vocab_max_piece_bytes(v_) + 1) * std::max<size_t>(a.size(), 1), '\0');
         int n = pk_detokenize(v_, a.data(), (int32_t)a.size(), &buf[0], (int32_t)buf.size());
         buf.resize(n < 0 ? 0 : std::min<size_t>((size_t)n, buf.size() - 1));
         return buf;
@@ -116,7 +116,7 @@ class Tokenizer {
         std::vector<int32_t> id(n), st(n), en(n);
         std::vector<float> cf(n), ws(n + 1), we(n + 1), wc(n + 1);
         for (int i = 0; i < n; ++i) { id[i] = t[i].token_id; st[i] = t[i].start_frame; en[i] = t[i].end_frame; cf[i] = t[i].confidence; }
-        std::string buf(64 + 64 * (size_t)n, '\0');
+        std::string buf(2 + ((size_t)pk_vocab_max_piece_bytes(v_) + 2) * std::max<size_t>((size_t)n, 1), '\0');
         int k = pk_group_words(v_, id.data(), st.data(), en.data(), cf.data(), n, &buf[0], (int32_t)buf.size(), ws.data(), we.data(), wc.data());
         std::vector<WordTimestamp> out;
         size_t pos = 0;
@@ -289,7 +289,20 @@ class TranscriberBase {
     }
     TranscribeResult transcribe(const std::vector<float> &samples, const TranscribeOptions &opts) { return transcribe(samples.data(), samples.size(), opts); }
     TranscribeResult transcribe(const float *samples, size_t n, const TranscribeOptions &opts) {
-        if (!opts.boost_phrases.empty()) throw std::runtime_error("phrase boosting is not available on the B200 path");
+        // phrase boosting (transcribe.hpp:110-137, :158-165): the ContextTrie and the boosted decode live on the device
+        struct BoostGuard {
+            pk_engine *e; bool on;
+            ~BoostGuard() { if (on) pk_set_boost(e, nullptr, nullptr, 0, 0.f); }
+        } guard{eng_->raw(), false};
+        if (!opts.boost_phrases.empty() && tokenizer_.loaded()) {
+            ContextTrie trie;
+            trie.build(opts.boost_phrases, tokenizer_);
+            if (!trie.empty()) {
+                if (pk_set_boost(eng_->raw(), trie.ids().data(), trie.offsets().data(), (int32_t)trie.offsets().size() - 1, opts.boost_score) != PK_OK)
+                    throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(eng_->raw()));
+                guard.on = true;
+            }
+        }
         auto toks = eng_->run({samples}, {n}, self().pick(opts.decoder))[0];
         return finish(toks, opts.timestamps);
     }

@@ -242,6 +242,8 @@ typedef struct pk_vocab pk_vocab;
 pk_status pk_vocab_load(const char *vocab_path, pk_vocab **out);
 void pk_vocab_free(pk_vocab *v);
 int32_t pk_vocab_size(const pk_vocab *v);
+/* Longest piece in bytes: pk_detokenize / pk_group_words never write more than n * (that + 1) + 1 bytes for n tokens. */
+int32_t pk_vocab_max_piece_bytes(const pk_vocab *v);
 /* Writes NUL-terminated UTF-8 into buf (truncated to cap-1); returns full length. */
 int32_t pk_detokenize(const pk_vocab *v, const int32_t *ids, int32_t n, char *buf, int32_t cap);
 /* Words are written '\n'-separated into buf; returns the number of words. */
@@ -263,6 +265,16 @@ int32_t pk_tokenize(const pk_vocab *v, const char *text, int32_t *ids, int32_t c
 int32_t pk_ctc_decode_boosted(const float *logprobs, int32_t n_frames, int32_t vocab, int32_t blank,
                               const int32_t *phrase_ids, const int32_t *phrase_off, int32_t n_phrases, float boost,
                               int32_t *ids, int32_t *start, int32_t *end, float *conf, int32_t cap);
+
+/* Phrase boosting ON THE DEVICE for both decoders (widening row: SURVEY.md section 8f(3)), replacing the decode loops of
+ * ctc_greedy_decode(_with_timestamps)_boosted and tdt_greedy_decode(_with_timestamps)_boosted (src/phrase_boost.cpp:70-352)
+ * as Transcriber::transcribe uses them when TranscribeOptions::boost_phrases is set (transcribe.hpp:110-137, :158-165).
+ * The phrases are token-id sequences (pk_tokenize), phrase p = phrase_ids[phrase_off[p] .. phrase_off[p+1]); the engine builds the
+ * ContextTrie (:9-66) and keeps it on the device.  While set, every decode of this engine (pk_transcribe_batch,
+ * pk_run_staged, pk_decode; CTC and TDT) adds `boost` to the label scores of the tokens that continue an active phrase;
+ * the trie state is per utterance and advances on emissions; confidences stay exp(raw log-prob).  n_phrases = 0 clears
+ * it.  (Not applied by pk_stream_step.)  At most 64 simultaneously active trie states per utterance. */
+pk_status pk_set_boost(pk_engine *e, const int32_t *phrase_ids, const int32_t *phrase_off, int32_t n_phrases, float boost);
 
 /* Sample-rate conversion (widening row: SURVEY.md section 8f(4)), replacing parakeet::resample / sinc_resample
  * (src/audio_io.cpp:123-195, :238-251): 32-tap Kaiser (beta 7.857) windowed sinc in double, output length

@@ -666,10 +666,18 @@ pk_status pk_engine::run_ctc(float *logprobs_dev) {
     ep.out_f32 = logits;
     ep.ldo = ldv;
     gemm(enc_operand(this), c.d_model, ctc_head, M, ep);
+    if (boost_on && !logprobs_dev) {
+        // boosted decode compares log-probs + boost (phrase_boost.cpp:94-102): they land in the (idle) qkv workspace
+        if ((size_t)M * c.vocab > (size_t)Bmax * Tmax * 3 * c.d_model) return fail(PK_ERR_CAPACITY, "boosted CTC decode: workspace too small for the log-probs");
+        logprobs_dev = qkv;
+    }
     {
         Scope sc(this, CAT_CTC);
         launch_ctc_frame_argmax(logits, M, c.vocab, ldv, best, bconf, logprobs_dev, stream);
-        launch_ctc_collapse(best, bconf, d_row_off, n_utt, c.vocab - 1, cap, tok, t_start, t_end, t_conf, stream);
+        if (boost_on)
+            launch_ctc_boosted_decode(logprobs_dev, d_row_off, n_utt, c.vocab, c.vocab - 1, cap, trie, boost, tok, t_start, t_end, t_conf, stream);
+        else
+            launch_ctc_collapse(best, bconf, d_row_off, n_utt, c.vocab - 1, cap, tok, t_start, t_end, t_conf, stream);
     }
     launches += 2;
     last_tdt = false;
@@ -701,6 +709,7 @@ pk_status pk_engine::run_tdt() {
     p.key_lab = tdt_keys; p.key_dur = tdt_keys + 3 * (size_t)Bpad;
     p.dbg = reinterpret_cast<long long *>(tdt_keys + 6 * (size_t)Bpad);
     p.tok = tok; p.t_start = t_start; p.t_end = t_end; p.t_conf = t_conf;
+    p.boost_on = boost_on ? 1 : 0; p.boost = boost; p.trie = trie; p.boost_bits = boost_bits; p.trie_active = trie_active; p.trie_nact = trie_nact;
     // initial state: zero LSTM state, token = blank (SOS), t = 0 (tdt.cpp:49-59)
     const size_t HS = (size_t)p.P * bp;
     PK_CUDA(cudaMemsetAsync(hbuf, 0, HS * 2 * p.L * sizeof(float), stream));
@@ -738,6 +747,57 @@ pk_status pk_engine::fetch(pk_tokens *out) {
         if (out->end) memcpy(out->end + b * out->cap, h_te + b * cap, (size_t)len * 4);
         if (out->conf) memcpy(out->conf + b * out->cap, h_tc + b * cap, (size_t)len * 4);
     }
+    return PK_OK;
+}
+
+// Runs `body` (a sequence of launches on the engine stream whose kernel arguments depend only on `key`) as ONE CUDA graph
+// once the key has been seen twice: first sight runs eagerly (which also completes every lazy one-time initialisation),
+// second sight captures + instantiates, later sights replay.  Falls back to plain launches if capture is not possible.
+pk_status pk_engine::run_graphed(const std::string &key, const std::function<pk_status()> &body) {
+    if (!use_graphs || prof_on) return body();
+    if (graphs.size() >= 32 && graphs.find(key) == graphs.end()) {
+        // Bound the cache at INSERTION: with variable-length audio nearly every batch shape is new.  Drop the
+        // entries that never got a graph first; if the instantiated graphs alone fill it, drop those too.
+        for (auto it = graphs.begin(); it != graphs.end();)
+            it = it->second.exec ? std::next(it) : graphs.erase(it);
+        if (graphs.size() >= 24) {
+            for (auto &kv : graphs) cudaGraphExecDestroy(kv.second.exec);
+            graphs.clear();
+        }
+    }
+    auto &g = graphs[key];
+    if (g.exec) {
+        cudaError_t ce = cudaGraphLaunch(g.exec, stream);
+        if (ce != cudaSuccess) return fail(PK_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce));
+        launches += g.launches;
+        return PK_OK;
+    }
+    if (g.seen++ == 0) return body();
+    const int64_t l0 = launches;
+    cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) return fail(PK_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce));
+    pk_status s = body();
+    cudaGraph_t graph = nullptr;
+    ce = cudaStreamEndCapture(stream, &graph);
+    if (s != PK_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        use_graphs = false;     // capture not possible here: stay on plain launches
+        launches = l0;
+        return body();
+    }
+    g.launches = launches - l0;
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        g.exec = nullptr;
+        cudaGetLastError();
+        use_graphs = false;
+        launches = l0;
+        return body();
+    }
+    ce = cudaGraphLaunch(g.exec, stream);
+    if (ce != cudaSuccess) return fail(PK_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce));
     return PK_OK;
 }
 
@@ -1150,54 +1210,11 @@ pk_status pk_run_staged(pk_engine *e, pk_decoder dec) {
         e->front_done = false;      // a second pk_run_staged of the same staged batch re-runs the front end
         if (fs) return fs;
     }
-    if (!e->use_graphs || e->prof_on) return run_pipeline(e, dec);
     std::string key(1, dec == PK_DECODER_CTC ? 'c' : 't');
+    const int32_t bg = e->boost_on ? e->boost_gen : 0;
+    key.append(reinterpret_cast<const char *>(&bg), sizeof(bg));
     key.append(reinterpret_cast<const char *>(e->frame_off.data()), e->frame_off.size() * sizeof(int32_t));
-    if (e->graphs.size() >= 32 && e->graphs.find(key) == e->graphs.end()) {
-        // Bound the cache at INSERTION: with variable-length audio nearly every batch shape is new.  Drop the
-        // entries that never got a graph first; if the instantiated graphs alone fill it, drop those too.
-        for (auto it = e->graphs.begin(); it != e->graphs.end();)
-            it = it->second.exec ? std::next(it) : e->graphs.erase(it);
-        if (e->graphs.size() >= 24) {
-            for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
-            e->graphs.clear();
-        }
-    }
-    auto &g = e->graphs[key];
-    if (g.exec) {
-        cudaError_t ce = cudaGraphLaunch(g.exec, e->stream);
-        if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce));
-        e->launches += g.launches;
-        return PK_OK;
-    }
-    if (g.seen++ == 0) return run_pipeline(e, dec);
-    auto &gg = g;
-    const int64_t l0 = e->launches;
-    cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
-    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce));
-    pk_status s = run_pipeline(e, dec);
-    cudaGraph_t graph = nullptr;
-    ce = cudaStreamEndCapture(e->stream, &graph);
-    if (s != PK_OK || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        e->use_graphs = false;     // capture not possible here: stay on plain launches
-        e->launches = l0;
-        return run_pipeline(e, dec);
-    }
-    gg.launches = e->launches - l0;
-    ce = cudaGraphInstantiate(&gg.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) {
-        gg.exec = nullptr;
-        cudaGetLastError();
-        e->use_graphs = false;
-        e->launches = l0;
-        return run_pipeline(e, dec);
-    }
-    ce = cudaGraphLaunch(gg.exec, e->stream);
-    if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce));
-    return PK_OK;
+    return e->run_graphed(key, [e, dec]() { return run_pipeline(e, dec); });
 }
 
 pk_status pk_fetch_tokens(pk_engine *e, pk_tokens *out) {
@@ -1448,6 +1465,61 @@ pk_status pk_resample_batch(pk_engine *e, const float *pcm, const int64_t *offse
                                  cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_resample_batch: ") + cudaGetErrorString(ce));
+    return PK_OK;
+}
+
+// ===================================================================== phrase boosting
+// ContextTrie (src/phrase_boost.cpp:9-66) built on the host from token-id phrases, flattened to CSR (children of a node
+// sorted by token) and uploaded; the decode kernels (ctc.cu: ctc_boosted_decode_kernel, tdt.cu: boost_on) walk it.
+pk_status pk_set_boost(pk_engine *e, const int32_t *phrase_ids, const int32_t *phrase_off, int32_t n_phrases, float boost) {
+    if (!e || n_phrases < 0 || (n_phrases > 0 && (!phrase_ids || !phrase_off))) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    ++e->boost_gen;
+    if (n_phrases == 0) {
+        e->boost_on = false;
+        return PK_OK;
+    }
+    std::vector<std::map<int32_t, int32_t>> ch(1);
+    for (int32_t p = 0; p < n_phrases; ++p) {
+        int32_t node = 0;
+        if (phrase_off[p + 1] < phrase_off[p]) return e->fail(PK_ERR_INVALID, "pk_set_boost: phrase_off must be non-decreasing");
+        for (int32_t i = phrase_off[p]; i < phrase_off[p + 1]; ++i) {
+            auto it = ch[node].find(phrase_ids[i]);
+            if (it == ch[node].end()) {
+                const int32_t nx = (int32_t)ch.size();
+                ch[node][phrase_ids[i]] = nx;
+                ch.emplace_back();
+                node = nx;
+            } else {
+                node = it->second;
+            }
+        }
+    }
+    std::vector<int32_t> first(ch.size() + 1, 0), tk, cd;
+    for (size_t i = 0; i < ch.size(); ++i) {
+        for (auto &kv : ch[i]) {
+            tk.push_back(kv.first);
+            cd.push_back(kv.second);
+        }
+        first[i + 1] = (int32_t)tk.size();
+    }
+    if (tk.empty()) {       // only empty phrases
+        e->boost_on = false;
+        return PK_OK;
+    }
+    int32_t *d_first = e->upload(first), *d_tok = e->upload(tk), *d_child = e->upload(cd);
+    if (!d_first || !d_tok || !d_child) return e->fail(PK_ERR_CUDA, "cudaMalloc failed (trie)");
+    e->trie.first = d_first; e->trie.tok = d_tok; e->trie.child = d_child; e->trie.n_nodes = (int32_t)ch.size();
+    if (!e->boost_bits) {
+        const size_t W = ((size_t)e->cfg.vocab + 31) / 32;
+        e->boost_bits = e->dalloc<uint32_t>((size_t)e->Bpad * W);
+        e->trie_active = e->dalloc<int32_t>((size_t)e->Bpad * 64);
+        e->trie_nact = e->dalloc<int32_t>(e->Bpad);
+        if (!e->boost_bits || !e->trie_active || !e->trie_nact) return e->fail(PK_ERR_CUDA, "cudaMalloc failed (boost state)");
+    }
+    e->boost = boost;
+    e->boost_on = true;
     return PK_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -159,6 +160,14 @@ struct pk_engine {
     bool last_tdt = false;                             // the token buffer holds a TDT decode (overflow flags are valid)
     int32_t truncated = 0;                             // utterances of the last fetch whose TDT hypothesis hit the token capacity
 
+    // ---- phrase boosting (pk_set_boost): ContextTrie on the device + per-utterance trie state of the TDT kernel
+    DeviceTrie trie{};
+    bool boost_on = false;
+    float boost = 0.f;
+    int boost_gen = 0;                                 // bumps on every pk_set_boost (part of the CUDA-graph key)
+    uint32_t *boost_bits = nullptr;                    // [Bpad][(V+31)/32]
+    int32_t *trie_active = nullptr, *trie_nact = nullptr;
+
     // ---- optional per-kernel-class timing (CUDA events on the engine stream)
     enum { CAT_MEL, CAT_SUBSAMPLE, CAT_GEMM, CAT_LAYERNORM, CAT_ATTENTION, CAT_DWCONV, CAT_CTC, CAT_TDT, CAT_N };
     struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
@@ -230,6 +239,7 @@ struct pk_engine {
     pk_status gemm_err = PK_OK;
     pk_status run_mel(int u0 = 0, int u1 = -1);
     pk_status run_conv1(int u0 = 0, int u1 = -1);
+    pk_status run_graphed(const std::string &key, const std::function<pk_status()> &body);
     pk_status run_subsample_tail();
     pk_status run_encoder(float *sub_out_host, float *layers_out_host);
     // streaming eou path (stream_engine.cu)

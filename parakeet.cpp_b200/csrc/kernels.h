@@ -108,7 +108,17 @@ bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_q
                                 int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
                                 int d_model, ActBuf out, cudaStream_t st);
 
+// ContextTrie (src/phrase_boost.cpp:9-66) in CSR form on the device: node 0 = root; the edges of node i are
+// [first[i], first[i+1]) = (token, child node), sorted by token.
+struct DeviceTrie {
+    const int32_t *first = nullptr, *tok = nullptr, *child = nullptr;
+    int32_t n_nodes = 0;
+};
+
 // ------------------------------------------------------------------ ctc.cu (K9)
+void launch_ctc_boosted_decode(const float *logprobs, const int32_t *row_off, int n_utt, int V, int blank, int cap,
+                               const DeviceTrie &trie, float boost, int32_t *tok, int32_t *t_start, int32_t *t_end, float *t_conf,
+                               cudaStream_t st);
 void launch_ctc_frame_argmax(const float *logits, int M, int V, int ld, int32_t *best, float *conf,
                              float *logprobs, cudaStream_t st);
 void launch_ctc_collapse(const int32_t *best, const float *conf, const int32_t *row_off, int n_utt, int blank,
@@ -147,6 +157,15 @@ struct TdtParams {
     float *c_state;
     int32_t *tok_state;
     const int32_t *frame_base;
+    // Phrase boosting (tdt_greedy_decode(_with_timestamps)_boosted, src/phrase_boost.cpp:177-352): boost_on = 1 adds `boost`
+    // to the label logits of the tokens that continue an active trie state of the utterance (durations are not boosted);
+    // boost_bits [Bpad][(V+31)/32] is the per-utterance bitmap of those tokens, trie_active [Bpad][64] / trie_nact [Bpad] the
+    // active states; all three are maintained by the CTA that owns the utterance.  Confidence stays exp(raw log-prob).
+    int boost_on;
+    float boost;
+    DeviceTrie trie;
+    uint32_t *boost_bits;
+    int32_t *trie_active, *trie_nact;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
 // fp32 [rows][K] -> [rows][2 K] bf16 = [hi: K][lo: K]

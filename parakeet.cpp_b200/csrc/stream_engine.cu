@@ -356,14 +356,27 @@ pk_status pk_stream_step(pk_engine *e, const float *pcm, const int64_t *offsets,
         // the active streams' frames as an ordinary packed batch (CausalConvSubsampling runs the plain zero-padded subsampling)
         if ((ps = e->set_batch_shapes(s.take.data(), nullptr, n_act))) return ps;
         if ((ps = e->upload_shapes())) return ps;
-        if ((ps = e->run_conv1())) return ps;
-        if ((ps = e->run_subsample_tail())) return ps;
-        if ((ps = e->run_stream_layers())) return ps;
+        auto body = [e, enc_out, st]() -> pk_status {
+            pk_status q;
+            if ((q = e->run_conv1())) return q;
+            if ((q = e->run_subsample_tail())) return q;
+            if ((q = e->run_stream_layers())) return q;
+            if (enc_out) {
+                cudaError_t c2 = cudaMemcpyAsync(enc_out, e->x, sizeof(float) * (size_t)e->M * e->cfg.d_model, cudaMemcpyDeviceToHost, st);
+                if (c2 != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_stream_step tap: ") + cudaGetErrorString(c2));
+            }
+            return e->run_stream_decode();
+        };
         if (enc_out) {
-            ce = cudaMemcpyAsync(enc_out, e->x, sizeof(float) * (size_t)e->M * c.d_model, cudaMemcpyDeviceToHost, st);
-            if (ce != cudaSuccess) return e->fail(PK_ERR_CUDA, std::string("pk_stream_step tap: ") + cudaGetErrorString(ce));
+            ps = body();                       // (debug taps: plain launches)
+        } else {
+            // every kernel argument of the step depends only on which streams take how many frames: one graph per pattern
+            std::string key(1, 's');
+            key.append(reinterpret_cast<const char *>(s.act.data()), s.act.size() * sizeof(int32_t));
+            key.append(reinterpret_cast<const char *>(s.take.data()), s.take.size() * sizeof(int32_t));
+            ps = e->run_graphed(key, body);
         }
-        if ((ps = e->run_stream_decode())) return ps;
+        if (ps) return ps;
         if (e->gemm_err) return e->gemm_err;
     }
     if (!out) return PK_OK;

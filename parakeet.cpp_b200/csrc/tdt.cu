@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
     int *s_cur = reinterpret_cast<int *>(csm + (size_t)L * 2 * ge.MU * Bpad);    // replicated decode state, [Bpad] each
     int *s_token = s_cur + Bpad, *s_tpos = s_token + Bpad, *s_active = s_tpos + Bpad, *s_ntok = s_active + Bpad;
     int *s_pend = s_ntok + Bpad;                   // slot of a token whose confidence is still pending (-1: none)
-    bf16 *wbf = reinterpret_cast<bf16 *>(s_pend + Bpad);
+    float *s_vraw = reinterpret_cast<float *>(s_pend + Bpad);   // raw (unboosted) logit of that token (phrase boosting)
+    bf16 *wbf = reinterpret_cast<bf16 *>(s_vraw + Bpad);
     // Weight rows in global memory are [hi: K][lo: K]; a CTA keeps columns [k0, k0 + KS) of its cluster's rows.
     auto stage_rows = [&](bf16 *dst, const bf16 *src, int rows, int K, int k0, int KS) {
         const int RS = 2 * (KS + 4), n8 = KS / 4;            // 8-byte pieces per half row
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
             for (int i = 0; i < QMAX; ++i)
                 if (m[i] > -INFINITY) s += sv[i] * expf(m[i] - gmax);
             s = warp_sum(s);
-            if (lane == 0) p.t_conf[(size_t)b * p.cap + slot] = 1.0f / s;
+            // exp(log-prob of the emitted token); without boosting the token IS the maximum: exp(0) / s
+            if (lane == 0) p.t_conf[(size_t)b * p.cap + slot] = p.boost_on ? expf(s_vraw[b] - gmax) / s : 1.0f / s;
         }
     };
     auto nox = [&](int) { return static_cast<const bf16 *>(nullptr); };
@@ -525,6 +527,9 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
         for (int bc = 0; bc < Bpad; bc += BCH) {
             float lmax = -INFINITY, lsum = 0.f, dmax = -INFINITY;
             int lidx = 0x7fffffff, didx = 0x7fffffff;
+            float kmax = -INFINITY;                       // phrase boosting: arg-max key on the BOOSTED logits,
+            int kidx = 0x7fffffff;                        // (lmax, lsum) stay raw for the softmax denominator
+            const int BW = (V + 31) >> 5;
             for (int rg = o0; rg < o1; rg += RG) {
                 const int R = min(RG, o1 - rg);
                 const int nmy = (R - rank + CL - 1) / CL;
@@ -550,6 +555,13 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                             } else {
                                 lsum += expf(v - lmax);
                             }
+                            if (p.boost_on && bc + tid < Bpad) {
+                                const float vb = v + (((p.boost_bits[(size_t)(bc + tid) * BW + (n >> 5)] >> (n & 31)) & 1u) ? p.boost : 0.0f);
+                                if (vb > kmax) {         // rows ascend within a CTA: strict '>' keeps the first maximum
+                                    kmax = vb;
+                                    kidx = n;
+                                }
+                            }
                         } else if (v > dmax) {
                             dmax = v;
                             didx = n - V;
@@ -564,7 +576,11 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                 p.pl_max[kb * PB + (size_t)g * Bpad + b] = lmax;
                 p.pl_sum[kb * PB + (size_t)g * Bpad + b] = lsum;
                 if (b < p.n_utt && s_active[b]) {
-                    if (lmax > -INFINITY) atomicMax(&p.key_lab[kb * KB + b], pack_key(lmax, lidx));
+                    if (p.boost_on) {
+                        if (kmax > -INFINITY) atomicMax(&p.key_lab[kb * KB + b], pack_key(kmax, kidx));
+                    } else if (lmax > -INFINITY) {
+                        atomicMax(&p.key_lab[kb * KB + b], pack_key(lmax, lidx));
+                    }
                     if (dmax > -INFINITY) atomicMax(&p.key_dur[kb * KB + b], pack_key(dmax, didx));
                 }
             }
@@ -598,6 +614,37 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                     row[0] = n + 1;
                 }
                 if (n < p.cap) s_pend[b] = n;
+                if (p.boost_on && (b % G) == g) {
+                    // raw logit of the emitted token (its key carries the boosted value), then ContextTrie::advance
+                    // (phrase_boost.cpp:53-66) and the bitmap of the next step's boosted tokens (:40-51)
+                    const int BW = (V + 31) >> 5;
+                    uint32_t *bits = p.boost_bits + (size_t)b * BW;
+                    s_vraw[b] = ((bits[lidx >> 5] >> (lidx & 31)) & 1u) ? lmax - p.boost : lmax;
+                    int32_t *act = p.trie_active + (size_t)b * 64;
+                    const int na = p.trie_nact[b];
+                    int32_t nxt[64];
+                    int nn = 1;
+                    nxt[0] = 0;
+                    for (int a = 0; a < na; ++a) {
+                        const int node = act[a];
+                        for (int e2 = p.trie.first[node]; e2 < p.trie.first[node + 1]; ++e2)
+                            if (p.trie.tok[e2] == lidx) {
+                                const int ch = p.trie.child[e2];
+                                bool dup = false;
+                                for (int q = 0; q < nn; ++q) dup |= nxt[q] == ch;
+                                if (!dup && nn < 64) nxt[nn++] = ch;
+                            }
+                    }
+                    for (int w = 0; w < BW; ++w) bits[w] = 0u;
+                    for (int q = 0; q < nn; ++q) {
+                        act[q] = nxt[q];
+                        for (int e2 = p.trie.first[nxt[q]]; e2 < p.trie.first[nxt[q] + 1]; ++e2) {
+                            const int tk = p.trie.tok[e2];
+                            if (tk >= 0 && tk < V) bits[tk >> 5] |= 1u << (tk & 31);
+                        }
+                    }
+                    p.trie_nact[b] = nn;
+                }
                 s_ntok[b] = n + 1;
                 s_token[b] = lidx;
                 s_cur[b] = 1 - s_cur[b];         // commit the new LSTM state
@@ -652,6 +699,17 @@ __global__ void tdt_init_kernel(TdtParams p) {
     if (b < p.n_utt) {
         p.tok[(size_t)b * (1 + p.cap)] = 0;
         p.overflow[b] = 0;
+        if (p.boost_on) {     // ContextTrie: only the root is active; its children are the boosted tokens of the first step
+            const int BW = (p.V + 31) >> 5;
+            uint32_t *bits = p.boost_bits + (size_t)b * BW;
+            for (int w = 0; w < BW; ++w) bits[w] = 0u;
+            for (int e = p.trie.first[0]; e < p.trie.first[1]; ++e) {
+                const int tk = p.trie.tok[e];
+                if (tk >= 0 && tk < p.V) bits[tk >> 5] |= 1u << (tk & 31);
+            }
+            p.trie_active[(size_t)b * 64] = 0;
+            p.trie_nact[b] = 1;
+        }
     }
 }
 
@@ -674,7 +732,7 @@ size_t tdt_smem_bytes(const TdtParams &p, int n_clusters, int CL, bool *out_in_s
     const size_t budget = 225 * 1024 / sizeof(float);
     const int KSmax = ge.KSP > ge.KSJ ? ge.KSP : ge.KSJ;
     size_t fixed = (size_t)RG * RLD + (size_t)MYMAX * BCH + (size_t)2 * BCH * (KSmax + 8) / 2 + (size_t)p.L * 2 * ge.MU * p.Bpad +
-                   6 * (size_t)p.Bpad;
+                   7 * (size_t)p.Bpad;
     // a staged weight row = [hi KS+4][lo KS+4] bf16 = KS + 4 floats
     const size_t hh = (size_t)p.L * ge.UPC * 4 * (ge.KSP + 4), ih = (size_t)(p.L - 1) * ge.UPC * 4 * (ge.KSP + 4);
     const size_t wp = (size_t)ge.JPC * (ge.KSP + 4), wo = (size_t)ge.OPC * (ge.KSJ + 4);

@@ -63,6 +63,13 @@ void pk_vocab_free(pk_vocab *v) { delete v; }
 
 int32_t pk_vocab_size(const pk_vocab *v) { return v ? (int32_t)v->pieces.size() : 0; }
 
+int32_t pk_vocab_max_piece_bytes(const pk_vocab *v) {
+    size_t m = 16;                                  // "[id]" placeholders of out-of-range ids (vocab.cpp:57-60)
+    if (v)
+        for (const auto &p : v->pieces) m = std::max(m, p.size());
+    return (int32_t)m;
+}
+
 int32_t pk_detokenize(const pk_vocab *v, const int32_t *ids, int32_t n, char *buf, int32_t cap) {
     if (!v) return -1;
     std::string joined;

@@ -49,7 +49,8 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_resample_len", "pk_resample",
            "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
            "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count",
-           "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count", "pk_stage_pcm_rate", "pk_resample_batch"]
+           "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count", "pk_stage_pcm_rate", "pk_resample_batch",
+           "pk_set_boost", "pk_vocab_max_piece_bytes"]
 
 _lib = None
 
@@ -106,6 +107,7 @@ def load_library():
     L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pk_vocab_free.argtypes = [vp]
     L.pk_vocab_size.argtypes = [vp]
+    L.pk_vocab_max_piece_bytes.argtypes = [vp]
     L.pk_detokenize.argtypes = [vp, i32p, C.c_int32, C.c_char_p, C.c_int32]
     L.pk_group_words.argtypes = [vp, i32p, i32p, i32p, f32p, C.c_int32, C.c_char_p, C.c_int32, f32p, f32p, f32p]
     L.pk_job_begin.argtypes = [vp, C.c_int64, C.c_int32]
@@ -121,6 +123,7 @@ def load_library():
     L.pk_stream_reset.argtypes = [vp, C.c_int32]
     L.pk_stream_step.argtypes = [vp, f32p, i64p, C.POINTER(_PkTokens), f32p, i32p, f32p, i32p]
     L.pk_stream_count.argtypes = [vp]
+    L.pk_set_boost.argtypes = [vp, i32p, i32p, C.c_int32, C.c_float]
     L.pk_stage_pcm_rate.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int32]
     L.pk_resample_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int32, C.c_int32, f32p, i64p]
     _lib = L
@@ -470,6 +473,16 @@ class Engine:
     def stream(self) -> int:
         return int(self.L.pk_stream(self.h) or 0)
 
+    # -- phrase boosting on the device
+    def set_boost(self, phrases: Sequence[Sequence[int]], boost: float = 5.0):
+        """phrases: token-id sequences; an empty list clears the boost."""
+        ids = np.array([t for ph in phrases for t in ph], np.int32)
+        off = np.zeros(len(phrases) + 1, np.int32)
+        off[1:] = np.cumsum([len(ph) for ph in phrases])
+        if len(ids) == 0:
+            ids = np.zeros(1, np.int32)
+        self._check(self.L.pk_set_boost(self.h, _i32p(ids), _i32p(off), len(phrases), float(boost)), "pk_set_boost")
+
     # -- non-16 kHz input: converted on the device (SURVEY.md section 8f row 4)
     def stage_rate(self, pcms: Sequence[np.ndarray], src_rate: int):
         buf, off = _pack(pcms)
@@ -580,7 +593,7 @@ class Tokenizer:
 
     def decode(self, ids: Sequence[int]) -> str:
         a = np.ascontiguousarray(ids, np.int32)
-        buf = C.create_string_buffer(64 + 64 * max(len(a), 1))
+        buf = C.create_string_buffer(2 + (self.L.pk_vocab_max_piece_bytes(self.h) + 1) * max(len(a), 1))
         self.L.pk_detokenize(self.h, _i32p(a), len(a), buf, len(buf))
         return buf.value.decode("utf-8")
 

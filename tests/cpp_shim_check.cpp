@@ -27,6 +27,23 @@ int main(int argc, char **argv) {
             for (auto &w : r.word_timestamps) std::cout << " " << w.word;
             std::cout << "\n";
         }
+        if (argc > 5) {      // TranscribeOptions::boost_phrases (transcribe.hpp:38-43): boosted decode on the device, then plain again
+            for (auto dec : {parakeet::Decoder::CTC, parakeet::Decoder::TDT}) {
+                parakeet::TranscribeOptions o;
+                o.decoder = dec;
+                o.timestamps = true;
+                o.boost_phrases = {argv[5]};
+                o.boost_score = 6.0f;
+                auto r = t.transcribe(std::string(argv[3]), o);
+                std::cout << "BOOST";
+                for (auto &tk : r.timestamped_tokens) std::cout << " " << tk.token_id << ":" << tk.start_frame << ":" << tk.end_frame;
+                std::cout << "\n";
+            }
+            auto r = t.transcribe(std::string(argv[3]), parakeet::Decoder::CTC, true);
+            std::cout << "PLAIN";
+            for (auto &tk : r.timestamped_tokens) std::cout << " " << tk.token_id << ":" << tk.start_frame << ":" << tk.end_frame;
+            std::cout << "\n";
+        }
         try {
             t.transcribe(std::string("/nonexistent.wav"));
             return 3;

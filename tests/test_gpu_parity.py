@@ -377,7 +377,7 @@ def test_error_statuses(pkg, eng_tiny, tiny, synth, tmp_path):
 
 
 # ------------------------------------------------------------------ the C++ drop-in shim (include/parakeet/transcribe.hpp)
-def test_cpp_shim(pkg, tiny, synth, golden, tmp_path):
+def test_cpp_shim(pkg, O, tiny, synth, golden, tmp_path):
     """Builds tests/cpp_shim_check.cpp (the reference-style usage: parakeet::Transcriber t(weights, vocab);
     t.to_gpu(); t.transcribe("audio.wav", Decoder, timestamps)) against the header-only shim + the C-ABI
     library and compares its tokens / text / words with the reference goldens."""
@@ -398,7 +398,9 @@ def test_cpp_shim(pkg, tiny, synth, golden, tmp_path):
         f.write(b"RIFF" + struct.pack("<I", 36 + 2 * len(i16)) + b"WAVEfmt " +
                 struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"data" + struct.pack("<I", 2 * len(i16)))
         f.write(i16.tobytes())
-    out = subprocess.run([exe, tiny.weights_path, tiny.vocab_path, wav, "tiny"], check=True, capture_output=True, text=True).stdout
+    # a phrase for TranscribeOptions::boost_phrases: three vocabulary pieces as text
+    phrase = "".join(tiny.pieces[i] for i in (7, 11, 5)).replace(O.SP_MARK, " ").strip()
+    out = subprocess.run([exe, tiny.weights_path, tiny.vocab_path, wav, "tiny", phrase], check=True, capture_output=True, text=True).stdout
     lines = out.strip().split("\n")
     tdt = [[int(x) for x in t.split(":")] for t in lines[0].split()[1:]]
     assert tdt == golden[k + "tdt_tok"].tolist()
@@ -407,7 +409,17 @@ def test_cpp_shim(pkg, tiny, synth, golden, tmp_path):
     ctc = [[int(x) for x in t.split(":")] for t in lines[3].split()[1:]]
     assert ctc == golden[k + "ctc_tok"].tolist()
     assert lines[4] == "TEXT " + bytes(golden[k + "ctc_text"]).decode()
-    assert lines[6].startswith("ERR Cannot open audio file")
+    # boosted decode through the shim == pk_set_boost on the same phrase through the ctypes binding; then plain again
+    tk = pkg.engine.Tokenizer(tiny.vocab_path)
+    e = pkg.Engine(tiny.cfg, tiny.weights_path, 0)
+    wav_pcm = i16.astype(np.float32) / np.float32(32768.0)
+    e.set_boost([tk.encode(phrase)], 6.0)
+    for li, dec in ((6, pkg.Decoder.CTC), (7, pkg.Decoder.TDT)):
+        want = e.transcribe_batch([wav_pcm], dec)[0]
+        assert lines[li].split()[1:] == [f"{t.token_id}:{t.start_frame}:{t.end_frame}" for t in want], li
+    e.close()
+    assert lines[8].split()[1:] == lines[3].split()[1:] and lines[8].startswith("PLAIN")
+    assert lines[9].startswith("ERR Cannot open audio file")
 
 
 # ------------------------------------------------------------------ tdt-600m preset (BASELINE config 3)
@@ -660,3 +672,38 @@ def test_gpu_resampler_matches_oracle_and_feeds_the_path(pkg, O, synth, tiny, re
     got = e.transcribe_batch_rate(pcm22, 22050, pkg.Decoder.TDT)
     assert [_tt(a) for a in got] == [_tt(b) for b in want]
     e.close()
+
+
+# ------------------------------------------------------------------ phrase-boosted decode on the device
+def test_boosted_decode_on_device_matches_reference_golden(pkg, eng_tiny, O, tiny, golden):
+    """pk_set_boost + pk_decode (CTC and TDT) against the compiled reference's ctc_/tdt_greedy_decode_with_timestamps_boosted
+    (golden_boost_v1.npz): boosted first-max argmax, trie advance on every emission, confidence = exp(raw log-prob);
+    a batch of all cases' utterances at once (per-utterance trie state), the livelocking TDT cases only through their
+    token capacity; and the boost is really off again after clearing it."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_boost_v1.npz"))
+    changed = 0
+    for n in range(int(g["n_cases"][0])):
+        k = f"boost.k{n}."
+        ci = int(g[k + "clip"][0])
+        boost = float(g[k + "boost"][0])
+        ids, lens = g[k + "ph_ids"], g[k + "ph_len"]
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        phrases = [ids[offs[i]:offs[i + 1]].tolist() for i in range(len(lens))]
+        enc = golden[f"tiny.c{ci}.enc"]
+        eng_tiny.set_boost(phrases, boost)
+        # the same utterance three times in one batch: every row keeps its own trie state
+        ctc = eng_tiny.decode([enc, enc[:max(4, len(enc) // 2)], enc], pkg.Decoder.CTC)
+        assert [list(t) for t in _tt(ctc[0])] == g[k + "ctc_tok"].tolist(), n
+        assert _tt(ctc[2]) == _tt(ctc[0])
+        assert np.allclose([t.confidence for t in ctc[0]], g[k + "ctc_conf"], rtol=1e-3, atol=1e-6)
+        if not int(g[k + "tdt_livelock"][0]):
+            tdt = eng_tiny.decode([enc, enc], pkg.Decoder.TDT)
+            assert [list(t) for t in _tt(tdt[0])] == g[k + "tdt_tok"].tolist(), n
+            assert _tt(tdt[1]) == _tt(tdt[0])
+            assert np.allclose([t.confidence for t in tdt[0]], g[k + "tdt_conf"], rtol=1e-3, atol=1e-6)
+        eng_tiny.set_boost([], 0.0)
+        plain = eng_tiny.decode([enc], pkg.Decoder.CTC)[0]
+        assert [list(t) for t in _tt(plain)] == golden[f"tiny.c{ci}.ctc_tok"].tolist()
+        changed += _tt(plain) != _tt(ctc[0])
+    assert changed >= 6
+    assert [list(t) for t in _tt(eng_tiny.decode([golden["tiny.c0.enc"]], pkg.Decoder.TDT)[0])] == golden["tiny.c0.tdt_tok"].tolist()
