@@ -172,8 +172,10 @@ inline std::vector<int> ctc_greedy_decode_boosted(const float *log_probs, int n_
     return ids;
 }
 
-// ─── minimal read_audio (audio_io.hpp): 16 kHz mono PCM16 / float32 WAV ──────
-inline std::vector<float> read_audio(const std::string &path) {
+// ─── minimal read_audio (audio_io.hpp): mono-mixed PCM16 / float32 WAV ───────
+// read_audio_native keeps the file's own sample rate (Transcriber::transcribe(path) converts on the DEVICE,
+// pk_stage_pcm_rate); read_audio resamples to 16 kHz on the host like the reference's (audio_io.cpp:227-232).
+inline std::vector<float> read_audio_native(const std::string &path, int &sample_rate) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("Cannot open audio file: " + path);
     std::vector<char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
@@ -216,6 +218,12 @@ inline std::vector<float> read_audio(const std::string &path) {
     } else {
         throw std::runtime_error("unsupported WAV encoding: " + path);
     }
+    sample_rate = (int)sr;
+    return mono;
+}
+inline std::vector<float> read_audio(const std::string &path) {
+    int sr = 16000;
+    auto mono = read_audio_native(path, sr);
     if (sr != 16000) {   // read_audio resamples to the target rate (audio_io.cpp:123-195, :227-232)
         std::vector<float> r((size_t)std::max<int64_t>(pk_resample_len((int64_t)mono.size(), (int32_t)sr, 16000), 0));
         pk_resample(mono.data(), (int64_t)mono.size(), (int32_t)sr, 16000, r.data(), (int64_t)r.size());
@@ -244,7 +252,8 @@ class EngineHolder {
     EngineHolder &operator=(const EngineHolder &) = delete;
     ~EngineHolder() { pk_engine_destroy(e_); }
 
-    std::vector<std::vector<TimestampedToken>> run(const std::vector<const float *> &pcm, const std::vector<size_t> &n, pk_decoder dec) {
+    std::vector<std::vector<TimestampedToken>> run(const std::vector<const float *> &pcm, const std::vector<size_t> &n, pk_decoder dec,
+                                                   int sample_rate = 16000) {
         const int B = (int)pcm.size();
         std::vector<int64_t> off(B + 1, 0);
         for (int i = 0; i < B; ++i) off[i + 1] = off[i] + (int64_t)n[i];
@@ -253,8 +262,12 @@ class EngineHolder {
         std::vector<int32_t> ids((size_t)B * cap_), st((size_t)B * cap_), en((size_t)B * cap_), len(B);
         std::vector<float> cf((size_t)B * cap_);
         pk_tokens t{cap_, ids.data(), st.data(), en.data(), cf.data(), len.data()};
-        if (pk_transcribe_batch(e_, buf.data(), off.data(), B, dec, &t) != PK_OK)
-            throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(e_));
+        // 16 kHz: the blocking whole-path call; any other rate: raw samples to the device, polyphase conversion there
+        const bool ok = sample_rate == 16000
+                            ? pk_transcribe_batch(e_, buf.data(), off.data(), B, dec, &t) == PK_OK
+                            : (pk_stage_pcm_rate(e_, buf.data(), off.data(), B, sample_rate) == PK_OK && pk_run_staged(e_, dec) == PK_OK &&
+                               pk_fetch_tokens(e_, &t) == PK_OK);
+        if (!ok) throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(e_));
         std::vector<std::vector<TimestampedToken>> out(B);
         for (int b = 0; b < B; ++b)
             for (int i = 0; i < len[b]; ++i)
@@ -284,11 +297,12 @@ class TranscriberBase {
     void to_gpu() {}   // the reference moves weights to Metal here (transcribe.hpp:68-71); we are always on the device
 
     TranscribeResult transcribe(const std::string &audio_path, const TranscribeOptions &opts) {
-        auto s = read_audio(audio_path);
-        return transcribe(s.data(), s.size(), opts);
+        int sr = 16000;
+        auto s = read_audio_native(audio_path, sr);
+        return transcribe(s.data(), s.size(), opts, sr);
     }
     TranscribeResult transcribe(const std::vector<float> &samples, const TranscribeOptions &opts) { return transcribe(samples.data(), samples.size(), opts); }
-    TranscribeResult transcribe(const float *samples, size_t n, const TranscribeOptions &opts) {
+    TranscribeResult transcribe(const float *samples, size_t n, const TranscribeOptions &opts, int sample_rate = 16000) {
         // phrase boosting (transcribe.hpp:110-137, :158-165): the ContextTrie and the boosted decode live on the device
         struct BoostGuard {
             pk_engine *e; bool on;
@@ -303,7 +317,7 @@ class TranscriberBase {
                 guard.on = true;
             }
         }
-        auto toks = eng_->run({samples}, {n}, self().pick(opts.decoder))[0];
+        auto toks = eng_->run({samples}, {n}, self().pick(opts.decoder), sample_rate)[0];
         return finish(toks, opts.timestamps);
     }
     // Not in the reference (batch-1 only): one call for many utterances.

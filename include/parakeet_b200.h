@@ -207,6 +207,11 @@ pk_status pk_stream_step(pk_engine *e, const float *pcm, const int64_t *offsets,
                          int32_t *n_mel, float *enc_out, int32_t *n_enc);
 int32_t pk_stream_count(const pk_engine *e);
 
+/* Host-only probe of the checkpoint reader (safetensors::load, axiom io_safetensors.cpp:16-160: F32 / F16 / BF16 / F64
+ * tensors, converted to fp32): opens the file (PK_ERR_IO + pk_last_error(NULL) on a malformed header), and if `name` is
+ * given converts that tensor into out[0 .. cap) and reports its element count.  Needs no device. */
+pk_status pk_safetensors_probe(const char *path, const char *name, float *out, int64_t cap, int64_t *numel);
+
 /* Number of utterances of the last pk_fetch_tokens whose TDT hypothesis was cut at the engine's token capacity
  * (2 T'max + 8 per utterance; only reachable on inputs that livelock the reference's tdt_greedy_decode, which
  * never forces an advance after max_symbols_per_step, src/tdt.cpp:66-104). */

@@ -453,8 +453,29 @@ pk_status pk_engine::upload_shapes() {
 
 // ===================================================================== pipeline
 
+const CUtensorMap *pk_engine::out_map(const void *ptr, bool is_f32, int rows, int ld) {
+    auto key = std::make_tuple(ptr, (int)is_f32, rows, ld);
+    auto it = out_maps.find(key);
+    if (it != out_maps.end()) return &it->second;
+    CUtensorMap m;
+    if (!make_tc_out_map(&m, ptr, is_f32, (uint64_t)rows, (uint64_t)ld)) return nullptr;
+    if (out_maps.size() > 4096) out_maps.clear();          // (shape-varying batches: bounded; maps are rebuilt on demand)
+    return &(out_maps[key] = m);
+}
+
 void pk_engine::gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiParams epi) {
     epi.bias = W.bias;
+    if (tma_out && cfg.math != PK_MATH_FP32 && epi.kind != EPI_RESID_F32 && M_ > 0) {
+        // results leave the SM through the TMA engine (UTMASTG) wherever the tile is interior (gemm_tc.cu: epilogue_slab64)
+        const bool act_kind = epi.kind == EPI_BIAS_RELU_ACT || epi.kind == EPI_BIAS_SILU_ACT || epi.kind == EPI_BIAS_ACT || epi.kind == EPI_QKV_ACT;
+        if (act_kind && epi.act.hi) {
+            const CUtensorMap *m0 = out_map(epi.act.hi, false, M_, epi.ldo), *m1 = epi.act.lo ? out_map(epi.act.lo, false, M_, epi.ldo) : nullptr;
+            if (m0 && (m1 || !epi.act.lo)) { epi.tma_out = 1; epi.tm_out0 = m0; epi.tm_out1 = m1; }
+        } else if (!act_kind && epi.out_f32) {
+            const CUtensorMap *m0 = out_map(epi.out_f32, true, M_, epi.ldo);
+            if (m0) { epi.tma_out = 1; epi.tm_out0 = m0; }
+        }
+    }
     Scope sc(this, CAT_GEMM, 2.0 * M_ * W.N * W.K);
     if (cfg.math == PK_MATH_FP32) {
         launch_gemm_simt(A.f32, lda, W.w, W.K, M_, W.N, W.K, epi, stream);
@@ -856,6 +877,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     e->cfg = c;
     if (const char *ev = getenv("PK_GRAPH")) e->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("PK_ATTN_TC")) e->attn_tc = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_GEMM_TMA_OUT")) e->tma_out = atoi(ev) != 0;
     e->device = device;
     if (cudaSetDevice(device) != cudaSuccess) {
         g_create_err = "cudaSetDevice failed";
@@ -1021,6 +1043,12 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
         ep.out_f32 = o_tc;
         ActBuf tc_act; tc_act.hi = oh; tc_act.lo = ol;
         ep.act = tc_act;
+        CUtensorMap om0, om1;
+        if (getenv("PK_GEMM_TMA_OUT") && atoi(getenv("PK_GEMM_TMA_OUT")) && epi_kind != EPI_RESID_F32) {
+            const bool ok = act_out ? (make_tc_out_map(&om0, oh, false, M, No) && make_tc_out_map(&om1, ol, false, M, No))
+                                    : make_tc_out_map(&om0, o_tc, true, M, No);
+            if (ok) { ep.tma_out = 1; ep.tm_out0 = &om0; ep.tm_out1 = act_out ? &om1 : nullptr; }
+        }
         if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st) != cudaSuccess) rc = PK_ERR_CUDA;
         if (rc == PK_OK && getenv("PK_SELFTEST_TIME")) {   // warm, back-to-back timing of the tcgen05 launch
             cudaEvent_t e0, e1;
@@ -1520,6 +1548,27 @@ pk_status pk_set_boost(pk_engine *e, const int32_t *phrase_ids, const int32_t *p
     }
     e->boost = boost;
     e->boost_on = true;
+    return PK_OK;
+}
+
+// Host-only probe of the checkpoint reader (safetensors.cpp): opens `path`, converts tensor `name` to fp32.  No device.
+pk_status pk_safetensors_probe(const char *path, const char *name, float *out, int64_t cap, int64_t *numel) {
+    if (!path) return PK_ERR_INVALID;
+    SafeTensors st;
+    std::string err;
+    if (!st.open(path, err)) {
+        g_create_err = err;
+        return PK_ERR_IO;
+    }
+    if (!name) return PK_OK;
+    std::vector<float> v;
+    if (!st.read_f32(name, v, -1, err)) {
+        g_create_err = err;
+        return st.find(name) ? PK_ERR_IO : PK_ERR_MISSING;
+    }
+    if (numel) *numel = (int64_t)v.size();
+    if (out)
+        for (int64_t i = 0; i < cap && i < (int64_t)v.size(); ++i) out[i] = v[i];
     return PK_OK;
 }
 

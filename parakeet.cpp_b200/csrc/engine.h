@@ -10,6 +10,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/parakeet_b200.h"
@@ -236,6 +237,10 @@ struct pk_engine {
     pk_status set_batch_shapes(const int32_t *n_frames_or_null, const int64_t *offsets_or_null, int n);
     pk_status upload_shapes();
     void gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiParams epi);
+    // output-side tensor maps of the TMA-store epilogue, keyed by (buffer, leading dimension, rows)
+    std::map<std::tuple<const void *, int, int, int>, CUtensorMap> out_maps;
+    const CUtensorMap *out_map(const void *ptr, bool is_f32, int rows, int ld);
+    bool tma_out = true;                       // PK_GEMM_TMA_OUT=0: results leave through st.global instead
     pk_status gemm_err = PK_OK;
     pk_status run_mel(int u0 = 0, int u1 = -1);
     pk_status run_conv1(int u0 = 0, int u1 = -1);

@@ -323,6 +323,24 @@ __device__ __forceinline__ void store_tile128(uint32_t stg_s, int lane, const ui
     __syncwarp();
 }
 
+// The same 32 x 128 B tile leaves through the TMA engine: staged exactly in the SWIZZLE_128B layout of the output map
+// (16-byte chunk c of row r at chunk c ^ (r & 7): what store_tile128 writes), one lane issues cp.async.bulk.tensor
+// shared -> global (rows past M are clipped by the map) and waits until the engine has read the tile.
+__device__ __forceinline__ void tma_store_tile(uint32_t stg_s, int lane, const uint32_t *r, const CUtensorMap *tm, int col, int row0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        sts128(stg_s + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(stg_s), "r"(col), "r"(row0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t &hi, uint32_t &lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     const float2 hf = __bfloat1622float2(h);
@@ -343,8 +361,9 @@ __device__ __forceinline__ bool wide_ok(const EpiParams &epi, int gcol0, int N) 
 
 template <int EK, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, int row0, int gcol0, int M, const EpiParams &epi_param,
-                                                int lane, ReleaseFn release, bool last_slab) {
+                                                int lane, ReleaseFn release, bool last_slab, const CUtensorMap *tm0, const CUtensorMap *tm1) {
     const EpiParams epi = epi_param;
+    const bool tma = epi.tma_out != 0;
     uint32_t a0[32], a1[32];
     tmem_ld32_issue(taddr, a0);
     tmem_ld32_issue(taddr + 32u, a1);
@@ -383,7 +402,8 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
             uint32_t r[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-            store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob, rb, ldb, row0, M);
+            if (tma && EK != EPI_RESID_F32) tma_store_tile(stg_s, lane, r, tm0, gcol0, row0);
+            else store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob, rb, ldb, row0, M);
         }
         {
             float v[32];
@@ -391,7 +411,8 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
             uint32_t r[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-            store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob + 128, rb + 128, ldb, row0, M);
+            if (tma && EK != EPI_RESID_F32) tma_store_tile(stg_s, lane, r, tm0, gcol0 + 32, row0);
+            else store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob + 128, rb + 128, ldb, row0, M);
         }
     } else if (EK == EPI_GLU_F32) {
         uint32_t r[32];
@@ -407,7 +428,8 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
 #pragma unroll
             for (int k = 0; k < 16; ++k) r[16 + k] = __float_as_uint(v[2 * k] * fast_sigmoid(v[2 * k + 1]));
         }
-        store_tile128<false>(stg_s, lane, r, reinterpret_cast<uint8_t *>(epi.out_f32 + (gcol0 >> 1)), nullptr, (size_t)epi.ldo * 4, row0, M);
+        if (tma) tma_store_tile(stg_s, lane, r, tm0, gcol0 >> 1, row0);
+        else store_tile128<false>(stg_s, lane, r, reinterpret_cast<uint8_t *>(epi.out_f32 + (gcol0 >> 1)), nullptr, (size_t)epi.ldo * 4, row0, M);
     } else {
         // bf16 hi / lo planes: 64 columns = 128 B per lane and plane
         const size_t ldb = (size_t)epi.ldo * 2;
@@ -441,8 +463,13 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
                 }
             }
             const int col = dcol + var * epi.qcols;
-            store_tile128<false>(stg_s, lane, hi, reinterpret_cast<uint8_t *>(epi.act.hi + col), nullptr, ldb, row0, M);
-            if (epi.act.lo) store_tile128<false>(stg_s, lane, lo, reinterpret_cast<uint8_t *>(epi.act.lo + col), nullptr, ldb, row0, M);
+            if (tma) {
+                tma_store_tile(stg_s, lane, hi, tm0, col, row0);
+                if (epi.act.lo) tma_store_tile(stg_s, lane, lo, tm1, col, row0);
+            } else {
+                store_tile128<false>(stg_s, lane, hi, reinterpret_cast<uint8_t *>(epi.act.hi + col), nullptr, ldb, row0, M);
+                if (epi.act.lo) store_tile128<false>(stg_s, lane, lo, reinterpret_cast<uint8_t *>(epi.act.lo + col), nullptr, ldb, row0, M);
+            }
         }
     }
 }
@@ -471,7 +498,8 @@ template <int BN, int NPASS, int EK>
 __global__ void __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-               int K, const __grid_constant__ EpiParams epi, int dbg) {
+               int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
+               const __grid_constant__ CUtensorMap tmO1) {
     using C = TcCfg<BN, NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -592,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             };
             if (BN == 128 && !(dbg & 64) && wide_ok<EK>(epi, n0 + half * 64, N))
-                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, n0 + half * 64, M, epi, lane, release, true);
+                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, n0 + half * 64, M, epi, lane, release, true, &tmO0, &tmO1);
             else
                 epilogue_slab<BN / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN / 2), M, N, epi, lane, release, dbg);
             if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
@@ -671,7 +699,8 @@ template <int NPASS, int EK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-                int K, const __grid_constant__ EpiParams epi, int dbg) {
+                int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
+                const __grid_constant__ CUtensorMap tmO1) {
     using C = Tc2Cfg<NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -796,8 +825,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             };
             const int gc = n0 + half * (BN2 / 2);
             if (!(dbg & 64) && wide_ok<EK>(epi, gc, N) && wide_ok<EK>(epi, gc + 64, N)) {
-                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, gc, M, epi, lane, release, false);
-                epilogue_slab64<EK>(taddr + 64u, stg_s, m0 + q * 32, gc + 64, M, epi, lane, release, true);
+                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, gc, M, epi, lane, release, false, &tmO0, &tmO1);
+                epilogue_slab64<EK>(taddr + 64u, stg_s, m0 + q * 32, gc + 64, M, epi, lane, release, true, &tmO0, &tmO1);
             } else {
                 epilogue_slab<BN2 / 2, EK>(taddr, stg_s, m0 + q * 32, gc, M, N, epi, lane, release, dbg);
             }
@@ -847,7 +876,12 @@ cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K
     const int num_tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
     dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    gemm_tc_kernel<BN, NPASS, EK><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi, g_dbg);
+    EpiParams ep = epi;
+    const bool tma = ep.tma_out && ep.tm_out0 && BN == 128;
+    ep.tma_out = tma ? 1 : 0;
+    const CUtensorMap &o0 = tma ? *static_cast<const CUtensorMap *>(ep.tm_out0) : A.hi;
+    const CUtensorMap &o1 = (tma && ep.tm_out1) ? *static_cast<const CUtensorMap *>(ep.tm_out1) : o0;
+    gemm_tc_kernel<BN, NPASS, EK><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1);
     return cudaGetLastError();
 }
 
@@ -869,7 +903,12 @@ cudaError_t launch_k2(const TcOperand &A, const TcOperand &W, int M, int N, int 
     const int num_tiles = ((N + BN2 - 1) / BN2) * ((M + 2 * BM - 1) / (2 * BM));
     const int pairs = num_tiles < num_sms / 2 ? num_tiles : num_sms / 2;
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    gemm_tc2_kernel<NPASS, EK><<<dim3(2 * pairs), TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, epi, g_dbg);
+    EpiParams ep = epi;
+    const bool tma = ep.tma_out && ep.tm_out0;
+    ep.tma_out = tma ? 1 : 0;
+    const CUtensorMap &o0 = tma ? *static_cast<const CUtensorMap *>(ep.tm_out0) : A.hi;
+    const CUtensorMap &o1 = (tma && ep.tm_out1) ? *static_cast<const CUtensorMap *>(ep.tm_out1) : o0;
+    gemm_tc2_kernel<NPASS, EK><<<dim3(2 * pairs), TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1);
     return cudaGetLastError();
 }
 
@@ -920,6 +959,19 @@ bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t ro
         return false;
     out->box_rows = box_rows;
     return true;
+}
+
+bool make_tc_out_map(CUtensorMap *out, const void *ptr, bool is_f32, uint64_t rows, uint64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    const uint64_t esz = is_f32 ? 4 : 2;
+    if (!fn || !ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esz) & 15) || rows == 0) return false;
+    const cuuint64_t gdim[2] = {ld, rows};
+    const cuuint64_t gstr[1] = {ld * esz};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int tc_tile_n(int N) { return N <= 64 ? 64 : 128; }

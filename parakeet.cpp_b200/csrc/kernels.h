@@ -81,6 +81,9 @@ struct TcOperand {
     uint32_t box_rows = 0;
 };
 bool make_tc_operand(TcOperand *out, const bf16 *hi, const bf16 *lo, uint64_t rows, uint64_t K, uint32_t box_rows);
+// Output-side tensor map for the TMA-store epilogue: [rows][ld] matrix of bf16 (is_f32 = false: box 64 x 32) or fp32
+// (box 32 x 32), 128-byte inner box, SWIZZLE_128B.
+bool make_tc_out_map(CUtensorMap *out, const void *ptr, bool is_f32, uint64_t rows, uint64_t ld);
 int tc_tile_n(int N);
 void tc_set_2cta(bool on);   // debug/measurement switch: use the cta_group::2 kernel for N >= 256 (default off; PK_GEMM_2CTA=1)   // N-tile (= box_rows of the weight operand) chosen for an [N][K] weight
 void tc_set_debug(int bits); // measurement aid (PK_GEMM_DBG): bit 0 = skip the epilogue's work, bit 1 = skip the TMA loads (results are garbage)

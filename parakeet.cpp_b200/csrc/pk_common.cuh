@@ -86,6 +86,11 @@ struct EpiParams {
     float alpha = 1.0f;
     const float *bias_u = nullptr, *bias_v = nullptr;   // EPI_QKV_ACT: pos_bias_u / pos_bias_v, [qcols]
     int qcols = 0;
+    // tcgen05 kernels only: results leave the SM by TMA (cp.async.bulk.tensor shared -> global) instead of st.global.
+    // tm_out0 / tm_out1 are HOST pointers to CUtensorMaps of the output (fp32 matrix, or the bf16 hi / lo planes) with a
+    // 32-row x 128-byte box, SWIZZLE_128B (make_tc_out_map); the launcher copies them into kernel parameters.
+    int tma_out = 0;
+    const void *tm_out0 = nullptr, *tm_out1 = nullptr;
 };
 
 // Generic (edge-tile / run-time-kind) path; out of line so that it does not bloat the hot loops.

@@ -16,6 +16,7 @@ namespace {
 struct JsonCur {
     const char *p, *e;
     bool fail = false;
+    int depth = 0;                 // nesting of skip_value (bounded: a hostile header must not overflow the stack)
     void ws() {
         while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
     }
@@ -41,7 +42,11 @@ struct JsonCur {
                 switch (*p) {
                 case 'n': s += '\n'; break;
                 case 't': s += '\t'; break;
-                case 'u': s += '?'; p += 4; break;
+                case 'u':
+                    s += '?';
+                    if (e - p < 5) { fail = true; return s; }      // \uXXXX must lie inside the header
+                    p += 4;
+                    break;
                 default: s += *p;
                 }
                 ++p;
@@ -53,15 +58,39 @@ struct JsonCur {
         ++p;
         return s;
     }
+    // JSON number inside [p, e): copied to a NUL-terminated buffer first (the mmap is not terminated)
     double num() {
         ws();
+        char buf[64];
+        size_t n = 0;
+        while (p + n < e && n < sizeof(buf) - 1 && (strchr("+-.eE", p[n]) || (p[n] >= '0' && p[n] <= '9'))) {
+            buf[n] = p[n];
+            ++n;
+        }
+        buf[n] = 0;
         char *end = nullptr;
-        double v = strtod(p, &end);
-        if (end == p) fail = true;
-        p = end;
+        double v = strtod(buf, &end);
+        if (n == 0 || end != buf + n) fail = true;
+        p += n;
+        return v;
+    }
+    // non-negative integer (shape entries, data offsets): digits only, overflow-checked
+    uint64_t uint() {
+        ws();
+        uint64_t v = 0;
+        const char *s0 = p;
+        while (p < e && *p >= '0' && *p <= '9') {
+            const uint64_t d = (uint64_t)(*p - '0');
+            if (v > (UINT64_MAX - d) / 10) { fail = true; return 0; }
+            v = v * 10 + d;
+            ++p;
+        }
+        if (p == s0) fail = true;          // (a '-' or any other character: not a valid size)
         return v;
     }
     void skip_value() {
+        struct Depth { int &d; Depth(int &x) : d(x) { ++d; } ~Depth() { --d; } } guard(depth);
+        if (depth > 64) { fail = true; return; }
         ws();
         if (p >= e) { fail = true; return; }
         if (*p == '"') { str(); return; }
@@ -83,9 +112,9 @@ struct JsonCur {
             if (!eat(']')) fail = true;
             return;
         }
-        if (!strncmp(p, "true", 4)) { p += 4; return; }
-        if (!strncmp(p, "false", 5)) { p += 5; return; }
-        if (!strncmp(p, "null", 4)) { p += 4; return; }
+        if (e - p >= 4 && !strncmp(p, "true", 4)) { p += 4; return; }
+        if (e - p >= 5 && !strncmp(p, "false", 5)) { p += 5; return; }
+        if (e - p >= 4 && !strncmp(p, "null", 4)) { p += 4; return; }
         num();
     }
 };
@@ -168,14 +197,18 @@ bool SafeTensors::open(const std::string &path, std::string &err) {
                 } else if (key == "shape") {
                     if (!c.eat('[')) { c.fail = true; break; }
                     if (!c.eat(']')) {
-                        do t.shape.push_back((int64_t)c.num()); while (!c.fail && c.eat(','));
+                        do {
+                            const uint64_t dim = c.uint();
+                            if (dim > (uint64_t)INT64_MAX) c.fail = true;
+                            t.shape.push_back((int64_t)dim);
+                        } while (!c.fail && c.eat(','));
                         if (!c.eat(']')) c.fail = true;
                     }
                 } else if (key == "data_offsets") {
                     if (!c.eat('[')) { c.fail = true; break; }
-                    t.begin = (uint64_t)c.num();
+                    t.begin = c.uint();
                     if (!c.eat(',')) c.fail = true;
-                    t.end = (uint64_t)c.num();
+                    t.end = c.uint();
                     if (!c.eat(']')) c.fail = true;
                 } else {
                     c.skip_value();
@@ -183,7 +216,7 @@ bool SafeTensors::open(const std::string &path, std::string &err) {
             } while (!c.fail && c.eat(','));
             if (!c.eat('}')) c.fail = true;
             if (c.fail) break;
-            if (t.end < t.begin || data_base_ + t.end > map_len_) {
+            if (t.end < t.begin || t.end > map_len_ - data_base_) {     // (no wrap-around: data_base_ <= map_len_)
                 err = "safetensors: tensor '" + name + "' data out of range";
                 return false;
             }
@@ -210,6 +243,10 @@ bool SafeTensors::read_f32(const std::string &name, std::vector<float> &out, int
         return false;
     }
     const int64_t n = t->numel();
+    if (n < 0) {
+        err = "tensor '" + name + "': shape overflows";
+        return false;
+    }
     if (expect_numel >= 0 && n != expect_numel) {
         err = "tensor '" + name + "' has " + std::to_string(n) + " elements, expected " + std::to_string(expect_numel);
         return false;

@@ -18,9 +18,12 @@ struct StTensor {
     std::string dtype;
     std::vector<int64_t> shape;
     uint64_t begin = 0, end = 0;   // byte offsets into the data section
-    int64_t numel() const {
+    int64_t numel() const {        // -1 on overflow
         int64_t n = 1;
-        for (auto s : shape) n *= s;
+        for (int64_t d : shape) {
+            if (d < 0 || (d != 0 && n > INT64_MAX / d)) return -1;
+            n *= d;
+        }
         return n;
     }
 };

@@ -50,7 +50,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
            "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count",
            "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count", "pk_stage_pcm_rate", "pk_resample_batch",
-           "pk_set_boost", "pk_vocab_max_piece_bytes"]
+           "pk_set_boost", "pk_vocab_max_piece_bytes", "pk_safetensors_probe"]
 
 _lib = None
 
@@ -124,6 +124,7 @@ def load_library():
     L.pk_stream_step.argtypes = [vp, f32p, i64p, C.POINTER(_PkTokens), f32p, i32p, f32p, i32p]
     L.pk_stream_count.argtypes = [vp]
     L.pk_set_boost.argtypes = [vp, i32p, i32p, C.c_int32, C.c_float]
+    L.pk_safetensors_probe.argtypes = [C.c_char_p, C.c_char_p, f32p, C.c_int64, i64p]
     L.pk_stage_pcm_rate.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int32]
     L.pk_resample_batch.argtypes = [vp, f32p, i64p, C.c_int32, C.c_int32, C.c_int32, f32p, i64p]
     _lib = L
@@ -249,6 +250,16 @@ class TranscribeOptions:              # transcribe.hpp:38-43
     timestamps: bool = False
     boost_phrases: List[str] = field(default_factory=list)
     boost_score: float = 5.0
+
+
+def safetensors_probe(path: str, name: Optional[str] = None, cap: int = 0):
+    """Host-only check of the checkpoint reader: -> (status, message, values | None)."""
+    L = load_library()
+    out = np.zeros(max(cap, 1), np.float32)
+    n = C.c_int64(0)
+    st = L.pk_safetensors_probe(path.encode(), name.encode() if name else None, _f32p(out), cap, C.byref(n))
+    msg = L.pk_last_error(None).decode() if st != 0 else ""
+    return st, msg, (out[:min(cap, n.value)].copy() if (st == 0 and name) else None)
 
 
 def selftest_gemm(M, N, K, epi_kind, math=0, seed=1, device=0):

@@ -44,6 +44,12 @@ int main(int argc, char **argv) {
             for (auto &tk : r.timestamped_tokens) std::cout << " " << tk.token_id << ":" << tk.start_frame << ":" << tk.end_frame;
             std::cout << "\n";
         }
+        if (argc > 6) {      // a WAV that is not 16 kHz: converted on the device (pk_stage_pcm_rate)
+            auto r = t.transcribe(std::string(argv[6]), parakeet::Decoder::TDT, true);
+            std::cout << "RATE";
+            for (auto &tk : r.timestamped_tokens) std::cout << " " << tk.token_id << ":" << tk.start_frame << ":" << tk.end_frame;
+            std::cout << "\n";
+        }
         try {
             t.transcribe(std::string("/nonexistent.wav"));
             return 3;

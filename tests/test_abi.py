@@ -194,3 +194,57 @@ def test_synth_checkpoint_layout(O, synth):
     assert len(specs) == 705
     n = sum(int(np.prod(s)) for _, s, k in specs if k != "i64")
     assert abs(n - 114.6e6) < 0.1e6
+
+
+def _write_st(path, header_json: bytes, data: bytes = b""):
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(header_json)) + header_json + data)
+
+
+def test_safetensors_reader_dtypes_and_hostile_headers(pkg, tmp_path):
+    """The checkpoint reader (csrc/safetensors.cpp) on the host: F32 / F16 / BF16 / F64 tensors convert to the expected fp32
+    values (safetensors::load, axiom io_safetensors.cpp:16-44), and malformed headers are refused instead of read out of
+    bounds: negative or overflowing sizes, offsets past the file, an unterminated escape, bottomless nesting."""
+    import json
+    from parakeet_cpp_b200.engine import safetensors_probe
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal(37) * 3).astype(np.float32)
+    import torch
+    parts = {"a32": (x.tobytes(), "F32"), "a16": (x.astype(np.float16).tobytes(), "F16"),
+             "ab16": (torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().tobytes(), "BF16"),
+             "a64": (x.astype(np.float64).tobytes(), "F64")}
+    hdr, blob = {"__metadata__": {"format": "pt", "nested": {"k": [1, 2, {"z": None}]}}}, b""
+    for k, (b, dt) in parts.items():
+        hdr[k] = {"dtype": dt, "shape": [37], "data_offsets": [len(blob), len(blob) + len(b)]}
+        blob += b
+    p = str(tmp_path / "ok.safetensors")
+    _write_st(p, json.dumps(hdr).encode(), blob)
+    st, msg, v = safetensors_probe(p, "a32", 37)
+    assert st == 0 and np.array_equal(v, x)
+    assert np.array_equal(safetensors_probe(p, "a16", 37)[2], x.astype(np.float16).astype(np.float32))
+    assert np.array_equal(safetensors_probe(p, "ab16", 37)[2], torch.from_numpy(x).to(torch.bfloat16).float().numpy())
+    assert np.array_equal(safetensors_probe(p, "a64", 37)[2], x)
+    assert safetensors_probe(p, "nope", 1)[0] == 4                                    # PK_ERR_MISSING
+    bad = {
+        "neg_shape": b'{"t":{"dtype":"F32","shape":[-4],"data_offsets":[0,16]}}',
+        "huge_offset": b'{"t":{"dtype":"F32","shape":[4],"data_offsets":[0,18446744073709551615]}}',
+        "overflow_offset": b'{"t":{"dtype":"F32","shape":[4],"data_offsets":[0,99999999999999999999999]}}',
+        "float_offset": b'{"t":{"dtype":"F32","shape":[4],"data_offsets":[0,1e30]}}',
+        "end_before_begin": b'{"t":{"dtype":"F32","shape":[4],"data_offsets":[16,0]}}',
+        "cut_escape": b'{"t\\u12',
+        "deep": b'{"__metadata__":' + b"[" * 5000 + b"]" * 5000 + b"}",
+        "not_object": b'[1,2,3]',
+    }
+    for name, h in bad.items():
+        q = str(tmp_path / (name + ".safetensors"))
+        _write_st(q, h, b"\0" * 16)
+        assert safetensors_probe(q)[0] == 2, name                                     # PK_ERR_IO, no crash
+    q = str(tmp_path / "shape_overflow.safetensors")
+    _write_st(q, b'{"t":{"dtype":"F32","shape":[4294967296,4294967296,4],"data_offsets":[0,16]}}', b"\0" * 16)
+    st, msg, _ = safetensors_probe(q, "t", 4)
+    assert st == 2 and "overflow" in msg
+    q = str(tmp_path / "hdr_len.safetensors")
+    with open(q, "wb") as f:
+        f.write(b"\xff" * 8 + b"{}")
+    assert safetensors_probe(q)[0] == 2

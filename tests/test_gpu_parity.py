@@ -400,7 +400,12 @@ def test_cpp_shim(pkg, O, tiny, synth, golden, tmp_path):
         f.write(i16.tobytes())
     # a phrase for TranscribeOptions::boost_phrases: three vocabulary pieces as text
     phrase = "".join(tiny.pieces[i] for i in (7, 11, 5)).replace(O.SP_MARK, " ").strip()
-    out = subprocess.run([exe, tiny.weights_path, tiny.vocab_path, wav, "tiny", phrase], check=True, capture_output=True, text=True).stdout
+    wav22 = str(tmp_path / "b.wav")                                      # the same samples declared as 22.05 kHz
+    with open(wav22, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + 2 * len(i16)) + b"WAVEfmt " +
+                struct.pack("<IHHIIHH", 16, 1, 1, 22050, 44100, 2, 16) + b"data" + struct.pack("<I", 2 * len(i16)))
+        f.write(i16.tobytes())
+    out = subprocess.run([exe, tiny.weights_path, tiny.vocab_path, wav, "tiny", phrase, wav22], check=True, capture_output=True, text=True).stdout
     lines = out.strip().split("\n")
     tdt = [[int(x) for x in t.split(":")] for t in lines[0].split()[1:]]
     assert tdt == golden[k + "tdt_tok"].tolist()
@@ -417,9 +422,12 @@ def test_cpp_shim(pkg, O, tiny, synth, golden, tmp_path):
     for li, dec in ((6, pkg.Decoder.CTC), (7, pkg.Decoder.TDT)):
         want = e.transcribe_batch([wav_pcm], dec)[0]
         assert lines[li].split()[1:] == [f"{t.token_id}:{t.start_frame}:{t.end_frame}" for t in want], li
+    e.set_boost([], 0.0)
+    want22 = e.transcribe_batch_rate([wav_pcm], 22050, pkg.Decoder.TDT)[0]
     e.close()
     assert lines[8].split()[1:] == lines[3].split()[1:] and lines[8].startswith("PLAIN")
-    assert lines[9].startswith("ERR Cannot open audio file")
+    assert lines[9].startswith("RATE") and lines[9].split()[1:] == [f"{t.token_id}:{t.start_frame}:{t.end_frame}" for t in want22]
+    assert lines[10].startswith("ERR Cannot open audio file")
 
 
 # ------------------------------------------------------------------ tdt-600m preset (BASELINE config 3)
@@ -707,3 +715,44 @@ def test_boosted_decode_on_device_matches_reference_golden(pkg, eng_tiny, O, tin
         changed += _tt(plain) != _tt(ctc[0])
     assert changed >= 6
     assert [list(t) for t in _tt(eng_tiny.decode([golden["tiny.c0.enc"]], pkg.Decoder.TDT)[0])] == golden["tiny.c0.tdt_tok"].tolist()
+
+
+def test_f16_and_bf16_checkpoints_load_like_their_f32_roundings(pkg, tiny, synth, tmp_path):
+    """Checkpoint dtypes other than F32 (safetensors::load, axiom io_safetensors.cpp:16-44): a half-precision file must give
+    exactly the engine an F32 file holding the same (rounded) values gives -- the loader converts on the way in."""
+    import struct as _s
+    import json as _j
+    import torch
+    W = tiny.W
+    pcms = [synth.make_audio(32000, 11), synth.make_audio(20000, 12)]
+
+    def save(path, conv, dtype_name):
+        header, off, blobs = {}, 0, []
+        for name, a in W.items():
+            a = np.ascontiguousarray(a)
+            if a.dtype == np.float32:
+                b, dt = conv(a), dtype_name
+            else:
+                b, dt = a.tobytes(), "I64"
+            header[name] = {"dtype": dt, "shape": list(a.shape), "data_offsets": [off, off + len(b)]}
+            off += len(b)
+            blobs.append(b)
+        hj = _j.dumps(header).encode()
+        with open(path, "wb") as f:
+            f.write(_s.pack("<Q", len(hj)) + hj + b"".join(blobs))
+
+    for tag, to_half, back in (("f16", lambda a: a.astype(np.float16).tobytes(), lambda a: a.astype(np.float16).astype(np.float32)),
+                               ("bf16", lambda a: torch.from_numpy(a).to(torch.bfloat16).view(torch.int16).numpy().tobytes(),
+                                lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy())):
+        ph, pf = str(tmp_path / (tag + ".safetensors")), str(tmp_path / (tag + "_as_f32.safetensors"))
+        save(ph, to_half, "F16" if tag == "f16" else "BF16")
+        save(pf, lambda a: back(a).tobytes(), "F32")
+        outs = []
+        for p in (ph, pf):
+            e = pkg.Engine(tiny.cfg, p, 0)
+            feats = e.mel(pcms)
+            outs.append((e.encode(feats), [_tt(t) for t in e.transcribe_batch(pcms, pkg.Decoder.TDT)]))
+            e.close()
+        for a, b in zip(outs[0][0], outs[1][0]):
+            assert np.array_equal(a, b), tag
+        assert outs[0][1] == outs[1][1] and sum(len(t) for t in outs[0][1]) > 0
