@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
         except Exception:
@@ -428,7 +428,6 @@ def main():
     sampler.start()
     time.sleep(0.3)
     ms, wall = timed(lambda: job_resident(K))
-    clocks = sampler.stop()
     launches = eng.launch_count() - l0
     rows_all = eng.job_fetch(world * K * BATCH, gathered=True) if world > 1 else eng.job_fetch(K * BATCH)
     mine = rows_all[rank * K * BATCH:(rank + 1) * K * BATCH]
@@ -505,6 +504,7 @@ def main():
 
     sync_wall, out = time_e2e(job_sync)
     e2e_wall, out = time_e2e(job_pipelined)
+    clocks = sampler.stop()            # sampled every 20 ms across the three timed regions (value, e2e sync, e2e pipelined)
     e2e_value = audio_s / e2e_wall
     n_tok = int(mine[:, 0].sum())
     W = 1 + eng.cap

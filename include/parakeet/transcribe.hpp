@@ -24,6 +24,7 @@
 #include <cstring>
 #include <algorithm>
 #include <fstream>
+#include <functional>
 #include <iterator>
 #include <memory>
 #include <stdexcept>
@@ -409,6 +410,124 @@ class TDTTranscriber : public detail::TranscriberBase<TDTTranscriber> {
         return TranscriberBase::transcribe(samples, o);
     }
     pk_decoder pick(Decoder) const { return PK_DECODER_TDT; }
+};
+
+
+// ─── streaming (reference include/parakeet/eou.hpp:25-141, streaming_encoder.hpp:18-24) ─────────────────────────
+struct StreamingEncoderConfig : EncoderConfig {
+    int att_context_left = 70, att_context_right = 0, chunk_size = 20;
+    bool xscaling = false;
+};
+struct EOUConfig {
+    StreamingEncoderConfig encoder;
+    PredictionConfig prediction;
+    JointConfig joint;
+    std::vector<int> durations = {0, 1, 2, 3, 4};
+    int eou_token_id = -1;
+    int ctc_vocab_size = 1025;
+};
+inline EOUConfig make_eou_120m_config() {      // eou.hpp:32-55
+    EOUConfig c;
+    c.encoder.hidden_size = 512; c.encoder.num_layers = 17; c.encoder.num_heads = 8; c.encoder.ffn_intermediate = 2048;
+    c.encoder.subsampling_channels = 256; c.encoder.conv_kernel_size = 9; c.encoder.att_context_left = 70; c.encoder.att_context_right = 1;
+    c.prediction.vocab_size = 1025; c.prediction.pred_hidden = 640; c.prediction.num_lstm_layers = 1;
+    c.joint.encoder_hidden = 512; c.joint.pred_hidden = 640; c.joint.joint_hidden = 640; c.joint.vocab_size = 1025;
+    c.eou_token_id = 1024;
+    return c;
+}
+
+/// parakeet::StreamingTranscriber (reference eou.hpp:101-141, src/eou.cpp:100-155): chunk-by-chunk transcription with
+/// carried state.  One object = one stream on the device (pk_stream_open with a single stream); for many concurrent
+/// streams that share every weight read use StreamingBatch below -- the reference has no counterpart to it.
+class StreamingBatch {
+  public:
+    StreamingBatch(const std::string &weights_path, const std::string &vocab_path, int n_streams, const EOUConfig &config = make_eou_120m_config(),
+                   int device = 0, int max_chunk_samples = 5120)
+        : n_(n_streams), tokens_(n_streams), stamped_(n_streams) {
+        if (config.encoder.xscaling) throw std::runtime_error("StreamingBatch: xscaling is not supported on the B200 path");
+        pk_config c;
+        pk_config_110m(&c);
+        detail::fill(c, config.encoder, config.prediction, config.joint, config.durations);
+        c.has_ctc = 0; c.joint_prefix_tdt = 0;                 // ParakeetEOU registers "joint_" (eou.cpp:9-13)
+        c.max_batch = std::max(n_streams, 8);
+        c.max_samples = 102400;                                 // 6.4 s: encoder-frame capacity >= left context + frames per chunk
+        eng_ = std::make_unique<detail::EngineHolder>(c, weights_path, device);
+        if (pk_stream_open(eng_->raw(), n_streams, max_chunk_samples, config.encoder.att_context_left, config.encoder.att_context_right) != PK_OK)
+            throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(eng_->raw()));
+        if (!vocab_path.empty()) tokenizer_.load(vocab_path);
+        cap_ = 2 * pk_encoder_frames(pk_mel_frames(c.max_samples)) + 8;
+    }
+    /// One step: stream s receives chunks[s] (may be empty).  Returns the text each stream produced in this step.
+    std::vector<std::string> transcribe_chunks(const std::vector<std::vector<float>> &chunks) {
+        if ((int)chunks.size() != n_) throw std::runtime_error("StreamingBatch: one chunk per stream expected");
+        std::vector<int64_t> off(n_ + 1, 0);
+        for (int i = 0; i < n_; ++i) off[i + 1] = off[i] + (int64_t)chunks[i].size();
+        std::vector<float> buf((size_t)off[n_] + 1);
+        for (int i = 0; i < n_; ++i) std::memcpy(buf.data() + off[i], chunks[i].data(), chunks[i].size() * sizeof(float));
+        std::vector<int32_t> ids((size_t)n_ * cap_), st((size_t)n_ * cap_), en((size_t)n_ * cap_), len(n_);
+        std::vector<float> cf((size_t)n_ * cap_);
+        pk_tokens t{cap_, ids.data(), st.data(), en.data(), cf.data(), len.data()};
+        if (pk_stream_step(eng_->raw(), buf.data(), off.data(), &t, nullptr, nullptr, nullptr, nullptr) != PK_OK)
+            throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(eng_->raw()));
+        std::vector<std::string> out(n_);
+        for (int s = 0; s < n_; ++s) {
+            std::vector<int> fresh;
+            for (int i = 0; i < len[s]; ++i) {
+                const size_t k = (size_t)s * cap_ + i;
+                fresh.push_back(ids[k]);
+                tokens_[s].push_back(ids[k]);
+                stamped_[s].push_back({ids[k], st[k], en[k], cf[k]});
+            }
+            if (!fresh.empty() && tokenizer_.loaded()) out[s] = tokenizer_.decode(fresh);
+        }
+        return out;
+    }
+    void reset(int stream = -1) {
+        if (pk_stream_reset(eng_->raw(), stream) != PK_OK) throw std::runtime_error(std::string("parakeet_b200: ") + pk_last_error(eng_->raw()));
+        for (int s = 0; s < n_; ++s)
+            if (stream < 0 || s == stream) { tokens_[s].clear(); stamped_[s].clear(); }
+    }
+    std::string get_text(int stream = 0) const { return (tokenizer_.loaded() && !tokens_[stream].empty()) ? tokenizer_.decode(tokens_[stream]) : std::string(); }
+    const std::vector<TimestampedToken> &get_timestamped_tokens(int stream = 0) const { return stamped_[stream]; }
+    const std::vector<int> &get_tokens(int stream = 0) const { return tokens_[stream]; }
+    const Tokenizer &tokenizer() const { return tokenizer_; }
+    int streams() const { return n_; }
+
+  private:
+    int n_;
+    int32_t cap_ = 0;
+    std::unique_ptr<detail::EngineHolder> eng_;
+    Tokenizer tokenizer_;
+    std::vector<std::vector<int>> tokens_;
+    std::vector<std::vector<TimestampedToken>> stamped_;
+};
+
+class StreamingTranscriber {
+  public:
+    using PartialResultCallback = std::function<void(const std::string &partial)>;
+    StreamingTranscriber(const std::string &weights_path, const std::string &vocab_path, const EOUConfig &config = make_eou_120m_config(), int device = 0)
+        : batch_(weights_path, vocab_path, 1, config, device) {}
+    void to_gpu() {}                                           // always on the device
+    std::string transcribe_chunk(const float *data, size_t num_samples) {
+        auto text = batch_.transcribe_chunks({std::vector<float>(data, data + num_samples)})[0];
+        if (!text.empty() && cb_) cb_(text);                  // eou.cpp:134-139
+        return text;
+    }
+    std::string transcribe_chunk(const std::vector<float> &samples) { return transcribe_chunk(samples.data(), samples.size()); }
+    std::string transcribe_chunk(const int16_t *data, size_t num_samples) {   // eou.hpp:123-129
+        std::vector<float> f(num_samples);
+        for (size_t i = 0; i < num_samples; ++i) f[i] = static_cast<float>(data[i]) / 32768.0f;
+        return transcribe_chunk(f.data(), f.size());
+    }
+    void reset() { batch_.reset(-1); }
+    void set_partial_callback(PartialResultCallback cb) { cb_ = std::move(cb); }
+    std::string get_text() const { return batch_.get_text(0); }
+    const std::vector<TimestampedToken> &get_timestamped_tokens() const { return batch_.get_timestamped_tokens(0); }
+    const Tokenizer &tokenizer() const { return batch_.tokenizer(); }
+
+  private:
+    StreamingBatch batch_;
+    PartialResultCallback cb_;
 };
 
 }  // namespace parakeet

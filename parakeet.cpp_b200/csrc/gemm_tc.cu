@@ -62,10 +62,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();   // ~seconds: protocol error, fail instead of hanging
     }
 }
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+// L2 eviction-priority hints of the TMA operand loads (the 64-bit policy words CUTLASS uses for createpolicy-free hints).
+// Measured (profiles/r02_b_gemm_analysis.md): the result stream of a GEMM (66 MB per fc1 launch) pushes the operand tiles
+// that all CTAs re-read out of the near L2 partition -- lts hit rate 91 % -> 74 %, every miss a trip to the far die --
+// which is what stretched the MMA interval when loads and stores ran together.  Operands are therefore loaded EVICT_LAST.
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ int g_l2_hint_mode;   // measurement aid (PK_GEMM_DBG bits 10-11): 0 = loads EVICT_LAST, 1 = no hints, 2 = + stores EVICT_FIRST
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, uint64_t policy = L2_EVICT_LAST) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
 // One elected lane of a fully active warp (the warp-specialised roles below run under it): unlike `lane == 0`, ptxas
@@ -333,6 +339,10 @@ __device__ __forceinline__ void tma_store_tile(uint32_t stg_s, int lane, const u
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
+        if (g_l2_hint_mode == 2)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                         ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(stg_s), "r"(col), "r"(row0), "l"(L2_EVICT_FIRST) : "memory");
+        else
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                      ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(stg_s), "r"(col), "r"(row0) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -537,6 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ===================== TMA producer =====================
         if (elect_one()) {
             uint32_t it = 0;   // global k-block counter across tiles
+            const uint64_t ld_policy = g_l2_hint_mode == 1 ? L2_EVICT_NORMAL : L2_EVICT_LAST;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -546,11 +557,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
                     if (dbg & 2) { mbar_arrive(&full[s]); continue; }      // measurement aid: MMAs on stale smem, no loads
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
-                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
+                    tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0, ld_policy);
+                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0, ld_policy);
                     if (NPASS == 3) {
-                        tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0);
-                        tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0);
+                        tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0, ld_policy);
+                        tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0, ld_policy);
                     }
                 }
             }
@@ -982,6 +993,8 @@ void tc_set_debug(int bits) {
     g_dbg = bits & 0xff;
     const int mode = (bits >> 8) & 3;
     cudaMemcpyToSymbol(g_store_mode, &mode, sizeof(int));
+    const int hint = (bits >> 10) & 3;
+    cudaMemcpyToSymbol(g_l2_hint_mode, &hint, sizeof(int));
 }
 void tc_print_timeline(int n_tiles) {   // after a 1-CTA launch with debug bit 5
     long long h[64][4];

@@ -756,3 +756,32 @@ def test_f16_and_bf16_checkpoints_load_like_their_f32_roundings(pkg, tiny, synth
         for a, b in zip(outs[0][0], outs[1][0]):
             assert np.array_equal(a, b), tag
         assert outs[0][1] == outs[1][1] and sum(len(t) for t in outs[0][1]) > 0
+
+
+def test_cpp_streaming_transcriber(pkg, O, synth, tmp_path):
+    """parakeet::StreamingTranscriber of the C++ drop-in (reference eou.hpp:101-141): transcribe_chunk per chunk of the golden
+    stream, tokens with absolute frames per chunk, get_text, the partial-result callback, reset."""
+    import subprocess
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_stream_v1.npz"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cpp_stream_check")
+    libdir = os.path.dirname(pkg.lib_path())
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp_stream_check.cpp"),
+                    "-L" + libdir, "-lparakeet_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    ocfg = O.make_tiny_stream_config()
+    wseed, aseed = (int(v) for v in g["tstream.seeds"])
+    sched = [int(v) for v in g["tstream.schedule"]]
+    wp, vp, pp = str(tmp_path / "ts.safetensors"), str(tmp_path / "ts.vocab.txt"), str(tmp_path / "pcm.f32")
+    synth.save_safetensors(wp, synth.make_weights(ocfg, seed=wseed))
+    pieces = synth.make_vocab(ocfg.vocab - 1, seed=wseed)
+    synth.save_vocab(vp, pieces)
+    synth.make_audio(sum(sched), aseed).astype(np.float32).tofile(pp)
+    out = subprocess.run([exe, wp, vp, pp, ",".join(str(n) for n in sched)], check=True, capture_output=True, text=True).stdout.strip().split("\n")
+    all_ids = []
+    for ci in range(len(sched)):
+        want = g[f"tstream.k{ci}.tok"].tolist()
+        assert out[ci].split()[1:] == [f"{a}:{b}:{c}" for a, b, c in want], ci
+        all_ids += [w[0] for w in want]
+    assert out[len(sched)] == "TEXT " + O.detokenize(all_ids, pieces)
+    assert int(out[len(sched) + 1].split()[1]) == sum(1 for ci in range(len(sched)) if len(g[f"tstream.k{ci}.tok"]))
+    assert out[len(sched) + 2] == "AFTER_RESET 0"
