@@ -144,6 +144,13 @@ pk_status pk_engine::load(const char *path) {
     if ((s = get_vec(st, sp + "dw1_.weight", C * 9, &dw1_w))) return s;
     if ((s = get_vec(st, sp + "dw1_.bias", C, &dw1_b))) return s;
     if ((s = get_vec(st, sp + "dw2_.weight", C * 9, &dw2_w))) return s;
+    {
+        std::vector<float> w, wt((size_t)C * 9);
+        if (!st.read_f32(sp + "dw2_.weight", w, (int64_t)C * 9, e)) return fail(PK_ERR_MISSING, e);
+        for (int ch = 0; ch < C; ++ch)
+            for (int k = 0; k < 9; ++k) wt[(size_t)k * C + ch] = w[(size_t)ch * 9 + k];
+        dw2_wt = upload(wt);
+    }
     if ((s = get_vec(st, sp + "dw2_.bias", C, &dw2_b))) return s;
     if ((s = make_weight(st, sp + "conv2_.weight", sp + "conv2_.bias", C, C, conv2))) return s;
     if ((s = make_weight(st, sp + "conv3_.weight", sp + "conv3_.bias", C, C, conv3))) return s;
@@ -252,6 +259,10 @@ pk_status pk_engine::load(const char *path) {
                 b[ch] = (float)(((double)b[ch] - (double)mu[ch]) * sc + (double)be[ch]);
             }
             L.dw_w = upload(w);
+            std::vector<float> wt((size_t)d * ks);
+            for (int ch = 0; ch < d; ++ch)
+                for (int j = 0; j < ks; ++j) wt[(size_t)j * d + ch] = w[(size_t)ch * ks + j];
+            L.dw_wt = upload(wt);
             L.dw_b = upload(b);
         }
         if ((s = get_vec(st, lp + "final_norm_.weight", d, &L.fin_ln_w))) return s;
@@ -530,7 +541,7 @@ pk_status pk_engine::run_subsample_tail() {
     }
     {
         Scope sc(this, CAT_SUBSAMPLE);
-        launch_subsample_dw(sub2, d_t2_rows, d_s2_off, d_row_off, n_utt, f2n, C, dw2_w, dw2_b, sub3, M * f3n, stream);
+        launch_subsample_dw(sub2, d_t2_rows, d_s2_off, d_row_off, n_utt, f2n, C, dw2_wt, dw2_b, sub3, M * f3n, stream);
     }
     ++launches;
     {
@@ -637,7 +648,7 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             gemm(ln, d, L.pw1, M, eg);
             {
                 Scope sc(this, CAT_DWCONV);
-                if (!launch_dwconv_bn_silu(glu, d_row_off, n_utt, maxT, d, c.conv_kernel, L.dw_w, L.dw_b, cv, stream))
+                if (!launch_dwconv_bn_silu(glu, d_row_off, n_utt, maxT, d, c.conv_kernel, L.dw_wt, L.dw_b, cv, stream))
                     return fail(PK_ERR_INVALID, "unsupported conv_kernel");
             }
             ++launches;

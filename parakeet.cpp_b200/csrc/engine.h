@@ -60,7 +60,8 @@ struct LayerW {
     bf16 *pp_hi = nullptr, *pp_lo = nullptr;   // its bf16 split planes (tensor-core attention)
     float *conv_ln_w, *conv_ln_b;
     GemmWeight pw1, pw2;
-    float *dw_w, *dw_b;  // BatchNorm folded
+    float *dw_w, *dw_b;  // BatchNorm folded; [d][k]
+    float *dw_wt;        // the same weights tap-major [k][d] (offline kernel: one float4 per tap and 4 channels)
     float *fin_ln_w, *fin_ln_b;
 };
 
@@ -94,6 +95,7 @@ struct pk_engine {
     // ---- weights
     MelTables mel_tb{};
     float *c1_w, *c1_b, *dw1_w, *dw1_b, *dw2_w, *dw2_b;
+    float *dw2_wt = nullptr;                   // dw2_ weights tap-major [9][C]: one float4 per tap and 4 channels
     GemmWeight conv2, conv3, proj;
     std::vector<LayerW> layers;
     GemmWeight ctc_head;

@@ -82,22 +82,20 @@ layernorm_kernel(const float *__restrict__ x, int M, int d, const float *__restr
 // SiLU (reference src/encoder.cpp:59-75).  A thread owns 4 channels and DW_TT consecutive frames and
 // slides the KS-tap window down the column: DW_TT + KS - 1 float4 loads and one read of its 4 x KS
 // taps for DW_TT x 4 outputs (the previous one-frame-per-thread version re-read both 9x).
-constexpr int DW_TT = 8;
+constexpr int DW_TT = 4;
 template <int KS>
 __global__ void __launch_bounds__(128)
 dwconv_bn_silu_kernel(const float *__restrict__ g, const int32_t *__restrict__ row_off, int d,
-                      const float *__restrict__ w /* [d][KS] folded */, const float *__restrict__ bias /* [d] folded */,
+                      const float *__restrict__ w /* tap-major [KS][d], BatchNorm folded */, const float *__restrict__ bias /* [d] folded */,
                       ActBuf out) {
     const int b = blockIdx.z;
     const int r0 = row_off[b], T = row_off[b + 1] - r0;
     const int t0 = blockIdx.y * DW_TT;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (t0 >= T || c >= d) return;
-    float wr[4][KS];
+    float4 wr[KS];                       // one float4 per tap (4 channels)
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int j = 0; j < KS; ++j) wr[q][j] = __ldg(w + (c + q) * KS + j);
+    for (int j = 0; j < KS; ++j) wr[j] = __ldg(reinterpret_cast<const float4 *>(w + (size_t)j * d + c));
     const float4 bs = *reinterpret_cast<const float4 *>(bias + c);
     float4 win[KS];                      // win[j] = g[t - KS/2 + j]
 #pragma unroll
@@ -118,10 +116,10 @@ dwconv_bn_silu_kernel(const float *__restrict__ g, const int32_t *__restrict__ r
         float4 acc = bs;
 #pragma unroll
         for (int j = 0; j < KS; ++j) {   // same tap order as the one-frame version (bit-identical sums)
-            acc.x = fmaf(wr[0][j], win[j].x, acc.x);
-            acc.y = fmaf(wr[1][j], win[j].y, acc.y);
-            acc.z = fmaf(wr[2][j], win[j].z, acc.z);
-            acc.w = fmaf(wr[3][j], win[j].w, acc.w);
+            acc.x = fmaf(wr[j].x, win[j].x, acc.x);
+            acc.y = fmaf(wr[j].y, win[j].y, acc.y);
+            acc.z = fmaf(wr[j].z, win[j].z, acc.z);
+            acc.w = fmaf(wr[j].w, win[j].w, acc.w);
         }
         store_act4(out, (size_t)(r0 + t) * d + c, make_float4(siluf_(acc.x), siluf_(acc.y), siluf_(acc.z), siluf_(acc.w)));
     }

@@ -111,7 +111,7 @@ subsample_conv1_dw1_kernel(const float *__restrict__ feats, const int32_t *__res
 __global__ void subsample_dw_kernel(const float *__restrict__ in, const int32_t *__restrict__ in_rows,
                                     const int32_t *__restrict__ in_off,
                                     const int32_t *__restrict__ out_off, int fin, int C,
-                                    const float *__restrict__ wd /* [C][9] */,
+                                    const float *__restrict__ wd /* tap-major [9][C] */,
                                     const float *__restrict__ bd, ActBuf out, int total_out_rows,
                                     int n_utt) {
     // one thread per (output row, 4 channels)
@@ -142,11 +142,11 @@ __global__ void subsample_dw_kernel(const float *__restrict__ in, const int32_t 
             const int fi = 2 * fo - 1 + j;
             if (fi < 0 || fi >= fin) continue;
             const float4 x = *reinterpret_cast<const float4 *>(base + ((size_t)ti * fin + fi) * C + c);
-            const int k = i * 3 + j;
-            acc.x = fmaf(wd[(c + 0) * 9 + k], x.x, acc.x);
-            acc.y = fmaf(wd[(c + 1) * 9 + k], x.y, acc.y);
-            acc.z = fmaf(wd[(c + 2) * 9 + k], x.z, acc.z);
-            acc.w = fmaf(wd[(c + 3) * 9 + k], x.w, acc.w);
+            const float4 wk = __ldg(reinterpret_cast<const float4 *>(wd + (size_t)(i * 3 + j) * C + c));   // (was 4 scalar loads per tap)
+            acc.x = fmaf(wk.x, x.x, acc.x);
+            acc.y = fmaf(wk.y, x.y, acc.y);
+            acc.z = fmaf(wk.z, x.z, acc.z);
+            acc.w = fmaf(wk.w, x.w, acc.w);
         }
     }
     store_act4(out, (size_t)orow * C + c, acc);
