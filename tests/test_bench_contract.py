@@ -7,7 +7,8 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_l_bench_n*.json")))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_l_bench_n*.json")) + glob.glob(os.path.join(ROOT, "profiles", "r02_*_bench_n*.json")) +
+               glob.glob(os.path.join(ROOT, "profiles", "r02_*_bench_600m*.json")))
 
 
 def _line(path):
@@ -25,7 +26,7 @@ def test_bench_line_has_the_contract_keys(path):
     assert d["warmup"] >= 3 and d["scaling"] == "weak" and d["higher_is_better"] is True
     assert "workload" in d["config"] and "l2" in d["config"]
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 160000 * 4 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] in (64 * 160000 * 4, 16 * 480000 * 4) and e["d2h_bytes_per_step"] > 0
     assert e["value"] <= d["value"] * 1.02                           # end to end cannot beat the device-resident number
     assert e["sync_call"]["value"] <= e["value"] * 1.02
     r = d["roofline"]
@@ -34,6 +35,9 @@ def test_bench_line_has_the_contract_keys(path):
     assert r["traffic"] is None or r["traffic"] > 0
     c = d["clocks"]
     assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not any("slowdown" in x for x in c["reasons"])
+    if "job_clips" in d["config"]:           # round 2: the timed region is a job of distinct clips with one all-gather
+        assert d["config"]["job_clips"] == d["steps"] * d["config"]["clips_per_gpu_per_step"] * d["n_gpus"]
+        assert d["config"]["distinct_hypotheses_in_job"] >= 0.9 * d["config"]["job_clips"]
     assert d["gpu_launches"] > 0
     if d["n_gpus"] == 1:
         b = d["cpu_baseline"]
@@ -41,8 +45,19 @@ def test_bench_line_has_the_contract_keys(path):
         assert b.get("tokens_match_gpu", True) is True
 
 
-def test_reference_arm_line():
-    p = os.path.join(ROOT, "profiles", "r01_l_bench_reference_arm.json")
+def test_streaming_bench_lines():
+    for p in glob.glob(os.path.join(ROOT, "profiles", "r02_*_bench_eou_stream_*.json")):
+        d = _line(p)
+        assert d["metric"].startswith("audio-seconds/sec (RTFx) eou-120m streaming") and d["value"] > 0 and d["higher_is_better"] is True
+        assert d["config"]["streams"] >= 1 and d["config"]["chunk_samples"] == 2560 and d["gpu_launches"] > 0
+        assert d["latency"]["ms_per_chunk_single_stream"] < d["latency"]["real_time_budget_ms"]
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["r01_l_bench_reference_arm.json", "r02_f_bench_reference_arm.json"])
+def test_reference_arm_line(name):
+    p = os.path.join(ROOT, "profiles", name)
     d = _line(p)
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "reference"
