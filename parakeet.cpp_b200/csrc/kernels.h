@@ -131,6 +131,7 @@ void launch_ctc_collapse(const int32_t *best, const float *conf, const int32_t *
 struct TdtParams {
     int P, J, V, D, L, Bpad, n_utt, cap, max_steps, n_dur;
     int out_in_smem, wih_in_smem, smem_lstm_floats;   // filled by launch_tdt_decode
+    int wstage_rows;                                  // rows of the shared-memory staging tile for weights that stay in L2 (0: none)
     int durations[8];
     const float *EP;                          // [M][J] enc_proj(enc) + bias
     const int32_t *row_off;                   // [n_utt+1]

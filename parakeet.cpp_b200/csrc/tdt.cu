@@ -62,6 +62,9 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -120,6 +123,7 @@ __device__ __forceinline__ float ld_cluster_f32(uint32_t a) {
 template <typename XSrc>
 __device__ __forceinline__ void stage_x(XSrc xsrc, size_t lo_off, int KS, int Bpad, int bc, bf16 *xs) {
     const int XLD = KS + 8, pieces = KS / 8;          // 16-byte pieces per row
+    const int xrows = min(BCH, Bpad);                 // rows per plane of the staging buffer (see tdt_smem_bytes)
     const uint32_t xs_s = smem_addr(xs);
     for (int idx = threadIdx.x; idx < BCH * pieces; idx += NTHR) {
         const int row = idx / pieces, pc = idx - row * pieces;
@@ -127,7 +131,7 @@ __device__ __forceinline__ void stage_x(XSrc xsrc, size_t lo_off, int KS, int Bp
         const bf16 *s = xsrc(bc + row) + pc * 8;
         const uint32_t dst = xs_s + (uint32_t)(row * XLD + pc * 8) * 2u;
         cp_async16(dst, s);
-        cp_async16(dst + (uint32_t)(BCH * XLD) * 2u, s + lo_off);
+        cp_async16(dst + (uint32_t)(xrows * XLD) * 2u, s + lo_off);
     }
     cp_async_commit_wait_all();
     __syncthreads();
@@ -137,12 +141,12 @@ __device__ __forceinline__ void stage_x(XSrc xsrc, size_t lo_off, int KS, int Bp
 //   W: row r at W + r * RS (bf16 elements): [hi ...][lo ...] with lo at +LO; k index 0 = first k of the slice
 //   warp w: utterance block (w & 3), n-blocks [ (w >> 2) * NBH, +NBH )
 template <int NBH, bool WS>
-__device__ __forceinline__ void mma_slice(float (&acc)[NBH][4], const bf16 *W, int RS, int LO, int R, int KS, const bf16 *xs) {
+__device__ __forceinline__ void mma_slice(float (&acc)[NBH][4], const bf16 *W, int RS, int LO, int R, int KS, const bf16 *xs, int xrows) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, cq = lane & 3;
     const int mb = warp & 3, nh = warp >> 2;
     const int XLD = KS + 8;
     const uint32_t a_base = smem_addr(xs) + (uint32_t)((mb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XLD + ((lane >> 4) & 1) * 8) * 2u;
-    const uint32_t lo_plane = (uint32_t)(BCH * XLD) * 2u;
+    const uint32_t lo_plane = (uint32_t)(xrows * XLD) * 2u;   // (m-blocks past xrows read stale shared memory: results discarded)
     const bf16 *wrow[NBH];
 #pragma unroll
     for (int nb = 0; nb < NBH; ++nb)
@@ -179,10 +183,13 @@ __device__ __forceinline__ void store_partials(const float (&acc)[NBH][4], float
 // (W1 . x1 [+ W2 . x2]), partial sums exchanged through DSMEM, rows finalised by their owner CTA.
 //   myrow(i) -> row (0..R-1) of the i-th row this CTA finalises, i < nmy (nmy <= MYMAX)
 //   pre(r, b) -> float operand of the epilogue, fetched before the products;  fin(i, r, b, sum, pre)
-template <int CL, int NBH, bool WS1, bool WS2, typename X1, typename X2, typename MyRow, typename Pre, typename Fin>
+//   post() runs right after the last product has read its weights (e.g. to start the asynchronous copy of the next
+//   weight tile into the staging buffer while the partial sums are exchanged and finalised)
+template <int CL, int NBH, bool WS1, bool WS2, typename X1, typename X2, typename MyRow, typename Pre, typename Fin, typename Post>
 __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X1 x1, const bf16 *W2, int RS2, int LO2, X2 x2,
                                              size_t lo_off, int R, int KS, int Bpad, int bc, bf16 *xs, float *red, int nmy,
-                                             MyRow myrow, Pre pre, Fin fin) {
+                                             MyRow myrow, Pre pre, Fin fin, Post post, bool stage_x1 = true) {
+    const int xrows = min(BCH, Bpad);
     float acc[NBH][4];
 #pragma unroll
     for (int nb = 0; nb < NBH; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
@@ -191,13 +198,14 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
     {
         const int XLD = KS + 8, pieces = KS / 8;
         const uint32_t xs_s = smem_addr(xs);
+        if (stage_x1)               // (false: xs still holds this slice from the previous pass of the same phase)
         for (int idx = threadIdx.x; idx < BCH * pieces; idx += NTHR) {
             const int row = idx / pieces, pc = idx - row * pieces;
             if (bc + row >= Bpad) continue;
             const bf16 *s = x1(bc + row) + pc * 8;
             const uint32_t dst = xs_s + (uint32_t)(row * XLD + pc * 8) * 2u;
             cp_async16(dst, s);
-            cp_async16(dst + (uint32_t)(BCH * XLD) * 2u, s + lo_off);
+            cp_async16(dst + (uint32_t)(xrows * XLD) * 2u, s + lo_off);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -208,12 +216,13 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    mma_slice<NBH, WS1>(acc, W1, RS1, LO1, R, KS, xs);
+    mma_slice<NBH, WS1>(acc, W1, RS1, LO1, R, KS, xs, xrows);
     if (W2 != nullptr) {
         __syncthreads();                              // everyone is done reading x1
         stage_x(x2, lo_off, KS, Bpad, bc, xs);
-        mma_slice<NBH, WS2>(acc, W2, RS2, LO2, R, KS, xs);
+        mma_slice<NBH, WS2>(acc, W2, RS2, LO2, R, KS, xs, xrows);
     }
+    post();
     store_partials<NBH>(acc, red);
     cluster_sync_all();                               // all CL partial buffers complete and visible
     uint32_t peer[CL];
@@ -234,14 +243,17 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
     __syncthreads();
 }
 
-template <int CL, bool WS1, bool WS2, typename X1, typename X2, typename MyRow, typename Pre, typename Fin>
+struct NoPost {
+    __device__ __forceinline__ void operator()() const {}
+};
+template <int CL, bool WS1, bool WS2, typename X1, typename X2, typename MyRow, typename Pre, typename Fin, typename Post = NoPost>
 __device__ __forceinline__ void cluster_pass_n(const bf16 *W1, int RS1, int LO1, X1 x1, const bf16 *W2, int RS2, int LO2, X2 x2,
                                                size_t lo_off, int R, int KS, int Bpad, int bc, bf16 *xs, float *red, int nmy,
-                                               MyRow myrow, Pre pre, Fin fin) {
-    if (R <= 16) cluster_pass<CL, 1, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
-    else if (R <= 32) cluster_pass<CL, 2, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
-    else if (R <= 48) cluster_pass<CL, 3, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
-    else cluster_pass<CL, 5, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin);
+                                               MyRow myrow, Pre pre, Fin fin, Post post = Post(), bool stage_x1 = true) {
+    if (R <= 16) cluster_pass<CL, 1, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin, post, stage_x1);
+    else if (R <= 32) cluster_pass<CL, 2, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin, post, stage_x1);
+    else if (R <= 48) cluster_pass<CL, 3, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin, post, stage_x1);
+    else cluster_pass<CL, 5, WS1, WS2>(W1, RS1, LO1, x1, W2, RS2, LO2, x2, lo_off, R, KS, Bpad, bc, xs, red, nmy, myrow, pre, fin, post, stage_x1);
 }
 
 // Monotonic-counter grid barrier (all CTAs are co-resident: cooperative launch), split into
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
     float *gsm = red + RG * RLD;                              // [MYMAX][BCH] gate pre-activations / logits of my rows
     bf16 *xs = reinterpret_cast<bf16 *>(gsm + MYMAX * BCH);   // [2][BCH][KSmax + 8]
     const int KSmax = max(KSP, KSJ);
-    float *csm = reinterpret_cast<float *>(xs + (size_t)2 * BCH * (KSmax + 8));  // [L][2][MU][Bpad] LSTM cell state
+    float *csm = reinterpret_cast<float *>(xs + (size_t)2 * min(BCH, Bpad) * (KSmax + 8));  // [L][2][MU][Bpad] LSTM cell state
     int *s_cur = reinterpret_cast<int *>(csm + (size_t)L * 2 * ge.MU * Bpad);    // replicated decode state, [Bpad] each
     int *s_token = s_cur + Bpad, *s_tpos = s_token + Bpad, *s_active = s_tpos + Bpad, *s_ntok = s_active + Bpad;
     int *s_pend = s_ntok + Bpad;                   // slot of a token whose confidence is still pending (-1: none)
@@ -367,6 +379,23 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
         w_o = p.Wout + (size_t)o0 * 2 * J + kJ0;              // global: row stride 2J, lo at +J
     }
     const int RSO = p.out_in_smem ? RSJ : 2 * J, LOO = p.out_in_smem ? KSJ + 4 : J;
+    // (48-80 rows per pass)  Weights that do not fit in shared memory (tdt-600m: the 8198-row output matrix) are streamed per pass through a
+    // staging tile by 8-byte cp.async in the layout of the resident weights, so that their products read shared memory
+    // like everyone else (the previous per-fragment ld.global made P3 57 % of a 600m decode step); the copy of pass i+1
+    // is started as soon as the products of pass i have read the tile and overlaps the partial-sum exchange.
+    bf16 *wstage = w_p + (size_t)ge.JPC * RSP + (p.out_in_smem ? (size_t)ge.OPC * RSJ : 0);
+    auto stage_rows_async = [&](bf16 *dst, const bf16 *src, int rows, int K, int k0, int KS) {
+        const int RS = 2 * (KS + 4), n8 = KS / 4;
+        const uint32_t d0 = smem_addr(dst);
+        for (int i = tid; i < rows * n8; i += blockDim.x) {
+            const int r = i / n8, pc = i - r * n8;
+            const bf16 *sp = src + (size_t)r * 2 * K + k0 + pc * 4;
+            const uint32_t dd = d0 + (uint32_t)(r * RS + pc * 4) * 2u;
+            cp_async8(dd, sp);
+            cp_async8(dd + (uint32_t)(KS + 4) * 2u, sp + K);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     for (int i = tid; i < L * 2 * ge.MU * Bpad; i += blockDim.x) csm[i] = 0.f;   // zero cell state (tdt.cpp:49-59)
     for (int b = tid; b < Bpad; b += blockDim.x) {                               // initial decode state
         s_cur[b] = 0;
@@ -445,7 +474,12 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                 p.key_dur[((step + 1) % 3) * KB + b] = 0ull;
             }
         // ================= P1: LSTM layers =================
+        // W_ih of an upper layer that is not resident is streamed through the staging tile (free until P3): with two
+        // layers its copy starts here and lands under layer 0's products; deeper stacks stage right before use.
+        const bool staged_ih = !p.wih_in_smem && L > 1 && p.wstage_rows >= nU * 4 && nU <= RG / 4 && KSP == KSJ;
+        if (staged_ih && L == 2) stage_rows_async(wstage, p.Wih[1] + (size_t)u0 * 4 * 2 * P, nU * 4, P, kP0, KSP);
         for (int l = 0; l < L; ++l) {
+            if (staged_ih && L > 2 && l >= 1) stage_rows_async(wstage, p.Wih[l] + (size_t)u0 * 4 * 2 * P, nU * 4, P, kP0, KSP);
             for (int bc = 0; bc < Bpad; bc += BCH)
                 for (int ug = 0; ug < nU; ug += RG / 4) {               // passes of <= 20 units (one for the 110m)
                     const int nu = min(RG / 4, nU - ug), R = nu * 4;
@@ -466,6 +500,9 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                         auto xh = [&](int b) { return hb + ((size_t)((l - 1) * 2 + (1 - s_cur[b]))) * HS + (size_t)b * P + kP0; };
                         if (p.wih_in_smem)
                             cluster_pass_n<CL, true, true>(W1, RSP, KSP + 4, xprev, w_ih[l] + (size_t)ug * 4 * RSP, RSP, KSP + 4, xh, h_lo, R,
+                                                           KSP, Bpad, bc, xs, red, myu * 4, myrow, pre_g, fin_g);
+                        else if (staged_ih)          // (one pass: nU <= 20 units; the tile holds rows [u0*4, u1*4) of W_ih[l])
+                            cluster_pass_n<CL, true, true>(W1, RSP, KSP + 4, xprev, wstage, RSP, KSP + 4, xh, h_lo, R,
                                                            KSP, Bpad, bc, xs, red, myu * 4, myrow, pre_g, fin_g);
                         else
                             cluster_pass_n<CL, true, false>(W1, RSP, KSP + 4, xprev, w_ih[l] + (size_t)ug * 4 * 2 * P, 2 * P, P, xh, h_lo, R,
@@ -524,25 +561,39 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
         grid_wait(p.bar, G * (++nbar));
         tick(3);
         // ================= P3: logits -> per-CTA partials + global arg-max keys =================
+        const bool staged_out = !p.out_in_smem && p.wstage_rows >= 16;
+        const int RGo = staged_out ? p.wstage_rows : RG;                 // rows per pass of the output matrix
         for (int bc = 0; bc < Bpad; bc += BCH) {
             float lmax = -INFINITY, lsum = 0.f, dmax = -INFINITY;
             int lidx = 0x7fffffff, didx = 0x7fffffff;
             float kmax = -INFINITY;                       // phrase boosting: arg-max key on the BOOSTED logits,
             int kidx = 0x7fffffff;                        // (lmax, lsum) stay raw for the softmax denominator
             const int BW = (V + 31) >> 5;
-            for (int rg = o0; rg < o1; rg += RG) {
-                const int R = min(RG, o1 - rg);
+            if (staged_out && o1 > o0) stage_rows_async(wstage, p.Wout + (size_t)o0 * 2 * J, min(RGo, o1 - o0), J, kJ0, KSJ);
+            for (int rg = o0; rg < o1; rg += RGo) {
+                const int R = min(RGo, o1 - rg);
                 const int nmy = (R - rank + CL - 1) / CL;
                 auto xz = [&](int b) { return zb + (size_t)b * J + kJ0; };
                 auto myrow = [&](int i) { return rank + CL * i; };
                 auto pb = [&](int r, int) { return p.bout[rg + r]; };
                 auto fl = [&](int i, int, int b, float v, float e) { gsm[i * BCH + (b - bc)] = v + e; };
-                if (p.out_in_smem)
+                const bool first_pass = rg == o0;          // z is staged once per (phase, utterance chunk): no pass overwrites xs in P3
+                if (p.out_in_smem) {
                     cluster_pass_n<CL, true, true>(w_o + (size_t)(rg - o0) * RSO, RSO, LOO, xz, nullptr, 0, 0, nox, z_lo, R, KSJ, Bpad, bc, xs,
-                                                   red, nmy, myrow, pb, fl);
-                else
+                                                   red, nmy, myrow, pb, fl, NoPost(), first_pass);
+                } else if (staged_out) {
+                    // (the x staging inside the pass waits for ALL outstanding cp.async groups: this tile included)
+                    auto next_tile = [&]() {
+                        const int rn = rg + RGo;
+                        __syncthreads();                  // every warp has finished reading the tile
+                        if (rn < o1) stage_rows_async(wstage, p.Wout + (size_t)rn * 2 * J, min(RGo, o1 - rn), J, kJ0, KSJ);
+                    };
+                    cluster_pass_n<CL, true, true>(wstage, RSJ, KSJ + 4, xz, nullptr, 0, 0, nox, z_lo, R, KSJ, Bpad, bc, xs, red, nmy, myrow, pb, fl,
+                                                   next_tile, first_pass);
+                } else {
                     cluster_pass_n<CL, false, true>(w_o + (size_t)(rg - o0) * RSO, RSO, LOO, xz, nullptr, 0, 0, nox, z_lo, R, KSJ, Bpad, bc, xs,
                                                     red, nmy, myrow, pb, fl);
+                }
                 if (tid < BCH) {
                     for (int i = 0; i < nmy; ++i) {
                         const float v = gsm[i * BCH + tid];
@@ -569,7 +620,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                     }
                 }
                 __syncthreads();
-                if (rg + RG < o1 || bc + BCH < Bpad) cluster_sync_all();
+                if (rg + RGo < o1 || bc + BCH < Bpad) cluster_sync_all();
             }
             if (tid < BCH && bc + tid < Bpad) {
                 const int b = bc + tid;
@@ -727,21 +778,37 @@ __global__ void tdt_split_rows_kernel(const float *__restrict__ src, int rows, i
 }
 
 // Shared memory of one CTA (bytes) for `n_clusters` clusters of CL; decides what stays in shared memory.
-size_t tdt_smem_bytes(const TdtParams &p, int n_clusters, int CL, bool *out_in_smem, bool *wih_in_smem, int *lstm_floats) {
+size_t tdt_smem_bytes(const TdtParams &p, int n_clusters, int CL, bool *out_in_smem, bool *wih_in_smem, int *lstm_floats, int *wstage_rows) {
     const TdtGeom ge = tdt_geom(p.P, p.J, p.V + p.D, n_clusters, CL);
     const size_t budget = 225 * 1024 / sizeof(float);
     const int KSmax = ge.KSP > ge.KSJ ? ge.KSP : ge.KSJ;
-    size_t fixed = (size_t)RG * RLD + (size_t)MYMAX * BCH + (size_t)2 * BCH * (KSmax + 8) / 2 + (size_t)p.L * 2 * ge.MU * p.Bpad +
+    const int xrows = p.Bpad < BCH ? p.Bpad : BCH;      // the x staging planes hold min(64, Bpad) utterance rows
+    size_t fixed = (size_t)RG * RLD + (size_t)MYMAX * BCH + (size_t)2 * xrows * (KSmax + 8) / 2 + (size_t)p.L * 2 * ge.MU * p.Bpad +
                    7 * (size_t)p.Bpad;
     // a staged weight row = [hi KS+4][lo KS+4] bf16 = KS + 4 floats
     const size_t hh = (size_t)p.L * ge.UPC * 4 * (ge.KSP + 4), ih = (size_t)(p.L - 1) * ge.UPC * 4 * (ge.KSP + 4);
     const size_t wp = (size_t)ge.JPC * (ge.KSP + 4), wo = (size_t)ge.OPC * (ge.KSJ + 4);
     size_t total = fixed + hh + wp;                 // always resident
     *wih_in_smem = (ih == 0) || (total + ih <= budget);
-    if (*wih_in_smem) total += ih;
     *lstm_floats = (int)(hh + (*wih_in_smem ? ih : 0));
-    *out_in_smem = total + wo <= budget;
-    if (*out_in_smem) total += wo;
+    *out_in_smem = total + (*wih_in_smem ? ih : 0) + wo <= budget;
+    *wstage_rows = 0;
+    if (*out_in_smem) {
+        total += (*wih_in_smem ? ih : 0) + wo;
+    } else {
+        // Large vocabulary (tdt-600m: 8198 output rows): the output matrix is streamed every step, so the staging tile
+        // comes first -- 80 rows per pass cost a third of the passes that 16 rows do, and each pass has a fixed cost of
+        // ~9k cycles (x staging, cluster barrier, DSMEM exchange).  W_ih of the upper layers stays resident only if it still
+        // fits; otherwise it is streamed through the same tile (P1 uses the tile before P3 needs it).
+        const size_t left = budget > total ? budget - total : 0;
+        int rows = (int)(left / (size_t)(ge.KSJ + 4));
+        rows = rows >= 80 ? 80 : (rows >= 64 ? 64 : (rows >= 48 ? 48 : (rows >= 32 ? 32 : (rows >= 16 ? 16 : 0))));
+        *wstage_rows = rows;
+        total += (size_t)rows * (ge.KSJ + 4);
+        *wih_in_smem = (ih == 0) || (total + ih <= budget);
+        *lstm_floats = (int)(hh + (*wih_in_smem ? ih : 0));
+        if (*wih_in_smem) total += ih;
+    }
     return total * sizeof(float);
 }
 
@@ -767,8 +834,8 @@ cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
     cudaError_t err;
     for (int iter = 0; iter < 2; ++iter) {
         bool out_in_smem, wih_in_smem;
-        int lstm_floats;
-        const size_t smem = tdt_smem_bytes(p, nc, CL, &out_in_smem, &wih_in_smem, &lstm_floats);
+        int lstm_floats, wstage_rows;
+        const size_t smem = tdt_smem_bytes(p, nc, CL, &out_in_smem, &wih_in_smem, &lstm_floats, &wstage_rows);
         if (smem > 227 * 1024) return cudaSuccess;
         err = cudaFuncSetAttribute(tdt_decode_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
@@ -781,6 +848,7 @@ cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
             p.out_in_smem = out_in_smem ? 1 : 0;
             p.wih_in_smem = wih_in_smem ? 1 : 0;
             p.smem_lstm_floats = lstm_floats;
+            p.wstage_rows = getenv("PK_TDT_NO_STAGE") ? 0 : wstage_rows;
             *fits = true;
             tdt_init_kernel<<<(3 * p.Bpad + 127) / 128, 128, 0, st>>>(p);
             return cudaLaunchKernelEx(&cfg, tdt_decode_kernel<CL>, p);
