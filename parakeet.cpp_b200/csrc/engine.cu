@@ -394,7 +394,11 @@ pk_status pk_engine::alloc_workspace() {
     const size_t PG = (size_t)3 * num_sms * Bpad;
     pl_max = dalloc<float>(PG);
     pl_sum = dalloc<float>(PG);
-    if (!pl_sum || !tdt_keys || !hbuf || !x || !sub2 || !d_pcm || !t_conf) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
+    skinny_ws_floats = (size_t)2 << 20;                                       // 8 MB: >= (2 SMs' worth of CTAs) x 128 x 32 fp32 tiles
+    skinny_ws = dalloc<float>(skinny_ws_floats);
+    skinny_tickets = dalloc<unsigned int>(SKINNY_TICKETS);
+    if (skinny_tickets) cudaMemsetAsync(skinny_tickets, 0, SKINNY_TICKETS * sizeof(unsigned int), stream);
+    if (!pl_sum || !tdt_keys || !hbuf || !x || !sub2 || !d_pcm || !t_conf || !skinny_ws || !skinny_tickets) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
     if (cfg.math != PK_MATH_FP32 && (!sub1.hi || !sub3.hi || !sub4.hi || !ln.hi || !ffh.hi || !ctx.hi || !cv.hi))
         return fail(PK_ERR_CUDA, "workspace: cudaMalloc or cuTensorMapEncodeTiled failed for an activation operand");
     PK_CUDA(cudaMallocHost(&h_pcm, (B * (size_t)c.max_samples + 8) * sizeof(float)));
@@ -490,6 +494,12 @@ void pk_engine::gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiPara
     Scope sc(this, CAT_GEMM, 2.0 * M_ * W.N * W.K);
     if (cfg.math == PK_MATH_FP32) {
         launch_gemm_simt(A.f32, lda, W.w, W.K, M_, W.N, W.K, epi, stream);
+    } else if (skinny && M_ <= 128 && skinny_ws && W.N <= 32 * SKINNY_TICKETS) {
+        // one row tile: weight-streaming bound -- split over N and K so that every SM pulls weights (gemm_skinny.cu)
+        epi.tma_out = 0;
+        cudaError_t ce = launch_gemm_skinny(A.hi, A.lo, lda, W.hi, W.lo, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, epi, skinny_ws, skinny_ws_floats,
+                                            skinny_tickets, SKINNY_TICKETS, num_sms, stream);
+        if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("skinny GEMM launch: ") + cudaGetErrorString(ce));
     } else {
         cudaError_t ce = launch_gemm_tc(A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, epi, stream);
         if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(ce));
@@ -889,6 +899,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     if (const char *ev = getenv("PK_GRAPH")) e->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("PK_ATTN_TC")) e->attn_tc = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_TMA_OUT")) e->tma_out = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_GEMM_SKINNY")) e->skinny = atoi(ev) != 0;
     e->device = device;
     if (cudaSetDevice(device) != cudaSuccess) {
         g_create_err = "cudaSetDevice failed";
@@ -1060,8 +1071,23 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
                                     : make_tc_out_map(&om0, o_tc, true, M, No);
             if (ok) { ep.tma_out = 1; ep.tm_out0 = &om0; ep.tm_out1 = act_out ? &om1 : nullptr; }
         }
-        if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st) != cudaSuccess) rc = PK_ERR_CUDA;
-        if (rc == PK_OK && getenv("PK_SELFTEST_TIME")) {   // warm, back-to-back timing of the tcgen05 launch
+        const bool use_skinny = getenv("PK_SELFTEST_SKINNY") && atoi(getenv("PK_SELFTEST_SKINNY")) && M <= 128;
+        float *sws = nullptr;
+        unsigned int *stk = nullptr;
+        if (use_skinny) {           // the few-row kernel (gemm_skinny.cu) on the same operands
+            cudaMalloc(&sws, ((size_t)2 << 20) * sizeof(float));
+            cudaMalloc(&stk, 1024 * sizeof(unsigned int));
+            cudaMemsetAsync(stk, 0, 1024 * sizeof(unsigned int), st);
+            int sms = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            ep.tma_out = 0;
+            for (int rep = 0; rep < 2 && rc == PK_OK; ++rep)      // twice: the tickets must come back to zero
+                if (launch_gemm_skinny(Ah, Al, K, Wh, Wl, M, N, K, math == PK_MATH_BF16X3, ep, sws, (size_t)2 << 20, stk, 1024, sms, st) != cudaSuccess) rc = PK_ERR_CUDA;
+            cudaStreamSynchronize(st);
+            cudaFree(sws);
+            cudaFree(stk);
+        } else if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st) != cudaSuccess) rc = PK_ERR_CUDA;
+        if (rc == PK_OK && !use_skinny && getenv("PK_SELFTEST_TIME")) {   // warm, back-to-back timing of the tcgen05 launch
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);
             const int reps = 20;

@@ -243,6 +243,12 @@ struct pk_engine {
     std::map<std::tuple<const void *, int, int, int>, CUtensorMap> out_maps;
     const CUtensorMap *out_map(const void *ptr, bool is_f32, int rows, int ld);
     bool tma_out = true;                       // PK_GEMM_TMA_OUT=0: results leave through st.global instead
+    // few-row GEMMs (M <= 128: streaming steps, short utterances) go to gemm_skinny.cu (PK_GEMM_SKINNY=0: never)
+    bool skinny = true;
+    float *skinny_ws = nullptr;
+    size_t skinny_ws_floats = 0;
+    unsigned int *skinny_tickets = nullptr;
+    static constexpr int SKINNY_TICKETS = 1024;
     pk_status gemm_err = PK_OK;
     pk_status run_mel(int u0 = 0, int u1 = -1);
     pk_status run_conv1(int u0 = 0, int u1 = -1);

@@ -92,6 +92,12 @@ void tc_print_timeline(int n_tiles);
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st);
 
+// ------------------------------------------------------------------ gemm_skinny.cu (M <= 128: the streaming path's GEMMs)
+size_t gemm_skinny_ws_floats(int max_n, int max_splits);
+cudaError_t launch_gemm_skinny(const bf16 *Ahi, const bf16 *Alo, int lda, const bf16 *Whi, const bf16 *Wlo, int M, int N, int K, bool split3,
+                               const EpiParams &epi, float *ws, size_t ws_floats, unsigned int *tickets, int n_tickets, int num_sms,
+                               cudaStream_t st);
+
 // ------------------------------------------------------------------ norm_conv.cu (K6, K8)
 // fp32 -> bf16 hi/lo operand planes (n multiple of 4)
 void launch_split(const float *x, size_t n, ActBuf out, cudaStream_t st);

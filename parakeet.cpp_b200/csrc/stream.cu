@@ -118,15 +118,19 @@ stream_attention_kernel(const float *__restrict__ qkv, int ld_qkv, const int32_t
             sc[j] = (ac + bd) * scale;
         }
         __syncthreads();
-        // softmax over kv (max-subtracted, cpu_operations.cpp:3101-3231), every thread redundantly over <= L + C values
+        // softmax over kv (max-subtracted, cpu_operations.cpp:3101-3231): thread j exponentiates its own score once; the
+        // maximum and the (sequential, in key order) sum are recomputed by every thread from shared memory
         float mx = -INFINITY;
         for (int j = 0; j < kv; ++j) mx = fmaxf(mx, sc[j]);
+        __syncthreads();
+        for (int j = tid; j < kv; j += nt) sc[j] = expf(sc[j] - mx);
+        __syncthreads();
         float sum = 0.f;
-        for (int j = 0; j < kv; ++j) sum += expf(sc[j] - mx);
+        for (int j = 0; j < kv; ++j) sum += sc[j];
         const float inv = 1.0f / sum;
         for (int c = tid; c < hd; c += nt) {
             float o = 0.f;
-            for (int j = 0; j < kv; ++j) o = fmaf(expf(sc[j] - mx) * inv, sv[j * (hd + 1) + c], o);
+            for (int j = 0; j < kv; ++j) o = fmaf(sc[j] * inv, sv[j * (hd + 1) + c], o);
             store_act(out, (size_t)(r0 + i) * d_model + h * hd + c, o);
         }
     }

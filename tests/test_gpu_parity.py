@@ -66,6 +66,21 @@ def test_tcgen05_gemm_matches_fp32_gemm(pkg, M, N, K, epi):
     assert err1 / ref < 2e-2                     # plain bf16 operands
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(1, 640, 512, "BIAS_F32"), (2, 2048, 512, "SILU_ACT"), (64, 512, 2048, "RESID"), (128, 1536, 512, "QKV"),
+                                       (100, 1024, 512, "GLU"), (126, 1025, 512, "BIAS_F32"), (17, 256, 256, "RELU_ACT"), (128, 512, 2560, "BIAS_F32"),
+                                       (77, 384, 128, "QKV"), (128, 64, 64, "BIAS_ACT")])
+def test_skinny_gemm_matches_fp32_gemm(pkg, M, N, K, epi, monkeypatch):
+    """The few-row GEMM of the streaming path (csrc/gemm_skinny.cu: N x K-split CTAs, mma.sync bf16x3, slices reduced in
+    a fixed order by the last CTA to arrive) against the fp32 CUDA-core GEMM, every epilogue kind, edge columns, two
+    launches in a row (tickets reset)."""
+    from parakeet_cpp_b200.engine import selftest_gemm
+    monkeypatch.setenv("PK_SELFTEST_SKINNY", "1")
+    err, ref = selftest_gemm(M, N, K, EPI[epi], 0)
+    assert err / ref < 5e-5, (err, ref)
+    err1, _ = selftest_gemm(M, N, K, EPI[epi], 1)
+    assert err1 / ref < 2e-2
+
+
 # ------------------------------------------------------------------ mel front end (K1/K2)
 @pytest.mark.parametrize("lengths", [[16000], [400], [401, 559, 560, 561], [32000, 20000, 64000, 12345, 8000, 16001]])
 def test_mel_matches_oracle(eng_tiny, O, synth, lengths):
