@@ -235,6 +235,9 @@ pk_status pk_flush_l2(pk_engine *e);
 /* Debug aid: cycles CTA 0 of the last TDT decode spent in {P1, B1, P2, B2, P3, B3, P4}; out8[7] =
  * number of lock-step decode steps. */
 pk_status pk_debug_tdt_phases(pk_engine *e, int64_t *out8);
+/* Debug aid: cycles CTA 0 spent in the sections of the decode kernel's passes since the previous call:
+ * {x staging, products, partial store + cluster barrier, DSMEM gather + finalise, number of passes, 0, 0, 0}. */
+pk_status pk_debug_tdt_passes(pk_engine *e, int64_t *out8);
 
 /* GPU self-check of the tcgen05 GEMM kernel against the fp32 CUDA-core GEMM on seeded
  * random data (epi_kind: EpiKind of csrc/pk_common.cuh; math: PK_MATH_BF16X3 | PK_MATH_BF16X1). */

@@ -1141,6 +1141,18 @@ pk_status pk_debug_tdt_phases(pk_engine *e, int64_t *out8) {
     return PK_OK;
 }
 
+// Debug aid: cycles CTA 0 spent in the sections of the decode kernel's passes since the last call
+// {x staging, products, partial store + cluster barrier, DSMEM gather + finalise, number of passes}.
+pk_status pk_debug_tdt_passes(pk_engine *e, int64_t *out8) {
+    if (!e || !out8) return PK_ERR_INVALID;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    long long v[8];
+    tdt_pass_profile(v, true);
+    for (int i = 0; i < 8; ++i) out8[i] = v[i];
+    return PK_OK;
+}
+
 pk_status pk_sync(pk_engine *e) {
     if (!e) return PK_ERR_INVALID;
     cudaError_t ce = cudaStreamSynchronize(e->stream);

@@ -178,6 +178,7 @@ struct TdtParams {
     int32_t *trie_active, *trie_nact;
 };
 cudaError_t launch_tdt_decode(TdtParams p, int num_sms, cudaStream_t st);
+void tdt_pass_profile(long long *out8, bool reset);   // measurement aid: section cycles of cluster_pass (CTA 0), summed since the last reset
 // fp32 [rows][K] -> [rows][2 K] bf16 = [hi: K][lo: K]
 void launch_tdt_split_rows(const float *src, int rows, int K, bf16 *dst, cudaStream_t st);
 

@@ -179,6 +179,11 @@ __device__ __forceinline__ void store_partials(const float (&acc)[NBH][4], float
     }
 }
 
+// measurement aid: cycles thread 0 of CTA 0 spent in the sections of cluster_pass, summed over a decode:
+// [0] x staging + operand prefetch until the staged slice is visible, [1] products, [2] partial store + cluster barrier,
+// [3] DSMEM gather + finalisation, [4] number of passes
+__device__ long long g_pass_clk[8];
+
 // One pass over R <= RG weight rows of the cluster: up to two products accumulated together
 // (W1 . x1 [+ W2 . x2]), partial sums exchanged through DSMEM, rows finalised by their owner CTA.
 //   myrow(i) -> row (0..R-1) of the i-th row this CTA finalises, i < nmy (nmy <= MYMAX)
@@ -190,6 +195,9 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
                                              size_t lo_off, int R, int KS, int Bpad, int bc, bf16 *xs, float *red, int nmy,
                                              MyRow myrow, Pre pre, Fin fin, Post post, bool stage_x1 = true) {
     const int xrows = min(BCH, Bpad);
+    const bool prof = blockIdx.x == 0 && threadIdx.x == 0;
+    long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
+    if (prof) pt0 = clock64();
     float acc[NBH][4];
 #pragma unroll
     for (int nb = 0; nb < NBH; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
@@ -216,6 +224,7 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (prof) pt1 = clock64();
     mma_slice<NBH, WS1>(acc, W1, RS1, LO1, R, KS, xs, xrows);
     if (W2 != nullptr) {
         __syncthreads();                              // everyone is done reading x1
@@ -223,8 +232,10 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
         mma_slice<NBH, WS2>(acc, W2, RS2, LO2, R, KS, xs, xrows);
     }
     post();
+    if (prof) pt2 = clock64();
     store_partials<NBH>(acc, red);
     cluster_sync_all();                               // all CL partial buffers complete and visible
+    if (prof) pt3 = clock64();
     uint32_t peer[CL];
 #pragma unroll
     for (int q = 0; q < CL; ++q) peer[q] = mapa_rank(smem_addr(red), (uint32_t)q);
@@ -241,6 +252,14 @@ __device__ __forceinline__ void cluster_pass(const bf16 *W1, int RS1, int LO1, X
         }
     }
     __syncthreads();
+    if (prof) {
+        const long long pt4 = clock64();
+        g_pass_clk[0] += pt1 - pt0;
+        g_pass_clk[1] += pt2 - pt1;
+        g_pass_clk[2] += pt3 - pt2;
+        g_pass_clk[3] += pt4 - pt3;
+        g_pass_clk[4] += 1;
+    }
 }
 
 struct NoPost {
@@ -259,6 +278,8 @@ __device__ __forceinline__ void cluster_pass_n(const bf16 *W1, int RS1, int LO1,
 // Monotonic-counter grid barrier (all CTAs are co-resident: cooperative launch), split into
 // arrive / wait so that work which does not depend on the other CTAs can sit in between.
 // Cheaper than cooperative_groups' grid.sync() and traps instead of hanging if a CTA never arrives.
+// (A hierarchical variant -- hardware cluster barrier, one atomic per cluster, second cluster barrier -- was measured
+// SLOWER: 5.4-6.1k cycles per use against 3.2-5.1k; two barrier.cluster round trips cost more than the 111 atomics saved.)
 __device__ __forceinline__ void grid_arrive(unsigned int *counter) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -864,6 +885,14 @@ cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
 int g_tdt_cl = 0;
 
 }  // namespace
+
+void tdt_pass_profile(long long *out8, bool reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, g_pass_clk, 8 * sizeof(long long));
+    if (reset) {
+        long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_pass_clk, z, sizeof(z));
+    }
+}
 
 void launch_tdt_split_rows(const float *src, int rows, int K, bf16 *dst, cudaStream_t st) {
     tdt_split_rows_kernel<<<256, 256, 0, st>>>(src, rows, K, dst);

@@ -50,7 +50,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
            "pk_job_fetch", "pk_job_stage_pcm", "pk_job_select", "pk_truncated_count",
            "pk_stream_open", "pk_stream_reset", "pk_stream_step", "pk_stream_count", "pk_stage_pcm_rate", "pk_resample_batch",
-           "pk_set_boost", "pk_vocab_max_piece_bytes", "pk_safetensors_probe"]
+           "pk_set_boost", "pk_vocab_max_piece_bytes", "pk_safetensors_probe", "pk_debug_tdt_passes"]
 
 _lib = None
 
@@ -103,6 +103,7 @@ def load_library():
     L.pk_profile_names.restype = C.c_char_p
     L.pk_flush_l2.argtypes = [vp]
     L.pk_debug_tdt_phases.argtypes = [vp, i64p]
+    L.pk_debug_tdt_passes.argtypes = [vp, i64p]
     L.pk_selftest_gemm.argtypes = [C.c_int] * 6 + [C.c_uint32, f32p, f32p]
     L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pk_vocab_free.argtypes = [vp]
@@ -476,6 +477,11 @@ class Engine:
     def tdt_phases(self):
         a = np.zeros(8, np.int64)
         self._check(self.L.pk_debug_tdt_phases(self.h, _i64p(a)), "pk_debug_tdt_phases")
+        return a
+
+    def tdt_passes(self):
+        a = np.zeros(8, np.int64)
+        self._check(self.L.pk_debug_tdt_passes(self.h, _i64p(a)), "pk_debug_tdt_passes")
         return a
 
     def launch_count(self) -> int:

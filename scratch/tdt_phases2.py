@@ -14,6 +14,10 @@ for name in sys.argv[1:] or ['110m-64x10s', '600m-16x30s']:
     eng.stage(buf, off)
     for _ in range(3): eng.run_staged(pkg.Decoder.TDT)
     eng.sync()
+    eng.tdt_passes()
+    eng.run_staged(pkg.Decoder.TDT)
+    ps = eng.tdt_passes()
+    print(name, 'passes', ps[4], 'cycles per pass: stage %.0f  mma %.0f  store+cluster-barrier %.0f  gather+fin %.0f' % tuple(ps[:4] / max(ps[4], 1)))
     a = eng.tdt_phases(); tot = a[:7].sum()
     print(name, 'steps', a[7], 'cycles/step', tot / a[7])
     for nm, v in zip(['P1', 'B1', 'P2', 'B2', 'P3', 'B3', 'P4'], a[:7]): print('   ', nm, f'{v / tot:.1%}', f'{v / a[7]:.0f} cycles/step')
