@@ -389,7 +389,7 @@ pk_status pk_engine::alloc_workspace() {
     const size_t HS = (size_t)c.pred_hidden * Bpad;
     hbuf = dalloc<float>(HS * 2 * c.lstm_layers);                  // bf16 hi + lo planes
     zbuf = dalloc<float>((size_t)c.joint_hidden * Bpad);           // bf16 hi + lo planes
-    tdt_ints = dalloc<int32_t>((size_t)Bpad + 4);
+    tdt_ints = dalloc<int32_t>((size_t)Bpad + 512);               // overflow flags | grid-barrier counters (8 lines)
     tdt_keys = dalloc<unsigned long long>((size_t)6 * Bpad + 8);
     const size_t PG = (size_t)3 * num_sms * Bpad;
     pl_max = dalloc<float>(PG);

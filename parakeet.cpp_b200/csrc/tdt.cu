@@ -280,21 +280,31 @@ __device__ __forceinline__ void cluster_pass_n(const bf16 *W1, int RS1, int LO1,
 // Cheaper than cooperative_groups' grid.sync() and traps instead of hanging if a CTA never arrives.
 // (A hierarchical variant -- hardware cluster barrier, one atomic per cluster, second cluster barrier -- was measured
 // SLOWER: 5.4-6.1k cycles per use against 3.2-5.1k; two barrier.cluster round trips cost more than the 111 atomics saved.)
+// Same-address atomics serialise in the L2 (~27 cycles each: 148 of them made a barrier 3.2-5.1k cycles), so the arrivals
+// are spread over GBAR counters on different 128-byte lines (CTA c -> counter c % GBAR) and lanes 0..GBAR-1 of warp 0
+// poll one counter each.
+constexpr int GBAR = 8, GBAR_STRIDE = 32;      // counters, uints between them
 __device__ __forceinline__ void grid_arrive(unsigned int *counter) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(counter, 1u);
+        atomicAdd(counter + (blockIdx.x % GBAR) * GBAR_STRIDE, 1u);
     }
 }
-__device__ __forceinline__ void grid_wait(unsigned int *counter, unsigned int target) {
-    if (threadIdx.x == 0) {
-        unsigned int v, spin = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (++spin > (1u << 28)) __trap();
-        } while (v < target);
-        __threadfence();
+__device__ __forceinline__ void grid_wait(unsigned int *counter, unsigned int round /* 1, 2, ... */) {
+    if (threadIdx.x < 32) {
+        const int l = threadIdx.x;
+        if (l < GBAR) {
+            const unsigned int members = (gridDim.x - l + GBAR - 1) / GBAR;     // CTAs that arrive on counter l
+            const unsigned int target = members * round;
+            unsigned int v, spin = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter + l * GBAR_STRIDE) : "memory");
+                if (++spin > (1u << 28)) __trap();
+            } while (v < target);
+        }
+        __syncwarp();
+        if (threadIdx.x == 0) __threadfence();
     }
     __syncthreads();
 }
@@ -555,7 +565,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
                 __syncthreads();
                 for (int b = tid; b < Bpad; b += blockDim.x) s_pend[b] = -1;
             }
-            grid_wait(p.bar, G * (++nbar));
+            grid_wait(p.bar, ++nbar);
             tick(1);
         }
         // ================= P2: joint hidden z = relu(EP[t] + Wp . h') =================
@@ -579,7 +589,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
             }
         tick(2);
         grid_arrive(p.bar);
-        grid_wait(p.bar, G * (++nbar));
+        grid_wait(p.bar, ++nbar);
         tick(3);
         // ================= P3: logits -> per-CTA partials + global arg-max keys =================
         const bool staged_out = !p.out_in_smem && p.wstage_rows >= 16;
@@ -659,7 +669,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
         }
         tick(4);
         grid_arrive(p.bar);
-        grid_wait(p.bar, G * (++nbar));
+        grid_wait(p.bar, ++nbar);
         tick(5);
         // ================= P4 (replicated in every CTA): state update =================
         int any = 0;
@@ -763,7 +773,7 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
 
 __global__ void tdt_init_kernel(TdtParams p) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) *p.bar = 0u;
+    if (b < GBAR * GBAR_STRIDE) p.bar[b] = 0u;
     if (b < 3 * p.Bpad) {
         p.key_lab[b] = 0ull;
         p.key_dur[b] = 0ull;
@@ -871,7 +881,7 @@ cudaError_t launch_cl(TdtParams p, int num_sms, cudaStream_t st, bool *fits) {
             p.smem_lstm_floats = lstm_floats;
             p.wstage_rows = getenv("PK_TDT_NO_STAGE") ? 0 : wstage_rows;
             *fits = true;
-            tdt_init_kernel<<<(3 * p.Bpad + 127) / 128, 128, 0, st>>>(p);
+            tdt_init_kernel<<<((3 * p.Bpad > GBAR * GBAR_STRIDE ? 3 * p.Bpad : GBAR * GBAR_STRIDE) + 127) / 128, 128, 0, st>>>(p);
             return cudaLaunchKernelEx(&cfg, tdt_decode_kernel<CL>, p);
         }
         if (max_clusters < 1) return cudaSuccess;
