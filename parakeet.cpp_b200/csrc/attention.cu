@@ -194,7 +194,8 @@ void launch_t(const float *qkv, int ld_qkv, const int32_t *row_off, int n_utt, i
               const float *pp, int tmax, const float *bu, const float *bv, int d_model, ActBuf out,
               cudaStream_t st) {
     using C = AttnCfg<HD, BQ, BKV>;
-    static bool attr_set = false;
+    static PerDeviceFlag attr_flag;
+    bool &attr_set = attr_flag.cur();
     if (!attr_set) {
         cudaFuncSetAttribute(relpos_attention_kernel<HD, BQ, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)C::SMEM);

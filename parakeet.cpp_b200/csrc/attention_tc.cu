@@ -349,7 +349,8 @@ template <int HD, bool QS>
 static bool launch_attn_t(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt, int max_T,
                           int n_heads, const bf16 *pp_hi, const bf16 *pp_lo, int tmax, int d_model, ActBuf out, cudaStream_t st) {
     using SM = AttnSmem<HD, QS>;
-    static bool attr = false;
+    static PerDeviceFlag attr_flag;
+    bool &attr = attr_flag.cur();
     if (!attr) {
         if (cudaFuncSetAttribute(relpos_attention_tc_kernel<HD, QS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(SM)) != cudaSuccess)

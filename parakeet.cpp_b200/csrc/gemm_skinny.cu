@@ -179,7 +179,8 @@ cudaError_t launch_gemm_skinny(const bf16 *Ahi, const bf16 *Alo, int lda, const 
         --nsplit;
         while (chunks % nsplit != 0) --nsplit;
     }
-    static bool attr = false;
+    static PerDeviceFlag attr_flag;
+    bool &attr = attr_flag.cur();
     if (!attr) {
         cudaError_t e1 = cudaFuncSetAttribute(gemm_skinny_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
         cudaError_t e2 = cudaFuncSetAttribute(gemm_skinny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);

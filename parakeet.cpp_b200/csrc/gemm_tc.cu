@@ -872,17 +872,20 @@ EncodeTiledFn encode_fn() {
 template <int BN, int NPASS, int EK>
 cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
     using C = TcCfg<BN, NPASS>;
-    static bool attr = false;
+    static PerDeviceFlag attr_flag;
+    bool &attr = attr_flag.cur();
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    static int num_sms = 0;
-    if (!num_sms) {
+    int num_sms = 0;
+    {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        static int sms_of[64] = {};
+        if (!sms_of[dev & 63]) cudaDeviceGetAttribute(&sms_of[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+        num_sms = sms_of[dev & 63];
     }
     const int num_tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
     dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);
@@ -899,17 +902,20 @@ cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K
 template <int NPASS, int EK>
 cudaError_t launch_k2(const TcOperand &A, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
     using C = Tc2Cfg<NPASS>;
-    static bool attr = false;
+    static PerDeviceFlag attr_flag;
+    bool &attr = attr_flag.cur();
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<NPASS, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    static int num_sms = 0;
-    if (!num_sms) {
+    int num_sms = 0;
+    {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        static int sms_of[64] = {};
+        if (!sms_of[dev & 63]) cudaDeviceGetAttribute(&sms_of[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+        num_sms = sms_of[dev & 63];
     }
     const int num_tiles = ((N + BN2 - 1) / BN2) * ((M + 2 * BM - 1) / (2 * BM));
     const int pairs = num_tiles < num_sms / 2 ? num_tiles : num_sms / 2;

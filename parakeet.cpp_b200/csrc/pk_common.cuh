@@ -8,6 +8,24 @@ namespace pk {
 
 typedef __nv_bfloat16 bf16;
 
+// cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (one pk_engine per device, e.g.
+// examples/sharded_transcribe.cpp) must set a kernel's attributes once on each of them.  Returns the flag of the
+// current device inside a caller-owned per-kernel table.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    size_t size[64] = {};
+    bool &cur() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return done[dev & 63];
+    }
+    size_t &cur_size() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return size[dev & 63];
+    }
+};
+
 // An activation that feeds a GEMM as the A operand.  In PK_MATH_FP32 mode only
 // `f32` is set; in the tcgen05 modes the producer kernel writes the bf16 hi/lo
 // split planes (hi = rn(x), lo = rn(x - hi)), which cost the same bytes as fp32.

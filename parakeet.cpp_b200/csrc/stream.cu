@@ -198,7 +198,8 @@ bool launch_stream_attention(const float *qkv, int ld_qkv, const int32_t *row_of
                              ActBuf out, cudaStream_t s) {
     const size_t smem = stream_attention_smem(L, max_C, hd);
     if (smem > 200 * 1024) return false;
-    static size_t attr = 0;
+    static PerDeviceFlag attr_flag;
+    size_t &attr = attr_flag.cur_size();
     if (smem > attr) {
         if (cudaFuncSetAttribute(stream_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         attr = smem;

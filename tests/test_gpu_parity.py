@@ -800,3 +800,17 @@ def test_cpp_streaming_transcriber(pkg, O, synth, tmp_path):
     assert out[len(sched)] == "TEXT " + O.detokenize(all_ids, pieces)
     assert int(out[len(sched) + 1].split()[1]) == sum(1 for ci in range(len(sched)) if len(g[f"tstream.k{ci}.tok"]))
     assert out[len(sched) + 2] == "AFTER_RESET 0"
+
+
+def test_cpp_sharded_example_world1(pkg, O, tiny, tmp_path):
+    """examples/sharded_transcribe.cpp (a C++ host: one thread per GPU, pk_comm_init_rank + pk_job_* + ONE
+    pk_allgather_tokens, NCCL by dlopen) built and run with one rank; on 2 GPUs the same job gives the same checksum
+    (profiles/r02_example_sharded_cpp_2gpu.txt)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "sharded_transcribe")
+    libdir = os.path.dirname(pkg.lib_path())
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "sharded_transcribe.cpp"),
+                    "-L" + libdir, "-lparakeet_b200", "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
+    out = subprocess.run([exe, tiny.weights_path, "1", "12", "tiny"], check=True, capture_output=True, text=True).stdout
+    assert "gathered 12 rows" in out and "identical on every rank" in out
