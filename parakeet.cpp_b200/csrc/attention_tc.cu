@@ -7,11 +7,12 @@
 // 126 x 126 x 64, far below a UMMA tile pipeline's break-even, and the rel_shift needs a per-row
 // skew that is natural in registers/shared memory.
 //
-// Operands arrive as bf16 hi/lo planes: the fused q/k/v projection (EPI_QKV_ACT epilogue of the
-// tcgen05 GEMM) writes [M, 4d] = [Qu | Qv | K | V] with Qu = q + pos_bias_u, Qv = q + pos_bias_v, and
-// PP = pos_emb . Wpos^T is split once at load.  So this kernel does no conversions on its inputs:
-// K / V / PP-window tiles are cp.async'ed (16 B) into shared memory, Q fragments are read straight
-// from global memory into registers, all fragments come from ldmatrix (V through .trans).
+// Operands: the fused q/k/v projection (EPI_QKV_ACT epilogue of the tcgen05 GEMM) writes K | V as bf16 hi/lo
+// planes [M, 2d] and q as fp32 [M, d]; PP = pos_emb . Wpos^T is split once at load.  K / V / PP-window tiles
+// are cp.async'ed (16 B) into shared memory and read through ldmatrix (V through .trans).  The CTA forms
+// Qu = q + pos_bias_u and Qv = q + pos_bias_v itself while it builds its Q fragments (one fp32 add and one hi/lo
+// split per element, once per CTA) -- when the GEMM epilogue produced both as planes, a q tile cost it four plane
+// stores and two passes of maths and the projection GEMM was epilogue-bound (profiles/r02_p_gemm_epilogue.txt).
 //
 // One CTA = (64-query tile, head, utterance), 4 warps x 16 query rows.  head_dim 64 (tdt-ctc-110m):
 // Q fragments live in registers, 93 KB smem -> 2 CTAs per SM (one CTA's tile loads overlap the other's
@@ -97,9 +98,12 @@ __device__ __forceinline__ uint32_t bfrag_t_addr(const bf16 *base, int k0, int n
 
 template <int HD, bool QS>
 __global__ void __launch_bounds__(TCA_THREADS, QS ? 1 : 2)
-relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restrict__ qkv_lo, int ld_qkv,
+relpos_attention_tc_kernel(const float *__restrict__ q32, const float *__restrict__ pos_u, const float *__restrict__ pos_v,
+                           const bf16 *__restrict__ qkv_hi, const bf16 *__restrict__ qkv_lo, int ld_qkv,
                            const int32_t *__restrict__ row_off, const bf16 *__restrict__ pp_hi,
                            const bf16 *__restrict__ pp_lo, int tmax, int d_model, ActBuf out) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) uint8_t smraw[];
     using SM = AttnSmem<HD, QS>;
     constexpr int LDS_ = SM::LDS_, KS = HD / 16, NBO = HD / 8, CH = HD / 8;   // k-steps, output n-blocks, 16 B chunks per row
@@ -114,33 +118,27 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
     // ---- Q fragments (A operand, rows wrow+g / wrow+g+8, KS k-steps): registers straight from the planes
     // (head_dim 64) or the Qu / Qv tiles staged in shared memory (head_dim 128)
     uint32_t qu_h[QS ? 1 : KS][4], qu_l[QS ? 1 : KS][4], qv_h[QS ? 1 : KS][4], qv_l[QS ? 1 : KS][4];
+    constexpr int NQ = QS ? BQ * (HD / 4) / TCA_THREADS : 1;
+    float4 qq[NQ];
+    float2 qraw[QS ? 1 : KS][4];
     if (!QS) {
         const int ia = i0 + wrow + g, ib = ia + 8;
-        const size_t oa = (size_t)(r0 + ia) * ld_qkv + h * HD + 2 * c, ob = (size_t)(r0 + ib) * ld_qkv + h * HD + 2 * c;
 #pragma unroll
         for (int ks = 0; ks < (QS ? 1 : KS); ++ks)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const bool okr = ((e & 1) ? ib : ia) < T;
-                const size_t o = ((e & 1) ? ob : oa) + ks * 16 + ((e >> 1) << 3);
-                qu_h[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_hi + o) : 0u;
-                qu_l[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_lo + o) : 0u;
-                qv_h[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_hi + o + d_model) : 0u;
-                qv_l[ks][e] = okr ? *reinterpret_cast<const uint32_t *>(qkv_lo + o + d_model) : 0u;
+                const int row = (e & 1) ? ib : ia;
+                const int col = h * HD + ks * 16 + ((e >> 1) << 3) + 2 * c;
+                qraw[ks][e] = make_float2(0.f, 0.f);
+                if (row < T) qraw[ks][e] = *reinterpret_cast<const float2 *>(q32 + (size_t)(r0 + row) * d_model + col);
             }
     } else {
-        // joins the first key tile's cp.async group (waited for before the first MMA)
-        const uint32_t sq0 = smem_addr(sm.q[0]), sq1 = smem_addr(sm.q[1]), sq2 = smem_addr(sm.q[2]), sq3 = smem_addr(sm.q[3]);
-        for (int idx = tid; idx < BQ * CH; idx += TCA_THREADS) {
-            const int i = idx / CH, ch = idx % CH;
-            const bool ok = (i0 + i < T);
-            const size_t o = (size_t)(r0 + (ok ? i0 + i : 0)) * ld_qkv + h * HD + ch * 8;
-            const uint32_t so = (uint32_t)(i * LDS_ + ch * 8) * 2u;
-            const int nb = ok ? 16 : 0;
-            cp_async16(sq0 + so, qkv_hi + o, nb);
-            cp_async16(sq1 + so, qkv_lo + o, nb);
-            cp_async16(sq2 + so, qkv_hi + o + d_model, nb);
-            cp_async16(sq3 + so, qkv_lo + o + d_model, nb);
+        // q rows of this tile: all loads in flight now, consumed after the first key tile's copies have been issued
+#pragma unroll
+        for (int it = 0; it < NQ; ++it) {
+            const int idx = tid + it * TCA_THREADS, i = idx / (HD / 4), c4 = (idx % (HD / 4)) * 4;
+            qq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i0 + i < T) qq[it] = *reinterpret_cast<const float4 *>(q32 + (size_t)(r0 + i0 + i) * d_model + h * HD + c4);
         }
     }
 
@@ -160,7 +158,7 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
         for (int idx = tid; idx < BKV * CH; idx += TCA_THREADS) {
             const int j = idx / CH, ch = idx % CH;
             const bool ok = (j0 + j < T);
-            const size_t o = (size_t)(r0 + (ok ? j0 + j : 0)) * ld_qkv + 2 * d_model + h * HD + ch * 8;
+            const size_t o = (size_t)(r0 + (ok ? j0 + j : 0)) * ld_qkv + h * HD + ch * 8;      // planes [k | v]
             const uint32_t so = (uint32_t)(j * LDS_ + ch * 8) * 2u;
             const int nb = ok ? 16 : 0;
             cp_async16(sk_hi + so, qkv_hi + o, nb);
@@ -180,6 +178,46 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
             cp_async16(sp_lo + so, pp_lo + o, nb);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        if (!QS && j0 == 0) {
+            // Q fragments: Qu = q + pos_bias_u, Qv = q + pos_bias_v, split hi/lo (rows past T stay zero)
+            const int ia = i0 + wrow + g, ib = ia + 8;
+#pragma unroll
+            for (int ks = 0; ks < (QS ? 1 : KS); ++ks)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = (e & 1) ? ib : ia;
+                    const int col = h * HD + ks * 16 + ((e >> 1) << 3) + 2 * c;
+                    const float2 bu = __ldg(reinterpret_cast<const float2 *>(pos_u + col)), bv = __ldg(reinterpret_cast<const float2 *>(pos_v + col));
+                    const float2 qv2 = qraw[ks][e];
+                    if (row < T) {
+                        split2(qv2.x + bu.x, qv2.y + bu.y, qu_h[ks][e], qu_l[ks][e]);
+                        split2(qv2.x + bv.x, qv2.y + bv.y, qv_h[ks][e], qv_l[ks][e]);
+                    } else {
+                        qu_h[ks][e] = qu_l[ks][e] = qv_h[ks][e] = qv_l[ks][e] = 0u;
+                    }
+                }
+        }
+        if (QS && j0 == 0) {
+            // Qu / Qv tiles (hi, lo) -> shared memory while the first key tile is on its way; visible after the barrier below
+#pragma unroll
+            for (int it = 0; it < NQ; ++it) {
+                const int idx = tid + it * TCA_THREADS, i = idx / (HD / 4), c4 = (idx % (HD / 4)) * 4;
+                const bool ok = (i0 + i < T);
+                const float4 bu = __ldg(reinterpret_cast<const float4 *>(pos_u + h * HD + c4)), bv = __ldg(reinterpret_cast<const float4 *>(pos_v + h * HD + c4));
+                uint2 uh = make_uint2(0u, 0u), ul = uh, vh = uh, vl = uh;
+                if (ok) {
+                    split2(qq[it].x + bu.x, qq[it].y + bu.y, uh.x, ul.x);
+                    split2(qq[it].z + bu.z, qq[it].w + bu.w, uh.y, ul.y);
+                    split2(qq[it].x + bv.x, qq[it].y + bv.y, vh.x, vl.x);
+                    split2(qq[it].z + bv.z, qq[it].w + bv.w, vh.y, vl.y);
+                }
+                const int so = i * LDS_ + c4;
+                *reinterpret_cast<uint2 *>(sm.q[0] + so) = uh;
+                *reinterpret_cast<uint2 *>(sm.q[QS ? 1 : 0] + so) = ul;
+                *reinterpret_cast<uint2 *>(sm.q[QS ? 2 : 0] + so) = vh;
+                *reinterpret_cast<uint2 *>(sm.q[QS ? 3 : 0] + so) = vl;
+            }
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
@@ -346,7 +384,8 @@ relpos_attention_tc_kernel(const bf16 *__restrict__ qkv_hi, const bf16 *__restri
 }  // namespace
 
 template <int HD, bool QS>
-static bool launch_attn_t(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt, int max_T,
+static bool launch_attn_t(const float *q32, const float *pos_u, const float *pos_v, const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv,
+                          const int32_t *row_off, int n_utt, int max_T,
                           int n_heads, const bf16 *pp_hi, const bf16 *pp_lo, int tmax, int d_model, ActBuf out, cudaStream_t st) {
     using SM = AttnSmem<HD, QS>;
     static PerDeviceFlag attr_flag;
@@ -358,19 +397,19 @@ static bool launch_attn_t(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, co
         attr = true;
     }
     dim3 grid((max_T + BQ - 1) / BQ, n_heads, n_utt);
-    relpos_attention_tc_kernel<HD, QS><<<grid, TCA_THREADS, sizeof(SM), st>>>(qkv_hi, qkv_lo, ld_qkv, row_off, pp_hi, pp_lo,
+    launch_pdl(relpos_attention_tc_kernel<HD, QS>, dim3(grid), dim3(TCA_THREADS), sizeof(SM), st, q32, pos_u, pos_v, qkv_hi, qkv_lo, ld_qkv, row_off, pp_hi, pp_lo,
                                                                               tmax, d_model, out);
     return true;
 }
 
-bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt,
-                                int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
-                                int d_model, ActBuf out, cudaStream_t st) {
-    if (!qkv_hi || !qkv_lo || !pp_hi || !pp_lo) return false;
+bool launch_relpos_attention_tc(const float *q32, const float *pos_u, const float *pos_v, const bf16 *qkv_hi, const bf16 *qkv_lo,
+                                int ld_qkv, const int32_t *row_off, int n_utt, int max_T, int n_heads, int head_dim, const bf16 *pp_hi,
+                                const bf16 *pp_lo, int tmax, int d_model, ActBuf out, cudaStream_t st) {
+    if (!q32 || !pos_u || !pos_v || !qkv_hi || !qkv_lo || !pp_hi || !pp_lo) return false;
     if (head_dim == 64)
-        return launch_attn_t<64, false>(qkv_hi, qkv_lo, ld_qkv, row_off, n_utt, max_T, n_heads, pp_hi, pp_lo, tmax, d_model, out, st);
+        return launch_attn_t<64, false>(q32, pos_u, pos_v, qkv_hi, qkv_lo, ld_qkv, row_off, n_utt, max_T, n_heads, pp_hi, pp_lo, tmax, d_model, out, st);
     if (head_dim == 128)
-        return launch_attn_t<128, true>(qkv_hi, qkv_lo, ld_qkv, row_off, n_utt, max_T, n_heads, pp_hi, pp_lo, tmax, d_model, out, st);
+        return launch_attn_t<128, true>(q32, pos_u, pos_v, qkv_hi, qkv_lo, ld_qkv, row_off, n_utt, max_T, n_heads, pp_hi, pp_lo, tmax, d_model, out, st);
     return false;
 }
 

@@ -369,8 +369,8 @@ pk_status pk_engine::alloc_workspace() {
     ffh = act_alloc(Mx, c.ff);
     qkv = dalloc<float>(Mx * 3 * d);
     if (cfg.math != PK_MATH_FP32 && (c.d_model / c.n_heads == 64 || c.d_model / c.n_heads == 128)) {
-        qkvp_hi = dalloc<bf16>(Mx * 4 * d);
-        qkvp_lo = dalloc<bf16>(Mx * 4 * d);
+        qkvp_hi = dalloc<bf16>(Mx * 2 * d);
+        qkvp_lo = dalloc<bf16>(Mx * 2 * d);
         if (!qkvp_hi || !qkvp_lo) return fail(PK_ERR_CUDA, "cudaMalloc failed (qkv planes)");
     }
     ctx = act_alloc(Mx, d);
@@ -485,7 +485,8 @@ void pk_engine::gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiPara
         const bool act_kind = epi.kind == EPI_BIAS_RELU_ACT || epi.kind == EPI_BIAS_SILU_ACT || epi.kind == EPI_BIAS_ACT || epi.kind == EPI_QKV_ACT;
         if (act_kind && epi.act.hi) {
             const CUtensorMap *m0 = out_map(epi.act.hi, false, M_, epi.ldo), *m1 = epi.act.lo ? out_map(epi.act.lo, false, M_, epi.ldo) : nullptr;
-            if (m0 && (m1 || !epi.act.lo)) { epi.tma_out = 1; epi.tm_out0 = m0; epi.tm_out1 = m1; }
+            const CUtensorMap *m2 = epi.kind == EPI_QKV_ACT ? out_map(epi.out_f32, true, M_, epi.qcols) : nullptr;
+            if (m0 && (m1 || !epi.act.lo) && (m2 || epi.kind != EPI_QKV_ACT)) { epi.tma_out = 1; epi.tm_out0 = m0; epi.tm_out1 = m1; epi.tm_out2 = m2; }
         } else if (!act_kind && epi.out_f32) {
             const CUtensorMap *m0 = out_map(epi.out_f32, true, M_, epi.ldo);
             if (m0) { epi.tma_out = 1; epi.tm_out0 = m0; }
@@ -618,13 +619,12 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             ++launches;
             const bool tc_attn = L.pp_hi && qkvp_hi && attn_tc;
             EpiParams eq;
-            if (tc_attn) {   // q/k/v land as bf16 hi/lo planes with the position biases already added
+            if (tc_attn) {   // k | v land as bf16 hi/lo planes [M, 2 d], q as fp32 [M, d] (the attention kernel adds pos_bias_u / _v)
                 eq.kind = EPI_QKV_ACT;
                 eq.act.hi = qkvp_hi;
                 eq.act.lo = qkvp_lo;
-                eq.ldo = 4 * d;
-                eq.bias_u = L.pos_u;
-                eq.bias_v = L.pos_v;
+                eq.ldo = 2 * d;
+                eq.out_f32 = qkv;
                 eq.qcols = d;
             } else {
                 eq.kind = EPI_BIAS_F32;
@@ -635,7 +635,7 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             {
                 Scope sc(this, CAT_ATTENTION);
                 const bool ok = tc_attn
-                    ? launch_relpos_attention_tc(qkvp_hi, qkvp_lo, 4 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, d, ctx, stream)
+                    ? launch_relpos_attention_tc(qkv, L.pos_u, L.pos_v, qkvp_hi, qkvp_lo, 2 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, d, ctx, stream)
                     : launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream);
                 if (!ok) return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
             }
@@ -1022,13 +1022,13 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     if (const char *ev = getenv("PK_GEMM_2CTA")) tc_set_2cta(atoi(ev) != 0);
     tc_set_debug(getenv("PK_GEMM_DBG") ? atoi(getenv("PK_GEMM_DBG")) : 0);
     if (K % 64 != 0 || (epi_kind == EPI_GLU_F32 && (N & 1))) return PK_ERR_INVALID;
-    const int qcols = epi_kind == EPI_QKV_ACT ? N / 3 : 0;     // fused q/k/v projection: N = 3 d, output [M, 4 d]
+    const int qcols = epi_kind == EPI_QKV_ACT ? N / 3 : 0;     // fused q/k/v projection: N = 3 d -> fp32 q [M, d] + planes [M, 2 d]
     if (epi_kind == EPI_QKV_ACT && (N % 3 != 0 || qcols % 16 != 0)) return PK_ERR_INVALID;
     cudaStream_t st;
     cudaStreamCreate(&st);
     const bool act_out = epi_kind == EPI_BIAS_RELU_ACT || epi_kind == EPI_BIAS_SILU_ACT || epi_kind == EPI_BIAS_ACT ||
                          epi_kind == EPI_QKV_ACT;
-    const int No = epi_kind == EPI_GLU_F32 ? N / 2 : N + qcols;
+    const int No = epi_kind == EPI_GLU_F32 ? N / 2 : N - qcols;
     std::vector<float> hA((size_t)M * K), hW((size_t)N * K), hb(N), hr((size_t)M * No);
     uint32_t sd = seed * 2654435761u + 12345u;
     auto rnd = [&]() { sd = sd * 1664525u + 1013904223u; return ((sd >> 8) & 0xffff) / 32768.0f - 1.0f; };
@@ -1036,8 +1036,9 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     for (auto &v : hW) v = rnd() * 0.1f;
     for (auto &v : hb) v = rnd();
     for (auto &v : hr) v = rnd();
-    float *dA, *dW, *db, *dr, *o_ref, *o_tc;
+    float *dA, *dW, *db, *dr, *o_ref, *o_tc, *q_ref = nullptr, *q_tc = nullptr;
     bf16 *Ah, *Al, *Wh, *Wl, *oh, *ol;
+    if (qcols) { cudaMalloc(&q_ref, (size_t)M * qcols * 4); cudaMalloc(&q_tc, (size_t)M * qcols * 4); }
     cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dW, hW.size() * 4); cudaMalloc(&db, hb.size() * 4);
     cudaMalloc(&dr, hr.size() * 4); cudaMalloc(&o_ref, hr.size() * 4); cudaMalloc(&o_tc, hr.size() * 4);
     cudaMalloc(&Ah, hA.size() * 2); cudaMalloc(&Al, hA.size() * 2); cudaMalloc(&Wh, hW.size() * 2); cudaMalloc(&Wl, hW.size() * 2);
@@ -1053,8 +1054,8 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     launch_split(dW, hW.size(), sw, st);
     EpiParams ep;
     ep.kind = epi_kind; ep.bias = db; ep.ldo = No; ep.resid = dr; ep.alpha = 0.5f;
-    ep.bias_u = dr; ep.bias_v = dr + qcols; ep.qcols = qcols;   // (dr holds >= 2 qcols random floats)
-    ep.out_f32 = o_ref;
+    ep.qcols = qcols;
+    ep.out_f32 = qcols ? q_ref : o_ref;
     ActBuf ref_act; ref_act.f32 = o_ref;
     ep.act = ref_act;
     launch_gemm_simt(dA, K, dW, K, M, N, K, ep, st);
@@ -1062,14 +1063,16 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     pk_status rc = PK_OK;
     if (!make_tc_operand(&ta, Ah, Al, M, K, 128) || !make_tc_operand(&tw, Wh, Wl, N, K, tc_tile_n(N))) rc = PK_ERR_CUDA;
     if (rc == PK_OK) {
-        ep.out_f32 = o_tc;
+        ep.out_f32 = qcols ? q_tc : o_tc;
         ActBuf tc_act; tc_act.hi = oh; tc_act.lo = ol;
         ep.act = tc_act;
-        CUtensorMap om0, om1;
+        CUtensorMap om0, om1, om2;
         if (getenv("PK_GEMM_TMA_OUT") && atoi(getenv("PK_GEMM_TMA_OUT")) && epi_kind != EPI_RESID_F32) {
             const bool ok = act_out ? (make_tc_out_map(&om0, oh, false, M, No) && make_tc_out_map(&om1, ol, false, M, No))
                                     : make_tc_out_map(&om0, o_tc, true, M, No);
-            if (ok) { ep.tma_out = 1; ep.tm_out0 = &om0; ep.tm_out1 = act_out ? &om1 : nullptr; }
+            if (ok && (!qcols || make_tc_out_map(&om2, q_tc, true, M, qcols))) {
+                ep.tma_out = 1; ep.tm_out0 = &om0; ep.tm_out1 = act_out ? &om1 : nullptr; ep.tm_out2 = qcols ? &om2 : nullptr;
+            }
         }
         const bool use_skinny = getenv("PK_SELFTEST_SKINNY") && atoi(getenv("PK_SELFTEST_SKINNY")) && M <= 128;
         float *sws = nullptr;
@@ -1122,11 +1125,21 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
             if (!(e <= me)) me = e;            // NaN-propagating max
             mr = std::max(mr, std::fabs(r[i]));
         }
+        if (qcols) {                           // the fp32 q columns of the fused projection
+            std::vector<float> qr((size_t)M * qcols), qt((size_t)M * qcols);
+            cudaMemcpy(qr.data(), q_ref, qr.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(qt.data(), q_tc, qt.size() * 4, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < qt.size(); ++i) {
+                const float e = std::fabs(qt[i] - qr[i]);
+                if (!(e <= me)) me = e;
+                mr = std::max(mr, std::fabs(qr[i]));
+            }
+        }
         *max_err = me;
         *max_ref = mr;
     }
     for (void *p : {(void *)dA, (void *)dW, (void *)db, (void *)dr, (void *)o_ref, (void *)o_tc, (void *)Ah, (void *)Al,
-                    (void *)Wh, (void *)Wl, (void *)oh, (void *)ol})
+                    (void *)Wh, (void *)Wl, (void *)oh, (void *)ol, (void *)q_ref, (void *)q_tc})
         cudaFree(p);
     cudaStreamDestroy(st);
     return rc;

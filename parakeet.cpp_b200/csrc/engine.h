@@ -117,7 +117,7 @@ struct pk_engine {
     float *logmel = nullptr, *feats = nullptr;
     Act sub1, sub3, sub4, ln, ffh, ctx, cv;
     float *sub2 = nullptr, *x = nullptr, *qkv = nullptr, *glu = nullptr, *logits = nullptr, *EP = nullptr;
-    bf16 *qkvp_hi = nullptr, *qkvp_lo = nullptr;   // [Mx, 4 d] planes [q+u | q+v | k | v] for the tensor-core attention
+    bf16 *qkvp_hi = nullptr, *qkvp_lo = nullptr;   // [Mx, 2 d] planes [k | v] for the tensor-core attention (q stays fp32 in `qkv`)
     int32_t *best = nullptr;
     float *bconf = nullptr;
     int32_t *tok = nullptr, *t_start = nullptr, *t_end = nullptr;

@@ -146,22 +146,17 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 // Global operands of one 16-column chunk (this lane: 4 rows x 4 columns), issued one chunk AHEAD of
 // their use so that the L2 round trip overlaps the previous chunk's transpose / math / stores.
 struct EpiOperands {
-    float4 b, bu, bv, r[4];
+    float4 b, r[4];
 };
 template <int EK>
 __device__ __forceinline__ void epi_load(const EpiParams &epi, int rb, int gc, int M, bool ok, EpiOperands &o) {
     o.b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (EK == EPI_QKV_ACT) o.bu = o.bv = o.b;
     if (EK == EPI_RESID_F32) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) o.r[i] = o.b;
     }
     if (ok) {
         if (epi.bias) o.b = __ldg(reinterpret_cast<const float4 *>(epi.bias + gc));
-        if (EK == EPI_QKV_ACT && gc < epi.qcols) {
-            o.bu = __ldg(reinterpret_cast<const float4 *>(epi.bias_u + gc));
-            o.bv = __ldg(reinterpret_cast<const float4 *>(epi.bias_v + gc));
-        }
         if (EK == EPI_RESID_F32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -216,11 +211,11 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
 #pragma unroll
             for (int i = 0; i < 4; ++i) val[i] = epi_math<EK>(val[i], oc.b, oc.r[i], epi.alpha);
             if (dbg & 8) {      // (measurement aid, bit 3: everything but the global stores)
-                if (val[0].x + val[1].y + val[2].z + val[3].w == 1.2345e-30f) epi_store<EK>(epi, rb, gc0 + cc, val[0], oc.bu, oc.bv);
+                if (val[0].x + val[1].y + val[2].z + val[3].w == 1.2345e-30f) epi_store<EK>(epi, rb, gc0 + cc, val[0]);
             } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (rb + i * 8 < M) epi_store<EK>(epi, rb + i * 8, gc0 + cc, val[i], oc.bu, oc.bv);
+                if (rb + i * 8 < M) epi_store<EK>(epi, rb + i * 8, gc0 + cc, val[i]);
             }
         } else {
 #pragma unroll
@@ -235,10 +230,6 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
 #pragma unroll
             for (int j = 0; j < 16; ++j) vc[j] = vn[j];
             oc.b = on.b;
-            if (EK == EPI_QKV_ACT) {
-                oc.bu = on.bu;
-                oc.bv = on.bv;
-            }
             if (EK == EPI_RESID_F32) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) oc.r[i] = on.r[i];
@@ -251,7 +242,7 @@ __device__ __forceinline__ void epilogue_slab(uint32_t taddr, uint32_t stg_s, in
 __device__ unsigned long long g_clk_probe[2];
 // measurement aid (debug bit 5): per-tile timeline of CTA 0 -- [tile][0..3] = MMA thread: accumulator free, last MMA issued;
 // epilogue warp 2: accumulator full seen, tile stored.  (clock64 of SM 0's CTA)
-__device__ long long g_timeline[64][4];
+__device__ long long g_timeline[64][8];   // [4..6]: epilogue sub-phases of warp 2 (TMEM loads landed, maths done, first plane handed to the store path)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -332,7 +323,12 @@ __device__ __forceinline__ void store_tile128(uint32_t stg_s, int lane, const ui
 // The same 32 x 128 B tile leaves through the TMA engine: staged exactly in the SWIZZLE_128B layout of the output map
 // (16-byte chunk c of row r at chunk c ^ (r & 7): what store_tile128 writes), one lane issues cp.async.bulk.tensor
 // shared -> global (rows past M are clipped by the map) and waits until the engine has read the tile.
+__device__ __forceinline__ void stg_acquire(int lane) {    // the TMA engine has finished READING this warp's staging tile
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
 __device__ __forceinline__ void tma_store_tile(uint32_t stg_s, int lane, const uint32_t *r, const CUtensorMap *tm, int col, int row0) {
+    stg_acquire(lane);          // waits for the PREVIOUS store of this warp only now: its read overlapped the maths in between
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         sts128(stg_s + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4)), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
@@ -346,9 +342,7 @@ __device__ __forceinline__ void tma_store_tile(uint32_t stg_s, int lane, const u
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                      ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(stg_s), "r"(col), "r"(row0) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    __syncwarp();
 }
 
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t &hi, uint32_t &lo) {
@@ -365,13 +359,14 @@ __device__ __forceinline__ bool wide_ok(const EpiParams &epi, int gcol0, int N) 
     if (gcol0 + 64 > N) return false;
     if (EK == EPI_BIAS_F32 || EK == EPI_BIAS_RELU_F32 || EK == EPI_RESID_F32) return (epi.ldo & 3) == 0;
     if (EK == EPI_GLU_F32) return (epi.ldo & 3) == 0;
-    if (EK == EPI_QKV_ACT) return (epi.ldo & 7) == 0 && (epi.qcols & 63) == 0 && epi.act.hi != nullptr;
+    if (EK == EPI_QKV_ACT) return (epi.ldo & 7) == 0 && (epi.qcols & 63) == 0 && epi.act.hi != nullptr && epi.out_f32 != nullptr;
     return (epi.ldo & 7) == 0 && epi.act.hi != nullptr;
 }
 
 template <int EK, typename ReleaseFn>
 __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, int row0, int gcol0, int M, const EpiParams &epi_param,
-                                                int lane, ReleaseFn release, bool last_slab, const CUtensorMap *tm0, const CUtensorMap *tm1) {
+                                                int lane, ReleaseFn release, bool last_slab, const CUtensorMap *tm0, const CUtensorMap *tm1,
+                                                const CUtensorMap *tm2, long long *tl = nullptr) {
     const EpiParams epi = epi_param;
     const bool tma = epi.tma_out != 0;
     uint32_t a0[32], a1[32];
@@ -379,6 +374,7 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
     tmem_ld32_issue(taddr + 32u, a1);
     tmem_wait_ld();
     if (last_slab) release();
+    if (tl) tl[4] = clock64();
     // row-wise on 32 columns [c0, c0 + 32) of the slab: + bias (warp-uniform float4 loads), activation
     auto rowmath = [&](const uint32_t (&a)[32], int c0, float (&v)[32]) {
 #pragma unroll
@@ -401,19 +397,24 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
             for (int j = 0; j < 32; ++j) v[j] *= epi.alpha;
         }
     };
-    if (EK == EPI_BIAS_F32 || EK == EPI_BIAS_RELU_F32 || EK == EPI_RESID_F32) {
-        // fp32 rows: 256 B per lane -> two 128-byte passes
+    const bool q_part = (EK == EPI_QKV_ACT) && gcol0 < epi.qcols;      // warp-uniform; compile-time false for the other kinds
+    if (EK == EPI_BIAS_F32 || EK == EPI_BIAS_RELU_F32 || EK == EPI_RESID_F32 || q_part) {
+        // fp32 rows: 256 B per lane -> two 128-byte passes  (EPI_QKV_ACT: the q columns, matrix [M, qcols])
+        const int ldf = (EK == EPI_QKV_ACT) ? epi.qcols : epi.ldo;
+        const CUtensorMap *tmf = (EK == EPI_QKV_ACT) ? tm2 : tm0;
         uint8_t *ob = reinterpret_cast<uint8_t *>(epi.out_f32 + gcol0);
         const uint8_t *rb = reinterpret_cast<const uint8_t *>(epi.resid + gcol0);
-        const size_t ldb = (size_t)epi.ldo * 4;
+        const size_t ldb = (size_t)ldf * 4;
         {
             float v[32];
             rowmath(a0, 0, v);
             uint32_t r[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-            if (tma && EK != EPI_RESID_F32) tma_store_tile(stg_s, lane, r, tm0, gcol0, row0);
+            if (tl) tl[5] = clock64();
+            if (tma && EK != EPI_RESID_F32) tma_store_tile(stg_s, lane, r, tmf, gcol0, row0);
             else store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob, rb, ldb, row0, M);
+            if (tl) tl[6] = clock64();
         }
         {
             float v[32];
@@ -421,7 +422,7 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
             uint32_t r[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-            if (tma && EK != EPI_RESID_F32) tma_store_tile(stg_s, lane, r, tm0, gcol0 + 32, row0);
+            if (tma && EK != EPI_RESID_F32) tma_store_tile(stg_s, lane, r, tmf, gcol0 + 32, row0);
             else store_tile128<EK == EPI_RESID_F32>(stg_s, lane, r, ob + 128, rb + 128, ldb, row0, M);
         }
     } else if (EK == EPI_GLU_F32) {
@@ -438,48 +439,35 @@ __device__ __forceinline__ void epilogue_slab64(uint32_t taddr, uint32_t stg_s, 
 #pragma unroll
             for (int k = 0; k < 16; ++k) r[16 + k] = __float_as_uint(v[2 * k] * fast_sigmoid(v[2 * k + 1]));
         }
+        if (tl) tl[5] = tl[6] = clock64();
         if (tma) tma_store_tile(stg_s, lane, r, tm0, gcol0 >> 1, row0);
         else store_tile128<false>(stg_s, lane, r, reinterpret_cast<uint8_t *>(epi.out_f32 + (gcol0 >> 1)), nullptr, (size_t)epi.ldo * 4, row0, M);
     } else {
-        // bf16 hi / lo planes: 64 columns = 128 B per lane and plane
+        // bf16 hi / lo planes: 64 columns = 128 B per lane and plane  (EPI_QKV_ACT: the k | v columns, planes [M, N - qcols])
         const size_t ldb = (size_t)epi.ldo * 2;
-        const bool q_part = (EK == EPI_QKV_ACT) && gcol0 < epi.qcols;
-        const int dcol = (EK == EPI_QKV_ACT) ? (q_part ? gcol0 : gcol0 + epi.qcols) : gcol0;
-        const int nvar = q_part ? 2 : 1;
-#pragma unroll 1
-        for (int var = 0; var < nvar; ++var) {
-            uint32_t hi[32], lo[32];
-            const float *pb = var == 0 ? epi.bias_u : epi.bias_v;
-            {
-                float v[32];
-                rowmath(a0, 0, v);
+        const int col = (EK == EPI_QKV_ACT) ? gcol0 - epi.qcols : gcol0;
+        uint32_t hi[32], lo[32];
+        {
+            float v[32];
+            rowmath(a0, 0, v);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q_part) b = __ldg(reinterpret_cast<const float4 *>(pb + gcol0 + j));
-                    split_pair(v[j] + b.x, v[j + 1] + b.y, hi[j >> 1], lo[j >> 1]);
-                    split_pair(v[j + 2] + b.z, v[j + 3] + b.w, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
-                }
-            }
-            {
-                float v[32];
-                rowmath(a1, 32, v);
+            for (int j = 0; j < 32; j += 2) split_pair(v[j], v[j + 1], hi[j >> 1], lo[j >> 1]);
+        }
+        {
+            float v[32];
+            rowmath(a1, 32, v);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q_part) b = __ldg(reinterpret_cast<const float4 *>(pb + gcol0 + 32 + j));
-                    split_pair(v[j] + b.x, v[j + 1] + b.y, hi[16 + (j >> 1)], lo[16 + (j >> 1)]);
-                    split_pair(v[j + 2] + b.z, v[j + 3] + b.w, hi[16 + (j >> 1) + 1], lo[16 + (j >> 1) + 1]);
-                }
-            }
-            const int col = dcol + var * epi.qcols;
-            if (tma) {
-                tma_store_tile(stg_s, lane, hi, tm0, col, row0);
-                if (epi.act.lo) tma_store_tile(stg_s, lane, lo, tm1, col, row0);
-            } else {
-                store_tile128<false>(stg_s, lane, hi, reinterpret_cast<uint8_t *>(epi.act.hi + col), nullptr, ldb, row0, M);
-                if (epi.act.lo) store_tile128<false>(stg_s, lane, lo, reinterpret_cast<uint8_t *>(epi.act.lo + col), nullptr, ldb, row0, M);
-            }
+            for (int j = 0; j < 32; j += 2) split_pair(v[j], v[j + 1], hi[16 + (j >> 1)], lo[16 + (j >> 1)]);
+        }
+        if (tl) tl[5] = clock64();
+        if (tma) {
+            tma_store_tile(stg_s, lane, hi, tm0, col, row0);
+            if (tl) tl[6] = clock64();
+            if (epi.act.lo) tma_store_tile(stg_s, lane, lo, tm1, col, row0);
+        } else {
+            store_tile128<false>(stg_s, lane, hi, reinterpret_cast<uint8_t *>(epi.act.hi + col), nullptr, ldb, row0, M);
+            if (tl) tl[6] = clock64();
+            if (epi.act.lo) store_tile128<false>(stg_s, lane, lo, reinterpret_cast<uint8_t *>(epi.act.lo + col), nullptr, ldb, row0, M);
         }
     }
 }
@@ -509,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
                int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
-               const __grid_constant__ CUtensorMap tmO1) {
+               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2) {
     using C = TcCfg<BN, NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -542,6 +530,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // barriers, TMEM and the role split are set up while the previous grid drains; now its results are visible
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -565,6 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                 }
             }
+            pdl_trigger_late();     // every operand load of this CTA has been issued
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -630,13 +621,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             };
-            if (BN == 128 && !(dbg & 64) && wide_ok<EK>(epi, n0 + half * 64, N))
-                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, n0 + half * 64, M, epi, lane, release, true, &tmO0, &tmO1);
-            else
+            if (BN == 128 && !(dbg & 64) && wide_ok<EK>(epi, n0 + half * 64, N)) {
+                long long *tl = ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) ? g_timeline[tcount] : nullptr;
+                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, n0 + half * 64, M, epi, lane, release, true, &tmO0, &tmO1, &tmO2, tl);
+            } else {
+                if (epi.tma_out) stg_acquire(lane);
                 epilogue_slab<BN / 2, EK>(taddr, stg_s, m0 + q * 32, n0 + half * (BN / 2), M, N, epi, lane, release, dbg);
+            }
             if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
         if (probe) { g_clk_probe[0] = (unsigned long long)(clock64() - pc0); g_clk_probe[1] = globaltimer_ns() - pg0; }
+        if (epi.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores have completed
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -711,7 +706,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS_P, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
                 int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
-                const __grid_constant__ CUtensorMap tmO1) {
+                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2) {
     using C = Tc2Cfg<NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -747,6 +742,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     cluster_sync();                              // barriers of both CTAs initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // barriers, TMEM and the role split are set up while the previous grid drains; now its results are visible
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -836,13 +833,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             };
             const int gc = n0 + half * (BN2 / 2);
             if (!(dbg & 64) && wide_ok<EK>(epi, gc, N) && wide_ok<EK>(epi, gc + 64, N)) {
-                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, gc, M, epi, lane, release, false, &tmO0, &tmO1);
-                epilogue_slab64<EK>(taddr + 64u, stg_s, m0 + q * 32, gc + 64, M, epi, lane, release, true, &tmO0, &tmO1);
+                epilogue_slab64<EK>(taddr, stg_s, m0 + q * 32, gc, M, epi, lane, release, false, &tmO0, &tmO1, &tmO2);
+                epilogue_slab64<EK>(taddr + 64u, stg_s, m0 + q * 32, gc + 64, M, epi, lane, release, true, &tmO0, &tmO1, &tmO2);
             } else {
+                if (epi.tma_out) stg_acquire(lane);
                 epilogue_slab<BN2 / 2, EK>(taddr, stg_s, m0 + q * 32, gc, M, N, epi, lane, release, dbg);
             }
             if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
+        if (epi.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tcgen05_fence_before();
     cluster_sync();                              // nobody leaves (or frees TMEM) while the peer may still signal it
@@ -891,11 +890,12 @@ cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K
     dim3 grid(num_tiles < num_sms ? num_tiles : num_sms);
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
     EpiParams ep = epi;
-    const bool tma = ep.tma_out && ep.tm_out0 && BN == 128;
+    const bool tma = ep.tma_out && ep.tm_out0 && BN == 128 && (EK != EPI_QKV_ACT || ep.tm_out2);
     ep.tma_out = tma ? 1 : 0;
     const CUtensorMap &o0 = tma ? *static_cast<const CUtensorMap *>(ep.tm_out0) : A.hi;
     const CUtensorMap &o1 = (tma && ep.tm_out1) ? *static_cast<const CUtensorMap *>(ep.tm_out1) : o0;
-    gemm_tc_kernel<BN, NPASS, EK><<<grid, TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1);
+    const CUtensorMap &o2 = (tma && ep.tm_out2) ? *static_cast<const CUtensorMap *>(ep.tm_out2) : o0;
+    launch_pdl(gemm_tc_kernel<BN, NPASS, EK>, dim3(grid), dim3(TC_THREADS_P), C::SMEM, st, A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1, o2);
     return cudaGetLastError();
 }
 
@@ -921,11 +921,12 @@ cudaError_t launch_k2(const TcOperand &A, const TcOperand &W, int M, int N, int 
     const int pairs = num_tiles < num_sms / 2 ? num_tiles : num_sms / 2;
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
     EpiParams ep = epi;
-    const bool tma = ep.tma_out && ep.tm_out0;
+    const bool tma = ep.tma_out && ep.tm_out0 && (EK != EPI_QKV_ACT || ep.tm_out2);
     ep.tma_out = tma ? 1 : 0;
     const CUtensorMap &o0 = tma ? *static_cast<const CUtensorMap *>(ep.tm_out0) : A.hi;
     const CUtensorMap &o1 = (tma && ep.tm_out1) ? *static_cast<const CUtensorMap *>(ep.tm_out1) : o0;
-    gemm_tc2_kernel<NPASS, EK><<<dim3(2 * pairs), TC_THREADS_P, C::SMEM, st>>>(A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1);
+    const CUtensorMap &o2 = (tma && ep.tm_out2) ? *static_cast<const CUtensorMap *>(ep.tm_out2) : o0;
+    launch_pdl(gemm_tc2_kernel<NPASS, EK>, dim3(dim3(2 * pairs)), dim3(TC_THREADS_P), C::SMEM, st, A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1, o2);
     return cudaGetLastError();
 }
 
@@ -1003,12 +1004,12 @@ void tc_set_debug(int bits) {
     cudaMemcpyToSymbol(g_l2_hint_mode, &hint, sizeof(int));
 }
 void tc_print_timeline(int n_tiles) {   // after a 1-CTA launch with debug bit 5
-    long long h[64][4];
+    long long h[64][8];
     if (cudaMemcpyFromSymbol(h, g_timeline, sizeof(h)) != cudaSuccess) return;
     const long long t0 = h[0][0];
     for (int i = 0; i < n_tiles && i < 64; ++i)
-        fprintf(stderr, "    tile %2d: acc free %7lld  mma issued %7lld | acc full seen %7lld  stored %7lld   (epilogue %lld cyc)\n", i,
-                h[i][0] - t0, h[i][1] - t0, h[i][2] - t0, h[i][3] - t0, h[i][3] - h[i][2]);
+        fprintf(stderr, "    tile %2d: acc free %7lld  mma issued %7lld | acc full seen %7lld  stored %7lld   (epilogue %lld cyc: tmem %lld, maths %lld, 1st plane %lld)\n", i,
+                h[i][0] - t0, h[i][1] - t0, h[i][2] - t0, h[i][3] - t0, h[i][3] - h[i][2], h[i][4] - h[i][2], h[i][5] - h[i][4], h[i][6] - h[i][5]);
 }
 double tc_probe_mhz() {   // effective SM clock seen by CTA 0 of the last 1-CTA launch with a non-zero debug mask (bit 4 = probe only)
     unsigned long long h[2] = {0, 0};

@@ -112,10 +112,11 @@ bool launch_relpos_attention(const float *qkv, int ld_qkv, const int32_t *row_of
                              const float *bv, int d_model, ActBuf out, cudaStream_t st);
 
 // tensor-core variant (attention_tc.cu, head_dim 64): pp as bf16 hi/lo planes
-// qkv_hi / qkv_lo: bf16 planes [M, ld_qkv = 4 d] = [q + u | q + v | k | v] from the EPI_QKV_ACT GEMM epilogue.
-bool launch_relpos_attention_tc(const bf16 *qkv_hi, const bf16 *qkv_lo, int ld_qkv, const int32_t *row_off, int n_utt,
-                                int max_T, int n_heads, int head_dim, const bf16 *pp_hi, const bf16 *pp_lo, int tmax,
-                                int d_model, ActBuf out, cudaStream_t st);
+// From the EPI_QKV_ACT GEMM epilogue: q32 = fp32 q [M, d] (the kernel adds pos_u / pos_v), kv_hi / kv_lo = bf16 planes
+// [M, ld_kv = 2 d] = [k | v].
+bool launch_relpos_attention_tc(const float *q32, const float *pos_u, const float *pos_v, const bf16 *kv_hi, const bf16 *kv_lo,
+                                int ld_kv, const int32_t *row_off, int n_utt, int max_T, int n_heads, int head_dim, const bf16 *pp_hi,
+                                const bf16 *pp_lo, int tmax, int d_model, ActBuf out, cudaStream_t st);
 
 // ContextTrie (src/phrase_boost.cpp:9-66) in CSR form on the device: node 0 = root; the edges of node i are
 // [first[i], first[i+1]) = (token, child node), sorted by token.

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 mel_logpower_kernel(const float *__restrict__ pcm, const int64_t *__restrict__ pcm_off,
                     const int32_t *__restrict__ frame_off, const int32_t *__restrict__ n_frames_arr, int n_mels, MelTables tb,
                     float *__restrict__ logmel) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float smem[];
     // layout: [window 400][tw256 512][tw512 514][fb weights nnz][per-warp: frame 512 | Z 512 | P 260]
     float *s_win = smem;
@@ -188,6 +190,8 @@ mel_logpower_kernel(const float *__restrict__ pcm, const int64_t *__restrict__ p
 __global__ void mel_normalize_kernel(const float *__restrict__ logmel,
                                      const int32_t *__restrict__ frame_off, int n_mels,
                                      float *__restrict__ feats) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float red[];  // [groups][n_mels]
     const int b = blockIdx.x;
     const int groups = blockDim.x / n_mels;
@@ -233,10 +237,10 @@ void launch_mel(const float *pcm, const int64_t *pcm_off, const int32_t *frame_o
                 int max_frames, int n_mels, const MelTables &tb, float *logmel, float *feats,
                 cudaStream_t st) {
     dim3 grid((max_frames + WARPS * 4 - 1) / (WARPS * 4), n_utt);
-    mel_logpower_kernel<false><<<grid, WARPS * 32, mel_smem_bytes(tb), st>>>(pcm, pcm_off, frame_off, nullptr, n_mels, tb,
+    launch_pdl(mel_logpower_kernel<false>, dim3(grid), dim3(WARPS * 32), mel_smem_bytes(tb), st, pcm, pcm_off, frame_off, nullptr, n_mels, tb,
                                                                              logmel);
     int groups = 640 / n_mels;  // 8 for 80 bins, 5 for 128
-    mel_normalize_kernel<<<n_utt, groups * n_mels, sizeof(float) * groups * n_mels, st>>>(
+    launch_pdl(mel_normalize_kernel, dim3(n_utt), dim3(groups * n_mels), sizeof(float) * groups * n_mels, st, 
         logmel, frame_off, n_mels, feats);
 }
 
@@ -244,7 +248,7 @@ void launch_mel_stream(const float *sig, const int64_t *sig_off, const int32_t *
                        int max_frames, int n_mels, const MelTables &tb, float *logmel, cudaStream_t st) {
     if (max_frames <= 0) return;
     dim3 grid((max_frames + WARPS * 4 - 1) / (WARPS * 4), n_streams);
-    mel_logpower_kernel<true><<<grid, WARPS * 32, mel_smem_bytes(tb), st>>>(sig, sig_off, out_row, n_frames, n_mels, tb, logmel);
+    launch_pdl(mel_logpower_kernel<true>, dim3(grid), dim3(WARPS * 32), mel_smem_bytes(tb), st, sig, sig_off, out_row, n_frames, n_mels, tb, logmel);
 }
 
 }  // namespace pk

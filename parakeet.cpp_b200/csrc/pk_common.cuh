@@ -3,10 +3,62 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <utility>
 
 namespace pk {
 
 typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the path starts with pdl_wait() (griddepcontrol.wait: returns once the preceding grid has completed and
+// its writes are visible; a no-op for a normal launch) and is launched through launch_pdl(); with PK_PDL=1 the launch
+// carries programmatic stream serialisation, so the next grid's CTAs are scheduled and do their input-independent set-up
+// (barrier init, TMEM allocation, index math) while the previous grid drains.  Because EVERY kernel waits before its
+// first global access, completion of a grid still implies completion of all its predecessors.
+// MEASURED (B200, profiles/r02_p_pdl.txt): with plain stream launches (PK_GRAPH=0) it helps (single-stream chunk 2.54 ->
+// 2.31 ms, 110m step 9.97 -> 9.90 ms); inside the CUDA graphs the product path replays it does not -- implicit trigger at
+// CTA exit: +-0.1 %; trigger at kernel entry: 2-8 % SLOWER (the early-resident CTAs of the next grid spin in
+// griddepcontrol.wait next to the running grid); trigger after the GEMM's last operand load: 1 % slower.  Graph edges
+// are already cheap, so the attribute is OFF by default (PK_PDL=1 turns it on).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef PK_PDL_TRIGGER
+#define PK_PDL_TRIGGER 1     // 0: implicit (at CTA exit); 1: at the top of every kernel; 2: only late in the GEMM (all loads issued)
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if PK_PDL_TRIGGER == 1
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger_late() {
+#if PK_PDL_TRIGGER == 2
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+inline int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PK_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (one pk_engine per device, e.g.
 // examples/sharded_transcribe.cpp) must set a kernel's attributes once on each of them.  Returns the flag of the
@@ -90,8 +142,10 @@ enum EpiKind : int {
     EPI_RESID_F32 = 4,     // out_f32[row, col] = resid[row, col] + alpha * (acc + bias)
     EPI_GLU_F32 = 5,       // columns interleaved (a0,b0,a1,b1..): out_f32[row, col/2] = a * sigmoid(b)
     EPI_BIAS_ACT = 6,      // acc + bias -> act
-    EPI_QKV_ACT = 7,       // fused q/k/v projection for the tensor-core attention: act planes [M, N + qcols] =
-                           // [q + bias_u | q + bias_v | k | v]  (q = acc + bias for col < qcols; encoder.cpp:129-140)
+    EPI_QKV_ACT = 7,       // fused q/k/v projection for the tensor-core attention (encoder.cpp:129-140): columns < qcols (q)
+                           // -> out_f32[M, qcols] (fp32: the attention kernel adds pos_bias_u / pos_bias_v and splits, so a q
+                           // tile costs the epilogue ONE fp32 tile instead of four bf16 planes); the rest (k | v) -> act planes
+                           // [M, N - qcols]
 };
 
 struct EpiParams {
@@ -102,13 +156,13 @@ struct EpiParams {
     ActBuf act;
     const float *resid = nullptr;
     float alpha = 1.0f;
-    const float *bias_u = nullptr, *bias_v = nullptr;   // EPI_QKV_ACT: pos_bias_u / pos_bias_v, [qcols]
-    int qcols = 0;
+    int qcols = 0;                // EPI_QKV_ACT: leading q columns (also the leading dimension of out_f32)
     // tcgen05 kernels only: results leave the SM by TMA (cp.async.bulk.tensor shared -> global) instead of st.global.
     // tm_out0 / tm_out1 are HOST pointers to CUtensorMaps of the output (fp32 matrix, or the bf16 hi / lo planes) with a
     // 32-row x 128-byte box, SWIZZLE_128B (make_tc_out_map); the launcher copies them into kernel parameters.
+    // EPI_QKV_ACT: tm_out2 = the fp32 q matrix.
     int tma_out = 0;
-    const void *tm_out0 = nullptr, *tm_out1 = nullptr;
+    const void *tm_out0 = nullptr, *tm_out1 = nullptr, *tm_out2 = nullptr;
 };
 
 // Generic (edge-tile / run-time-kind) path; out of line so that it does not bloat the hot loops.
@@ -165,12 +219,8 @@ static __device__ __noinline__ void epilogue4(const EpiParams &p, int row, int c
     case EPI_QKV_ACT:
         for (int i = 0; i < 4 && col0 + i < N; ++i) {
             const int cidx = col0 + i;
-            if (cidx < p.qcols) {
-                store_act(p.act, (size_t)row * p.ldo + cidx, v[i] + p.bias_u[cidx]);
-                store_act(p.act, (size_t)row * p.ldo + cidx + p.qcols, v[i] + p.bias_v[cidx]);
-            } else {
-                store_act(p.act, (size_t)row * p.ldo + cidx + p.qcols, v[i]);
-            }
+            if (cidx < p.qcols) p.out_f32[(size_t)row * p.qcols + cidx] = v[i];
+            else store_act(p.act, (size_t)row * p.ldo + cidx - p.qcols, v[i]);
         }
         break;
     case EPI_GLU_F32: {
@@ -212,16 +262,11 @@ __device__ __forceinline__ float4 epi_math(float4 v, const float4 &b, const floa
     return v;
 }
 template <int KIND>
-__device__ __forceinline__ void epi_store(const EpiParams &p, int row, int col0, const float4 &v, const float4 &bu,
-                                          const float4 &bv) {
+__device__ __forceinline__ void epi_store(const EpiParams &p, int row, int col0, const float4 &v) {
     const size_t base = (size_t)row * p.ldo + col0;
     if (KIND == EPI_QKV_ACT) {
-        if (col0 < p.qcols) {
-            store_act4(p.act, base, make_float4(v.x + bu.x, v.y + bu.y, v.z + bu.z, v.w + bu.w));
-            store_act4(p.act, base + p.qcols, make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w));
-        } else {
-            store_act4(p.act, base + p.qcols, v);
-        }
+        if (col0 < p.qcols) *reinterpret_cast<float4 *>(p.out_f32 + (size_t)row * p.qcols + col0) = v;
+        else store_act4(p.act, base - p.qcols, v);
     } else if (KIND == EPI_BIAS_F32 || KIND == EPI_BIAS_RELU_F32 || KIND == EPI_RESID_F32) {
         *reinterpret_cast<float4 *>(p.out_f32 + base) = v;
     } else if (KIND == EPI_GLU_F32) {

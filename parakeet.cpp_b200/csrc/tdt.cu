@@ -772,6 +772,8 @@ __global__ void __launch_bounds__(NTHR, 1) tdt_decode_kernel(TdtParams p) {
 }
 
 __global__ void tdt_init_kernel(TdtParams p) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < GBAR * GBAR_STRIDE) p.bar[b] = 0u;
     if (b < 3 * p.Bpad) {
@@ -797,6 +799,8 @@ __global__ void tdt_init_kernel(TdtParams p) {
 
 // fp32 rows [rows][K] -> pre-split rows [rows][2 K] = [hi: K][lo: K] bf16
 __global__ void tdt_split_rows_kernel(const float *__restrict__ src, int rows, int K, bf16 *__restrict__ dst) {
+    pdl_wait();
+    pdl_trigger();
     const size_t n = (size_t)rows * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / K;

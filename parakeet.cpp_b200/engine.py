@@ -25,7 +25,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libparakeet_b200.so")
+    # PK_LIB: a developer knob to load a variant build of the same sources (scratch/build_variant.py)
+    return os.environ.get("PK_LIB") or os.path.join(_HERE, "libparakeet_b200.so")
 
 
 class _PkConfig(C.Structure):
