@@ -243,6 +243,11 @@ pk_status pk_debug_tdt_passes(pk_engine *e, int64_t *out8);
  * random data (epi_kind: EpiKind of csrc/pk_common.cuh; math: PK_MATH_BF16X3 | PK_MATH_BF16X1). */
 pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int math, uint32_t seed,
                            float *max_err, float *max_ref);
+/* GPU self-check of the residual GEMM with the LayerNorm fused into its epilogue (csrc/gemm_tc_ln.cu, N = 512, run in place)
+ * against the fp32 GEMM followed by the stand-alone LayerNorm kernel.  mode 0: x = resid + a(A W^T + b), planes = LN1(x);
+ * 1: x = LN1(.), planes = LN2(x);  2: x = LN1(.), planes = split(x);  3: mode 0 without a residual.
+ * err4 = {max |x - x_ref|, max |x_ref|, max |planes - planes_ref|, max |planes_ref|}. */
+pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint32_t seed, float *err4);
 
 /* Host-side text helpers (pure C++ host code; no device work):
  * Tokenizer::load/decode (src/vocab.cpp:10-64), group_timestamps (src/timestamp.cpp:24-75). */

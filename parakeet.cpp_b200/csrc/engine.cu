@@ -539,8 +539,43 @@ pk_status pk_engine::run_conv1(int u0, int u1) {
         launch_layernorm(__VA_ARGS__);          \
     } while (0)
 
+pk_status pk_engine::gemm_ln(const Act &A, int lda, const GemmWeight &W, int M_, bool resid_in_x, float alpha, const float *ln1_w,
+                             const float *ln1_b, bool out_ln1, const float *ln2_w, const float *ln2_b, ActBuf planes) {
+    const int d = cfg.d_model;
+    const bool fused = fuse_ln && cfg.math != PK_MATH_FP32 && W.N == d && gemm_tc_ln_supported(d) && lda == W.K && W.tc.box_rows == 128 &&
+                       !(skinny && M_ <= 128 && skinny_ws) && planes.hi != nullptr;
+    if (fused) {
+        LnEpi le;
+        le.bias = W.bias;
+        le.resid = resid_in_x ? x : nullptr;
+        le.alpha = alpha;
+        le.out_f32 = x;
+        le.ln1_w = ln1_w; le.ln1_b = ln1_b; le.ln2_w = ln2_w; le.ln2_b = ln2_b;
+        le.out_ln1 = out_ln1;
+        le.planes = planes;
+        Scope sc(this, CAT_GEMM, 2.0 * M_ * W.N * W.K);
+        cudaError_t ce = launch_gemm_tc_ln(A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, le, num_sms, stream);
+        if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("tcgen05 GEMM+LayerNorm launch: ") + cudaGetErrorString(ce));
+        ++launches;
+        return PK_OK;
+    }
+    EpiParams ep;
+    ep.kind = resid_in_x ? EPI_RESID_F32 : EPI_BIAS_F32;
+    ep.out_f32 = x;
+    ep.resid = resid_in_x ? x : nullptr;
+    ep.ldo = d;
+    ep.alpha = alpha;
+    gemm(A, lda, W, M_, ep);
+    ActBuf none;
+    if (!out_ln1) PK_LN(x, M_, d, ln1_w, ln1_b, nullptr, planes, nullptr, nullptr, none, stream);
+    else if (ln2_w) PK_LN(x, M_, d, ln1_w, ln1_b, x, none, ln2_w, ln2_b, planes, stream);
+    else PK_LN(x, M_, d, ln1_w, ln1_b, x, planes, nullptr, nullptr, none, stream);
+    ++launches;
+    return PK_OK;
+}
+
 // conv2_ .. proj_ of ConvSubsampling (encoder.cpp:219-241) on the staged batch; conv1_/dw1_ already ran (run_conv1)
-pk_status pk_engine::run_subsample_tail() {
+pk_status pk_engine::run_subsample_tail(bool with_first_ln) {
     const pk_config &c = cfg;
     const int C = c.sub_channels, d = c.d_model;
     {
@@ -562,7 +597,10 @@ pk_status pk_engine::run_subsample_tail() {
         ep.ldo = C;
         gemm(sub3, C, conv3, M * f3n, ep);
     }
-    {
+    if (with_first_ln) {       // proj_ + the first block's ffn1_.norm_ (encoder.cpp:40)
+        pk_status q = gemm_ln(sub4, C * f3n, proj, M, false, 1.0f, layers[0].ffn_ln_w[0], layers[0].ffn_ln_b[0], false, nullptr, nullptr, ln);
+        if (q) return q;
+    } else {
         EpiParams ep;
         ep.kind = EPI_BIAS_F32;
         ep.out_f32 = x;
@@ -577,7 +615,7 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
     const pk_config &c = cfg;
     const int d = c.d_model, H = c.n_heads, hd = d / H;
     {
-        pk_status ss = run_subsample_tail();
+        pk_status ss = run_subsample_tail(true);
         if (ss) return ss;
     }
     PK_CUDA(cudaGetLastError());
@@ -585,38 +623,37 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
         PK_CUDA(cudaMemcpyAsync(sub_out_host, x, (size_t)M * d * 4, cudaMemcpyDeviceToHost, stream));
         PK_CUDA(cudaStreamSynchronize(stream));
     }
-    // ---- Conformer blocks (encoder.cpp:196-204)
+    // ---- Conformer blocks (encoder.cpp:196-204).  Every residual GEMM carries the LayerNorm that consumes its result
+    // (gemm_ln: one kernel when fuse_ln applies): ffn1 -> attention norm, attention out -> conv norm, conv pw2 -> ffn2 norm,
+    // ffn2 -> final_norm_ chained with the next block's ffn1_.norm_.
     ActBuf none;
     // PK_DEBUG_SUBBLOCKS=n (bisecting aid): stop after n residual sub-blocks; x is returned as is.
     int dbg_stop = -1, dbg_cnt = 0;
     if (const char *ev = getenv("PK_DEBUG_SUBBLOCKS")) dbg_stop = atoi(ev);
-    PK_LN(x, M, d, layers[0].ffn_ln_w[0], layers[0].ffn_ln_b[0], nullptr, ln, nullptr, nullptr, none, stream);
-    ++launches;
     for (int i = 0; i < c.n_layers; ++i) {
         const LayerW &L = layers[i];
+        const bool last = (i + 1 == c.n_layers);
+        pk_status q;
         for (int f = 0; f < 2; ++f) {
-            if (f == 1) {
-                PK_LN(x, M, d, L.ffn_ln_w[1], L.ffn_ln_b[1], nullptr, ln, nullptr, nullptr, none, stream);
-                ++launches;
-            }
             // FeedForward (encoder.cpp:39-46): x += 0.5 * fc2(silu(fc1(LN(x))))
             EpiParams e1;
             e1.kind = EPI_BIAS_SILU_ACT;
             e1.act = ffh;
             e1.ldo = c.ff;
             gemm(ln, d, L.fc1[f], M, e1);
-            EpiParams e2;
-            e2.kind = EPI_RESID_F32;
-            e2.out_f32 = x;
-            e2.resid = x;
-            e2.ldo = d;
-            e2.alpha = 0.5f;
-            gemm(ffh, c.ff, L.fc2[f], M, e2);
+            if (f == 0) {
+                q = gemm_ln(ffh, c.ff, L.fc2[f], M, true, 0.5f, L.att_ln_w, L.att_ln_b, false, nullptr, nullptr, ln);
+            } else if (!last) {
+                // final_norm_ of this block chained with the next block's ffn1_.norm_
+                q = gemm_ln(ffh, c.ff, L.fc2[f], M, true, 0.5f, L.fin_ln_w, L.fin_ln_b, true, layers[i + 1].ffn_ln_w[0], layers[i + 1].ffn_ln_b[0], ln);
+            } else {
+                // after the last block the normalised output is also written in GEMM-operand form for the heads
+                q = gemm_ln(ffh, c.ff, L.fc2[f], M, true, 0.5f, L.fin_ln_w, L.fin_ln_b, true, nullptr, nullptr, cfg.math == PK_MATH_FP32 ? none : (ActBuf)ln);
+            }
+            if (q) return q;
             if (++dbg_cnt == dbg_stop) return PK_OK;
             if (f == 1) break;
             // ConformerAttention (encoder.cpp:111-186)
-            PK_LN(x, M, d, L.att_ln_w, L.att_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
-            ++launches;
             const bool tc_attn = L.pp_hi && qkvp_hi && attn_tc;
             EpiParams eq;
             if (tc_attn) {   // k | v land as bf16 hi/lo planes [M, 2 d], q as fp32 [M, d] (the attention kernel adds pos_bias_u / _v)
@@ -640,17 +677,9 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
                 if (!ok) return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
             }
             ++launches;
-            EpiParams eo;
-            eo.kind = EPI_RESID_F32;
-            eo.out_f32 = x;
-            eo.resid = x;
-            eo.ldo = d;
-            eo.alpha = 1.0f;
-            gemm(ctx, d, L.out, M, eo);
+            if ((q = gemm_ln(ctx, d, L.out, M, true, 1.0f, L.conv_ln_w, L.conv_ln_b, false, nullptr, nullptr, ln))) return q;
             if (++dbg_cnt == dbg_stop) return PK_OK;
             // ConformerConvModule (encoder.cpp:59-75)
-            PK_LN(x, M, d, L.conv_ln_w, L.conv_ln_b, nullptr, ln, nullptr, nullptr, none, stream);
-            ++launches;
             EpiParams eg;
             eg.kind = EPI_GLU_F32;
             eg.out_f32 = glu;
@@ -662,25 +691,9 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
                     return fail(PK_ERR_INVALID, "unsupported conv_kernel");
             }
             ++launches;
-            EpiParams ec;
-            ec.kind = EPI_RESID_F32;
-            ec.out_f32 = x;
-            ec.resid = x;
-            ec.ldo = d;
-            ec.alpha = 1.0f;
-            gemm(cv, d, L.pw2, M, ec);
+            if ((q = gemm_ln(cv, d, L.pw2, M, true, 1.0f, L.ffn_ln_w[1], L.ffn_ln_b[1], false, nullptr, nullptr, ln))) return q;
             if (++dbg_cnt == dbg_stop) return PK_OK;
         }
-        // final_norm_ of this block chained with the next block's ffn1_.norm_; after the last
-        // block the normalised output is also written in GEMM-operand form for the heads.
-        const bool last = (i + 1 == c.n_layers);
-        if (!last)
-            PK_LN(x, M, d, L.fin_ln_w, L.fin_ln_b, x, none, layers[i + 1].ffn_ln_w[0],
-                             layers[i + 1].ffn_ln_b[0], ln, stream);
-        else
-            PK_LN(x, M, d, L.fin_ln_w, L.fin_ln_b, x, cfg.math == PK_MATH_FP32 ? none : ln, nullptr,
-                             nullptr, none, stream);
-        ++launches;
         if (layers_out_host) {
             PK_CUDA(cudaMemcpyAsync(layers_out_host + (size_t)i * M * d, x, (size_t)M * d * 4, cudaMemcpyDeviceToHost, stream));
         }
@@ -900,6 +913,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     if (const char *ev = getenv("PK_ATTN_TC")) e->attn_tc = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_TMA_OUT")) e->tma_out = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_SKINNY")) e->skinny = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_FUSE_LN")) e->fuse_ln = atoi(ev) != 0;
     e->device = device;
     if (cudaSetDevice(device) != cudaSuccess) {
         g_create_err = "cudaSetDevice failed";
@@ -1140,6 +1154,117 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     }
     for (void *p : {(void *)dA, (void *)dW, (void *)db, (void *)dr, (void *)o_ref, (void *)o_tc, (void *)Ah, (void *)Al,
                     (void *)Wh, (void *)Wl, (void *)oh, (void *)ol, (void *)q_ref, (void *)q_tc})
+        cudaFree(p);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+// GPU self-check of the fused residual-GEMM + LayerNorm kernel (gemm_tc_ln.cu) against the fp32 CUDA-core GEMM followed by
+// layernorm_kernel, N = 512.  mode 0: x = resid + a (A W^T + b), planes = LN1(x);  1: x = LN1(.), planes = LN2(x) (block end);
+// 2: x = LN1(.), planes = split(x) (last block);  3: mode 0 without a residual (proj_).  The fused kernel runs IN PLACE
+// (out = resid), as the encoder uses it.  err4 = {max |x - x_ref|, max |x_ref|, max |planes - planes_ref|, max |planes_ref|}.
+pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint32_t seed, float *err4) {
+    if (cudaSetDevice(device) != cudaSuccess) return PK_ERR_CUDA;
+    const int N = 512;
+    if (K % 64 != 0 || M < 1 || mode < 0 || mode > 3 || !err4) return PK_ERR_INVALID;
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    std::vector<float> hA((size_t)M * K), hW((size_t)N * K), hb(N), hr((size_t)M * N), hl(4 * N);
+    uint32_t sd = seed * 2654435761u + 777u;
+    auto rnd = [&]() { sd = sd * 1664525u + 1013904223u; return ((sd >> 8) & 0xffff) / 32768.0f - 1.0f; };
+    for (auto &v : hA) v = rnd();
+    for (auto &v : hW) v = rnd() * 0.1f;
+    for (auto &v : hb) v = rnd();
+    for (auto &v : hr) v = rnd() + 0.25f;
+    for (int i = 0; i < 4 * N; ++i) hl[i] = (i / N) % 2 == 0 ? 1.0f + 0.5f * rnd() : 0.3f * rnd();   // w1, b1, w2, b2
+    float *dA, *dW, *db, *dr, *dl, *x_ref, *x_tc, *p_ref;
+    bf16 *Ah, *Al, *Wh, *Wl, *ph, *pl;
+    cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dW, hW.size() * 4); cudaMalloc(&db, hb.size() * 4); cudaMalloc(&dr, hr.size() * 4);
+    cudaMalloc(&dl, hl.size() * 4); cudaMalloc(&x_ref, hr.size() * 4); cudaMalloc(&x_tc, hr.size() * 4); cudaMalloc(&p_ref, hr.size() * 4);
+    cudaMalloc(&Ah, hA.size() * 2); cudaMalloc(&Al, hA.size() * 2); cudaMalloc(&Wh, hW.size() * 2); cudaMalloc(&Wl, hW.size() * 2);
+    cudaMalloc(&ph, hr.size() * 2); cudaMalloc(&pl, hr.size() * 2);
+    cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, hW.data(), hW.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dr, hr.data(), hr.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dl, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(x_tc, hr.data(), hr.size() * 4, cudaMemcpyHostToDevice);      // in place: starts as the residual
+    cudaMemset(ph, 0, hr.size() * 2); cudaMemset(pl, 0, hr.size() * 2);
+    cudaDeviceSynchronize();
+    const float *w1 = dl, *b1 = dl + N, *w2 = dl + 2 * N, *b2 = dl + 3 * N;
+    const bool has_resid = mode != 3, out_ln1 = mode == 1 || mode == 2, two = mode == 1;
+    ActBuf sa; sa.hi = Ah; sa.lo = Al;
+    ActBuf sw; sw.hi = Wh; sw.lo = Wl;
+    launch_split(dA, hA.size(), sa, st);
+    launch_split(dW, hW.size(), sw, st);
+    // reference: fp32 GEMM (+ residual), then the stand-alone LayerNorm kernel
+    EpiParams ep;
+    ep.kind = has_resid ? EPI_RESID_F32 : EPI_BIAS_F32; ep.bias = db; ep.ldo = N; ep.resid = has_resid ? dr : nullptr; ep.alpha = has_resid ? 0.5f : 1.0f;
+    ep.out_f32 = x_ref;
+    launch_gemm_simt(dA, K, dW, K, M, N, K, ep, st);
+    ActBuf none, refp; refp.f32 = p_ref;
+    if (!out_ln1) launch_layernorm(x_ref, M, N, w1, b1, nullptr, refp, nullptr, nullptr, none, st);
+    else if (two) launch_layernorm(x_ref, M, N, w1, b1, x_ref, none, w2, b2, refp, st);
+    else launch_layernorm(x_ref, M, N, w1, b1, x_ref, refp, nullptr, nullptr, none, st);
+    TcOperand ta, tw;
+    pk_status rc = PK_OK;
+    if (!make_tc_operand(&ta, Ah, Al, M, K, 128) || !make_tc_operand(&tw, Wh, Wl, N, K, 128)) rc = PK_ERR_CUDA;
+    LnEpi le;
+    le.bias = db; le.resid = has_resid ? x_tc : nullptr; le.alpha = ep.alpha; le.out_f32 = x_tc;
+    le.ln1_w = w1; le.ln1_b = b1; le.ln2_w = two ? w2 : nullptr; le.ln2_b = two ? b2 : nullptr; le.out_ln1 = out_ln1;
+    le.planes.hi = ph; le.planes.lo = math == PK_MATH_BF16X3 ? pl : nullptr;
+    if (rc == PK_OK && launch_gemm_tc_ln(ta, tw, M, N, K, math == PK_MATH_BF16X3, le, sms, st) != cudaSuccess) rc = PK_ERR_CUDA;
+    if (rc == PK_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PK_ERR_CUDA;
+    if (rc == PK_OK) {
+        std::vector<float> xr(hr.size()), xt(hr.size()), pr(hr.size());
+        std::vector<bf16> h(hr.size()), l(hr.size());
+        cudaMemcpy(xr.data(), x_ref, xr.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(xt.data(), x_tc, xt.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(pr.data(), p_ref, pr.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h.data(), ph, h.size() * 2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(l.data(), pl, l.size() * 2, cudaMemcpyDeviceToHost);
+        float e0 = 0.f, r0 = 0.f, e1 = 0.f, r1 = 0.f;
+        for (size_t i = 0; i < xr.size(); ++i) {
+            const float ex = std::fabs(xt[i] - xr[i]);
+            if (!(ex <= e0)) e0 = ex;
+            r0 = std::max(r0, std::fabs(xr[i]));
+            const float pv = __bfloat162float(h[i]) + (math == PK_MATH_BF16X3 ? __bfloat162float(l[i]) : 0.f);
+            const float epv = std::fabs(pv - pr[i]);
+            if (!(epv <= e1)) e1 = epv;
+            r1 = std::max(r1, std::fabs(pr[i]));
+        }
+        err4[0] = e0; err4[1] = r0; err4[2] = e1; err4[3] = r1;
+    }
+    if (rc == PK_OK && getenv("PK_SELFTEST_TIME")) {   // warm back-to-back: the fused kernel vs residual GEMM + layernorm_kernel
+        cudaEvent_t e0, e1, e2;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        const int reps = 20;
+        EpiParams er;
+        er.kind = EPI_RESID_F32; er.bias = db; er.ldo = N; er.resid = x_tc; er.out_f32 = x_tc; er.alpha = 0.5f;
+        ActBuf tp; tp.hi = ph; tp.lo = pl;
+        for (int w = 0; w < 2; ++w) {
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < reps; ++i) launch_gemm_tc_ln(ta, tw, M, N, K, math == PK_MATH_BF16X3, le, sms, st);
+            cudaEventRecord(e1, st);
+            for (int i = 0; i < reps; ++i) {
+                launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, er, st);
+                if (two) launch_layernorm(x_tc, M, N, w1, b1, x_tc, none, w2, b2, tp, st);
+                else launch_layernorm(x_tc, M, N, w1, b1, out_ln1 ? x_tc : nullptr, tp, nullptr, nullptr, none, st);
+            }
+            cudaEventRecord(e2, st);
+            cudaStreamSynchronize(st);
+        }
+        float ms0 = 0.f, ms1 = 0.f;
+        cudaEventElapsedTime(&ms0, e0, e1);
+        cudaEventElapsedTime(&ms1, e1, e2);
+        fprintf(stderr, "gemm_tc_ln M=%d N=%d K=%d mode=%d math=%d: fused %.1f us | gemm_tc + layernorm %.1f us\n", M, N, K, mode, math,
+                1e3 * ms0 / reps, 1e3 * ms1 / reps);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    }
+    for (void *p : {(void *)dA, (void *)dW, (void *)db, (void *)dr, (void *)dl, (void *)x_ref, (void *)x_tc, (void *)p_ref, (void *)Ah, (void *)Al,
+                    (void *)Wh, (void *)Wl, (void *)ph, (void *)pl})
         cudaFree(p);
     cudaStreamDestroy(st);
     return rc;

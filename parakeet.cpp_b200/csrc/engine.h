@@ -239,6 +239,12 @@ struct pk_engine {
     pk_status set_batch_shapes(const int32_t *n_frames_or_null, const int64_t *offsets_or_null, int n);
     pk_status upload_shapes();
     void gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiParams epi);
+    // x = resid + alpha * (A . W^T + b) followed by LayerNorm(s): ONE kernel (gemm_tc_ln.cu) when fuse_ln applies,
+    // else the residual GEMM and layernorm_kernel.  resid_in_x: the residual is x itself (false: x = A . W^T + b).
+    // out_ln1: x receives LayerNorm_1 of the sum (block end) instead of the sum; planes = split of the last LayerNorm.
+    pk_status gemm_ln(const Act &A, int lda, const GemmWeight &W, int M_, bool resid_in_x, float alpha, const float *ln1_w, const float *ln1_b,
+                      bool out_ln1, const float *ln2_w, const float *ln2_b, ActBuf planes);
+    bool fuse_ln = false;                      // PK_FUSE_LN=1: LayerNorm in the epilogue of the GEMM that produces its input
     // output-side tensor maps of the TMA-store epilogue, keyed by (buffer, leading dimension, rows)
     std::map<std::tuple<const void *, int, int, int>, CUtensorMap> out_maps;
     const CUtensorMap *out_map(const void *ptr, bool is_f32, int rows, int ld);
@@ -253,7 +259,7 @@ struct pk_engine {
     pk_status run_mel(int u0 = 0, int u1 = -1);
     pk_status run_conv1(int u0 = 0, int u1 = -1);
     pk_status run_graphed(const std::string &key, const std::function<pk_status()> &body);
-    pk_status run_subsample_tail();
+    pk_status run_subsample_tail(bool with_first_ln = false);
     pk_status run_encoder(float *sub_out_host, float *layers_out_host);
     // streaming eou path (stream_engine.cu)
     struct StreamSet *ss = nullptr;

@@ -31,117 +31,16 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "tc_prims.cuh"
 
 namespace pk {
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int UMMA_K = 16;
+using namespace tc;
 
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (spin > (1u << 26)) __trap();   // ~seconds: protocol error, fail instead of hanging
-    }
-}
-// L2 eviction-priority hints of the TMA operand loads (the 64-bit policy words CUTLASS uses for createpolicy-free hints).
-// Measured (profiles/r02_b_gemm_analysis.md): the result stream of a GEMM (66 MB per fc1 launch) pushes the operand tiles
-// that all CTAs re-read out of the near L2 partition -- lts hit rate 91 % -> 74 %, every miss a trip to the far die --
-// which is what stretched the MMA interval when loads and stores ran together.  Operands are therefore loaded EVICT_LAST.
-constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
 __device__ int g_l2_hint_mode;   // measurement aid (PK_GEMM_DBG bits 10-11): 0 = loads EVICT_LAST, 1 = no hints, 2 = + stores EVICT_FIRST
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, uint64_t policy = L2_EVICT_LAST) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
-// One elected lane of a fully active warp (the warp-specialised roles below run under it): unlike `lane == 0`, ptxas
-// then knows that exactly one thread executes the region and issues UTCHMMA / UTMALDG from uniform registers directly
-// instead of wrapping every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-
-// K-major operand tile in shared memory, rows of 128 B, SWIZZLE_128B (as written by TMA):
-// 8-row core groups are 1024 B apart (SBO); LBO unused for swizzled K-major (1);
-// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  (cute mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address  [0,14)
-    d |= (uint64_t)1 << 16;                           // leading byte offset (>>4) [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset (>>4)  [32,46)
-    d |= (uint64_t)1 << 46;                           // version = 1               [46,48)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B              [61,64)
-    return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread.  Issue only; the caller overlaps
-// the TMEM read latency with other work and calls tmem_wait_ld() before touching v[].
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 constexpr int STG_LD = 20;                      // epilogue staging row stride (floats): 16 columns + pad
-// Explicit shared-space accesses for the epilogue staging (the compiler otherwise emits generic
-// LD/ST: the pointer is derived from a uintptr_t-aligned base).
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-    return v;
-}
 
 // Global operands of one 16-column chunk (this lane: 4 rows x 4 columns), issued one chunk AHEAD of
 // their use so that the L2 round trip overlaps the previous chunk's transpose / math / stores.
@@ -259,22 +158,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // into the warp's 4 KB staging tile (16-byte pieces XOR-swizzled by the row: conflict-free both ways), and the warp
 // reads the tile back transposed -- lane = (row it*4 + lane/8, piece lane%8) -- so 8 lanes cover one 128-byte line.
 // The accumulator buffer is released as soon as the two TMEM loads have landed, long before the stores.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-    return v;
-}
 constexpr int STGW_BYTES = 4096;                // per-warp staging tile of the wide epilogue: 32 rows x 128 B
 
 // lane's 128-byte row segment (32 words) -> staging; then the warp stores the 32 x 128 B tile to global memory, rows
@@ -345,13 +228,6 @@ __device__ __forceinline__ void tma_store_tile(uint32_t stg_s, int lane, const u
     }
 }
 
-__device__ __forceinline__ void split_pair(float x, float y, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
-}
 
 // Can the slab [gcol0, gcol0 + 64) of this launch take the wide path?  (warp-uniform)
 template <int EK>
@@ -652,22 +528,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // lanes; the leader's acc_empty barrier collects the arrivals of both epilogues.
 constexpr int BN2 = 256;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 __device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *tm, uint32_t leader_bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -92,6 +92,23 @@ void tc_print_timeline(int n_tiles);
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
                            const EpiParams &epi, cudaStream_t st);
 
+// ------------------------------------------------------------------ gemm_tc_ln.cu (K5b: residual GEMM + fused LayerNorm)
+//     v = resid + alpha * (A . W^T + bias)   (resid may be null);   y1 = LN1(v);   y2 = LN2(y1) if ln2_w
+//     out_f32 = out_ln1 ? y1 : v   (may alias resid);   planes = hi/lo split of the last LayerNorm's result
+// N must be a full LayerNorm row of 4 x 128 columns (one 4-CTA cluster per 128-row block; statistics through DSMEM).
+struct LnEpi {
+    const float *bias = nullptr, *resid = nullptr;
+    float alpha = 1.0f;
+    float *out_f32 = nullptr;
+    const float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+    bool out_ln1 = false;
+    ActBuf planes;
+    float eps = 1e-5f;
+};
+bool gemm_tc_ln_supported(int N);
+cudaError_t launch_gemm_tc_ln(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3, const LnEpi &epi, int num_sms,
+                              cudaStream_t st);
+
 // ------------------------------------------------------------------ gemm_skinny.cu (M <= 128: the streaming path's GEMMs)
 size_t gemm_skinny_ws_floats(int max_n, int max_splits);
 cudaError_t launch_gemm_skinny(const bf16 *Ahi, const bf16 *Alo, int lda, const bf16 *Whi, const bf16 *Wlo, int M, int N, int K, bool split3,

@@ -81,6 +81,20 @@ def test_skinny_gemm_matches_fp32_gemm(pkg, M, N, K, epi, monkeypatch):
     assert err1 / ref < 2e-2
 
 
+@pytest.mark.parametrize("M,K,mode", [(8064, 2048, 0), (8064, 512, 0), (8064, 2048, 1), (8064, 2048, 2), (8064, 2560, 3), (777, 512, 1),
+                                      (129, 512, 0), (4000, 2048, 1)])
+def test_fused_gemm_layernorm_matches_gemm_then_layernorm(pkg, M, K, mode):
+    """csrc/gemm_tc_ln.cu: the residual GEMM with the following LayerNorm(s) in its epilogue (4-CTA clusters along N = 512,
+    row statistics exchanged through distributed shared memory, run in place on the residual stream) against the fp32
+    CUDA-core GEMM followed by the stand-alone LayerNorm kernel: the residual stream and the operand planes, the chained
+    block-end pair, the last block, the residual-free proj_ case, a ragged last row block."""
+    from parakeet_cpp_b200.engine import selftest_gemm_ln
+    xe, xr, pe, pr = selftest_gemm_ln(M, K, mode, 0)
+    assert xe / xr < 5e-5 and pe / pr < 5e-5, (xe, xr, pe, pr)
+    xe1, _, pe1, _ = selftest_gemm_ln(M, K, mode, 1)
+    assert xe1 / xr < 2e-2 and pe1 / pr < 5e-2          # plain bf16 operands, bf16 hi plane only
+
+
 # ------------------------------------------------------------------ mel front end (K1/K2)
 @pytest.mark.parametrize("lengths", [[16000], [400], [401, 559, 560, 561], [32000, 20000, 64000, 12345, 8000, 16001]])
 def test_mel_matches_oracle(eng_tiny, O, synth, lengths):
@@ -352,6 +366,41 @@ def test_transcribe_110m_more_clips_tokens_match_reference(pkg, m110, synth, mat
             assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == gx[k + tag + "_tok"].tolist(), (tag, ci)
             assert np.allclose([x.confidence for x in r.timestamped_tokens], gx[k + tag + "_conf"], rtol=1e-3, atol=1e-6)
             assert r.text == bytes(gx[k + tag + "_text"]).decode()
+    t.engine.close()
+
+
+def test_fused_layernorm_engine_equals_unfused_and_reference(pkg, O, m110, synth, monkeypatch):
+    """PK_FUSE_LN: the encoder with every LayerNorm inside the epilogue of the GEMM that produces its input (gemm_tc_ln.cu)
+    against the same engine with stand-alone LayerNorm kernels -- per-layer activations of a ragged batch -- and against the
+    compiled reference's tokens on the twenty full-size clips (CTC and TDT, bit-exact)."""
+    import dataclasses
+    cfg = dataclasses.replace(m110.cfg, math=MATH["bf16x3"])
+    feats = [O.preprocess_audio(synth.make_audio(n, 4200 + i)) for i, n in enumerate((160000, 112000, 48000, 81234))]
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PK_FUSE_LN", flag)
+        e = pkg.Engine(cfg, m110.weights_path, 0)
+        outs[flag] = e.encode(feats, taps=True)
+        e.close()
+    for b in range(len(feats)):
+        assert _rel(outs["1"][1][b], outs["0"][1][b]) < 1e-6                      # subsampling output (proj_ without / with the fused norm)
+        for i in range(len(outs["0"][2][b])):
+            assert _rel(outs["1"][2][b][i], outs["0"][2][b][i]) < 2e-5, (b, i)     # every block's output
+        assert _rel(outs["1"][0][b], outs["0"][0][b]) < 2e-5
+    monkeypatch.setenv("PK_FUSE_LN", "1")
+    gx = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_110m_extra_v1.npz"))
+    n_clips = int(gx["n_clips"][0])
+    t = pkg.Transcriber(m110.weights_path, m110.vocab_path, cfg)
+    pcms = []
+    for ci in range(n_clips):
+        n, aseed = (int(v) for v in gx[f"x110.c{ci}.n_samples"])
+        pcms.append(synth.make_audio(n, aseed))
+    for dec, tag in ((pkg.Decoder.CTC, "ctc"), (pkg.Decoder.TDT, "tdt")):
+        rs = t.transcribe_batch(pcms, dec, True)
+        for ci, r in enumerate(rs):
+            k = f"x110.c{ci}."
+            assert [[x.token_id, x.start_frame, x.end_frame] for x in r.timestamped_tokens] == gx[k + tag + "_tok"].tolist(), (tag, ci)
+            assert np.allclose([x.confidence for x in r.timestamped_tokens], gx[k + tag + "_conf"], rtol=1e-3, atol=1e-6)
     t.engine.close()
 
 
