@@ -363,7 +363,7 @@ pk_status pk_engine::alloc_workspace() {
     sub2 = dalloc<float>(rows2 * C);
     sub3 = act_alloc(rows3, C);
     sub4 = act_alloc(rows3, C);
-    if (cfg.math != PK_MATH_FP32 && sub4.hi && !make_tc_operand(&sub4.tc, sub4.hi, sub4.lo, Mx, (size_t)C * f3n, 128)) sub4.hi = nullptr;   // viewed as [M][C*F'] by proj_
+    if (cfg.math != PK_MATH_FP32 && sub4.hi && (!make_tc_operand(&sub4.tc, sub4.hi, sub4.lo, Mx, (size_t)C * f3n, 128) || !make_tc_operand(&sub4.tc32, sub4.hi, sub4.lo, Mx, (size_t)C * f3n, 32))) sub4.hi = nullptr;   // viewed as [M][C*F'] by proj_
     x = dalloc<float>(Mx * d);
     ln = act_alloc(Mx, d);
     ffh = act_alloc(Mx, c.ff);
@@ -542,7 +542,7 @@ pk_status pk_engine::run_conv1(int u0, int u1) {
 pk_status pk_engine::gemm_ln(const Act &A, int lda, const GemmWeight &W, int M_, bool resid_in_x, float alpha, const float *ln1_w,
                              const float *ln1_b, bool out_ln1, const float *ln2_w, const float *ln2_b, ActBuf planes) {
     const int d = cfg.d_model;
-    const bool fused = fuse_ln && cfg.math != PK_MATH_FP32 && W.N == d && gemm_tc_ln_supported(d) && lda == W.K && W.tc.box_rows == 128 &&
+    const bool fused = fuse_ln && W.K >= fuse_ln_min_k && cfg.math != PK_MATH_FP32 && W.N == d && gemm_tc_ln_supported(d) && lda == W.K && W.tc.box_rows == 128 &&
                        !(skinny && M_ <= 128 && skinny_ws) && planes.hi != nullptr;
     if (fused) {
         LnEpi le;
@@ -554,7 +554,7 @@ pk_status pk_engine::gemm_ln(const Act &A, int lda, const GemmWeight &W, int M_,
         le.out_ln1 = out_ln1;
         le.planes = planes;
         Scope sc(this, CAT_GEMM, 2.0 * M_ * W.N * W.K);
-        cudaError_t ce = launch_gemm_tc_ln(A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, le, num_sms, stream);
+        cudaError_t ce = launch_gemm_tc_ln(ln_mcast ? A.tc32 : A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, le, num_sms, stream);
         if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("tcgen05 GEMM+LayerNorm launch: ") + cudaGetErrorString(ce));
         ++launches;
         return PK_OK;
@@ -914,6 +914,8 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     if (const char *ev = getenv("PK_GEMM_TMA_OUT")) e->tma_out = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_SKINNY")) e->skinny = atoi(ev) != 0;
     if (const char *ev = getenv("PK_FUSE_LN")) e->fuse_ln = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_LN_MCAST")) e->ln_mcast = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_FUSE_LN_MINK")) e->fuse_ln_min_k = atoi(ev);
     e->device = device;
     if (cudaSetDevice(device) != cudaSuccess) {
         g_create_err = "cudaSetDevice failed";
@@ -1210,7 +1212,10 @@ pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint
     else launch_layernorm(x_ref, M, N, w1, b1, x_ref, refp, nullptr, nullptr, none, st);
     TcOperand ta, tw;
     pk_status rc = PK_OK;
-    if (!make_tc_operand(&ta, Ah, Al, M, K, 128) || !make_tc_operand(&tw, Wh, Wl, N, K, 128)) rc = PK_ERR_CUDA;
+    const bool mcast = getenv("PK_LN_MCAST") && atoi(getenv("PK_LN_MCAST")) != 0;
+    TcOperand ta128;                              // (the unfused comparison launch needs the 128-row box)
+    if (!make_tc_operand(&ta, Ah, Al, M, K, mcast ? 32 : 128) || !make_tc_operand(&ta128, Ah, Al, M, K, 128) || !make_tc_operand(&tw, Wh, Wl, N, K, 128)) rc = PK_ERR_CUDA;
+    gemm_tc_ln_set_debug(getenv("PK_LN_DBG") ? atoi(getenv("PK_LN_DBG")) : 0);
     LnEpi le;
     le.bias = db; le.resid = has_resid ? x_tc : nullptr; le.alpha = ep.alpha; le.out_f32 = x_tc;
     le.ln1_w = w1; le.ln1_b = b1; le.ln2_w = two ? w2 : nullptr; le.ln2_b = two ? b2 : nullptr; le.out_ln1 = out_ln1;
@@ -1249,7 +1254,7 @@ pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint
             for (int i = 0; i < reps; ++i) launch_gemm_tc_ln(ta, tw, M, N, K, math == PK_MATH_BF16X3, le, sms, st);
             cudaEventRecord(e1, st);
             for (int i = 0; i < reps; ++i) {
-                launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, er, st);
+                launch_gemm_tc(ta128, tw, M, N, K, math == PK_MATH_BF16X3, er, st);
                 if (two) launch_layernorm(x_tc, M, N, w1, b1, x_tc, none, w2, b2, tp, st);
                 else launch_layernorm(x_tc, M, N, w1, b1, out_ln1 ? x_tc : nullptr, tp, nullptr, nullptr, none, st);
             }
@@ -1261,6 +1266,7 @@ pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint
         cudaEventElapsedTime(&ms1, e1, e2);
         fprintf(stderr, "gemm_tc_ln M=%d N=%d K=%d mode=%d math=%d: fused %.1f us | gemm_tc + layernorm %.1f us\n", M, N, K, mode, math,
                 1e3 * ms0 / reps, 1e3 * ms1 / reps);
+        if (getenv("PK_LN_DBG") && atoi(getenv("PK_LN_DBG"))) gemm_tc_ln_print_timeline(2);
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     }
     for (void *p : {(void *)dA, (void *)dW, (void *)db, (void *)dr, (void *)dl, (void *)x_ref, (void *)x_tc, (void *)p_ref, (void *)Ah, (void *)Al,

@@ -49,9 +49,11 @@ struct LnCfg {
     static constexpr int STG_BYTES = LN_EPI_WARPS * LN_STGW;
     static constexpr int NSRC = 2 * CLN;                               // partial statistics per row (two 64-column slabs per CTA)
     static constexpr int STATS_BYTES = 2 * BM * NSRC * 8;              // [slot][row][source] float2
-    static constexpr int AVAIL = 227 * 1024 - STG_BYTES - STATS_BYTES - 1024 - 256;
+    static constexpr int PAR_BYTES = 3 * LN_BN * 4;                    // bias | ln1 weight | ln1 bias of this CTA's 128 columns
+    static constexpr int AVAIL = 227 * 1024 - STG_BYTES - STATS_BYTES - PAR_BYTES - 1024 - 256;
     static constexpr int STAGES = AVAIL / STAGE_BYTES > 8 ? 8 : AVAIL / STAGE_BYTES;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + STATS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + STATS_BYTES + PAR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static constexpr int TMEM_COLS = 2 * LN_BN;
     static_assert(STAGES >= 2, "pipeline depth");
 };
@@ -65,10 +67,14 @@ struct LnEpiDev {                  // LnEpi as the kernel sees it
     int out_ln1;
 };
 
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+// 8 bytes into the shared memory of a CTA of the cluster; completion is signalled as 8 transaction bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_b64(uint32_t cluster_addr, uint64_t v, uint32_t cluster_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(cluster_addr), "l"(v), "r"(cluster_mbar) : "memory");
 }
-__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+// measurement aid (dbg != 0): clock64 of CTA 0's first epilogue warp per tile -- [0] tile start (residual loads issued), [1] accumulator
+// ready, [2] TMEM drained + bias, [3] residual added, [4] statistics sent, [5] x stored, [6] statistics received, [7] normalised (+ second
+// LayerNorm), [8] planes stored
+__device__ long long g_ln_tl[8][16];
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {   // acquire at cluster scope: remote st.shared::cluster before the arrivals are visible
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
@@ -84,62 +90,46 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
     }
 }
 
-// ---- the 32-row x 64-byte staging tile of a warp.  Chunk c (16 B) of row r sits at r * 64 + ((c ^ ((r >> 1) & 3)) << 4):
-// conflict-free for "lane = row" accesses (8 lanes of a phase: 2 row parities x 4 swizzle values) and for the transposed
-// ones (8 lanes = 2 rows x 4 chunks).
-__device__ __forceinline__ uint32_t stg_rowwise(uint32_t stg, int lane, int c) { return stg + (uint32_t)(lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)); }
-__device__ __forceinline__ uint32_t stg_transposed(uint32_t stg, int lane, int it, int &row) {
-    row = it * 8 + (lane >> 2);
-    return stg + (uint32_t)(row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
+// ---- the 2 KB staging tile of a warp: 16 rows x 128 B, 16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4) (the
+// SWIZZLE_128B pattern: conflict-free for "lane = row" accesses and for the transposed ones, where 8 lanes cover one row).
+// A warp's 32-row slab passes through it in two halves (h = 0, 1: rows 16 h .. 16 h + 15, held by lanes 16 h .. 16 h + 15), so
+// that every global access of the epilogue is a FULL 128-byte line per 8 lanes (measured: 64-byte pieces made the x / plane
+// stores of a tile cost 7.4k of the epilogue's 13k cycles).
+__device__ __forceinline__ uint32_t stg_row(uint32_t stg, int lane, int c) { return stg + (uint32_t)((lane & 15) * 128 + ((c ^ (lane & 7)) << 4)); }
+__device__ __forceinline__ uint32_t stg_tr(uint32_t stg, int lane, int it, int &row) {
+    row = it * 4 + (lane >> 3);
+    return stg + (uint32_t)(row * 128 + (((lane & 7) ^ (row & 7)) << 4));
 }
-// global tile (rows row0.., 64 B per row at base + row * ld_bytes) -> r[16] = the 64 bytes of THIS lane's row (zeros past M)
-__device__ __forceinline__ void load_tile64(uint32_t stg, int lane, const uint8_t *base, size_t ld_bytes, int row0, int M, uint32_t (&r)[16]) {
-    uint4 t[4];
+// lanes of half h hold w[32] = 128 bytes of their row; the warp writes rows row0 + 16 h .. + 15 at base + row * ld_bytes
+__device__ __forceinline__ void store_half128(uint32_t stg, int lane, int h, const uint32_t (&w)[32], uint8_t *base, size_t ld_bytes, int row0, int M) {
+    if ((lane >> 4) == h) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int row = it * 8 + (lane >> 2);
-        t[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (row0 + row < M) t[it] = *reinterpret_cast<const uint4 *>(base + (size_t)(row0 + row) * ld_bytes + ((lane & 3) << 4));
+        for (int c = 0; c < 8; ++c) sts128(stg_row(stg, lane, c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
     }
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        int row;
-        const uint32_t a = stg_transposed(stg, lane, it, row);
-        sts128(a, t[it].x, t[it].y, t[it].z, t[it].w);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const uint4 v = lds128u(stg_rowwise(stg, lane, c));
-        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
-    }
-    __syncwarp();
-}
-__device__ __forceinline__ void store_tile64(uint32_t stg, int lane, const uint32_t (&r)[16], uint8_t *base, size_t ld_bytes, int row0, int M) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sts128(stg_rowwise(stg, lane, c), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         int row;
-        const uint4 v = lds128u(stg_transposed(stg, lane, it, row));
-        if (row0 + row < M) *reinterpret_cast<uint4 *>(base + (size_t)(row0 + row) * ld_bytes + ((lane & 3) << 4)) = v;
+        const uint4 v = lds128u(stg_tr(stg, lane, it, row));
+        const int grow = row0 + 16 * h + row;
+        if (grow < M) *reinterpret_cast<uint4 *>(base + (size_t)grow * ld_bytes + ((lane & 7) << 4)) = v;
     }
     __syncwarp();
 }
 
-template <int NPASS, int CLN>
+template <int NPASS, int CLN, bool MC>
 __global__ void __cluster_dims__(CLN, 1, 1) __launch_bounds__(LN_THREADS, 1)
 gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int K,
-                  const __grid_constant__ LnEpiDev epi) {
+                  const __grid_constant__ LnEpiDev epi, int dbg) {
     using C = LnCfg<NPASS, CLN>;
     constexpr int N = CLN * LN_BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *staging = tiles + (size_t)C::STAGES * C::STAGE_BYTES;
     uint8_t *stats = staging + C::STG_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stats + C::STATS_BYTES);
+    float *par = reinterpret_cast<float *>(stats + C::STATS_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stats + C::STATS_BYTES + C::PAR_BYTES);
     uint64_t *full = bars, *empty = bars + C::STAGES, *acc_full = bars + 2 * C::STAGES, *acc_empty = acc_full + 2, *ln_bar = acc_empty + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ln_bar + 2);
 
@@ -153,12 +143,12 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC ? CLN : 1);             // MC: the stage is written by every CTA of the cluster, so all of them must have consumed it
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], LN_EPI_WARPS);
-            mbar_init(&ln_bar[b], LN_EPI_WARPS * CLN);      // one arrival per epilogue warp of the cluster
+            mbar_init(&ln_bar[b], 1);                       // armed once per exchange round; the data arrives as transaction bytes
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -166,8 +156,16 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // Per-column epilogue operands of this CTA's 128 columns -> shared memory (weights: not written by the preceding grid).
+    // Measured: as warp-uniform __ldg they queued behind the epilogue's own global stores (normalise: 2.0-2.6k cycles).
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + LN_BN) {
+        const int i = threadIdx.x - 64;
+        par[i] = epi.bias[n0 + i];
+        par[LN_BN + i] = epi.w1[n0 + i];
+        par[2 * LN_BN + i] = epi.b1[n0 + i];
+    }
     tcgen05_fence_before();
-    cluster_sync();                               // every CTA's barriers exist before any remote arrival
+    cluster_sync();                               // every CTA's barriers exist before any remote arrival (and `par` is visible)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
@@ -185,12 +183,19 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
-                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
-                    if (NPASS == 3) {
-                        tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0);
-                        tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0);
+                    if (MC) {
+                        // The A tile is the same for all CLN CTAs: each loads a quarter of its rows (tmA_* then have a 32-row
+                        // box) and MULTICASTS it into the stage of every CTA -- 1/CLN of the L2 -> SM operand traffic for A.
+                        constexpr int SL = BM / CLN, SLB = SL * BK * 2;
+                        constexpr uint16_t mask = (uint16_t)((1u << CLN) - 1u);
+                        tma_load_2d_mcast(st + rank * SLB, &tmA_hi, &full[s], kb * BK, m0 + rank * SL, mask);
+                        if (NPASS == 3) tma_load_2d_mcast(st + C::A_BYTES + C::W_BYTES + rank * SLB, &tmA_lo, &full[s], kb * BK, m0 + rank * SL, mask);
+                    } else {
+                        tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0);
+                        if (NPASS == 3) tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0);
                     }
+                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0);
+                    if (NPASS == 3) tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0);
                 }
             }
             pdl_trigger_late();
@@ -223,7 +228,8 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             umma_bf16(tmem_d, a_lo + koff, w_hi + koff, idesc, 1);
                         }
                     }
-                    umma_commit(&empty[s]);
+                    if (MC) umma_commit_mcast(&empty[s], (uint16_t)((1u << CLN) - 1u));
+                    else umma_commit(&empty[s]);
                 }
                 umma_commit(&acc_full[buf]);
             }
@@ -245,8 +251,11 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             peer_stats[d] = mapa_rank(stats_s, (uint32_t)d);
             peer_bar[d] = mapa_rank(smem_u32(&ln_bar[0]), (uint32_t)d);
         }
-        // (mean, 1/std) of this lane's row of `v` over all N columns of the cluster
-        auto row_stats = [&](const float (&v)[64], float &mean, float &rstd) {
+        const bool tl_on = dbg && blockIdx.x == 0 && threadIdx.x == 64;
+        // Statistics exchange, split so that independent stores can sit between the two halves.  send: the partial pair of this
+        // lane's row goes to every CTA of the cluster by st.async -- the write completes 8 bytes of the transaction count of the
+        // DESTINATION's mbarrier, so no fence / arrive is needed; one thread per CTA arms its barrier with the bytes of a round.
+        auto stats_send = [&](const float (&v)[64]) {
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j) s += v[j];
@@ -257,17 +266,16 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const float dlt = v[j] - ml;
                 m2 = fmaf(dlt, dlt, m2);
             }
+            const uint32_t slot = xr & 1u;
+            if (ew == 0 && lane == 0) mbar_expect_tx(&ln_bar[slot], (uint32_t)(LN_EPI_WARPS * CLN * 32 * 8));
+            const uint32_t off = ((slot * BM + (uint32_t)trow) * C::NSRC + (uint32_t)my_src) * 8u;
+            const uint64_t pair = ((uint64_t)__float_as_uint(m2) << 32) | (uint64_t)__float_as_uint(s);
+#pragma unroll
+            for (int d = 0; d < CLN; ++d) st_async_b64(peer_stats[d] + off, pair, peer_bar[d] + slot * 8u);
+        };
+        auto stats_recv = [&](float &mean, float &rstd) {
             const uint32_t slot = xr & 1u, par = (xr >> 1) & 1u;
             ++xr;
-            const uint32_t off = ((slot * BM + (uint32_t)trow) * C::NSRC + (uint32_t)my_src) * 8u;
-#pragma unroll
-            for (int d = 0; d < CLN; ++d) st_cluster_f32x2(peer_stats[d] + off, s, m2);
-            fence_acq_rel_cluster();
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int d = 0; d < CLN; ++d) mbar_arrive_cluster(peer_bar[d] + slot * 8u);
-            }
             mbar_wait_cluster(&ln_bar[slot], par);
             float ps[C::NSRC], pm[C::NSRC];
             const uint32_t rbase = stats_s + ((slot * BM + (uint32_t)trow) * C::NSRC) * 8u;
@@ -288,7 +296,19 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             }
             rstd = rsqrtf(M2 * (1.0f / (float)N) + epi.eps);
         };
-        auto normalise = [&](float (&v)[64], float mean, float rstd, const float *__restrict__ w, const float *__restrict__ b) {
+        const uint32_t par_s = smem_u32(par) + (uint32_t)(half * 64) * 4u;   // this warp's 64 columns of [bias | w1 | b1]
+        auto normalise1 = [&](float (&v)[64], float mean, float rstd) {         // LayerNorm_1: operands from shared memory (broadcast reads)
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+                const float4 g = lds128(par_s + (uint32_t)(LN_BN + j) * 4u);
+                const float4 bb = lds128(par_s + (uint32_t)(2 * LN_BN + j) * 4u);
+                v[j] = (v[j] - mean) * rstd * g.x + bb.x;
+                v[j + 1] = (v[j + 1] - mean) * rstd * g.y + bb.y;
+                v[j + 2] = (v[j + 2] - mean) * rstd * g.z + bb.z;
+                v[j + 3] = (v[j + 3] - mean) * rstd * g.w + bb.w;
+            }
+        };
+        auto normalise2 = [&](float (&v)[64], float mean, float rstd, const float *__restrict__ w, const float *__restrict__ b) {
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
                 const float4 g = __ldg(reinterpret_cast<const float4 *>(w + gcol0 + j));
@@ -299,12 +319,33 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 v[j + 3] = (v[j + 3] - mean) * rstd * g.w + bb.w;
             }
         };
+        const size_t ldf = (size_t)N * 4, ldp = (size_t)N * 2;
         uint32_t tcount = 0;
         for (int rb = cid; rb < tiles_m; rb += ncl, ++tcount) {
             const int row0 = rb * BM + q * 32;
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
+            long long *tl = (tl_on && tcount < 8) ? g_ln_tl[tcount] : nullptr;
+            if (tl) tl[0] = clock64();
+            // residual slab: issued BEFORE the accumulator is waited for (it does not depend on it), in the coalesced pattern
+            // (half h, 128-byte column group t2: lane -> row 16 h + it*4 + lane/8, 16-byte chunk lane%8)
+            uint4 rr[2][2][4];
+            if (epi.resid) {
+                const uint8_t *rbp = reinterpret_cast<const uint8_t *>(epi.resid + gcol0) + ((lane & 7) << 4);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = row0 + 16 * h + it * 4 + (lane >> 3);
+#pragma unroll
+                        for (int t2 = 0; t2 < 2; ++t2) {
+                            rr[h][t2][it] = make_uint4(0u, 0u, 0u, 0u);
+                            if (row < M) rr[h][t2][it] = *reinterpret_cast<const uint4 *>(rbp + (size_t)row * ldf + t2 * 128);
+                        }
+                    }
+            }
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
+            if (tl) tl[1] = clock64();
             const uint32_t taddr = tmem_base + buf * LN_BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
             float v[64];
             {
@@ -317,8 +358,8 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(epi.bias + gcol0 + j));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(epi.bias + gcol0 + 32 + j));
+                    const float4 b0 = lds128(par_s + (uint32_t)j * 4u);
+                    const float4 b1 = lds128(par_s + (uint32_t)(32 + j) * 4u);
                     v[j] = (__uint_as_float(a0[j]) + b0.x) * epi.alpha;
                     v[j + 1] = (__uint_as_float(a0[j + 1]) + b0.y) * epi.alpha;
                     v[j + 2] = (__uint_as_float(a0[j + 2]) + b0.z) * epi.alpha;
@@ -329,46 +370,70 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     v[32 + j + 3] = (__uint_as_float(a1[j + 3]) + b1.w) * epi.alpha;
                 }
             }
-            const size_t ldf = (size_t)N * 4, ldp = (size_t)N * 2;
-            if (epi.resid) {                          // + residual (coalesced loads, transposed to "lane = row" through the staging tile)
-                const uint8_t *rbp = reinterpret_cast<const uint8_t *>(epi.resid + gcol0);
+            if (tl) tl[2] = clock64();
+            if (epi.resid) {                          // + residual, transposed to "lane = row" through the staging tile
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    uint32_t r[16];
-                    load_tile64(stg_s, lane, rbp + t * 64, ldf, row0, M, r);
+                for (int t2 = 0; t2 < 2; ++t2)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[16 * t + i] += __uint_as_float(r[i]);
-                }
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            int row;
+                            const uint32_t a = stg_tr(stg_s, lane, it, row);
+                            sts128(a, rr[h][t2][it].x, rr[h][t2][it].y, rr[h][t2][it].z, rr[h][t2][it].w);
+                        }
+                        __syncwarp();
+                        if ((lane >> 4) == h) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 r4 = lds128(stg_row(stg_s, lane, c));
+                                v[32 * t2 + 4 * c] += r4.x; v[32 * t2 + 4 * c + 1] += r4.y; v[32 * t2 + 4 * c + 2] += r4.z; v[32 * t2 + 4 * c + 3] += r4.w;
+                            }
+                        }
+                        __syncwarp();
+                    }
             }
+            if (tl) tl[3] = clock64();
             auto store_f32 = [&]() {
                 uint8_t *ob = reinterpret_cast<uint8_t *>(epi.out_f32 + gcol0);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    uint32_t r[16];
+                for (int t2 = 0; t2 < 2; ++t2) {
+                    uint32_t w[32];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[16 * t + i]);
-                    store_tile64(stg_s, lane, r, ob + t * 64, ldf, row0, M);
+                    for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(v[32 * t2 + i]);
+                    store_half128(stg_s, lane, 0, w, ob + t2 * 128, ldf, row0, M);
+                    store_half128(stg_s, lane, 1, w, ob + t2 * 128, ldf, row0, M);
                 }
             };
             float mean, rstd;
-            if (!epi.out_ln1) store_f32();            // the residual stream keeps v
-            row_stats(v, mean, rstd);
-            normalise(v, mean, rstd, epi.w1, epi.b1);
-            if (epi.out_ln1) store_f32();             // block end: the residual stream is LayerNorm_1(v)
-            if (epi.w2) {
-                row_stats(v, mean, rstd);
-                normalise(v, mean, rstd, epi.w2, epi.b2);
+            stats_send(v);
+            if (tl) tl[4] = clock64();
+            if (!epi.out_ln1) store_f32();            // the residual stream keeps v (stored while the statistics travel)
+            if (tl) tl[5] = clock64();
+            stats_recv(mean, rstd);
+            if (tl) tl[6] = clock64();
+            normalise1(v, mean, rstd);
+            if (epi.w2) {                             // block end: x = LayerNorm_1(v), planes = LayerNorm_2(x)
+                stats_send(v);
+                store_f32();
+                stats_recv(mean, rstd);
+                normalise2(v, mean, rstd, epi.w2, epi.b2);
+            } else if (epi.out_ln1) {
+                store_f32();
             }
-            if (epi.hi) {                             // operand planes of the next GEMM
+            if (tl) tl[7] = clock64();
+            if (epi.hi) {                             // operand planes of the next GEMM: 64 bf16 = 128 B per row and plane
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) split_pair(v[32 * t + 2 * i], v[32 * t + 2 * i + 1], hi[i], lo[i]);
-                    store_tile64(stg_s, lane, hi, reinterpret_cast<uint8_t *>(epi.hi + gcol0) + t * 64, ldp, row0, M);
-                    if (epi.lo) store_tile64(stg_s, lane, lo, reinterpret_cast<uint8_t *>(epi.lo + gcol0) + t * 64, ldp, row0, M);
+                for (int i = 0; i < 32; ++i) split_pair(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                store_half128(stg_s, lane, 0, hi, reinterpret_cast<uint8_t *>(epi.hi + gcol0), ldp, row0, M);
+                store_half128(stg_s, lane, 1, hi, reinterpret_cast<uint8_t *>(epi.hi + gcol0), ldp, row0, M);
+                if (epi.lo) {
+                    store_half128(stg_s, lane, 0, lo, reinterpret_cast<uint8_t *>(epi.lo + gcol0), ldp, row0, M);
+                    store_half128(stg_s, lane, 1, lo, reinterpret_cast<uint8_t *>(epi.lo + gcol0), ldp, row0, M);
                 }
             }
+            if (tl) tl[8] = clock64();
         }
     }
     tcgen05_fence_before();
@@ -378,7 +443,10 @@ gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
 }
 
-template <int NPASS, int CLN>
+int g_ln_dbg = 0;
+int g_ln_clusters = 0;     // clusters of the last launch (reported by the timeline dump)
+
+template <int NPASS, int CLN, bool MC>
 cudaError_t launch_ln_k(const TcOperand &A, const TcOperand &W, int M, int K, const LnEpiDev &ep, int num_sms, cudaStream_t st) {
     using C = LnCfg<NPASS, CLN>;
     static PerDeviceFlag attr_flag;
@@ -386,7 +454,7 @@ cudaError_t launch_ln_k(const TcOperand &A, const TcOperand &W, int M, int K, co
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_flag.cur()) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_ln_kernel<NPASS, CLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_ln_kernel<NPASS, CLN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         // how many clusters can be resident at once (GPC boundaries can leave a few SMs without a full cluster)
         cudaLaunchConfig_t q = {};
@@ -394,7 +462,7 @@ cudaError_t launch_ln_k(const TcOperand &A, const TcOperand &W, int M, int K, co
         q.blockDim = dim3(LN_THREADS);
         q.dynamicSmemBytes = C::SMEM;
         int mc = 0;
-        if (cudaOccupancyMaxActiveClusters(&mc, gemm_tc_ln_kernel<NPASS, CLN>, &q) != cudaSuccess || mc < 1) {
+        if (cudaOccupancyMaxActiveClusters(&mc, gemm_tc_ln_kernel<NPASS, CLN, MC>, &q) != cudaSuccess || mc < 1) {
             cudaGetLastError();
             mc = num_sms / CLN;
         }
@@ -405,18 +473,33 @@ cudaError_t launch_ln_k(const TcOperand &A, const TcOperand &W, int M, int K, co
     int ncl = max_clusters[dev & 63];
     if (ncl > num_sms / CLN) ncl = num_sms / CLN;
     if (ncl > tiles_m) ncl = tiles_m;
+    g_ln_clusters = ncl;
     const CUtensorMap &alo = (NPASS == 3) ? A.lo : A.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
-    return launch_pdl(gemm_tc_ln_kernel<NPASS, CLN>, dim3((unsigned)(ncl * CLN)), dim3(LN_THREADS), C::SMEM, st, A.hi, alo, W.hi, wlo, M, K, ep);
+    return launch_pdl(gemm_tc_ln_kernel<NPASS, CLN, MC>, dim3((unsigned)(ncl * CLN)), dim3(LN_THREADS), C::SMEM, st, A.hi, alo, W.hi, wlo, M, K, ep, g_ln_dbg);
 }
 
 }  // namespace
 
 bool gemm_tc_ln_supported(int N) { return N == 4 * LN_BN; }
 
+void gemm_tc_ln_set_debug(int on) { g_ln_dbg = on; }
+void gemm_tc_ln_print_timeline(int n_tiles) {
+    long long h[8][16];
+    if (cudaMemcpyFromSymbol(h, g_ln_tl, sizeof(h)) != cudaSuccess) return;
+    fprintf(stderr, "    gemm_tc_ln: %d clusters; epilogue of CTA 0 warp 2, cycles since the tile's start\n", g_ln_clusters);
+    for (int i = 0; i < n_tiles && i < 8; ++i) {
+        fprintf(stderr, "    tile %d:", i);
+        static const char *nm[9] = {"start", "acc ready", "tmem+bias", "resid", "stats sent", "x stored", "stats recv", "normalised", "planes"};
+        for (int k = 1; k < 9; ++k) fprintf(stderr, "  %s %lld", nm[k], h[i][k] - h[i][0]);
+        fprintf(stderr, "   (next tile starts %lld after)\n", i + 1 < n_tiles ? h[i + 1][0] - h[i][8] : 0LL);
+    }
+}
+
 cudaError_t launch_gemm_tc_ln(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3, const LnEpi &epi, int num_sms,
                               cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    if (!gemm_tc_ln_supported(N) || K % BK != 0 || A.box_rows != BM || W.box_rows != LN_BN) return cudaErrorInvalidValue;
+    const bool mc = A.box_rows == BM / 4;        // a 32-row box: the A tile is fetched in quarters and multicast across the cluster
+    if (!gemm_tc_ln_supported(N) || K % BK != 0 || (A.box_rows != BM && !mc) || W.box_rows != LN_BN) return cudaErrorInvalidValue;
     if (split3 && !(A.has_lo && W.has_lo)) return cudaErrorInvalidValue;
     if (!epi.bias || !epi.out_f32 || !epi.ln1_w || !epi.ln1_b || (epi.ln2_w && !epi.ln2_b)) return cudaErrorInvalidValue;
     LnEpiDev d;
@@ -424,7 +507,8 @@ cudaError_t launch_gemm_tc_ln(const TcOperand &A, const TcOperand &W, int M, int
     d.w1 = epi.ln1_w; d.b1 = epi.ln1_b; d.w2 = epi.ln2_w; d.b2 = epi.ln2_b;
     d.hi = epi.planes.hi; d.lo = epi.planes.lo;
     d.alpha = epi.alpha; d.eps = epi.eps; d.out_ln1 = epi.out_ln1 ? 1 : 0;
-    return split3 ? launch_ln_k<3, 4>(A, W, M, K, d, num_sms, st) : launch_ln_k<1, 4>(A, W, M, K, d, num_sms, st);
+    if (mc) return split3 ? launch_ln_k<3, 4, true>(A, W, M, K, d, num_sms, st) : launch_ln_k<1, 4, true>(A, W, M, K, d, num_sms, st);
+    return split3 ? launch_ln_k<3, 4, false>(A, W, M, K, d, num_sms, st) : launch_ln_k<1, 4, false>(A, W, M, K, d, num_sms, st);
 }
 
 }  // namespace pk

@@ -106,6 +106,8 @@ struct LnEpi {
     float eps = 1e-5f;
 };
 bool gemm_tc_ln_supported(int N);
+void gemm_tc_ln_set_debug(int on);            // measurement aid (PK_LN_DBG=1): per-tile epilogue timeline of CTA 0
+void gemm_tc_ln_print_timeline(int n_tiles);
 cudaError_t launch_gemm_tc_ln(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3, const LnEpi &epi, int num_sms,
                               cudaStream_t st);
 

@@ -46,6 +46,15 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// The same load MULTICAST to the CTAs of `cta_mask` in this cluster: the tile lands at the same shared-memory offset in each of
+// them and completes its bytes on the mbarrier at the same offset in each of them (CUTLASS SM90_TMA_LOAD_MULTICAST_2D).
+__device__ __forceinline__ void tma_load_2d_mcast(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, uint16_t cta_mask,
+                                                  uint64_t policy = L2_EVICT_LAST) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 // One elected lane of a fully active warp (the warp-specialised roles below run under it): unlike `lane == 0`, ptxas
 // then knows that exactly one thread executes the region and issues UTCHMMA / UTMALDG from uniform registers directly
 // instead of wrapping every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop.
@@ -87,6 +96,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrives on `bar` (same offset) in every CTA of `cta_mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_mcast(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread.  Issue only; the caller overlaps
 // the TMEM read latency with other work and calls tmem_wait_ld() before touching v[].

@@ -83,12 +83,15 @@ def test_skinny_gemm_matches_fp32_gemm(pkg, M, N, K, epi, monkeypatch):
 
 @pytest.mark.parametrize("M,K,mode", [(8064, 2048, 0), (8064, 512, 0), (8064, 2048, 1), (8064, 2048, 2), (8064, 2560, 3), (777, 512, 1),
                                       (129, 512, 0), (4000, 2048, 1)])
-def test_fused_gemm_layernorm_matches_gemm_then_layernorm(pkg, M, K, mode):
+@pytest.mark.parametrize("mcast", ["1", "0"])
+def test_fused_gemm_layernorm_matches_gemm_then_layernorm(pkg, M, K, mode, mcast, monkeypatch):
     """csrc/gemm_tc_ln.cu: the residual GEMM with the following LayerNorm(s) in its epilogue (4-CTA clusters along N = 512,
     row statistics exchanged through distributed shared memory, run in place on the residual stream) against the fp32
     CUDA-core GEMM followed by the stand-alone LayerNorm kernel: the residual stream and the operand planes, the chained
-    block-end pair, the last block, the residual-free proj_ case, a ragged last row block."""
+    block-end pair, the last block, the residual-free proj_ case, a ragged last row block; with the A tile fetched in quarters
+    and TMA-multicast across the cluster (PK_LN_MCAST=1, default) and loaded whole by every CTA."""
     from parakeet_cpp_b200.engine import selftest_gemm_ln
+    monkeypatch.setenv("PK_LN_MCAST", mcast)
     xe, xr, pe, pr = selftest_gemm_ln(M, K, mode, 0)
     assert xe / xr < 5e-5 and pe / pr < 5e-5, (xe, xr, pe, pr)
     xe1, _, pe1, _ = selftest_gemm_ln(M, K, mode, 1)
