@@ -248,6 +248,10 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
  * 1: x = LN1(.), planes = LN2(x);  2: x = LN1(.), planes = split(x);  3: mode 0 without a residual.
  * err4 = {max |x - x_ref|, max |x_ref|, max |planes - planes_ref|, max |planes_ref|}. */
 pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint32_t seed, float *err4);
+/* GPU self-check of the tcgen05 attention kernel (csrc/attention_umma.cu: head_dim 64, <= 128 frames per utterance) against the
+ * fp32 CUDA-core attention kernel on seeded random inputs (d_model 512, 8 heads), utterance lengths lens[0..n).  mode bit 0:
+ * zero position table; bit 1: zero keys.  err2 = {max |ctx - ctx_ref|, max |ctx_ref|}. */
+pk_status pk_selftest_attention(int device, const int32_t *lens, int n, int tmax, int mode, uint32_t seed, float *err2);
 
 /* Host-side text helpers (pure C++ host code; no device work):
  * Tokenizer::load/decode (src/vocab.cpp:10-64), group_timestamps (src/timestamp.cpp:24-75). */

@@ -227,6 +227,7 @@ pk_status pk_engine::load(const char *path) {
                 sp.lo = L.pp_lo;
                 launch_split(L.pp, (size_t)NP * d, sp, stream);
                 ++launches;
+                L.pp_tc_ok = hd == 64 && make_tc_operand(&L.pp_tc, L.pp_hi, L.pp_lo, (uint64_t)NP, (uint64_t)d, 256);
             }
         }
         const std::string cp = lp + "conv_.";
@@ -671,9 +672,22 @@ pk_status pk_engine::run_encoder(float *sub_out_host, float *layers_out_host) {
             gemm(ln, d, L.qkv, M, eq);
             {
                 Scope sc(this, CAT_ATTENTION);
-                const bool ok = tc_attn
-                    ? launch_relpos_attention_tc(qkv, L.pos_u, L.pos_v, qkvp_hi, qkvp_lo, 2 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, d, ctx, stream)
-                    : launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream);
+                bool ok = false;
+                if (tc_attn && attn_umma && L.pp_tc_ok && relpos_attention_umma_supported(hd, maxT) && ctx.hi) {
+                    // tcgen05 kernel: the k | v planes as a TMA operand of exactly M rows (rows past the batch read as zeros)
+                    auto it = kv_maps.find(M);
+                    if (it == kv_maps.end()) {
+                        if (kv_maps.size() > 256) kv_maps.clear();
+                        TcOperand op;
+                        if (make_tc_operand(&op, qkvp_hi, qkvp_lo, (uint64_t)M, (uint64_t)2 * d, 128)) it = kv_maps.emplace(M, op).first;
+                    }
+                    if (it != kv_maps.end())
+                        ok = launch_relpos_attention_umma(qkv, L.pos_u, L.pos_v, it->second, L.pp_tc, d_row_off, n_utt, maxT, H, hd, Tmax, d, num_sms, ctx, stream);
+                }
+                if (!ok)
+                    ok = tc_attn
+                        ? launch_relpos_attention_tc(qkv, L.pos_u, L.pos_v, qkvp_hi, qkvp_lo, 2 * d, d_row_off, n_utt, maxT, H, hd, L.pp_hi, L.pp_lo, Tmax, d, ctx, stream)
+                        : launch_relpos_attention(qkv, 3 * d, d_row_off, n_utt, maxT, H, hd, L.pp, Tmax, L.pos_u, L.pos_v, d, ctx, stream);
                 if (!ok) return fail(PK_ERR_INVALID, "unsupported head_dim " + std::to_string(hd));
             }
             ++launches;
@@ -911,6 +925,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     e->cfg = c;
     if (const char *ev = getenv("PK_GRAPH")) e->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("PK_ATTN_TC")) e->attn_tc = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_ATTN_UMMA")) e->attn_umma = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_TMA_OUT")) e->tma_out = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_SKINNY")) e->skinny = atoi(ev) != 0;
     if (const char *ev = getenv("PK_FUSE_LN")) e->fuse_ln = atoi(ev) != 0;
@@ -1271,6 +1286,111 @@ pk_status pk_selftest_gemm_ln(int device, int M, int K, int mode, int math, uint
     }
     for (void *p : {(void *)dA, (void *)dW, (void *)db, (void *)dr, (void *)dl, (void *)x_ref, (void *)x_tc, (void *)p_ref, (void *)Ah, (void *)Al,
                     (void *)Wh, (void *)Wl, (void *)ph, (void *)pl})
+        cudaFree(p);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+// GPU self-check of the tcgen05 attention kernel (attention_umma.cu) against the fp32 CUDA-core attention kernel on seeded
+// random q | k | v, position table and biases: d_model 512, 8 heads of 64, utterance lengths lens[0..n) (<= 128), table for
+// `tmax` frames.  mode bit 0: zero position table (isolates Qu.K^T -> softmax -> P.V); bit 1: zero keys (isolates the
+// rel_shift path).  err2 = {max |ctx - ctx_ref|, max |ctx_ref|}.
+pk_status pk_selftest_attention(int device, const int32_t *lens, int n, int tmax, int mode, uint32_t seed, float *err2) {
+    if (cudaSetDevice(device) != cudaSuccess) return PK_ERR_CUDA;
+    const int d = 512, H = 8, hd = 64;
+    if (!lens || n < 1 || !err2 || tmax < 1) return PK_ERR_INVALID;
+    std::vector<int32_t> off(n + 1, 0);
+    int maxT = 0;
+    for (int i = 0; i < n; ++i) {
+        if (lens[i] < 0 || lens[i] > 128 || lens[i] > tmax) return PK_ERR_INVALID;
+        off[i + 1] = off[i] + lens[i];
+        maxT = std::max(maxT, (int)lens[i]);
+    }
+    const int M = off[n], NP = 2 * tmax - 1;
+    if (M < 1) return PK_ERR_INVALID;
+    cudaStream_t st;
+    cudaStreamCreate(&st);
+    uint32_t sd = seed * 2654435761u + 4242u;
+    auto rnd = [&]() { sd = sd * 1664525u + 1013904223u; return ((sd >> 8) & 0xffff) / 32768.0f - 1.0f; };
+    std::vector<float> hq((size_t)M * 3 * d), hpp((size_t)NP * d), hu(d), hv(d);
+    for (auto &v : hq) v = rnd();
+    for (auto &v : hpp) v = (mode & 1) ? 0.f : rnd();
+    for (auto &v : hu) v = 0.3f * rnd();
+    for (auto &v : hv) v = 0.3f * rnd();
+    if (mode & 2)
+        for (int r = 0; r < M; ++r)
+            for (int c = 0; c < d; ++c) hq[(size_t)r * 3 * d + d + c] = 0.f;
+    std::vector<float> hq32((size_t)M * d), hkv((size_t)M * 2 * d);
+    for (int r = 0; r < M; ++r) {
+        memcpy(&hq32[(size_t)r * d], &hq[(size_t)r * 3 * d], (size_t)d * 4);
+        memcpy(&hkv[(size_t)r * 2 * d], &hq[(size_t)r * 3 * d + d], (size_t)2 * d * 4);
+    }
+    float *dq, *dq32, *dkv, *dpp, *du, *dv, *c_ref;
+    bf16 *kvh, *kvl, *pph, *ppl, *ch, *cl;
+    int32_t *doff;
+    cudaMalloc(&dq, hq.size() * 4); cudaMalloc(&dq32, hq32.size() * 4); cudaMalloc(&dkv, hkv.size() * 4); cudaMalloc(&dpp, hpp.size() * 4);
+    cudaMalloc(&du, d * 4); cudaMalloc(&dv, d * 4); cudaMalloc(&c_ref, (size_t)M * d * 4);
+    cudaMalloc(&kvh, hkv.size() * 2); cudaMalloc(&kvl, hkv.size() * 2); cudaMalloc(&pph, hpp.size() * 2); cudaMalloc(&ppl, hpp.size() * 2);
+    cudaMalloc(&ch, (size_t)M * d * 2); cudaMalloc(&cl, (size_t)M * d * 2); cudaMalloc(&doff, (n + 1) * 4);
+    cudaMemcpy(dq, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dq32, hq32.data(), hq32.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dkv, hkv.data(), hkv.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dpp, hpp.data(), hpp.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(du, hu.data(), d * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dv, hv.data(), d * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(doff, off.data(), (n + 1) * 4, cudaMemcpyHostToDevice);
+    cudaMemset(ch, 0, (size_t)M * d * 2); cudaMemset(cl, 0, (size_t)M * d * 2);
+    cudaDeviceSynchronize();
+    ActBuf skv; skv.hi = kvh; skv.lo = kvl;
+    ActBuf spp; spp.hi = pph; spp.lo = ppl;
+    launch_split(dkv, hkv.size(), skv, st);
+    launch_split(dpp, hpp.size(), spp, st);
+    ActBuf ref; ref.f32 = c_ref;
+    pk_status rc = PK_OK;
+    if (!launch_relpos_attention(dq, 3 * d, doff, n, maxT, H, hd, dpp, tmax, du, dv, d, ref, st)) rc = PK_ERR_INVALID;
+    TcOperand kv, pp;
+    if (rc == PK_OK && (!make_tc_operand(&kv, kvh, kvl, (uint64_t)M, (uint64_t)2 * d, 128) || !make_tc_operand(&pp, pph, ppl, (uint64_t)NP, (uint64_t)d, 256))) rc = PK_ERR_CUDA;
+    ActBuf got; got.hi = ch; got.lo = cl;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    relpos_attention_umma_set_debug(getenv("PK_AU_DBG") ? atoi(getenv("PK_AU_DBG")) : 0);
+    if (rc == PK_OK && !launch_relpos_attention_umma(dq32, du, dv, kv, pp, doff, n, maxT, H, hd, tmax, d, sms, got, st)) rc = PK_ERR_INVALID;
+    if (rc == PK_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PK_ERR_CUDA;
+    if (rc == PK_OK) {
+        std::vector<float> r((size_t)M * d);
+        std::vector<bf16> h((size_t)M * d), l((size_t)M * d);
+        cudaMemcpy(r.data(), c_ref, r.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h.data(), ch, h.size() * 2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(l.data(), cl, l.size() * 2, cudaMemcpyDeviceToHost);
+        float me = 0.f, mr = 0.f;
+        for (size_t i = 0; i < r.size(); ++i) {
+            const float e = std::fabs(__bfloat162float(h[i]) + __bfloat162float(l[i]) - r[i]);
+            if (!(e <= me)) me = e;
+            mr = std::max(mr, std::fabs(r[i]));
+        }
+        err2[0] = me; err2[1] = mr;
+    }
+    if (rc == PK_OK && getenv("PK_SELFTEST_TIME")) {
+        cudaEvent_t e0, e1, e2;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        const int reps = 20;
+        for (int w = 0; w < 2; ++w) {
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < reps; ++i) launch_relpos_attention_umma(dq32, du, dv, kv, pp, doff, n, maxT, H, hd, tmax, d, sms, got, st);
+            cudaEventRecord(e1, st);
+            for (int i = 0; i < reps; ++i) launch_relpos_attention_tc(dq32, du, dv, kvh, kvl, 2 * d, doff, n, maxT, H, hd, pph, ppl, tmax, d, got, st);
+            cudaEventRecord(e2, st);
+            cudaStreamSynchronize(st);
+        }
+        float ms0 = 0.f, ms1 = 0.f;
+        cudaEventElapsedTime(&ms0, e0, e1);
+        cudaEventElapsedTime(&ms1, e1, e2);
+        fprintf(stderr, "attention n_utt=%d maxT=%d: tcgen05 %.1f us | mma.sync %.1f us\n", n, maxT, 1e3 * ms0 / reps, 1e3 * ms1 / reps);
+        if (getenv("PK_AU_DBG") && atoi(getenv("PK_AU_DBG"))) relpos_attention_umma_print_timeline(n < 32 ? 1 : 4);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    }
+    for (void *p : {(void *)dq, (void *)dq32, (void *)dkv, (void *)dpp, (void *)du, (void *)dv, (void *)c_ref, (void *)kvh, (void *)kvl, (void *)pph,
+                    (void *)ppl, (void *)ch, (void *)cl, (void *)doff})
         cudaFree(p);
     cudaStreamDestroy(st);
     return rc;

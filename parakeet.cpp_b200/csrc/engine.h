@@ -59,6 +59,8 @@ struct LayerW {
     float *pos_u, *pos_v;
     float *pp;  // [(2*Tmax-1)][d] projected relative-position table
     bf16 *pp_hi = nullptr, *pp_lo = nullptr;   // its bf16 split planes (tensor-core attention)
+    TcOperand pp_tc;                           // their TMA maps, box 64 x 256 (tcgen05 attention: one box = every relative position of a 128 x 128 tile)
+    bool pp_tc_ok = false;
     float *conv_ln_w, *conv_ln_b;
     GemmWeight pw1, pw2;
     float *dw_w, *dw_b;  // BatchNorm folded; [d][k]
@@ -138,6 +140,8 @@ struct pk_engine {
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;
+    bool attn_umma = false;                    // PK_ATTN_UMMA=1: tcgen05 attention (attention_umma.cu) for head_dim 64 and batches of <= 128-frame utterances
+    std::map<int, TcOperand> kv_maps;          // TMA maps of the k | v planes, keyed by the number of rows of the batch
     bool attn_tc = true;                       // mma.sync attention for head_dim 64 / 128 (PK_ATTN_TC=0: fp32 kernel)
 
     // ---- the staged batch

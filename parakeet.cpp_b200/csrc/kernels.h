@@ -137,6 +137,16 @@ bool launch_relpos_attention_tc(const float *q32, const float *pos_u, const floa
                                 int ld_kv, const int32_t *row_off, int n_utt, int max_T, int n_heads, int head_dim, const bf16 *pp_hi,
                                 const bf16 *pp_lo, int tmax, int d_model, ActBuf out, cudaStream_t st);
 
+// tcgen05 variant (attention_umma.cu): head_dim 64, utterances of <= 128 frames, one CTA per (utterance, head).
+// kv = tensor maps of the [M][2 d] k | v planes (box 64 x 128, rows = M exactly); pp = of the [2 tmax - 1][d] planes of
+// the projected position table (box 64 x 256).
+bool relpos_attention_umma_supported(int head_dim, int max_T);
+bool launch_relpos_attention_umma(const float *q32, const float *pos_u, const float *pos_v, const TcOperand &kv, const TcOperand &pp,
+                                  const int32_t *row_off, int n_utt, int max_T, int n_heads, int head_dim, int tmax, int d_model, int num_sms, ActBuf out,
+                                  cudaStream_t st);
+void relpos_attention_umma_set_debug(int on);          // measurement aid (PK_AU_DBG=1): per-item timeline of CTA 0
+void relpos_attention_umma_print_timeline(int n_items);
+
 // ContextTrie (src/phrase_boost.cpp:9-66) in CSR form on the device: node 0 = root; the edges of node i are
 // [first[i], first[i+1]) = (token, child node), sorted by token.
 struct DeviceTrie {

@@ -45,7 +45,7 @@ EXPORTS = ["pk_config_110m", "pk_config_tdt_600m", "pk_engine_create", "pk_engin
            "pk_mel_frames", "pk_encoder_frames", "pk_mel", "pk_encode", "pk_decode", "pk_ctc_logprobs",
            "pk_transcribe_batch", "pk_stage_pcm", "pk_prefetch_pcm", "pk_run_staged", "pk_fetch_tokens", "pk_sync",
            "pk_token_buffer", "pk_stream", "pk_launch_count", "pk_profile_begin", "pk_profile_end",
-           "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_selftest_gemm_ln", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
+           "pk_profile_names", "pk_flush_l2", "pk_selftest_gemm", "pk_selftest_gemm_ln", "pk_selftest_attention", "pk_debug_tdt_phases", "pk_vocab_load", "pk_vocab_free", "pk_vocab_size",
            "pk_detokenize", "pk_group_words", "pk_tokenize", "pk_ctc_decode_boosted",
            "pk_resample_len", "pk_resample",
            "pk_job_begin", "pk_job_append", "pk_nccl_unique_id", "pk_comm_init_rank", "pk_allgather_tokens",
@@ -107,6 +107,7 @@ def load_library():
     L.pk_debug_tdt_passes.argtypes = [vp, i64p]
     L.pk_selftest_gemm.argtypes = [C.c_int] * 6 + [C.c_uint32, f32p, f32p]
     L.pk_selftest_gemm_ln.argtypes = [C.c_int] * 5 + [C.c_uint32, f32p]
+    L.pk_selftest_attention.argtypes = [C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_uint32, f32p]
     L.pk_vocab_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.pk_vocab_free.argtypes = [vp]
     L.pk_vocab_size.argtypes = [vp]
@@ -273,6 +274,17 @@ def selftest_gemm(M, N, K, epi_kind, math=0, seed=1, device=0):
     if st != 0:
         raise RuntimeError(f"pk_selftest_gemm failed ({st})")
     return e.value, r.value
+
+
+def selftest_attention(lens, tmax=126, mode=0, seed=1, device=0):
+    """-> (max_abs_err, max_abs_ref) of the tcgen05 attention kernel vs the fp32 attention kernel."""
+    L = load_library()
+    ln = np.ascontiguousarray(lens, np.int32)
+    out = np.zeros(2, np.float32)
+    st = L.pk_selftest_attention(device, _i32p(ln), len(ln), tmax, mode, seed, _f32p(out))
+    if st != 0:
+        raise RuntimeError(f"pk_selftest_attention failed ({st})")
+    return float(out[0]), float(out[1])
 
 
 def selftest_gemm_ln(M, K, mode, math=0, seed=1, device=0):

@@ -98,6 +98,17 @@ def test_fused_gemm_layernorm_matches_gemm_then_layernorm(pkg, M, K, mode, mcast
     assert xe1 / xr < 2e-2 and pe1 / pr < 5e-2          # plain bf16 operands, bf16 hi plane only
 
 
+@pytest.mark.parametrize("lens,tmax,mode", [([126], 126, 0), ([126], 126, 1), ([126], 126, 2), ([128, 1, 77, 126, 33], 128, 0),
+                                            ([50, 126, 126, 9], 501, 0), ([64] * 20, 100, 0)])
+def test_tcgen05_attention_matches_fp32_attention(pkg, lens, tmax, mode):
+    """csrc/attention_umma.cu (UMMA tiles in TMEM, K / position window / V by TMA, rel_shift by a register barrel shifter,
+    V as an MN-major operand) against the fp32 CUDA-core attention kernel on random inputs: the content term alone (zero
+    position table), the position term alone (zero keys), ragged batches, a position table longer / shorter than the tile."""
+    from parakeet_cpp_b200.engine import selftest_attention
+    err, ref = selftest_attention(lens, tmax, mode)
+    assert err / ref < 2e-4, (err, ref)
+
+
 # ------------------------------------------------------------------ mel front end (K1/K2)
 @pytest.mark.parametrize("lengths", [[16000], [400], [401, 559, 560, 561], [32000, 20000, 64000, 12345, 8000, 16001]])
 def test_mel_matches_oracle(eng_tiny, O, synth, lengths):
@@ -372,16 +383,19 @@ def test_transcribe_110m_more_clips_tokens_match_reference(pkg, m110, synth, mat
     t.engine.close()
 
 
-def test_fused_layernorm_engine_equals_unfused_and_reference(pkg, O, m110, synth, monkeypatch):
-    """PK_FUSE_LN: the encoder with every LayerNorm inside the epilogue of the GEMM that produces its input (gemm_tc_ln.cu)
-    against the same engine with stand-alone LayerNorm kernels -- per-layer activations of a ragged batch -- and against the
-    compiled reference's tokens on the twenty full-size clips (CTC and TDT, bit-exact)."""
+@pytest.mark.parametrize("switch", ["PK_FUSE_LN", "PK_ATTN_UMMA"])
+def test_alternative_kernels_engine_equals_default_and_reference(pkg, O, m110, synth, monkeypatch, switch):
+    """Kernel variants behind an engine switch, each against the same engine without it -- per-layer activations of a ragged
+    batch -- and against the compiled reference's tokens on the twenty full-size clips (CTC and TDT, bit-exact):
+    PK_FUSE_LN: every LayerNorm inside the epilogue of the GEMM that produces its input (gemm_tc_ln.cu);
+    PK_ATTN_UMMA: the tcgen05 attention (attention_umma.cu: UMMA tiles in TMEM, rel_shift by a register barrel shifter,
+    V as an MN-major operand) instead of the mma.sync kernel."""
     import dataclasses
     cfg = dataclasses.replace(m110.cfg, math=MATH["bf16x3"])
     feats = [O.preprocess_audio(synth.make_audio(n, 4200 + i)) for i, n in enumerate((160000, 112000, 48000, 81234))]
     outs = {}
     for flag in ("0", "1"):
-        monkeypatch.setenv("PK_FUSE_LN", flag)
+        monkeypatch.setenv(switch, flag)
         e = pkg.Engine(cfg, m110.weights_path, 0)
         outs[flag] = e.encode(feats, taps=True)
         e.close()
@@ -390,7 +404,7 @@ def test_fused_layernorm_engine_equals_unfused_and_reference(pkg, O, m110, synth
         for i in range(len(outs["0"][2][b])):
             assert _rel(outs["1"][2][b][i], outs["0"][2][b][i]) < 2e-5, (b, i)     # every block's output
         assert _rel(outs["1"][0][b], outs["0"][0][b]) < 2e-5
-    monkeypatch.setenv("PK_FUSE_LN", "1")
+    monkeypatch.setenv(switch, "1")
     gx = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_110m_extra_v1.npz"))
     n_clips = int(gx["n_clips"][0])
     t = pkg.Transcriber(m110.weights_path, m110.vocab_path, cfg)
