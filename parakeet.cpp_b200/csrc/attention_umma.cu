@@ -16,10 +16,14 @@
 // (186 selects per chunk) -- no shared-memory patch.  Softmax in base 2 on the whole row (one tile: no online rescaling),
 // P unnormalised in [0, 1] split hi/lo, 1 / sum applied to O.
 //
-// Roles (192 threads): warp 0 TMA (K + PP window, then V), warp 1 TMEM allocation + MMA issue, warps 2..5 one query row
-// per thread (TMEM lane = row): form Qu = q + pos_bias_u and Qv = q + pos_bias_v from the fp32 q of the projection GEMM
-// and write them as swizzled operand tiles, softmax, P, output.  192 KB of shared memory (Qu/Qv 64 KB, reused for P; K
-// 32; PP window 64; V 32) -> one CTA per SM.
+// Roles (320 threads): warp 0 TMA (position window once per CTA, K and V per utterance), warp 1 TMEM allocation + MMA issue,
+// warps 2..9 the row work: two threads per query row (TMEM lane = row; each takes 64 of the 128 keys and 32 of the 64 output
+// columns; row maximum and sum meet through 2 KB of shared memory and a 64-thread named barrier).  They also form
+// Qu = q + pos_bias_u and Qv = q + pos_bias_v from the fp32 q of the projection GEMM (coalesced: 8 lanes per row) and write them
+// as swizzled operand tiles, and they pass O through a 32 KB staging tile so that the ctx planes are stored in full 128-byte
+// lines.  The CTA is persistent: it serves one head (the position window stays resident) and the utterances slot, slot +
+// nslots, ...; K and V of the next utterance are fetched as soon as the products that read the current ones have retired, its
+// q rows travel under P . V.  Shared memory: Qu/Qv 64 KB (reused for P) | K 32 | PP window 64 | V 32 | O staging 32.
 // Longer utterances and other head sizes take the mma.sync kernel (attention_tc.cu).
 #include <cuda.h>
 
@@ -35,12 +39,15 @@ using namespace tc;
 
 constexpr int AU_T = 128;                 // queries = keys = one UMMA tile
 constexpr int AU_HD = 64;
-constexpr int AU_THREADS = 192;
+constexpr int AU_THREADS = 320;
+constexpr int AU_ROWTHR = 256;            // row threads (warps 2..9)
 constexpr int AU_TILE = AU_T * AU_HD * 2; // one bf16 plane of a 128 x 64 tile: 16 KB
-// Q (later P) 64 KB | K 2 x 32 KB (double buffered) | PP window 64 KB (resident: it depends on the head only) | V 32 KB
-constexpr int AU_SMEM = 4 * AU_TILE + 2 * 2 * AU_TILE + 4 * AU_TILE + 2 * AU_TILE + 1024 + 128;
+// Q (later P) 64 KB | K 32 KB | PP window 64 KB (resident: it depends on the head only) | V 32 KB | O staging 32 KB | row max / sum 2 KB
+constexpr int AU_RED = 2 * 2 * AU_T * 4;
+constexpr int AU_LAYOUT = 4 * AU_TILE + 2 * AU_TILE + 4 * AU_TILE + 2 * AU_TILE + 2 * AU_TILE + AU_RED + 128;
+constexpr int AU_SMEM = 227 * 1024;       // (the slack after AU_LAYOUT absorbs the alignment of the base to 1024 B; checked in the kernel)
 constexpr uint32_t AU_COL_S = 0, AU_COL_G = 128, AU_COL_O = 384, AU_TMEM_COLS = 512;
-static_assert(AU_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(AU_LAYOUT + 512 <= AU_SMEM, "shared memory budget");
 
 __device__ __forceinline__ void tmem_ld64_issue(uint32_t taddr, uint32_t *v) {
     asm volatile(
@@ -71,8 +78,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int m, int n) { retur
 // [4] O ready, [5] O stored; MMA thread: [6] S products issued, [7] P.V issued
 __device__ long long g_au_tl[8][8];
 
-// Persistent: CTA c serves head c % H and the utterances slot, slot + nslots, ... (slot = c / H, nslots = gridDim.x / H), so the
-// position window stays in shared memory and the K tile of the next utterance is fetched under the current one.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Persistent: CTA c serves head c % H and the utterances slot, slot + nslots, ... (slot = c / H, nslots = gridDim.x / H).
 __global__ void __launch_bounds__(AU_THREADS, 1)
 relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const __grid_constant__ CUtensorMap tmKV_lo,
                              const __grid_constant__ CUtensorMap tmPP_hi, const __grid_constant__ CUtensorMap tmPP_lo,
@@ -80,28 +88,29 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
                              const int32_t *__restrict__ row_off, int n_utt, int n_heads, int tmax, int d_model, ActBuf out, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if ((base - smem_raw) + AU_LAYOUT > AU_SMEM) __trap();      // (the dynamic window starts 1024-aligned in practice)
     uint8_t *sQ = base;                          // Qu_hi | Qu_lo | Qv_hi | Qv_lo ; then P_hi (2 atoms) | P_lo (2 atoms)
-    uint8_t *sK = sQ + 4 * AU_TILE;              // 2 x (K_hi | K_lo)
-    uint8_t *sPP = sK + 4 * AU_TILE;             // PP_hi (256 rows) | PP_lo
+    uint8_t *sK = sQ + 4 * AU_TILE;              // K_hi | K_lo
+    uint8_t *sPP = sK + 2 * AU_TILE;             // PP_hi (256 rows) | PP_lo
     uint8_t *sV = sPP + 4 * AU_TILE;             // V_hi | V_lo   ([key][dim])
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sV + 2 * AU_TILE);
-    uint64_t *bar_pp = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 6, *q_full = bars + 7, *s_full = bars + 8,
-             *p_full = bars + 9, *o_full = bars + 10;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+    uint8_t *sO = sV + 2 * AU_TILE;              // O_hi | O_lo staging (128-byte rows, swizzled)
+    float *red = reinterpret_cast<float *>(sO + 2 * AU_TILE);   // [max | sum][half][row]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(red) + AU_RED);
+    uint64_t *bar_pp = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4, *q_full = bars + 5, *s_full = bars + 6,
+             *p_full = bars + 7, *o_full = bars + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x % n_heads, slot = blockIdx.x / n_heads, nslots = gridDim.x / n_heads;
     if (threadIdx.x == 0) {
         mbar_init(bar_pp, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&k_full[i], 1);
-            mbar_init(&k_empty[i], 1);
-        }
+        mbar_init(k_full, 1);
+        mbar_init(k_empty, 1);
         mbar_init(v_full, 1);
         mbar_init(v_empty, 1);
-        mbar_init(q_full, 128);
+        mbar_init(q_full, AU_ROWTHR);
         mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(p_full, AU_ROWTHR);
         mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -118,8 +127,8 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
     // Every role walks the same item list: utterances slot, slot + nslots, ... that have frames.
 
     if (warp == 0) {
-        // ===================== TMA: the position window once, then K (double buffered) and V of every item =====================
-        if (slot < nslots && elect_one()) {
+        // ===================== TMA: the position window once, then K and V of every item =====================
+        if (elect_one()) {
             bool first = true;
             uint32_t n = 0;
             for (int b = slot; b < n_utt; b += nslots) {
@@ -132,11 +141,10 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
                     tma_load_2d(sPP + 2 * AU_TILE, &tmPP_lo, bar_pp, h * AU_HD, tmax - AU_T);
                     first = false;
                 }
-                const uint32_t kb = n & 1u;
-                mbar_wait(&k_empty[kb], ((n >> 1) & 1u) ^ 1u);          // the S products of item n - 2 have read this buffer
-                mbar_expect_tx(&k_full[kb], 2 * AU_TILE);
-                tma_load_2d(sK + kb * 2 * AU_TILE, &tmKV_hi, &k_full[kb], h * AU_HD, r0);
-                tma_load_2d(sK + kb * 2 * AU_TILE + AU_TILE, &tmKV_lo, &k_full[kb], h * AU_HD, r0);
+                mbar_wait(k_empty, (n & 1u) ^ 1u);                      // the S products of item n - 1 have read K
+                mbar_expect_tx(k_full, 2 * AU_TILE);
+                tma_load_2d(sK, &tmKV_hi, k_full, h * AU_HD, r0);
+                tma_load_2d(sK + AU_TILE, &tmKV_lo, k_full, h * AU_HD, r0);
                 mbar_wait(v_empty, (n & 1u) ^ 1u);                      // P . V of item n - 1 has read V
                 mbar_expect_tx(v_full, 2 * AU_TILE);
                 tma_load_2d(sV, &tmKV_hi, v_full, d_model + h * AU_HD, r0);
@@ -146,17 +154,16 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
         }
     } else if (warp == 1) {
         // ===================== MMA issue =====================
-        if (slot < nslots && elect_one()) {
-            const uint32_t q_s = smem_u32(sQ), pp_s = smem_u32(sPP), v_s = smem_u32(sV);
+        if (elect_one()) {
+            const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), pp_s = smem_u32(sPP), v_s = smem_u32(sV);
             constexpr uint32_t id_s = umma_idesc_bf16(AU_T, 128), id_g = umma_idesc_bf16(AU_T, 256), id_o = umma_idesc_bf16_bmn(AU_T, AU_HD);
             uint32_t n = 0;
             for (int b = slot; b < n_utt; b += nslots) {
                 if (row_off[b + 1] - row_off[b] <= 0) continue;
-                const uint32_t kb = n & 1u, par = n & 1u;
-                const uint32_t k_s = smem_u32(sK) + kb * 2 * AU_TILE;
+                const uint32_t par = n & 1u;
                 if (n == 0) mbar_wait(bar_pp, 0);
                 mbar_wait(q_full, par);
-                mbar_wait(&k_full[kb], (n >> 1) & 1u);
+                mbar_wait(k_full, par);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < AU_HD / UMMA_K; ++ks) {          // AC = Qu . K^T
@@ -177,7 +184,7 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
                     umma_bf16(tmem_base + AU_COL_G, ql, ph, id_g, 1);
                 }
                 umma_commit(s_full);                                    // S and G complete ...
-                umma_commit(&k_empty[kb]);                              // ... and this K buffer (and the Q tiles) have been read
+                umma_commit(k_empty);                                   // ... and K (and the Q tiles) have been read
                 if (dbg && blockIdx.x == 0 && n < 8) g_au_tl[n][6] = clock64();
                 mbar_wait(p_full, par);
                 mbar_wait(v_full, par);
@@ -198,35 +205,43 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
                 ++n;
             }
         }
-    } else if (slot < nslots) {
-        // ===================== one query row per thread =====================
+    } else {
+        // ===================== the row work: thread = (query row, key / output-column half) =====================
         const int qd = warp & 3;                     // TMEM lane quarter of this warp
+        const int hf = (warp - 2) >> 2;              // keys 64 hf .. 64 hf + 63, output columns 32 hf .. 32 hf + 31
         const int i = qd * 32 + lane;                // query row
+        const int rt = threadIdx.x - 64;             // 0 .. 255: cooperative (coalesced) passes
+        const int cch = rt & 7, crow = rt >> 3;      // those passes: 16-byte chunk of a 128-byte row, row crow + 32 k
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
         const uint32_t sw = (uint32_t)(i & 7);
         const uint32_t row_s = smem_u32(sQ) + (uint32_t)i * 128u;
+        const uint32_t q_s = smem_u32(sQ), o_s = smem_u32(sO);
+        float *red_max = red, *red_sum = red + 2 * AU_T;
         const bool tl_on = dbg && blockIdx.x == 0 && threadIdx.x == 64;
-        float4 qa[8], qb[8];                         // this row of q (fp32), fetched one item ahead
+        // pos_bias_u / pos_bias_v of this thread's 8 dims (chunk cch of every row it prepares)
+        const float4 u0 = __ldg(reinterpret_cast<const float4 *>(pos_u + h * AU_HD + 8 * cch)), u1 = __ldg(reinterpret_cast<const float4 *>(pos_u + h * AU_HD + 8 * cch + 4));
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(pos_v + h * AU_HD + 8 * cch)), v1 = __ldg(reinterpret_cast<const float4 *>(pos_v + h * AU_HD + 8 * cch + 4));
+        float4 qa[4], qb[4];                         // q (fp32): dims 8 cch .. + 7 of rows crow + 32 k, fetched one item ahead (8 lanes = one 256-byte row)
         auto q_fetch = [&](int bb) {
             const int r0 = row_off[bb], T = row_off[bb + 1] - r0;
-            const float *qrow = q32 + (size_t)(r0 + i) * d_model + h * AU_HD;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                qa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                qb[c] = qa[c];
-                if (i < T) {
-                    qa[c] = *reinterpret_cast<const float4 *>(qrow + 8 * c);
-                    qb[c] = *reinterpret_cast<const float4 *>(qrow + 8 * c + 4);
+            for (int k = 0; k < 4; ++k) {
+                const int row = crow + 32 * k;
+                qa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                qb[k] = qa[k];
+                if (row < T) {
+                    const float *qp = q32 + (size_t)(r0 + row) * d_model + h * AU_HD + 8 * cch;
+                    qa[k] = *reinterpret_cast<const float4 *>(qp);
+                    qb[k] = *reinterpret_cast<const float4 *>(qp + 4);
                 }
             }
         };
         // Qu = q + pos_bias_u, Qv = q + pos_bias_v as swizzled K-major tiles (rows past T: q = 0 was fetched -> finite scores, never stored)
         auto q_write = [&]() {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {            // 8 dims = one 16-byte chunk per plane
-                const float4 u0 = __ldg(reinterpret_cast<const float4 *>(pos_u + h * AU_HD + 8 * c)), u1 = __ldg(reinterpret_cast<const float4 *>(pos_u + h * AU_HD + 8 * c + 4));
-                const float4 v0 = __ldg(reinterpret_cast<const float4 *>(pos_v + h * AU_HD + 8 * c)), v1 = __ldg(reinterpret_cast<const float4 *>(pos_v + h * AU_HD + 8 * c + 4));
-                const float4 a = qa[c], bq = qb[c];
+            for (int k = 0; k < 4; ++k) {
+                const int row = crow + 32 * k;
+                const float4 a = qa[k], bq = qb[k];
                 uint32_t uh[4], ul[4], vh[4], vl[4];
                 split_pair(a.x + u0.x, a.y + u0.y, uh[0], ul[0]);
                 split_pair(a.z + u0.z, a.w + u0.w, uh[1], ul[1]);
@@ -236,11 +251,11 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
                 split_pair(a.z + v0.z, a.w + v0.w, vh[1], vl[1]);
                 split_pair(bq.x + v1.x, bq.y + v1.y, vh[2], vl[2]);
                 split_pair(bq.z + v1.z, bq.w + v1.w, vh[3], vl[3]);
-                const uint32_t off = (((uint32_t)c ^ sw) << 4);
-                sts128(row_s + off, uh[0], uh[1], uh[2], uh[3]);
-                sts128(row_s + AU_TILE + off, ul[0], ul[1], ul[2], ul[3]);
-                sts128(row_s + 2 * AU_TILE + off, vh[0], vh[1], vh[2], vh[3]);
-                sts128(row_s + 3 * AU_TILE + off, vl[0], vl[1], vl[2], vl[3]);
+                const uint32_t a0 = q_s + (uint32_t)row * 128u + (((uint32_t)cch ^ (uint32_t)(row & 7)) << 4);
+                sts128(a0, uh[0], uh[1], uh[2], uh[3]);
+                sts128(a0 + AU_TILE, ul[0], ul[1], ul[2], ul[3]);
+                sts128(a0 + 2 * AU_TILE, vh[0], vh[1], vh[2], vh[3]);
+                sts128(a0 + 3 * AU_TILE, vl[0], vl[1], vl[2], vl[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the UMMA reads
             mbar_arrive(q_full);
@@ -262,20 +277,20 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
             const int bn = next_item(b);
             long long *tl = (tl_on && n < 8) ? g_au_tl[n] : nullptr;
             if (tl) tl[0] = tl[1] = clock64();
-            // ---- S = (AC + skew(G)) * scale, whole row in registers
+            // ---- S = (AC + skew(G)) * scale for this thread's 64 keys
             mbar_wait(s_full, par);
             tcgen05_fence_after();
             if (tl) tl[2] = clock64();
             constexpr float kScale = 0.125f * 1.4426950408889634f;     // 1 / sqrt(64), folded with log2 e
-            float s[4][32];
+            uint32_t su[2][32];                          // scores, then probabilities (fp32 bit patterns)
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = 2 * hf + cc;               // 32-key chunk
                 uint32_t R[64];
                 const int gbase = 32 * (qd - c) + 96;    // window columns gbase + lane + m, m = 31 - jj
                 tmem_ld64_issue(lane_addr + AU_COL_G + (uint32_t)gbase, R);
-                uint32_t A[32];
-                tmem_ld32_issue(lane_addr + AU_COL_S + (uint32_t)(32 * c), A);
+                tmem_ld32_issue(lane_addr + AU_COL_S + (uint32_t)(32 * c), su[cc]);
                 tmem_wait_ld();
                 // barrel shifter: R[m] <- R[lane + m]
 #pragma unroll
@@ -290,32 +305,37 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
                 for (int k = 0; k < 32; ++k) R[k] = (lane & 1) ? R[k + 1] : R[k];
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
-                    float v = (__uint_as_float(A[jj]) + __uint_as_float(R[31 - jj])) * kScale;
+                    float v = (__uint_as_float(su[cc][jj]) + __uint_as_float(R[31 - jj])) * kScale;
                     v = (32 * c + jj < T) ? v : -INFINITY;
-                    s[c][jj] = v;
+                    su[cc][jj] = __float_as_uint(v);
                     mx = fmaxf(mx, v);
                 }
             }
-            float sum = 0.f;                             // key 0 is always valid: mx is finite
+            // row maximum over both halves (the other half of this row lives in the warp with the same lane quarter)
+            red_max[hf * AU_T + i] = mx;
+            named_bar_sync(1 + qd, 64);
+            mx = fmaxf(mx, red_max[(hf ^ 1) * AU_T + i]);   // key 0 is always valid: finite
+            float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
-                    const float p = ex2_approx(s[c][jj] - mx);
-                    s[c][jj] = p;
+                    const float p = ex2_approx(__uint_as_float(su[cc][jj]) - mx);
+                    su[cc][jj] = __float_as_uint(p);
                     sum += p;
                 }
-            // ---- P (unnormalised) as the A operand of P . V: plane, 64-key atom, row i, 8 keys per 16-byte chunk
+            red_sum[hf * AU_T + i] = sum;
+            // ---- P (unnormalised) as the A operand of P . V: plane, 64-key atom hf, row i, 8 keys per 16-byte chunk
             // (the S products have retired: the Q tiles are dead)
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
                 for (int k8 = 0; k8 < 4; ++k8) {
                     uint32_t ph[4], pl[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split_pair(s[c][8 * k8 + 2 * e], s[c][8 * k8 + 2 * e + 1], ph[e], pl[e]);
-                    const int j = 32 * c + 8 * k8;
-                    const uint32_t off = (uint32_t)(j >> 6) * AU_TILE + ((((uint32_t)(j & 63) >> 3) ^ sw) << 4);
+                    for (int e = 0; e < 4; ++e)
+                        split_pair(__uint_as_float(su[cc][8 * k8 + 2 * e]), __uint_as_float(su[cc][8 * k8 + 2 * e + 1]), ph[e], pl[e]);
+                    const uint32_t off = (uint32_t)hf * AU_TILE + ((((uint32_t)(4 * cc + k8)) ^ sw) << 4);
                     sts128(row_s + off, ph[0], ph[1], ph[2], ph[3]);
                     sts128(row_s + 2 * AU_TILE + off, pl[0], pl[1], pl[2], pl[3]);
                 }
@@ -323,37 +343,41 @@ relpos_attention_umma_kernel(const __grid_constant__ CUtensorMap tmKV_hi, const 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(p_full);
             if (tl) tl[3] = clock64();
-            if (bn < n_utt) q_fetch(bn);                 // the next item's q row travels under P . V
+            if (bn < n_utt) q_fetch(bn);                 // the next item's q rows travel under P . V
             // ---- O: out of TMEM, then the next item's Q tiles (P . V has read P), then the stores
             mbar_wait(o_full, par);
             tcgen05_fence_after();
             if (tl) tl[4] = clock64();
-            uint32_t o[64];
-            tmem_ld64_issue(lane_addr + AU_COL_O, o);
+            uint32_t o[32];
+            tmem_ld32_issue(lane_addr + AU_COL_O + (uint32_t)(32 * hf), o);
             tmem_wait_ld();
             tcgen05_fence_before();
             if (bn < n_utt) q_write();
-            if (i < T) {
-                const float inv = 1.0f / sum;
-                const size_t idx = (size_t)(r0 + i) * d_model + h * AU_HD;
+            named_bar_sync(1 + qd, 64);                  // the other half's sum is in red_sum (and it has read this half's maximum)
+            {
+                const float inv = 1.0f / (sum + red_sum[(hf ^ 1) * AU_T + i]);
+                // this thread's 32 columns -> bf16 hi / lo, 4 chunks of the row's 128-byte staging line per plane
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float x[8];
+                for (int cq = 0; cq < 4; ++cq) {
+                    uint4 hh, ll;
+                    split_pair(__uint_as_float(o[8 * cq]) * inv, __uint_as_float(o[8 * cq + 1]) * inv, hh.x, ll.x);
+                    split_pair(__uint_as_float(o[8 * cq + 2]) * inv, __uint_as_float(o[8 * cq + 3]) * inv, hh.y, ll.y);
+                    split_pair(__uint_as_float(o[8 * cq + 4]) * inv, __uint_as_float(o[8 * cq + 5]) * inv, hh.z, ll.z);
+                    split_pair(__uint_as_float(o[8 * cq + 6]) * inv, __uint_as_float(o[8 * cq + 7]) * inv, hh.w, ll.w);
+                    const uint32_t a0 = o_s + (uint32_t)i * 128u + ((((uint32_t)(4 * hf + cq)) ^ sw) << 4);
+                    sts128(a0, hh.x, hh.y, hh.z, hh.w);
+                    sts128(a0 + AU_TILE, ll.x, ll.y, ll.z, ll.w);
+                }
+            }
+            named_bar_sync(5, AU_ROWTHR);                // the whole O tile is staged
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(o[8 * c + e]) * inv;
-                    if (out.f32) {
-                        *reinterpret_cast<float4 *>(out.f32 + idx + 8 * c) = make_float4(x[0], x[1], x[2], x[3]);
-                        *reinterpret_cast<float4 *>(out.f32 + idx + 8 * c + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                    }
-                    if (out.hi) {
-                        uint4 hh, ll;
-                        split_pair(x[0], x[1], hh.x, ll.x);
-                        split_pair(x[2], x[3], hh.y, ll.y);
-                        split_pair(x[4], x[5], hh.z, ll.z);
-                        split_pair(x[6], x[7], hh.w, ll.w);
-                        *reinterpret_cast<uint4 *>(out.hi + idx + 8 * c) = hh;
-                        if (out.lo) *reinterpret_cast<uint4 *>(out.lo + idx + 8 * c) = ll;
-                    }
+            for (int k = 0; k < 4; ++k) {                // 8 lanes = one 128-byte line of a ctx plane
+                const int row = crow + 32 * k;
+                if (row < T) {
+                    const uint32_t a0 = o_s + (uint32_t)row * 128u + (((uint32_t)cch ^ (uint32_t)(row & 7)) << 4);
+                    const size_t idx = (size_t)(r0 + row) * d_model + h * AU_HD + 8 * cch;
+                    *reinterpret_cast<uint4 *>(out.hi + idx) = lds128u(a0);
+                    if (out.lo) *reinterpret_cast<uint4 *>(out.lo + idx) = lds128u(a0 + AU_TILE);
                 }
             }
             if (tl) tl[5] = clock64();

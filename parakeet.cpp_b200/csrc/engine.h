@@ -140,7 +140,7 @@ struct pk_engine {
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
     std::map<std::string, GraphEntry> graphs;
     bool use_graphs = true;
-    bool attn_umma = false;                    // PK_ATTN_UMMA=1: tcgen05 attention (attention_umma.cu) for head_dim 64 and batches of <= 128-frame utterances
+    bool attn_umma = true;                     // tcgen05 attention (attention_umma.cu) for head_dim 64 and batches of <= 128-frame utterances (PK_ATTN_UMMA=0: mma.sync kernel)
     std::map<int, TcOperand> kv_maps;          // TMA maps of the k | v planes, keyed by the number of rows of the batch
     bool attn_tc = true;                       // mma.sync attention for head_dim 64 / 128 (PK_ATTN_TC=0: fp32 kernel)
 
