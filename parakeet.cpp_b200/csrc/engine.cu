@@ -503,7 +503,8 @@ void pk_engine::gemm(const Act &A, int lda, const GemmWeight &W, int M_, EpiPara
                                             skinny_tickets, SKINNY_TICKETS, num_sms, stream);
         if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("skinny GEMM launch: ") + cudaGetErrorString(ce));
     } else {
-        cudaError_t ce = launch_gemm_tc(A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, epi, stream);
+        const int cl = (gemm_cluster == 2 || gemm_cluster == 4) && lda == W.K ? gemm_cluster : 1;
+        cudaError_t ce = launch_gemm_tc(A.tc, W.tc, M_, W.N, W.K, cfg.math == PK_MATH_BF16X3, epi, stream, cl, cl == 4 ? &A.tc32 : &A.tc64);
         if (ce != cudaSuccess && gemm_err == PK_OK) gemm_err = fail(PK_ERR_CUDA, std::string("tcgen05 GEMM launch: ") + cudaGetErrorString(ce));
     }
     ++launches;
@@ -929,6 +930,7 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     if (const char *ev = getenv("PK_GEMM_TMA_OUT")) e->tma_out = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_SKINNY")) e->skinny = atoi(ev) != 0;
     if (const char *ev = getenv("PK_FUSE_LN")) e->fuse_ln = atoi(ev) != 0;
+    if (const char *ev = getenv("PK_GEMM_CLUSTER")) e->gemm_cluster = atoi(ev);
     if (const char *ev = getenv("PK_LN_MCAST")) e->ln_mcast = atoi(ev) != 0;
     if (const char *ev = getenv("PK_FUSE_LN_MINK")) e->fuse_ln_min_k = atoi(ev);
     e->device = device;
@@ -1092,7 +1094,10 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
     launch_gemm_simt(dA, K, dW, K, M, N, K, ep, st);
     TcOperand ta, tw;
     pk_status rc = PK_OK;
+    const int cl = getenv("PK_GEMM_CLUSTER") ? atoi(getenv("PK_GEMM_CLUSTER")) : 1;
+    TcOperand ta_sl;
     if (!make_tc_operand(&ta, Ah, Al, M, K, 128) || !make_tc_operand(&tw, Wh, Wl, N, K, tc_tile_n(N))) rc = PK_ERR_CUDA;
+    if (rc == PK_OK && (cl == 2 || cl == 4) && !make_tc_operand(&ta_sl, Ah, Al, M, K, 128 / cl)) rc = PK_ERR_CUDA;
     if (rc == PK_OK) {
         ep.out_f32 = qcols ? q_tc : o_tc;
         ActBuf tc_act; tc_act.hi = oh; tc_act.lo = ol;
@@ -1120,13 +1125,13 @@ pk_status pk_selftest_gemm(int device, int M, int N, int K, int epi_kind, int ma
             cudaStreamSynchronize(st);
             cudaFree(sws);
             cudaFree(stk);
-        } else if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st) != cudaSuccess) rc = PK_ERR_CUDA;
+        } else if (launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st, cl, &ta_sl) != cudaSuccess) rc = PK_ERR_CUDA;
         if (rc == PK_OK && !use_skinny && getenv("PK_SELFTEST_TIME")) {   // warm, back-to-back timing of the tcgen05 launch
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);
             const int reps = 20;
             cudaEventRecord(e0, st);
-            for (int i = 0; i < reps; ++i) launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st);
+            for (int i = 0; i < reps; ++i) launch_gemm_tc(ta, tw, M, N, K, math == PK_MATH_BF16X3, ep, st, cl, &ta_sl);
             cudaEventRecord(e1, st);
             cudaStreamSynchronize(st);
             float ms = 0.f;

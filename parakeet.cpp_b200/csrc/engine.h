@@ -48,7 +48,7 @@ struct GemmWeight {
 // An activation buffer that feeds GEMMs, with its TMA tensor maps (tcgen05 modes).
 struct Act : ActBuf {
     TcOperand tc;
-    TcOperand tc32;   // the same planes with a 32-row box (A tiles fetched in quarters and multicast across a 4-CTA cluster, gemm_tc_ln.cu)
+    TcOperand tc32, tc64;   // the same planes with a 32- / 64-row box (A tiles fetched in slices and TMA-multicast across a 4- / 2-CTA cluster)
 };
 
 struct LayerW {
@@ -229,7 +229,7 @@ struct pk_engine {
         } else {
             a.hi = dalloc<bf16>(n);
             if (cfg.math == PK_MATH_BF16X3) a.lo = dalloc<bf16>(n);
-            if (a.hi && (!make_tc_operand(&a.tc, a.hi, a.lo, rows, K, 128) || !make_tc_operand(&a.tc32, a.hi, a.lo, rows, K, 32))) a.hi = nullptr;   // reported by the caller
+            if (a.hi && (!make_tc_operand(&a.tc, a.hi, a.lo, rows, K, 128) || !make_tc_operand(&a.tc32, a.hi, a.lo, rows, K, 32) || !make_tc_operand(&a.tc64, a.hi, a.lo, rows, K, 64))) a.hi = nullptr;   // reported by the caller
         }
         return a;
     }
@@ -249,6 +249,7 @@ struct pk_engine {
     // out_ln1: x receives LayerNorm_1 of the sum (block end) instead of the sum; planes = split of the last LayerNorm.
     pk_status gemm_ln(const Act &A, int lda, const GemmWeight &W, int M_, bool resid_in_x, float alpha, const float *ln1_w, const float *ln1_b,
                       bool out_ln1, const float *ln2_w, const float *ln2_b, ActBuf planes);
+    int gemm_cluster = 0;                      // PK_GEMM_CLUSTER=2|4: wide GEMMs (fc1, q/k/v, pw1) run as clusters of 2 | 4 CTAs along N with the A tile multicast
     bool ln_mcast = false;                     // PK_LN_MCAST=1: the A tile is fetched in quarters and TMA-multicast across the cluster (measured: no gain)
     int fuse_ln_min_k = 0;                     // PK_FUSE_LN_MINK: fuse only GEMMs with K >= this (short-K launches are epilogue-bound either way)
     bool fuse_ln = false;                      // PK_FUSE_LN=1: LayerNorm in the epilogue of the GEMM that produces its input

@@ -368,12 +368,18 @@ struct TcCfg {
 // Persistent: grid = min(#tiles, #SMs); CTA c takes tiles c, c+grid, ...  (n-tile fastest so
 // concurrently running CTAs share the same A rows through L2).  The accumulator is double
 // buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int NPASS, int EK>
-__global__ void __launch_bounds__(TC_THREADS_P, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
-               int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
-               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2) {
+// CL > 1 (gemm_tc_cl_kernel): thread-block clusters of CL CTAs along N.  The CL CTAs of a cluster work on the SAME 128-row
+// block and on adjacent column tiles, so the A tile of a k-block is identical for all of them: each CTA fetches 128 / CL of
+// its rows (tmA_* then have a 128 / CL-row box) and TMA-MULTICASTS the slice into the stage of every CTA of the cluster.  A
+// stage is then written by all CTAs, so its "empty" barrier collects one tcgen05.commit (multicast) from each of them.
+// Why: with three 64 KB stages a CTA has 192 KB of operands in flight; at the ~1.5 us L2 latency of a loaded chip that is
+// 69 B/clk/SM (Little's law) against the 71 B/clk/SM that back-to-back UMMAs consume -- any extra latency (result stores
+// sharing the L2) stalls the MMA warp (measured: 7.3k -> 9.4k cycles per tile).  Multicast cuts the bytes a CTA has to pull
+// per k-block from 64 KB to 32 + 32 / CL KB, i.e. the same bytes in flight cover 1.33x (CL = 2) / 1.6x (CL = 4) the latency.
+template <int BN, int NPASS, int EK, int CL>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap &tmA_hi, const CUtensorMap &tmA_lo, const CUtensorMap &tmW_hi, const CUtensorMap &tmW_lo,
+                                             int M, int N, int K, const EpiParams &epi, int dbg, const CUtensorMap &tmO0, const CUtensorMap &tmO1,
+                                             const CUtensorMap &tmO2) {
     using C = TcCfg<BN, NPASS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -385,12 +391,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = K / BK;
     const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
-    const int num_tiles = tiles_n * tiles_m;
+    // work units of a CTA: tile = first + i * step; CL > 1: the cluster walks (row block, group of CL column tiles) and this
+    // CTA takes column tile `rank` of the group (tiles_n % CL == 0, checked by the launcher)
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int first_unit = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x, unit_step = CL > 1 ? (int)(gridDim.x / CL) : (int)gridDim.x;
+    const int num_tiles = CL > 1 ? (tiles_n / CL) * tiles_m : tiles_n * tiles_m;      // units
+    auto unit_m0 = [&](int u) { return CL > 1 ? (u / (tiles_n / CL)) * BM : (u / tiles_n) * BM; };
+    auto unit_n0 = [&](int u) { return CL > 1 ? ((u % (tiles_n / CL)) * CL + rank) * BN : (u % tiles_n) * BN; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -403,7 +415,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync();      // every CTA's barriers exist before a peer multicasts into this CTA
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();      // barriers, TMEM and the role split are set up while the previous grid drains; now its results are visible
@@ -414,8 +427,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (elect_one()) {
             uint32_t it = 0;   // global k-block counter across tiles
             const uint64_t ld_policy = g_l2_hint_mode == 1 ? L2_EVICT_NORMAL : L2_EVICT_LAST;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            for (int tile = first_unit; tile < num_tiles; tile += unit_step) {
+                const int m0 = unit_m0(tile), n0 = unit_n0(tile);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
@@ -423,12 +436,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     uint8_t *st = tiles + (size_t)s * C::STAGE_BYTES;
                     if (dbg & 2) { mbar_arrive(&full[s]); continue; }      // measurement aid: MMAs on stale smem, no loads
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0, ld_policy);
-                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0, ld_policy);
-                    if (NPASS == 3) {
-                        tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0, ld_policy);
-                        tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0, ld_policy);
+                    if (CL > 1) {       // this CTA's slice of the A rows, into the stage of every CTA of the cluster
+                        constexpr int SL = BM / CL, SLB = SL * BK * 2;
+                        constexpr uint16_t mask = (uint16_t)((1u << CL) - 1u);
+                        tma_load_2d_mcast(st + rank * SLB, &tmA_hi, &full[s], kb * BK, m0 + rank * SL, mask, ld_policy);
+                        if (NPASS == 3) tma_load_2d_mcast(st + C::A_BYTES + C::W_BYTES + rank * SLB, &tmA_lo, &full[s], kb * BK, m0 + rank * SL, mask, ld_policy);
+                    } else {
+                        tma_load_2d(st, &tmA_hi, &full[s], kb * BK, m0, ld_policy);
+                        if (NPASS == 3) tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tmA_lo, &full[s], kb * BK, m0, ld_policy);
                     }
+                    tma_load_2d(st + C::A_BYTES, &tmW_hi, &full[s], kb * BK, n0, ld_policy);
+                    if (NPASS == 3) tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tmW_lo, &full[s], kb * BK, n0, ld_policy);
                 }
             }
             pdl_trigger_late();     // every operand load of this CTA has been issued
@@ -438,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            for (int tile = first_unit; tile < num_tiles; tile += unit_step, ++tcount) {
                 const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
@@ -462,7 +480,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             umma_bf16(tmem_d, a_lo + koff, w_hi + koff, idesc, 1);
                         }
                     }
-                    umma_commit(&empty[s]);          // frees the stage when these MMAs retire
+                    if (CL > 1) umma_commit_mcast(&empty[s], (uint16_t)((1u << CL) - 1u));   // ... in every CTA of the cluster (they all write it)
+                    else umma_commit(&empty[s]);     // frees the stage when these MMAs retire
                 }
                 umma_commit(&acc_full[buf]);         // accumulator of this tile complete
                 if ((dbg & 32) && blockIdx.x == 0 && tcount < 64) g_timeline[tcount][1] = clock64();
@@ -479,8 +498,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         long long pc0 = 0;
         unsigned long long pg0 = 0;
         if (probe) { pc0 = clock64(); pg0 = globaltimer_ns(); }
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int tile = first_unit; tile < num_tiles; tile += unit_step, ++tcount) {
+            const int m0 = unit_m0(tile), n0 = unit_n0(tile);
             const uint32_t buf = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&acc_full[buf], aph);
             tcgen05_fence_after();
@@ -507,13 +526,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
         if (probe) { g_clk_probe[0] = (unsigned long long)(clock64() - pc0); g_clk_probe[1] = globaltimer_ns() - pg0; }
-        if (epi.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores have completed
+        if (epi.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this warp's TMA stores have completed
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync();      // nobody leaves while a peer may still multicast into it / signal its barriers
+    else __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
+}
+
+template <int BN, int NPASS, int EK>
+__global__ void __launch_bounds__(TC_THREADS_P, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
+               int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
+               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2) {
+    gemm_tc_body<BN, NPASS, EK, 1>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, M, N, K, epi, dbg, tmO0, tmO1, tmO2);
+}
+
+// clusters of CL CTAs along N with the A tile multicast (see gemm_tc_body); 128-column tiles only
+template <int NPASS, int EK, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS_P, 1)
+gemm_tc_cl_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int M, int N,
+                  int K, const __grid_constant__ EpiParams epi, int dbg, const __grid_constant__ CUtensorMap tmO0,
+                  const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2) {
+    gemm_tc_body<128, NPASS, EK, CL>(tmA_hi, tmA_lo, tmW_hi, tmW_lo, M, N, K, epi, dbg, tmO0, tmO1, tmO2);
 }
 
 // =====================================================================================
@@ -701,7 +740,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
             if ((dbg & 32) && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 64) g_timeline[tcount][3] = clock64();
         }
-        if (epi.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (epi.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tcgen05_fence_before();
     cluster_sync();                              // nobody leaves (or frees TMEM) while the peer may still signal it
@@ -757,6 +796,45 @@ cudaError_t launch_k(const TcOperand &A, const TcOperand &W, int M, int N, int K
     const CUtensorMap &o2 = (tma && ep.tm_out2) ? *static_cast<const CUtensorMap *>(ep.tm_out2) : o0;
     launch_pdl(gemm_tc_kernel<BN, NPASS, EK>, dim3(grid), dim3(TC_THREADS_P), C::SMEM, st, A.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1, o2);
     return cudaGetLastError();
+}
+
+// cluster / multicast variant: A_sl = the A operand with a 128 / CL-row box
+template <int NPASS, int EK, int CL>
+cudaError_t launch_kcl(const TcOperand &A_sl, const TcOperand &W, int M, int N, int K, const EpiParams &epi, cudaStream_t st) {
+    using C = TcCfg<128, NPASS>;
+    static PerDeviceFlag attr_flag;
+    static int max_clusters[64] = {};
+    int dev = 0, num_sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!attr_flag.cur()) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_cl_kernel<NPASS, EK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)(num_sms / CL * CL));
+        q.blockDim = dim3(TC_THREADS_P);
+        q.dynamicSmemBytes = C::SMEM;
+        int mc = 0;
+        if (cudaOccupancyMaxActiveClusters(&mc, gemm_tc_cl_kernel<NPASS, EK, CL>, &q) != cudaSuccess || mc < 1) {
+            cudaGetLastError();
+            mc = num_sms / CL;
+        }
+        max_clusters[dev & 63] = mc;
+        attr_flag.cur() = true;
+    }
+    const int units = ((N / 128) / CL) * ((M + BM - 1) / BM);
+    int ncl = max_clusters[dev & 63];
+    if (ncl > num_sms / CL) ncl = num_sms / CL;
+    if (ncl > units) ncl = units;
+    const CUtensorMap &alo = (NPASS == 3) ? A_sl.lo : A_sl.hi, &wlo = (NPASS == 3) ? W.lo : W.hi;
+    EpiParams ep = epi;
+    const bool tma = ep.tma_out && ep.tm_out0 && (EK != EPI_QKV_ACT || ep.tm_out2);
+    ep.tma_out = tma ? 1 : 0;
+    const CUtensorMap &o0 = tma ? *static_cast<const CUtensorMap *>(ep.tm_out0) : A_sl.hi;
+    const CUtensorMap &o1 = (tma && ep.tm_out1) ? *static_cast<const CUtensorMap *>(ep.tm_out1) : o0;
+    const CUtensorMap &o2 = (tma && ep.tm_out2) ? *static_cast<const CUtensorMap *>(ep.tm_out2) : o0;
+    return launch_pdl(gemm_tc_cl_kernel<NPASS, EK, CL>, dim3((unsigned)(ncl * CL)), dim3(TC_THREADS_P), C::SMEM, st, A_sl.hi, alo, W.hi, wlo, M, N, K, ep, g_dbg, o0, o1,
+                      o2);
 }
 
 template <int NPASS, int EK>
@@ -877,11 +955,23 @@ double tc_probe_mhz() {   // effective SM clock seen by CTA 0 of the last 1-CTA 
     return 1e3 * (double)h[0] / (double)h[1];
 }
 
+bool gemm_tc_cluster_supported(int N, int epi_kind, int cl) {
+    return (cl == 2 || cl == 4) && N % (128 * cl) == 0 && (epi_kind == EPI_BIAS_SILU_ACT || epi_kind == EPI_GLU_F32 || epi_kind == EPI_QKV_ACT);
+}
+
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
-                           const EpiParams &epi, cudaStream_t st) {
+                           const EpiParams &epi, cudaStream_t st, int cl, const TcOperand *A_slice) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (K % BK != 0 || A.box_rows != BM) return cudaErrorInvalidValue;
     if (split3 && !(A.has_lo && W.has_lo)) return cudaErrorInvalidValue;
+    if (cl > 1 && split3 && A_slice && A_slice->has_lo && (int)A_slice->box_rows * cl == BM && W.box_rows == 128 && gemm_tc_cluster_supported(N, epi.kind, cl)) {
+        // clusters of `cl` CTAs along N, A tile multicast (gemm_tc_body, CL > 1)
+        switch (epi.kind) {
+        case EPI_BIAS_SILU_ACT: return cl == 2 ? launch_kcl<3, EPI_BIAS_SILU_ACT, 2>(*A_slice, W, M, N, K, epi, st) : launch_kcl<3, EPI_BIAS_SILU_ACT, 4>(*A_slice, W, M, N, K, epi, st);
+        case EPI_GLU_F32: return cl == 2 ? launch_kcl<3, EPI_GLU_F32, 2>(*A_slice, W, M, N, K, epi, st) : launch_kcl<3, EPI_GLU_F32, 4>(*A_slice, W, M, N, K, epi, st);
+        default: return cl == 2 ? launch_kcl<3, EPI_QKV_ACT, 2>(*A_slice, W, M, N, K, epi, st) : launch_kcl<3, EPI_QKV_ACT, 4>(*A_slice, W, M, N, K, epi, st);
+        }
+    }
     if (W.box_rows == 128 && N >= 256 && g_use_2cta)
         return split3 ? launch_t2<3>(A, W, M, N, K, epi, st) : launch_t2<1>(A, W, M, N, K, epi, st);
     if (W.box_rows == 128) return split3 ? launch_t<128, 3>(A, W, M, N, K, epi, st) : launch_t<128, 1>(A, W, M, N, K, epi, st);

@@ -89,8 +89,11 @@ void tc_set_2cta(bool on);   // debug/measurement switch: use the cta_group::2 k
 void tc_set_debug(int bits); // measurement aid (PK_GEMM_DBG): bit 0 = skip the epilogue's work, bit 1 = skip the TMA loads (results are garbage)
 double tc_probe_mhz();
 void tc_print_timeline(int n_tiles);
+// cl = 2 | 4 with A_slice = the A operand with a 128 / cl-row box: clusters of cl CTAs along N that share (TMA multicast) the
+// A tile; taken when gemm_tc_cluster_supported(N, epi.kind, cl), else the plain persistent kernel.
+bool gemm_tc_cluster_supported(int N, int epi_kind, int cl);
 cudaError_t launch_gemm_tc(const TcOperand &A, const TcOperand &W, int M, int N, int K, bool split3,
-                           const EpiParams &epi, cudaStream_t st);
+                           const EpiParams &epi, cudaStream_t st, int cl = 1, const TcOperand *A_slice = nullptr);
 
 // ------------------------------------------------------------------ gemm_tc_ln.cu (K5b: residual GEMM + fused LayerNorm)
 //     v = resid + alpha * (A . W^T + bias)   (resid may be null);   y1 = LN1(v);   y2 = LN2(y1) if ln2_w

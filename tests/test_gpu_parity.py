@@ -66,6 +66,18 @@ def test_tcgen05_gemm_matches_fp32_gemm(pkg, M, N, K, epi):
     assert err1 / ref < 2e-2                     # plain bf16 operands
 
 
+@pytest.mark.parametrize("cl", ["2", "4"])
+@pytest.mark.parametrize("M,N,K,epi", [(8064, 2048, 512, "SILU_ACT"), (8064, 1536, 512, "QKV"), (8064, 1024, 512, "GLU"), (777, 2048, 512, "SILU_ACT"),
+                                       (130, 1024, 1024, "GLU"), (6016, 4096, 1024, "SILU_ACT")])
+def test_tcgen05_gemm_cluster_multicast_matches_fp32_gemm(pkg, M, N, K, epi, cl, monkeypatch):
+    """The wide GEMMs as clusters of 2 / 4 CTAs along N (PK_GEMM_CLUSTER): every CTA fetches a slice of the shared A tile and
+    TMA-multicasts it into the stage of all CTAs of the cluster; stage release by a multicast tcgen05.commit from each of them."""
+    from parakeet_cpp_b200.engine import selftest_gemm
+    monkeypatch.setenv("PK_GEMM_CLUSTER", cl)
+    err, ref = selftest_gemm(M, N, K, EPI[epi], 0)
+    assert err / ref < 5e-5, (err, ref)
+
+
 @pytest.mark.parametrize("M,N,K,epi", [(1, 640, 512, "BIAS_F32"), (2, 2048, 512, "SILU_ACT"), (64, 512, 2048, "RESID"), (128, 1536, 512, "QKV"),
                                        (100, 1024, 512, "GLU"), (126, 1025, 512, "BIAS_F32"), (17, 256, 256, "RELU_ACT"), (128, 512, 2560, "BIAS_F32"),
                                        (77, 384, 128, "QKV"), (128, 64, 64, "BIAS_ACT")])
@@ -383,7 +395,7 @@ def test_transcribe_110m_more_clips_tokens_match_reference(pkg, m110, synth, mat
     t.engine.close()
 
 
-@pytest.mark.parametrize("switch", ["PK_FUSE_LN", "PK_ATTN_UMMA"])
+@pytest.mark.parametrize("switch", ["PK_FUSE_LN", "PK_ATTN_UMMA", "PK_GEMM_CLUSTER"])
 def test_alternative_kernels_engine_equals_default_and_reference(pkg, O, m110, synth, monkeypatch, switch):
     """Kernel variants behind an engine switch, each against the same engine without it -- per-layer activations of a ragged
     batch -- and against the compiled reference's tokens on the twenty full-size clips (CTC and TDT, bit-exact):
@@ -394,17 +406,18 @@ def test_alternative_kernels_engine_equals_default_and_reference(pkg, O, m110, s
     cfg = dataclasses.replace(m110.cfg, math=MATH["bf16x3"])
     feats = [O.preprocess_audio(synth.make_audio(n, 4200 + i)) for i, n in enumerate((160000, 112000, 48000, 81234))]
     outs = {}
-    for flag in ("0", "1"):
+    on = "2" if switch == "PK_GEMM_CLUSTER" else "1"
+    for flag in ("0", on):
         monkeypatch.setenv(switch, flag)
         e = pkg.Engine(cfg, m110.weights_path, 0)
-        outs[flag] = e.encode(feats, taps=True)
+        outs["1" if flag == on else "0"] = e.encode(feats, taps=True)
         e.close()
     for b in range(len(feats)):
         assert _rel(outs["1"][1][b], outs["0"][1][b]) < 1e-6                      # subsampling output (proj_ without / with the fused norm)
         for i in range(len(outs["0"][2][b])):
             assert _rel(outs["1"][2][b][i], outs["0"][2][b][i]) < 2e-5, (b, i)     # every block's output
         assert _rel(outs["1"][0][b], outs["0"][0][b]) < 2e-5
-    monkeypatch.setenv(switch, "1")
+    monkeypatch.setenv(switch, on)
     gx = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_110m_extra_v1.npz"))
     n_clips = int(gx["n_clips"][0])
     t = pkg.Transcriber(m110.weights_path, m110.vocab_path, cfg)
