@@ -528,10 +528,8 @@ pk_status pk_engine::run_conv1(int u0, int u1) {
     if (u1 <= u0) return PK_OK;
     const pk_config &c = cfg;
     Scope sc(this, CAT_SUBSAMPLE);
-    if (!(conv1_umma && cfg.math != PK_MATH_FP32 && sub1.hi &&
-          launch_subsample_conv1_dw1_umma(feats, d_frame_off + u0, d_s2_off + u0, u1 - u0, c.mel_bins, c.sub_channels, c1_w, c1_b, dw1_w, dw1_b, sub1, num_sms, stream)))
-        launch_subsample_conv1_dw1(feats, d_frame_off + u0, d_s2_off + u0, u1 - u0, maxT2, c.mel_bins, c.sub_channels, c1_w, c1_b,
-                                   dw1_w, dw1_b, sub1, stream);
+    launch_subsample_conv1_dw1(feats, d_frame_off + u0, d_s2_off + u0, u1 - u0, maxT2, c.mel_bins, c.sub_channels, c1_w, c1_b,
+                               dw1_w, dw1_b, sub1, stream);
     ++launches;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
@@ -933,7 +931,6 @@ pk_status pk_engine_create(const pk_config *cfg, const char *path, int device, p
     if (const char *ev = getenv("PK_GEMM_SKINNY")) e->skinny = atoi(ev) != 0;
     if (const char *ev = getenv("PK_FUSE_LN")) e->fuse_ln = atoi(ev) != 0;
     if (const char *ev = getenv("PK_GEMM_CLUSTER")) e->gemm_cluster = atoi(ev);
-    if (const char *ev = getenv("PK_CONV1_UMMA")) e->conv1_umma = atoi(ev) != 0;
     if (const char *ev = getenv("PK_LN_MCAST")) e->ln_mcast = atoi(ev) != 0;
     if (const char *ev = getenv("PK_FUSE_LN_MINK")) e->fuse_ln_min_k = atoi(ev);
     e->device = device;

@@ -249,7 +249,6 @@ struct pk_engine {
     // out_ln1: x receives LayerNorm_1 of the sum (block end) instead of the sum; planes = split of the last LayerNorm.
     pk_status gemm_ln(const Act &A, int lda, const GemmWeight &W, int M_, bool resid_in_x, float alpha, const float *ln1_w, const float *ln1_b,
                       bool out_ln1, const float *ln2_w, const float *ln2_b, ActBuf planes);
-    bool conv1_umma = false;                   // PK_CONV1_UMMA=1: conv1 + ReLU + dw1 with conv1 on tcgen05 (subsample_umma.cu)
     int gemm_cluster = 0;                      // PK_GEMM_CLUSTER=2|4: wide GEMMs (fc1, q/k/v, pw1) run as clusters of 2 | 4 CTAs along N with the A tile multicast
     bool ln_mcast = false;                     // PK_LN_MCAST=1: the A tile is fetched in quarters and TMA-multicast across the cluster (measured: no gain)
     int fuse_ln_min_k = 0;                     // PK_FUSE_LN_MINK: fuse only GEMMs with K >= this (short-K launches are epilogue-bound either way)

@@ -65,10 +65,6 @@ bool launch_resample(const float *in, const int64_t *in_off, const int64_t *out_
 void launch_subsample_conv1_dw1(const float *feats, const int32_t *frame_off, const int32_t *s2_off, int n_utt,
                                 int max_t2, int mel, int C, const float *w1, const float *b1, const float *wd,
                                 const float *bd, ActBuf out, cudaStream_t st);
-// tcgen05 variant of conv1 + ReLU + dw1 (subsample_umma.cu): conv1 as a K = 16 GEMM per dw1 output row; 256 channels, 3 f1n <= 128
-bool subsample_umma_supported(int mel, int C);
-bool launch_subsample_conv1_dw1_umma(const float *feats, const int32_t *frame_off, const int32_t *s2_off, int n_utt, int mel, int C, const float *w1,
-                                     const float *b1, const float *wd, const float *bd, ActBuf out, int num_sms, cudaStream_t st);
 void launch_subsample_dw(const float *in, const int32_t *in_rows, const int32_t *in_off, const int32_t *out_off,
                          int n_utt, int fin, int C, const float *wd, const float *bd, ActBuf out,
                          int total_out_rows, cudaStream_t st);
