@@ -1,6 +1,6 @@
 // attention_umma.cu -- K7 on the 5th-generation tensor cores: the relative-position attention of reference
 // src/encoder.cpp:111-178 (rel_shift :85-109) for head_dim 64 and utterances of up to 128 encoder frames (a 10 s clip
-// has 126), one CTA per (utterance, head):
+// has 126), persistent CTAs that each serve one head and a share of the utterances:
 //     S[i,j] = ((q_i + u) . k_j + (q_i + v) . PP[i - j]) / sqrt(hd),   ctx_i = softmax_j(S[i,:]) V
 // Every product is a tcgen05.mma (UMMA M = 128, kind::f16, fp32 accumulators in TMEM) on the bf16 hi/lo operand split
 // of the GEMMs (hi.hi + hi.lo + lo.hi):

@@ -5,8 +5,9 @@
 //     y1     = LayerNorm_1(v)                                         (nn::LayerNorm, axiom operations.cpp:1796-1809:
 //     y2     = LayerNorm_2(y1)            [optional]                   biased variance, eps inside the root)
 //     out_f32 = v  or  y1 ;   planes = bf16 hi/lo split of the last LayerNorm's result (A operand of the next GEMM)
-// It replaces the pair  gemm_tc_kernel<EPI_RESID_F32>  +  layernorm_kernel  (86 stand-alone LayerNorm launches per
-// 110m step, each re-reading the fp32 residual stream from L2 and writing the operand planes).
+// It replaces the pair  gemm_tc_kernel<EPI_RESID_F32>  +  layernorm_kernel  (69 stand-alone LayerNorm launches per
+// 110m step, each re-reading the fp32 residual stream from L2 and writing the operand planes).  MEASURED (DESIGN.md
+// section 4): equal to the pair in isolation, not faster inside the step graph -> opt-in (PK_FUSE_LN=1).
 //
 // A LayerNorm row spans all N = d_model columns, i.e. CLN = N / 128 accumulator tiles that live in the TMEM of CLN
 // different SMs.  The kernel therefore runs as thread-block CLUSTERS of CLN CTAs along N: cluster c walks the row
@@ -14,15 +15,17 @@
 // TMA -> smem -> tcgen05.mma -> TMEM pipeline and warp roles as gemm_tc_kernel (warp 0 producer, warp 1 MMA issuer,
 // warps 2..9 epilogue, double-buffered accumulator).  In the epilogue a warp holds a 32-row x 64-column slab of v in
 // registers (one row per lane), reduces it to the pair (sum, centred sum of squares about its OWN mean), and writes that
-// pair into the statistics table of EVERY CTA of the cluster through distributed shared memory (st.shared::cluster),
-// followed by one release-arrive per destination on that CTA's mbarrier.  After an acquire-wait on the local mbarrier a
-// lane combines the 2 CLN partials of its row in a fixed order with Chan's parallel formula
+// pair into the statistics table of EVERY CTA of the cluster through distributed shared memory with st.async: the write
+// completes 8 transaction bytes on the DESTINATION's mbarrier (armed once per round by one thread of that CTA), so no
+// fence and no arrive are needed.  After an acquire-wait on the local mbarrier a lane combines the 2 CLN partials of its
+// row in a fixed order with Chan's parallel formula
 //     mean = (sum_i s_i) / N,   M2 = sum_i M2_i + 64 sum_i (s_i / 64 - mean)^2,   var = M2 / N
 // -- one exchange per LayerNorm, numerically equivalent to the reference's two passes (no E[x^2] - mean^2
 // cancellation) and deterministic.  Two table slots / two mbarriers alternate, which is enough: a warp can only be one
-// exchange ahead of the slowest warp of its cluster (it needs everybody's arrival to pass the exchange in between).
-// Global traffic stays coalesced: residual loads and all stores go through a 2 KB per-warp staging tile (32 rows x 64
-// B, 16-byte chunks XOR-swizzled) that transposes between "lane = row" and "4 lanes = 64 contiguous bytes of a row".
+// exchange ahead of the slowest warp of its cluster (it needs everybody's data to pass the exchange in between).
+// Global traffic stays coalesced: the residual (fetched BEFORE the accumulator is waited for) and all stores go through a
+// 2 KB per-warp staging tile (16 rows x 128 B, SWIZZLE_128B pattern) that transposes between "lane = row" and "8 lanes =
+// one full 128-byte line"; bias / LayerNorm weights of the CTA's 128 columns sit in shared memory.
 #include <cuda.h>
 
 #include <cstdio>
