@@ -359,6 +359,7 @@ pk_status pk_engine::alloc_workspace() {
     d_row_off = dalloc<int32_t>(B + 1);
     d_t2_rows = dalloc<int32_t>(B + 1);
     logmel = dalloc<float>(B * (size_t)Fmax * c.mel_bins);
+    mel_part = dalloc<float>(mel_part_floats((int)B, c.mel_bins));
     feats = dalloc<float>(B * (size_t)Fmax * c.mel_bins);
     sub1 = act_alloc(rows2, C);
     sub2 = dalloc<float>(rows2 * C);
@@ -399,7 +400,7 @@ pk_status pk_engine::alloc_workspace() {
     skinny_ws = dalloc<float>(skinny_ws_floats);
     skinny_tickets = dalloc<unsigned int>(SKINNY_TICKETS);
     if (skinny_tickets) cudaMemsetAsync(skinny_tickets, 0, SKINNY_TICKETS * sizeof(unsigned int), stream);
-    if (!pl_sum || !tdt_keys || !hbuf || !x || !sub2 || !d_pcm || !t_conf || !skinny_ws || !skinny_tickets) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
+    if (!pl_sum || !tdt_keys || !hbuf || !x || !sub2 || !d_pcm || !t_conf || !skinny_ws || !skinny_tickets || !mel_part) return fail(PK_ERR_CUDA, "cudaMalloc failed (workspace)");
     if (cfg.math != PK_MATH_FP32 && (!sub1.hi || !sub3.hi || !sub4.hi || !ln.hi || !ffh.hi || !ctx.hi || !cv.hi))
         return fail(PK_ERR_CUDA, "workspace: cudaMalloc or cuTensorMapEncodeTiled failed for an activation operand");
     PK_CUDA(cudaMallocHost(&h_pcm, (B * (size_t)c.max_samples + 8) * sizeof(float)));
@@ -516,8 +517,9 @@ pk_status pk_engine::run_mel(int u0, int u1) {
     if (u1 < 0) u1 = n_utt;
     if (u1 <= u0) return PK_OK;
     Scope sc(this, CAT_MEL);
-    launch_mel(pcm_src ? pcm_src : d_pcm, d_pcm_off + u0, d_frame_off + u0, u1 - u0, maxF, cfg.mel_bins, mel_tb, logmel, feats, stream);
-    launches += 2;
+    launch_mel(pcm_src ? pcm_src : d_pcm, d_pcm_off + u0, d_frame_off + u0, u1 - u0, maxF, cfg.mel_bins, mel_tb, logmel, feats,
+               mel_part + mel_part_floats(u0, cfg.mel_bins), stream);
+    launches += 3;
     PK_CUDA(cudaGetLastError());
     return PK_OK;
 }

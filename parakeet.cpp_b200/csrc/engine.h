@@ -118,6 +118,7 @@ struct pk_engine {
     int64_t *d_pcm_off = nullptr;
     int32_t *d_frame_off = nullptr, *d_s2_off = nullptr, *d_row_off = nullptr, *d_t2_rows = nullptr;
     float *logmel = nullptr, *feats = nullptr;
+    float *mel_part = nullptr;                 // per-chunk statistics of the mel normalisation (mel.cu K2), one slice per utterance
     Act sub1, sub3, sub4, ln, ffh, ctx, cv;
     float *sub2 = nullptr, *x = nullptr, *qkv = nullptr, *glu = nullptr, *logits = nullptr, *EP = nullptr;
     bf16 *qkvp_hi = nullptr, *qkvp_lo = nullptr;   // [Mx, 2 d] planes [k | v] for the tensor-core attention (q stays fp32 in `qkv`)

@@ -18,8 +18,10 @@ struct MelTables {
     int fb_nnz;
 };
 size_t mel_smem_bytes(const MelTables &tb);
+// part: scratch of mel_part_floats(n_utt, n_mels) floats (per-chunk statistics of the normalisation), one slice per utterance
+size_t mel_part_floats(int n_utt, int n_mels);
 void launch_mel(const float *pcm, const int64_t *pcm_off, const int32_t *frame_off, int n_utt, int max_frames,
-                int n_mels, const MelTables &tb, float *logmel, float *feats, cudaStream_t st);
+                int n_mels, const MelTables &tb, float *logmel, float *feats, float *part, cudaStream_t st);
 
 // streaming variant (StreamingAudioPreprocessor::process_chunk, src/audio.cpp:195-259): `sig` holds, per stream, the
 // already pre-emphasised samples [overlap | chunk]; frame f = window . sig[f*160 .. f*160+512) (center = False, no

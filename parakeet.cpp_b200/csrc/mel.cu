@@ -186,45 +186,91 @@ mel_logpower_kernel(const float *__restrict__ pcm, const int64_t *__restrict__ p
     }
 }
 
-// One block per utterance; threads = (groups x n_mels).  Two-pass mean / unbiased variance.
-__global__ void mel_normalize_kernel(const float *__restrict__ logmel,
-                                     const int32_t *__restrict__ frame_off, int n_mels,
-                                     float *__restrict__ feats) {
+// K2: per-utterance, per-bin normalisation (audio.cpp:138-150: mean over the frames, UNBIASED variance, eps outside the root).
+// Round 1 ran it as one block per utterance (64 blocks on 148 SMs, three serial sweeps over the frames: 41 us).  Now every
+// utterance is cut into MEL_CH frame chunks: mel_stats_kernel reduces a chunk to (mean_c, M2_c = sum (x - mean_c)^2) per bin with
+// two sweeps over its own frames, mel_apply_kernel combines the MEL_CH partials of an utterance in a fixed order with Chan's
+// formula (mean = sum n_c mean_c / F, M2 = sum M2_c + n_c (mean_c - mean)^2: the accuracy of the two-pass form, deterministic,
+// independent of the batch) and normalises its chunk.  threads = (groups x n_mels).
+constexpr int MEL_CH = 16;
+
+__device__ __forceinline__ void mel_chunk(int c, int F, int &f0, int &f1) {
+    f0 = (int)((long long)c * F / MEL_CH);
+    f1 = (int)((long long)(c + 1) * F / MEL_CH);
+}
+
+__global__ void mel_stats_kernel(const float *__restrict__ logmel, const int32_t *__restrict__ frame_off, int n_mels,
+                                 float *__restrict__ part /* [utterance][MEL_CH][2][n_mels] */) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ float red[];  // [groups][n_mels]
-    const int b = blockIdx.x;
+    const int b = blockIdx.y, c = blockIdx.x;
     const int groups = blockDim.x / n_mels;
     const int m = threadIdx.x % n_mels, g = threadIdx.x / n_mels;
     const int F0 = frame_off[b], F = frame_off[b + 1] - F0;
+    int f0, f1;
+    mel_chunk(c, F, f0, f1);
+    const int nc = f1 - f0;
     const bool active = g < groups;
     const float *src = logmel + (size_t)F0 * n_mels;
-    float *dst = feats + (size_t)F0 * n_mels;
 
     float s = 0.f;
     if (active)
-        for (int f = g; f < F; f += groups) s += src[(size_t)f * n_mels + m];
+        for (int f = f0 + g; f < f1; f += groups) s += src[(size_t)f * n_mels + m];
     if (active) red[g * n_mels + m] = s;
     __syncthreads();
     float mean = 0.f;
     for (int i = 0; i < groups; ++i) mean += red[i * n_mels + m];
-    mean /= (float)F;
+    mean = nc > 0 ? mean / (float)nc : 0.f;
     __syncthreads();
     float q = 0.f;
     if (active)
-        for (int f = g; f < F; f += groups) {
+        for (int f = f0 + g; f < f1; f += groups) {
             float d = src[(size_t)f * n_mels + m] - mean;
             q = fmaf(d, d, q);
         }
     if (active) red[g * n_mels + m] = q;
     __syncthreads();
-    float var = 0.f;
-    for (int i = 0; i < groups; ++i) var += red[i * n_mels + m];
-    var /= (float)(F - 1);                       // unbiased, audio.cpp:146-147
+    if (g == 0) {
+        float m2 = 0.f;
+        for (int i = 0; i < groups; ++i) m2 += red[i * n_mels + m];
+        float *p = part + ((size_t)(b * MEL_CH + c) * 2) * n_mels;
+        p[m] = mean;
+        p[n_mels + m] = m2;
+    }
+}
+
+__global__ void mel_apply_kernel(const float *__restrict__ logmel, const int32_t *__restrict__ frame_off, int n_mels,
+                                 const float *__restrict__ part, float *__restrict__ feats) {
+    pdl_wait();
+    pdl_trigger();
+    const int b = blockIdx.y, c = blockIdx.x;
+    const int groups = blockDim.x / n_mels;
+    const int m = threadIdx.x % n_mels, g = threadIdx.x / n_mels;
+    const int F0 = frame_off[b], F = frame_off[b + 1] - F0;
+    if (g >= groups) return;
+    const float *pb = part + ((size_t)b * MEL_CH * 2) * n_mels;
+    float tot = 0.f;
+    for (int k = 0; k < MEL_CH; ++k) {
+        int a0, a1;
+        mel_chunk(k, F, a0, a1);
+        tot = fmaf((float)(a1 - a0), pb[(size_t)(2 * k) * n_mels + m], tot);
+    }
+    const float mean = tot / (float)F;
+    float m2 = 0.f;
+    for (int k = 0; k < MEL_CH; ++k) {
+        int a0, a1;
+        mel_chunk(k, F, a0, a1);
+        const float d = pb[(size_t)(2 * k) * n_mels + m] - mean;
+        m2 += pb[(size_t)(2 * k + 1) * n_mels + m] + (float)(a1 - a0) * d * d;
+    }
+    const float var = m2 / (float)(F - 1);          // unbiased, audio.cpp:146-147
     const float inv = 1.0f / (sqrtf(var) + 1e-5f);  // eps outside the sqrt, :148
-    if (active)
-        for (int f = g; f < F; f += groups)
-            dst[(size_t)f * n_mels + m] = (src[(size_t)f * n_mels + m] - mean) * inv;
+    int f0, f1;
+    mel_chunk(c, F, f0, f1);
+    const float *src = logmel + (size_t)F0 * n_mels;
+    float *dst = feats + (size_t)F0 * n_mels;
+    for (int f = f0 + g; f < f1; f += groups) dst[(size_t)f * n_mels + m] = (src[(size_t)f * n_mels + m] - mean) * inv;
 }
 
 }  // namespace
@@ -233,15 +279,17 @@ size_t mel_smem_bytes(const MelTables &tb) {
     return sizeof(float) * (WIN + 512 + 514 + ((tb.fb_nnz + 3) & ~3) + WARPS * (512 + 512 + 260));
 }
 
+size_t mel_part_floats(int n_utt, int n_mels) { return (size_t)n_utt * MEL_CH * 2 * n_mels; }
+
 void launch_mel(const float *pcm, const int64_t *pcm_off, const int32_t *frame_off, int n_utt,
-                int max_frames, int n_mels, const MelTables &tb, float *logmel, float *feats,
+                int max_frames, int n_mels, const MelTables &tb, float *logmel, float *feats, float *part,
                 cudaStream_t st) {
     dim3 grid((max_frames + WARPS * 4 - 1) / (WARPS * 4), n_utt);
     launch_pdl(mel_logpower_kernel<false>, dim3(grid), dim3(WARPS * 32), mel_smem_bytes(tb), st, pcm, pcm_off, frame_off, nullptr, n_mels, tb,
                                                                              logmel);
     int groups = 640 / n_mels;  // 8 for 80 bins, 5 for 128
-    launch_pdl(mel_normalize_kernel, dim3(n_utt), dim3(groups * n_mels), sizeof(float) * groups * n_mels, st, 
-        logmel, frame_off, n_mels, feats);
+    launch_pdl(mel_stats_kernel, dim3(MEL_CH, n_utt), dim3(groups * n_mels), sizeof(float) * groups * n_mels, st, logmel, frame_off, n_mels, part);
+    launch_pdl(mel_apply_kernel, dim3(MEL_CH, n_utt), dim3(groups * n_mels), 0, st, logmel, frame_off, n_mels, part, feats);
 }
 
 void launch_mel_stream(const float *sig, const int64_t *sig_off, const int32_t *n_frames, const int32_t *out_row, int n_streams,
